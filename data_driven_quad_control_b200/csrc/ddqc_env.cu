@@ -1,0 +1,536 @@
+// ddqc_env.cu -- fused vectorized drone-environment step for sm_100a.
+//
+// One thread owns one environment: it loads the env's struct-of-arrays state with fully
+// coalesced 32-bit loads (one 128 B line per warp per component), keeps it in registers
+// across the action decode, the CTBR rate controller, the `decimation` rigid-body substeps,
+// the termination / auto-reset logic, the rewards and the observation, and streams the new
+// state and the outputs back.  The kernel is HBM-bound (357 B / env-step of algorithmic
+// traffic for CTBR_FIXED_YAW, ~1 kFLOP), so nothing here goes near the tensor cores.
+//
+// Arithmetic contract: this translation unit is compiled with -fmad=false and mirrors,
+// operation for operation, the fp32 restatement in oracle/env_oracle.py +
+// oracle/drone_physics.py, so positions, rewards and reset masks are bit-identical to
+// the oracle (libm calls -- atan2/asin/exp/log/cos -- are within 2 ulp).
+//
+// Reference behaviour reproduced (src/data_driven_quad_control/envs/hover_env.py:376-547,
+// 556-595 and SURVEY.md Appendix A1-A24), including the two batch-global quirks:
+//   A17  any reset in step t zeroes every env's rate-PID state before step t+1
+//        -> `ctl->pid_reset_pending`, written by the last CTA of step t, read in t+1;
+//   A16  rel_pos / last_rel_pos are refreshed for all envs only on steps with >=1 reset
+//        -> envs whose target was resampled without a reset append the "fresh" variant of
+//           their reward / sums / obs to a fix-up list that the last CTA applies iff
+//           n_reset > 0.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ddqc_device.cuh"
+
+using namespace ddqc;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---- the fused step kernel -------------------------------------------------------------
+template <int ACT>
+__global__ void __launch_bounds__(kThreads)
+env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O, DdqcEnvCtl* __restrict__ ctl,
+                const float* __restrict__ actions, const float* __restrict__ meas_override, const int n) {
+  constexpr int A = (ACT == DDQC_ACT_CTBR_FIXED_YAW) ? 3 : 4;
+  constexpr int NOBS = 13 + A;
+  constexpr bool USES_CTBR = (ACT != DDQC_ACT_ROTOR_RPMS);
+
+  __shared__ float s_sums[8];
+  __shared__ unsigned int s_cnt[2];
+  __shared__ bool s_last;
+  if (threadIdx.x < 8) s_sums[threadIdx.x] = 0.0f;
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0u;
+  __syncthreads();
+
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  const bool live = i < n;
+  const uint64_t ev = ctl->rng_event;
+  const bool pid_pending = ctl->pid_reset_pending != 0u;
+
+  float rew_total = 0.0f;
+  bool did_reset = false, did_timeout = false;
+
+  if (live) {
+    // ------------------------------------------------------------------ load state
+    V3 p{S.pos[i], S.pos[n + i], S.pos[2 * n + i]};
+    Q4 q{S.quat[i], S.quat[n + i], S.quat[2 * n + i], S.quat[3 * n + i]};
+    V3 v{S.vel[i], S.vel[n + i], S.vel[2 * n + i]};
+    V3 w{S.ang[i], S.ang[n + i], S.ang[2 * n + i]};
+    V3 cmd{S.commands[i], S.commands[n + i], S.commands[2 * n + i]};
+    float last_act[A], act[A];
+#pragma unroll
+    for (int j = 0; j < A; ++j) {
+      last_act[j] = S.last_actions[j * n + i];
+      act[j] = clipf(actions[(size_t)i * A + j], -P.clip_actions, P.clip_actions);  // A1
+    }
+    int ep_len = S.episode_length[i];
+    int hover = S.hover_counter[i];
+    float sums[DDQC_NUM_REWARDS];
+#pragma unroll
+    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) sums[k] = S.episode_sums[k * n + i];
+
+    // ------------------------------------------------------------------ action -> rpm
+    float rpm[4];
+    {
+      float y[A];
+#pragma unroll
+      for (int j = 0; j < A; ++j) {
+        float ex = (P.flags & DDQC_F_ACTION_LATENCY) ? last_act[j] : act[j];  // A2
+        y[j] = P.act_lo[j] + ((ex - (-1.0f)) * P.act_span[j]) / 2.0f;         // A3
+      }
+      if (USES_CTBR) {
+        float integ[3] = {0.0f, 0.0f, 0.0f}, prev[3] = {0.0f, 0.0f, 0.0f};
+        if (!pid_pending) {  // A17: a reset anywhere in the previous launch zeroed every PID
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            integ[j] = S.pid_integral[j * n + i];
+            prev[j] = S.pid_prev_error[j * n + i];
+          }
+        }
+        V3 meas;
+        if (meas_override) {
+          meas = V3{meas_override[i], meas_override[n + i], meas_override[2 * n + i]};
+        } else {  // A5: body rates as refreshed at the end of the previous step
+          Q4 qc{q.w, -q.x, -q.y, -q.z};
+          meas = rotate_by_quat(rotate_by_quat(w, q), qc);
+        }
+        float sp[3];
+        sp[0] = y[1];
+        sp[1] = y[2];
+        sp[2] = (ACT == DDQC_ACT_CTBR) ? y[A - 1] : 0.0f;  // A4
+        float ms[3] = {meas.x, meas.y, meas.z};
+        float c[4];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float err = sp[j] - ms[j];
+          integ[j] = integ[j] + err * P.step_dt;  // A6
+          float deriv = (err - prev[j]) / P.step_dt;
+          prev[j] = err;
+          c[j] = (P.pid_kp[j] * err + P.pid_ki[j] * integ[j]) + P.pid_kd[j] * deriv;
+          S.pid_integral[j * n + i] = integ[j];
+          S.pid_prev_error[j * n + i] = prev[j];
+        }
+        c[3] = y[0];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float f = ((P.mixer[4 * r + 0] * c[0] + P.mixer[4 * r + 1] * c[1]) + P.mixer[4 * r + 2] * c[2]) +
+                    P.mixer[4 * r + 3] * c[3];
+          f = f < 0.0f ? 0.0f : f;  // A7
+          rpm[r] = sqrtf(f) * P.inv_sqrt_kf;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rpm[r] = y[r < A ? r : 0];
+      }
+    }
+    if (P.actuator_noise_std > 0.0f) {
+      float z[4];
+      philox_normals<4>((uint32_t)i, ev, DDQC_STREAM_ACT_NOISE, P.seed, z);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) rpm[r] = fminf(fmaxf(rpm[r] + z[r] * P.actuator_noise_std, P.min_rpm), P.max_rpm);
+    }
+    if (O.rpm) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) O.rpm[r * n + i] = rpm[r];
+    }
+
+    // ------------------------------------------------------------------ physics (A8)
+    const V3 last_pos = p;
+    for (int sidx = 0; sidx < P.decimation; ++sidx) substep(P, p, q, v, w, rpm);
+
+    // ------------------------------------------------------------------ buffers (A9-A12)
+    ep_len += 1;
+    V3 rel{cmd.x - p.x, cmd.y - p.y, cmd.z - p.z};
+    V3 last_rel{cmd.x - last_pos.x, cmd.y - last_pos.y, cmd.z - last_pos.z};
+    V3 euler{0.0f, 0.0f, 0.0f};
+    if (P.flags & DDQC_F_NEED_EULER) {
+      Q4 r = quat_mul(q, Q4{P.inv_init_quat[0], P.inv_init_quat[1], P.inv_init_quat[2], P.inv_init_quat[3]});
+      const float rad2deg = 57.29577951308232f;
+      euler.x = atan2f((r.w * r.x + r.y * r.z) * 2.0f, 1.0f - (r.x * r.x + r.y * r.y) * 2.0f) * rad2deg;
+      euler.y = asinf(clipf((r.w * r.y - r.z * r.x) * 2.0f, -1.0f, 1.0f)) * rad2deg;
+      euler.z = atan2f((r.w * r.z + r.x * r.y) * 2.0f, 1.0f - (r.y * r.y + r.z * r.z) * 2.0f) * rad2deg;
+    }
+    Q4 qc{q.w, -q.x, -q.y, -q.z};
+    V3 lin_b = rotate_by_quat(v, qc);
+    V3 ang_b = rotate_by_quat(rotate_by_quat(w, q), qc);
+
+    // ------------------------------------------------------------------ hover / resample (A13-A15)
+    bool hover_resampled = false;
+    V3 cmd_new = cmd;
+    if (P.flags & DDQC_F_AUTO_TARGET) {
+      bool at_target = sqrtf(sumsq3(rel)) < P.at_target_threshold;
+      bool fire;
+      if (P.min_hover_steps > 0) {
+        hover = at_target ? hover + 1 : 0;
+        fire = hover >= P.min_hover_steps;
+      } else {
+        fire = at_target;
+      }
+      if (fire) {
+        cmd_new = resample_command(P, (uint32_t)i, ev, DDQC_STREAM_HOVER);
+        hover = 0;
+        hover_resampled = true;
+      }
+    }
+
+    // ------------------------------------------------------------------ termination (A8, A9)
+    bool crash = (fabsf(euler.y) > P.term_pitch) | (fabsf(euler.x) > P.term_roll) | (fabsf(rel.x) > P.term_x) |
+                 (fabsf(rel.y) > P.term_y) | (fabsf(rel.z) > P.term_z) | (p.z < P.term_ground) |
+                 (fabsf(ang_b.x) > P.term_ang_vel) | (fabsf(ang_b.y) > P.term_ang_vel) |
+                 (fabsf(ang_b.z) > P.term_ang_vel) | (fabsf(lin_b.x) > P.term_lin_vel) |
+                 (fabsf(lin_b.y) > P.term_lin_vel) | (fabsf(lin_b.z) > P.term_lin_vel);
+    did_timeout = ep_len > P.max_episode_length;
+    did_reset = did_timeout | crash;
+
+    float last_act_obs[A];
+#pragma unroll
+    for (int j = 0; j < A; ++j) last_act_obs[j] = last_act[j];
+    Q4 q_obs = q;
+
+    if (did_reset) {  // reset_idx (hover_env.py:556-595)
+      V3 ip{P.init_pos[0], P.init_pos[1], P.init_pos[2]};
+      p = ip;
+      rel = V3{cmd_new.x - ip.x, cmd_new.y - ip.y, cmd_new.z - ip.z};  // A16, old (pre-reset-resample) command
+      last_rel = rel;
+      q = Q4{P.init_quat[0], P.init_quat[1], P.init_quat[2], P.init_quat[3]};
+      q_obs = q;
+      v = V3{0.0f, 0.0f, 0.0f};
+      w = V3{0.0f, 0.0f, 0.0f};
+      lin_b = V3{0.0f, 0.0f, 0.0f};
+      ang_b = V3{0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int j = 0; j < A; ++j) last_act_obs[j] = 0.0f;
+      ep_len = 0;
+      hover = 0;
+#pragma unroll
+      for (int k = 0; k < DDQC_NUM_REWARDS; ++k) {  // A18
+        atomicAdd(&s_sums[k], sums[k]);
+        sums[k] = 0.0f;
+      }
+      cmd_new = resample_command(P, (uint32_t)i, ev, DDQC_STREAM_RESET);
+      hover_resampled = false;
+    }
+
+    // ------------------------------------------------------------------ rewards (A19)
+    float r_target = sumsq3(last_rel) - sumsq3(rel);
+    float r_close = (P.at_target_threshold_sq - sumsq3(rel)) / P.at_target_threshold_sq;
+    r_close = r_close < 0.0f ? 0.0f : r_close;
+    float r_hover = (float)hover;
+    float r_smooth;
+    {
+      float d0 = act[0] - last_act_obs[0];
+      r_smooth = d0 * d0;
+#pragma unroll
+      for (int j = 1; j < A; ++j) {
+        float d = act[j] - last_act_obs[j];
+        r_smooth = r_smooth + d * d;
+      }
+    }
+    float r_yaw = 0.0f;
+    if (P.flags & DDQC_F_NEED_EULER) {
+      float yaw = euler.z;
+      yaw = (yaw > 180.0f ? yaw - 360.0f : yaw) / 180.0f * 3.14159f;
+      r_yaw = expf(P.yaw_lambda * fabsf(yaw));
+    }
+    float r_ang = sqrtf(sumsq3(V3{ang_b.x / 3.14159f, ang_b.y / 3.14159f, ang_b.z / 3.14159f}));
+    float r_crash = crash ? 1.0f : 0.0f;
+
+    float rk[DDQC_NUM_REWARDS] = {r_target * P.rew_scale[0], r_close * P.rew_scale[1], r_hover * P.rew_scale[2],
+                                  r_smooth * P.rew_scale[3], r_yaw * P.rew_scale[4],  r_ang * P.rew_scale[5],
+                                  r_crash * P.rew_scale[6]};
+    const float sum0_pre = sums[0], sum1_pre = sums[1];
+    float rew = 0.0f;
+#pragma unroll
+    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) {
+      rew = rew + rk[k];
+      sums[k] = sums[k] + rk[k];
+    }
+    rew_total = rew;
+
+    // ------------------------------------------------------------------ observations (A20)
+    float obs[NOBS];
+    obs[0] = clipf(rel.x * P.obs_scale_pos, -1.0f, 1.0f);
+    obs[1] = clipf(rel.y * P.obs_scale_pos, -1.0f, 1.0f);
+    obs[2] = clipf(rel.z * P.obs_scale_pos, -1.0f, 1.0f);
+    obs[3] = q_obs.w;
+    obs[4] = q_obs.x;
+    obs[5] = q_obs.y;
+    obs[6] = q_obs.z;
+    obs[7] = clipf(lin_b.x * P.obs_scale_lin, -1.0f, 1.0f);
+    obs[8] = clipf(lin_b.y * P.obs_scale_lin, -1.0f, 1.0f);
+    obs[9] = clipf(lin_b.z * P.obs_scale_lin, -1.0f, 1.0f);
+    obs[10] = clipf(ang_b.x * P.obs_scale_ang, -1.0f, 1.0f);
+    obs[11] = clipf(ang_b.y * P.obs_scale_ang, -1.0f, 1.0f);
+    obs[12] = clipf(ang_b.z * P.obs_scale_ang, -1.0f, 1.0f);
+#pragma unroll
+    for (int j = 0; j < A; ++j) obs[13 + j] = last_act_obs[j];
+    if (P.obs_noise_std > 0.0f) {
+      float z[13];
+      philox_normals<13>((uint32_t)i, ev, DDQC_STREAM_OBS_NOISE, P.seed, z);
+      const float s = P.obs_noise_std;
+      obs[0] = obs[0] + z[0] * s;
+      obs[1] = obs[1] + z[1] * s;
+      obs[2] = obs[2] + z[2] * s;
+      obs[7] = obs[7] + z[3] * s;
+      obs[8] = obs[8] + z[4] * s;
+      obs[9] = obs[9] + z[5] * s;
+      obs[10] = obs[10] + z[6] * s;
+      obs[11] = obs[11] + z[7] * s;
+      obs[12] = obs[12] + z[8] * s;
+      float a = obs[3] + z[9] * s, b = obs[4] + z[10] * s, c = obs[5] + z[11] * s, d = obs[6] + z[12] * s;
+      float nrm = sqrtf(((a * a + b * b) + c * c) + d * d);
+      obs[3] = a / nrm;
+      obs[4] = b / nrm;
+      obs[5] = c / nrm;
+      obs[6] = d / nrm;
+    }
+
+    // A15/A16 fix-up record: the values this env would have if some other env reset this step
+    if (hover_resampled) {
+      V3 rel_f{cmd_new.x - p.x, cmd_new.y - p.y, cmd_new.z - p.z};
+      V3 lrel_f{cmd_new.x - last_pos.x, cmd_new.y - last_pos.y, cmd_new.z - last_pos.z};
+      float rt = (sumsq3(lrel_f) - sumsq3(rel_f)) * P.rew_scale[0];
+      float rc = (P.at_target_threshold_sq - sumsq3(rel_f)) / P.at_target_threshold_sq;
+      rc = (rc < 0.0f ? 0.0f : rc) * P.rew_scale[1];
+      float rw = 0.0f + rt;
+      rw = rw + rc;
+#pragma unroll
+      for (int k = 2; k < DDQC_NUM_REWARDS; ++k) rw = rw + rk[k];
+      unsigned int slot = atomicAdd(&ctl->fixup_count, 1u);
+      O.fixup_idx[slot] = i;
+      float* fv = O.fixup_val + (size_t)slot * 8;
+      fv[0] = rw;
+      fv[1] = sum0_pre + rt;
+      fv[2] = sum1_pre + rc;
+      fv[3] = clipf(rel_f.x * P.obs_scale_pos, -1.0f, 1.0f);
+      fv[4] = clipf(rel_f.y * P.obs_scale_pos, -1.0f, 1.0f);
+      fv[5] = clipf(rel_f.z * P.obs_scale_pos, -1.0f, 1.0f);
+      fv[6] = 0.0f;
+      fv[7] = 0.0f;
+    }
+
+    // ------------------------------------------------------------------ store
+    S.pos[i] = p.x;
+    S.pos[n + i] = p.y;
+    S.pos[2 * n + i] = p.z;
+    S.quat[i] = q.w;
+    S.quat[n + i] = q.x;
+    S.quat[2 * n + i] = q.y;
+    S.quat[3 * n + i] = q.z;
+    S.vel[i] = v.x;
+    S.vel[n + i] = v.y;
+    S.vel[2 * n + i] = v.z;
+    S.ang[i] = w.x;
+    S.ang[n + i] = w.y;
+    S.ang[2 * n + i] = w.z;
+    S.commands[i] = cmd_new.x;
+    S.commands[n + i] = cmd_new.y;
+    S.commands[2 * n + i] = cmd_new.z;
+#pragma unroll
+    for (int j = 0; j < A; ++j) S.last_actions[j * n + i] = act[j];  // hover_env.py:544, all envs
+    S.episode_length[i] = ep_len;
+    S.hover_counter[i] = hover;
+#pragma unroll
+    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) S.episode_sums[k * n + i] = sums[k];
+
+    if (NOBS == 16) {
+      float4* o4 = reinterpret_cast<float4*>(O.obs + (size_t)i * 16);
+      o4[0] = make_float4(obs[0], obs[1], obs[2], obs[3]);
+      o4[1] = make_float4(obs[4], obs[5], obs[6], obs[7]);
+      o4[2] = make_float4(obs[8], obs[9], obs[10], obs[11]);
+      o4[3] = make_float4(obs[12], obs[13], obs[14], obs[15]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NOBS; ++j) O.obs[(size_t)i * NOBS + j] = obs[j];
+    }
+    O.rew[i] = rew;
+    O.reset[i] = did_reset ? 1 : 0;
+    O.time_outs[i] = did_timeout ? 1.0f : 0.0f;
+
+    if (O.base_lin_vel) {
+      O.base_lin_vel[i] = lin_b.x;
+      O.base_lin_vel[n + i] = lin_b.y;
+      O.base_lin_vel[2 * n + i] = lin_b.z;
+    }
+    if (O.base_ang_vel) {
+      O.base_ang_vel[i] = ang_b.x;
+      O.base_ang_vel[n + i] = ang_b.y;
+      O.base_ang_vel[2 * n + i] = ang_b.z;
+    }
+    if (O.rel_pos) {
+      O.rel_pos[i] = rel.x;
+      O.rel_pos[n + i] = rel.y;
+      O.rel_pos[2 * n + i] = rel.z;
+    }
+    if (O.last_rel_pos) {
+      O.last_rel_pos[i] = last_rel.x;
+      O.last_rel_pos[n + i] = last_rel.y;
+      O.last_rel_pos[2 * n + i] = last_rel.z;
+    }
+    if (O.base_euler) {
+      O.base_euler[i] = euler.x;
+      O.base_euler[n + i] = euler.y;
+      O.base_euler[2 * n + i] = euler.z;
+    }
+    if (O.crash) O.crash[i] = crash ? 1 : 0;
+    if (O.last_base_pos) {
+      O.last_base_pos[i] = did_reset ? P.init_pos[0] : last_pos.x;
+      O.last_base_pos[n + i] = did_reset ? P.init_pos[1] : last_pos.y;
+      O.last_base_pos[2 * n + i] = did_reset ? P.init_pos[2] : last_pos.z;
+    }
+  }
+
+  // -------------------------------------------------------------------- statistics
+  // warp-level: reset / timeout counts by ballot, reward total by shuffle tree
+  {
+    unsigned int rmask = __ballot_sync(0xffffffffu, did_reset);
+    unsigned int tmask = __ballot_sync(0xffffffffu, did_timeout);
+    float r = rew_total;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if ((threadIdx.x & 31) == 0) {
+      if (rmask) atomicAdd(&s_cnt[0], (unsigned int)__popc(rmask));
+      if (tmask) atomicAdd(&s_cnt[1], (unsigned int)__popc(tmask));
+      atomicAdd(&s_sums[7], r);
+    }
+  }
+  __syncthreads();
+  const int copy = blockIdx.x % DDQC_STAT_COPIES;
+  if (threadIdx.x < 8) {
+    float val = s_sums[threadIdx.x];
+    if (val != 0.0f) atomicAdd(&ctl->acc_sums[copy][threadIdx.x], val);
+  } else if (threadIdx.x == 8) {
+    if (s_cnt[0]) atomicAdd(&ctl->acc_reset[copy], s_cnt[0]);
+  } else if (threadIdx.x == 9) {
+    if (s_cnt[1]) atomicAdd(&ctl->acc_timeout[copy], s_cnt[1]);
+  }
+
+  // -------------------------------------------------------------------- last-CTA finalisation
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int ticket = atomicAdd(&ctl->blocks_done, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  __shared__ float f_sums[8];
+  __shared__ unsigned int f_cnt[2];
+  if (threadIdx.x < 8) {
+    float acc = 0.0f;
+    for (int c = 0; c < DDQC_STAT_COPIES; ++c) {
+      acc += __ldcg(&ctl->acc_sums[c][threadIdx.x]);
+      ctl->acc_sums[c][threadIdx.x] = 0.0f;
+    }
+    f_sums[threadIdx.x] = acc;
+  } else if (threadIdx.x < 10) {
+    unsigned int* src = (threadIdx.x == 8) ? ctl->acc_reset : ctl->acc_timeout;
+    unsigned int acc = 0;
+    for (int c = 0; c < DDQC_STAT_COPIES; ++c) {
+      acc += __ldcg(&src[c]);
+      src[c] = 0u;
+    }
+    f_cnt[threadIdx.x - 8] = acc;
+  }
+  __syncthreads();
+  const unsigned int n_reset = f_cnt[0];
+  const unsigned int n_fix = __ldcg(&ctl->fixup_count);
+
+  // A16: some env reset this step -> envs that only resampled their target see fresh rel_pos
+  if (n_reset > 0) {
+    for (unsigned int s = threadIdx.x; s < n_fix; s += kThreads) {
+      int e = __ldcg(&O.fixup_idx[s]);
+      const float* fv = O.fixup_val + (size_t)s * 8;
+      O.rew[e] = __ldcg(&fv[0]);
+      S.episode_sums[0 * n + e] = __ldcg(&fv[1]);
+      S.episode_sums[1 * n + e] = __ldcg(&fv[2]);
+      float o0 = __ldcg(&fv[3]), o1 = __ldcg(&fv[4]), o2 = __ldcg(&fv[5]);
+      if (P.obs_noise_std > 0.0f) {  // same noise words as the main pass
+        float z[13];
+        philox_normals<13>((uint32_t)e, ev, DDQC_STREAM_OBS_NOISE, P.seed, z);
+        o0 = o0 + z[0] * P.obs_noise_std;
+        o1 = o1 + z[1] * P.obs_noise_std;
+        o2 = o2 + z[2] * P.obs_noise_std;
+      }
+      O.obs[(size_t)e * NOBS + 0] = o0;
+      O.obs[(size_t)e * NOBS + 1] = o1;
+      O.obs[(size_t)e * NOBS + 2] = o2;
+      if (O.rel_pos && O.last_rel_pos && O.last_base_pos) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float cm = __ldcg(&S.commands[c * n + e]);
+          O.rel_pos[c * n + e] = cm - __ldcg(&S.pos[c * n + e]);
+          O.last_rel_pos[c * n + e] = cm - __ldcg(&O.last_base_pos[c * n + e]);
+        }
+      }
+    }
+  }
+
+  if (threadIdx.x == 0) {
+    const uint32_t row = (ctl->ep_row + 1) % DDQC_EP_RING;
+    const uint32_t prev_row = ctl->ep_row;
+    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) {
+      float val = ctl->ep_ring[prev_row][k];
+      if (n_reset > 0) val = (f_sums[k] / (float)n_reset) / P.episode_length_s;
+      ctl->ep_ring[row][k] = val;
+      if (n_reset > 0) ctl->total_episode_sums[k] += (double)f_sums[k];
+    }
+    ctl->ep_ring[row][7] = (float)n_reset;
+    ctl->ep_row = row;
+    ctl->n_reset_last = n_reset;
+    ctl->pid_reset_pending = USES_CTBR ? (n_reset > 0 ? 1u : 0u) : 0u;
+    ctl->total_resets += n_reset;
+    ctl->total_timeouts += f_cnt[1];
+    ctl->total_env_steps += (uint64_t)n;
+    ctl->total_reward += (double)f_sums[7];
+    ctl->step_count += 1;
+    ctl->rng_event = ev + 1;
+    ctl->fixup_count = 0u;
+    ctl->blocks_done = 0u;
+  }
+}
+
+}  // namespace
+
+static int check_env_args(const DdqcEnvParams* P, const DdqcEnvState* S, int64_t n) {
+  if (!P || !S) return DDQC_E_NULL;
+  if (n <= 0 || n > 0x7fffffff / 8) return DDQC_E_SHAPE;
+  if (P->action_type < 0 || P->action_type > 2) return DDQC_E_CONFIG;
+  if (P->decimation < 1) return DDQC_E_CONFIG;
+  if (!S->pos || !S->quat || !S->vel || !S->ang || !S->commands || !S->last_actions || !S->episode_sums ||
+      !S->episode_length || !S->hover_counter)
+    return DDQC_E_NULL;
+  if (P->action_type != DDQC_ACT_ROTOR_RPMS && (!S->pid_integral || !S->pid_prev_error)) return DDQC_E_NULL;
+  return 0;
+}
+
+extern "C" int ddqc_env_step(const DdqcEnvParams* P, const DdqcEnvState* S, const DdqcEnvOut* O, DdqcEnvCtl* ctl,
+                             const float* actions, const float* meas_override, int64_t n_env, void* stream) {
+  int rc = check_env_args(P, S, n_env);
+  if (rc) return rc;
+  if (!O || !ctl || !actions || !O->obs || !O->rew || !O->reset || !O->time_outs || !O->fixup_idx || !O->fixup_val)
+    return DDQC_E_NULL;
+  if (P->action_type == DDQC_ACT_CTBR_FIXED_YAW && (reinterpret_cast<uintptr_t>(O->obs) & 15u)) return DDQC_E_ALIGN;
+  const int n = (int)n_env;
+  dim3 grid((n + kThreads - 1) / kThreads), block(kThreads);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (P->action_type) {
+    case DDQC_ACT_ROTOR_RPMS:
+      env_step_kernel<DDQC_ACT_ROTOR_RPMS><<<grid, block, 0, st>>>(*P, *S, *O, ctl, actions, meas_override, n);
+      break;
+    case DDQC_ACT_CTBR:
+      env_step_kernel<DDQC_ACT_CTBR><<<grid, block, 0, st>>>(*P, *S, *O, ctl, actions, meas_override, n);
+      break;
+    default:
+      env_step_kernel<DDQC_ACT_CTBR_FIXED_YAW><<<grid, block, 0, st>>>(*P, *S, *O, ctl, actions, meas_override, n);
+      break;
+  }
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,214 @@
+"""GPU parity of the fused env-step kernel against the numpy oracle (bit-exact contract)."""
+
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import default_cfgs
+
+pytestmark = pytest.mark.gpu
+
+
+def _make_pair(N, at_name, auto=True, seed=5, env_over=None, obs_over=None, reward_cfg=None, materialize=True):
+    import env_oracle as eo
+    from data_driven_quad_control_b200.controllers.ctbr.ctbr_controller import build_ctbr_matrices
+    from data_driven_quad_control_b200.envs.hover_env import HoverEnv
+    from data_driven_quad_control_b200.envs.hover_env_config import EnvCTBRControllerConfig, EnvDroneParams
+
+    env_cfg, obs_cfg, rew_cfg, cmd_cfg, at = default_cfgs(at_name)
+    if reward_cfg is not None:
+        rew_cfg = reward_cfg
+    env_cfg.update(env_over or {})
+    obs_cfg.update(obs_over or {})
+    cfgs_o = copy.deepcopy((env_cfg, obs_cfg, rew_cfg, cmd_cfg))
+    env = HoverEnv(N, env_cfg, obs_cfg, rew_cfg, cmd_cfg, device="cuda", action_type=at, auto_target_updates=auto,
+                   seed=seed, materialize_buffers=materialize)
+    mats = build_ctbr_matrices(EnvDroneParams.get())
+    orc = eo.EnvOracle(N, *cfgs_o, action_type=at.value, auto_target_updates=auto, mixer=mats["mixer"].numpy(),
+                       inv_sqrt_kf=float(mats["inv_sqrt_KF"]),
+                       rate_pid_gains=EnvCTBRControllerConfig.get()["ctbr_controller_params"]["rate_pid_gains"],
+                       rng=eo.PhiloxRng(seed))
+    return env, orc
+
+
+def _actions(T, N, A, seed, gentle_frac=0.25):
+    a = np.random.RandomState(seed).uniform(-1.3, 1.3, (T, N, A)).astype(np.float32)  # also exercises the clip
+    a[:, : int(N * gentle_frac)] *= 0.03
+    return a
+
+
+def _compare_step(env, orc, t, exact=True, yaw_tol=0.0):
+    o = env.obs_buf.cpu().numpy()
+    assert np.array_equal(env.reset_buf.cpu().numpy(), orc.reset_buf), f"reset mask differs at step {t}"
+    assert np.array_equal(env.extras["time_outs"].cpu().numpy(), orc.time_outs), f"time_outs differ at step {t}"
+    assert np.array_equal(env.episode_length_buf.cpu().numpy(), orc.episode_length_buf)
+    assert np.array_equal(env.hover_counter.cpu().numpy(), orc.hover_counter), f"hover counter differs at step {t}"
+    if exact:
+        assert np.array_equal(env.base_pos.cpu().numpy(), orc.base_pos), f"pos differs at step {t}"
+        assert np.array_equal(env.base_quat.cpu().numpy(), orc.base_quat)
+        assert np.array_equal(env.commands.cpu().numpy(), orc.commands), f"commands differ at step {t}"
+        assert np.array_equal(o, orc.obs_buf), f"obs differs at step {t}: {np.abs(o - orc.obs_buf).max()}"
+        assert np.array_equal(env.base_lin_vel.cpu().numpy(), orc.base_lin_vel)
+        assert np.array_equal(env.base_ang_vel.cpu().numpy(), orc.base_ang_vel)
+    r = env.rew_buf.cpu().numpy()
+    if yaw_tol == 0.0:
+        assert np.array_equal(r, orc.rew_buf), f"rew differs at step {t}: {np.abs(r - orc.rew_buf).max()}"
+    else:
+        np.testing.assert_allclose(r, orc.rew_buf, rtol=0, atol=yaw_tol)
+
+
+@pytest.mark.parametrize("at_name", ["CTBR_FIXED_YAW", "CTBR", "ROTOR_RPMS"])
+@pytest.mark.parametrize("auto", [True, False])
+def test_random_rollout_bit_exact(build_lib, at_name, auto):
+    """600 random-action steps x 96 envs, ~1.5k resets: trajectories, obs, rewards (yaw term: 1e-6),
+    reset masks, time-outs, counters and resampled commands identical to the oracle."""
+    N, T = 96, 600
+    env, orc = _make_pair(N, at_name, auto)
+    acts = _actions(T, N, env.num_actions, 1)
+    env.reset()
+    orc.reset()
+    assert np.array_equal(env.commands.cpu().numpy(), orc.commands)
+    # yaw reward (exp/atan2 from libm) only contributes when its scale is non-zero
+    yaw_tol = 0.0 if at_name == "CTBR_FIXED_YAW" else 2e-6
+    nres = 0
+    for t in range(T):
+        env.step(torch.from_numpy(acts[t]).cuda())
+        orc.step(acts[t])
+        _compare_step(env, orc, t, yaw_tol=yaw_tol)
+        nres += int(orc.reset_buf.sum())
+        for k, v in orc.extras_episode.items():
+            assert abs(float(env.extras["episode"][k]) - v) <= 1e-5 * max(1.0, abs(v)), (t, k)
+    assert nres > 500
+    for name, s in orc.episode_sums.items():
+        np.testing.assert_allclose(env.episode_sums[name].cpu().numpy(), s, rtol=0, atol=1e-5 if yaw_tol else 0)
+
+
+def test_hover_resample_and_fixup(build_lib):
+    """Envs parked on their target exercise the hover counter, the Philox target resample and the
+    A15/A16 stale-vs-fresh rel_pos rule on steps with and without a reset elsewhere."""
+    N, T = 64, 120
+    env, orc = _make_pair(N, "CTBR_FIXED_YAW", True)
+    acts = _actions(T, N, 3, 2, gentle_frac=0.0)
+    acts[:, :16] = 0.0  # zero action = hover thrust, zero rates
+    acts[:20] = 0.0  # phase 1: nobody crashes, so the first hover events happen on reset-free steps
+    env.reset()
+    orc.reset()
+    n_hover_events = 0
+    n_fix_with_reset = n_fix_without_reset = 0
+    for t in range(T):
+        if t % 20 == 0:  # park the first 16 drones' targets on their current position
+            idx = np.arange(16)
+            tgt = orc.base_pos[idx].copy()
+            orc.update_target_pos(idx, tgt)
+            env.update_target_pos(torch.arange(16, device="cuda"), torch.from_numpy(tgt).cuda())
+        env.step(torch.from_numpy(acts[t]).cuda())
+        orc.step(acts[t])
+        _compare_step(env, orc, t)
+        if orc.hover_resampled.any():
+            n_hover_events += int(orc.hover_resampled.sum())
+            if orc.reset_buf.any():
+                n_fix_with_reset += 1
+            else:
+                n_fix_without_reset += 1
+        np.testing.assert_array_equal(env.rel_pos.cpu().numpy(), orc.rel_pos)
+        np.testing.assert_array_equal(env.last_rel_pos.cpu().numpy(), orc.last_rel_pos)
+    assert n_hover_events >= 16
+    assert n_fix_with_reset > 0 and n_fix_without_reset > 0
+
+
+def test_lazy_buffers_match_materialized(build_lib):
+    """materialize_buffers=False (the large-N mode) gives the same trajectory and the same
+    body-frame velocities on demand."""
+    N, T = 128, 60
+    env_a, orc = _make_pair(N, "CTBR", True, materialize=False)
+    acts = _actions(T, N, 4, 3)
+    env_a.reset()
+    orc.reset()
+    for t in range(T):
+        env_a.step(torch.from_numpy(acts[t]).cuda())
+        orc.step(acts[t])
+        _compare_step(env_a, orc, t, yaw_tol=2e-6)
+    with pytest.raises(AttributeError):
+        _ = env_a.base_euler
+
+
+def test_timeouts_and_episode_length_assignment(build_lib):
+    """Zero actions hover forever: every env times out on step max_episode_length+1 (strict >)."""
+    env, orc = _make_pair(8, "CTBR_FIXED_YAW", False, env_over={"episode_length_s": 0.4})
+    env.reset()
+    orc.reset()
+    z = np.zeros((8, 3), np.float32)
+    assert env.max_episode_length == 10
+    for t in range(25):
+        env.step(torch.from_numpy(z).cuda())
+        orc.step(z)
+        _compare_step(env, orc, t)
+        if t == 10:
+            assert env.reset_buf.all() and (env.extras["time_outs"] == 1.0).all()
+    # rsl_rl-style assignment keeps working (init_at_random_ep_len)
+    new = torch.randint(0, 10, (8,), device="cuda")
+    env.episode_length_buf = new
+    assert torch.equal(env.episode_length_buf, new.to(torch.int32))
+
+
+def test_obs_noise_statistics(build_lib):
+    env, orc = _make_pair(4096, "CTBR_FIXED_YAW", False, obs_over={"obs_noise_std": 0.05})
+    env.reset()
+    orc.reset()
+    z = np.zeros((4096, 3), np.float32)
+    env.step(torch.from_numpy(z).cuda())
+    orc.step(z)
+    o, oo = env.obs_buf.cpu().numpy(), orc.obs_buf
+    # same Philox words, libm-level differences only
+    np.testing.assert_allclose(o, oo, rtol=0, atol=5e-6)
+    noise = o[:, 7:10]  # lin vel is ~0 while hovering
+    assert abs(noise.std() - 0.05) < 0.004 and abs(noise.mean()) < 0.004
+    assert np.array_equal(env.base_pos.cpu().numpy(), orc.base_pos)  # noise never touches the state
+
+
+def test_actuator_noise(build_lib):
+    env, orc = _make_pair(2048, "CTBR_FIXED_YAW", False, env_over={"actuator_noise_std": 50.0})
+    env.reset()
+    orc.reset()
+    z = np.zeros((2048, 3), np.float32)
+    env.step(torch.from_numpy(z).cuda())
+    orc.step(z)
+    np.testing.assert_allclose(env.rotor_rpms.cpu().numpy(), orc.last_rpm, rtol=0, atol=2e-2)
+    np.testing.assert_allclose(env.base_pos.cpu().numpy(), orc.base_pos, rtol=0, atol=1e-6)
+
+
+def test_state_save_restore_matches_oracle(build_lib):
+    """get_current_state -> steps -> restore_from_state -> steps, against the oracle (incl. the
+    body-frame-velocities-into-dofs quirk and the whole-batch PID state)."""
+    import env_oracle as eo
+
+    N = 6
+    env, orc = _make_pair(N, "CTBR", False)
+    acts = _actions(40, N, 4, 7, gentle_frac=1.0) * 10  # moderate actions, few resets
+    env.reset()
+    orc.reset()
+    for t in range(8):
+        env.step(torch.from_numpy(acts[t]).cuda())
+        orc.step(acts[t])
+    idx = [2]
+    s_env = env.get_current_state(torch.tensor(idx, device="cuda"))
+    s_orc = orc.get_current_state(idx)
+    for name in ("base_pos", "base_quat", "base_lin_vel", "base_ang_vel", "commands", "episode_length", "last_actions"):
+        assert np.array_equal(getattr(s_env, name).cpu().numpy(), getattr(s_orc, name)), name
+    assert np.array_equal(s_env.ctbr_controller_state.integral.cpu().numpy(), s_orc.pid_integral)
+    assert np.array_equal(s_env.ctbr_controller_state.prev_error.cpu().numpy(), s_orc.pid_prev_error)
+    for t in range(8, 16):
+        env.step(torch.from_numpy(acts[t]).cuda())
+        orc.step(acts[t])
+    env.restore_from_state(torch.tensor(idx, device="cuda"), s_env)
+    orc.restore_from_state(idx, s_orc)
+    again = env.get_current_state(torch.tensor(idx, device="cuda"))
+    for name in ("base_pos", "base_quat", "base_lin_vel", "base_ang_vel", "commands", "episode_length", "last_actions"):
+        assert torch.equal(getattr(again, name), getattr(s_env, name)), name  # reference test_drone_utilities.py
+    assert bool(env.reset_buf[2])
+    for t in range(16, 40):
+        env.step(torch.from_numpy(acts[t]).cuda())
+        orc.step(acts[t])
+        _compare_step(env, orc, t, yaw_tol=2e-6)
