@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libddqc.so")
+LIB_PATH = os.environ.get("DDQC_LIB", os.path.join(_HERE, "libddqc.so"))  # DDQC_LIB: kernel-variant experiments
 
 NUM_REWARDS = 7
 STAT_COPIES = 32
@@ -35,6 +35,7 @@ class EnvParams(C.Structure):
         ("act_lo", f32 * 4),
         ("act_span", f32 * 4),
         ("step_dt", f32),
+        ("inv_step_dt", f32),
         ("pid_kp", f32 * 3),
         ("pid_ki", f32 * 3),
         ("pid_kd", f32 * 3),
@@ -42,21 +43,17 @@ class EnvParams(C.Structure):
         ("inv_sqrt_kf", f32),
         ("dt", f32),
         ("half_dt", f32),
+        ("dt_g", f32),
         ("kf", f32),
-        ("km", f32),
-        ("inv_mass", f32),
-        ("gravity", f32),
-        ("jxx", f32),
-        ("jyy", f32),
-        ("jzz", f32),
-        ("inv_jxx", f32),
-        ("inv_jyy", f32),
-        ("inv_jzz", f32),
-        ("rotor_x", f32 * 4),
-        ("rotor_y", f32 * 4),
-        ("spin", f32 * 4),
-        ("cos_coef", f32 * 7),
-        ("sinc_coef", f32 * 7),
+        ("dt_over_m", f32),
+        ("two_dt_over_m", f32),
+        ("k_w", f32 * 3),
+        ("b_w", f32 * 3),
+        ("arm_x", f32 * 4),
+        ("arm_y", f32 * 4),
+        ("km_spin", f32 * 4),
+        ("cos_coef", f32 * 5),
+        ("sinc_coef", f32 * 5),
         ("actuator_noise_std", f32),
         ("min_rpm", f32),
         ("max_rpm", f32),
@@ -74,6 +71,9 @@ class EnvParams(C.Structure):
         ("inv_init_quat", f32 * 4),
         ("at_target_threshold", f32),
         ("at_target_threshold_sq", f32),
+        ("inv_at_target_threshold_sq", f32),
+        ("inv_pi_lit", f32),
+        ("inv_180", f32),
         ("cmd_lo", f32 * 3),
         ("cmd_span", f32 * 3),
         ("obs_scale_pos", f32),

@@ -4,7 +4,8 @@
 //   DroneTrackingController.compute   (controllers/tracking/tracking_controller.py:90-164)
 // One thread per drone; inputs are addressed with explicit element strides so (N,k) tensors and
 // their transposed struct-of-arrays views are both read without a copy.  Compiled with
-// -fmad=false: the op order follows the reference's elementwise torch expressions.
+// -fmad=false: the op order follows the reference's elementwise torch expressions; tensor / scalar
+// divisions follow torch's CUDA semantics, x * (1.0f / s).
 #include "ddqc_device.cuh"
 
 using namespace ddqc;
@@ -21,10 +22,10 @@ struct Mixer {
 };
 
 __device__ __forceinline__ float pid_update(float sp, float meas, float& integ, float& prev, float kp, float ki,
-                                            float kd, float dt) {
+                                            float kd, float dt, float inv_dt) {
   float err = sp - meas;
   integ = integ + err * dt;
-  float deriv = (err - prev) / dt;
+  float deriv = (err - prev) * inv_dt;
   prev = err;
   return (kp * err + ki * integ) + kd * deriv;
 }
@@ -38,7 +39,7 @@ pid_kernel(const float* __restrict__ sp, int64_t sp_rs, int64_t sp_cs, const flo
   for (int j = 0; j < k; ++j) {
     float integ = integral[i * k + j], prev = prev_error[i * k + j];
     out[i * k + j] = pid_update(sp[i * sp_rs + j * sp_cs], ms[i * ms_rs + j * ms_cs], integ, prev, g.kp[j], g.ki[j],
-                                g.kd[j], dt);
+                                g.kd[j], dt, 1.0f / dt);
     integral[i * k + j] = integ;
     prev_error[i * k + j] = prev;
   }
@@ -55,7 +56,7 @@ ctbr_kernel(const float* __restrict__ meas, int64_t m_rs, int64_t m_cs, const fl
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     float integ = integral[i * 3 + j], prev = prev_error[i * 3 + j];
-    c[j] = pid_update(sp[i * s_rs + j * s_cs], meas[i * m_rs + j * m_cs], integ, prev, g.kp[j], g.ki[j], g.kd[j], dt);
+    c[j] = pid_update(sp[i * s_rs + j * s_cs], meas[i * m_rs + j * m_cs], integ, prev, g.kp[j], g.ki[j], g.kd[j], dt, 1.0f / dt);
     integral[i * 3 + j] = integ;
     prev_error[i * 3 + j] = prev;
   }
@@ -91,7 +92,7 @@ tracking_kernel(const float* __restrict__ pos, int64_t p_rs, int64_t p_cs, const
   for (int j = 0; j < 3; ++j) {
     float integ = integral[i * 3 + j], prev = prev_error[i * 3 + j];
     acc[j] = pid_update(pos_sp[i * ps_rs + j * ps_cs], pos[i * p_rs + j * p_cs], integ, prev, g.kp[j], g.ki[j],
-                        g.kd[j], dt);
+                        g.kd[j], dt, 1.0f / dt);
     integral[i * 3 + j] = integ;
     prev_error[i * 3 + j] = prev;
   }

@@ -15,35 +15,36 @@ struct V3 {
   float x, y, z;
 };
 
+// fm(a,b,c) = round(a*b + c): the only fused operation in these translation units
+// (-fmad=false keeps every other * and + separately rounded, as written).
+__device__ __forceinline__ float fm(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+// Hamilton product a (x) b -- oracle/drone_physics.py: quat_mul
 __device__ __forceinline__ Q4 quat_mul(Q4 a, Q4 b) {
   Q4 r;
-  r.w = ((a.w * b.w - a.x * b.x) - a.y * b.y) - a.z * b.z;
-  r.x = ((a.w * b.x + a.x * b.w) + a.y * b.z) - a.z * b.y;
-  r.y = ((a.w * b.y - a.x * b.z) + a.y * b.w) + a.z * b.x;
-  r.z = ((a.w * b.z + a.x * b.y) - a.y * b.x) + a.z * b.w;
+  r.w = fm(-a.z, b.z, fm(-a.y, b.y, fm(-a.x, b.x, a.w * b.w)));
+  r.x = fm(-a.z, b.y, fm(a.y, b.z, fm(a.x, b.w, a.w * b.x)));
+  r.y = fm(a.z, b.x, fm(a.y, b.w, fm(-a.x, b.z, a.w * b.y)));
+  r.z = fm(a.z, b.w, fm(-a.y, b.x, fm(a.x, b.y, a.w * b.z)));
   return r;
 }
 
-// genesis.utils.geom.transform_by_quat: v + w t + qv x t, t = 2 qv x v
+// genesis.utils.geom.transform_by_quat: v + 2 (w u + qv x u), u = qv x v -- oracle: rotate_by_quat
 __device__ __forceinline__ V3 rotate_by_quat(V3 v, Q4 q) {
-  float tx = (q.y * v.z - q.z * v.y) * 2.0f;
-  float ty = (q.z * v.x - q.x * v.z) * 2.0f;
-  float tz = (q.x * v.y - q.y * v.x) * 2.0f;
-  V3 r;
-  r.x = (v.x + q.w * tx) + (q.y * tz - q.z * ty);
-  r.y = (v.y + q.w * ty) + (q.z * tx - q.x * tz);
-  r.z = (v.z + q.w * tz) + (q.x * ty - q.y * tx);
-  return r;
+  float ux = fm(q.y, v.z, -(q.z * v.y));
+  float uy = fm(q.z, v.x, -(q.x * v.z));
+  float uz = fm(q.x, v.y, -(q.y * v.x));
+  float sx = fm(q.y, uz, fm(-q.z, uy, q.w * ux));
+  float sy = fm(q.z, ux, fm(-q.x, uz, q.w * uy));
+  float sz = fm(q.x, uy, fm(-q.y, ux, q.w * uz));
+  return V3{fm(2.0f, sx, v.x), fm(2.0f, sy, v.y), fm(2.0f, sz, v.z)};
 }
 
-__device__ __forceinline__ float horner7(const float* c, float s) {
-  float acc = s * c[6] + c[5];
-  acc = acc * s + c[4];
-  acc = acc * s + c[3];
-  acc = acc * s + c[2];
-  acc = acc * s + c[1];
-  acc = acc * s + c[0];
-  return acc;
+__device__ __forceinline__ float horner5(const float* c, float s) {
+  float acc = fm(s, c[4], c[3]);
+  acc = fm(acc, s, c[2]);
+  acc = fm(acc, s, c[1]);
+  return fm(acc, s, c[0]);
 }
 
 __device__ __forceinline__ float clipf(float x, float lo, float hi) {
@@ -109,43 +110,45 @@ __device__ __forceinline__ V3 resample_command(const DdqcEnvParams& P, uint32_t 
   return c;
 }
 
-// ---- one rigid-body substep (oracle/drone_physics.py: substep) ------------------------
-__device__ __forceinline__ void substep(const DdqcEnvParams& P, V3& p, Q4& q, V3& v, V3& w, const float rpm[4]) {
-  float t0 = (rpm[0] * rpm[0]) * P.kf, t1 = (rpm[1] * rpm[1]) * P.kf;
-  float t2 = (rpm[2] * rpm[2]) * P.kf, t3 = (rpm[3] * rpm[3]) * P.kf;
+// ---- rigid body (oracle/drone_physics.py: rotor_wrench, substep) ---------------------------
+struct Wrench {
+  float ax, ay, az;  // per-substep body-rate increments from the rotor torques
+  float cxy, cz;     // 2 dt F/m and dt F/m
+};
+
+__device__ __forceinline__ Wrench rotor_wrench(const DdqcEnvParams& P, const float rpm[4]) {
+  float s0 = rpm[0] * rpm[0], s1 = rpm[1] * rpm[1], s2 = rpm[2] * rpm[2], s3 = rpm[3] * rpm[3];
+  float t0 = s0 * P.kf, t1 = s1 * P.kf, t2 = s2 * P.kf, t3 = s3 * P.kf;
   float fz = ((t0 + t1) + t2) + t3;
-  float tau_x = ((t0 * P.rotor_y[0] + t1 * P.rotor_y[1]) + t2 * P.rotor_y[2]) + t3 * P.rotor_y[3];
-  float tau_y = ((t0 * (-P.rotor_x[0]) + t1 * (-P.rotor_x[1])) + t2 * (-P.rotor_x[2])) + t3 * (-P.rotor_x[3]);
-  float m0 = ((rpm[0] * rpm[0]) * P.km) * P.spin[0], m1 = ((rpm[1] * rpm[1]) * P.km) * P.spin[1];
-  float m2 = ((rpm[2] * rpm[2]) * P.km) * P.spin[2], m3 = ((rpm[3] * rpm[3]) * P.km) * P.spin[3];
-  float tau_z = ((m0 + m1) + m2) + m3;
+  float tau_x = fm(t3, P.arm_x[3], fm(t2, P.arm_x[2], fm(t1, P.arm_x[1], t0 * P.arm_x[0])));
+  float tau_y = fm(t3, P.arm_y[3], fm(t2, P.arm_y[2], fm(t1, P.arm_y[1], t0 * P.arm_y[0])));
+  float tau_z = fm(s3, P.km_spin[3], fm(s2, P.km_spin[2], fm(s1, P.km_spin[1], s0 * P.km_spin[0])));
+  return Wrench{P.k_w[0] * tau_x, P.k_w[1] * tau_y, P.k_w[2] * tau_z, P.two_dt_over_m * fz, P.dt_over_m * fz};
+}
 
-  float jwx = w.x * P.jxx, jwy = w.y * P.jyy, jwz = w.z * P.jzz;
-  float gx = w.y * jwz - w.z * jwy;
-  float gy = w.z * jwx - w.x * jwz;
-  float gz = w.x * jwy - w.y * jwx;
-  w.x = w.x + ((tau_x - gx) * P.inv_jxx) * P.dt;
-  w.y = w.y + ((tau_y - gy) * P.inv_jyy) * P.dt;
-  w.z = w.z + ((tau_z - gz) * P.inv_jzz) * P.dt;
-
-  float r13 = (q.x * q.z + q.w * q.y) * 2.0f;
-  float r23 = (q.y * q.z - q.w * q.x) * 2.0f;
-  float r33 = ((q.w * q.w - q.x * q.x) - q.y * q.y) + q.z * q.z;
-  float acc = fz * P.inv_mass;
-  v.x = v.x + (r13 * acc) * P.dt;
-  v.y = v.y + (r23 * acc) * P.dt;
-  v.z = v.z + (r33 * acc - P.gravity) * P.dt;
-
-  p.x = p.x + v.x * P.dt;
-  p.y = p.y + v.y * P.dt;
-  p.z = p.z + v.z * P.dt;
-
+__device__ __forceinline__ void substep(const DdqcEnvParams& P, const Wrench& W, V3& p, Q4& q, V3& v, V3& w) {
+  // body-frame Euler equations, gyroscopic term with the old rates
+  float nwx = fm(-P.b_w[0], w.y * w.z, w.x + W.ax);
+  float nwy = fm(-P.b_w[1], w.z * w.x, w.y + W.ay);
+  float nwz = fm(-P.b_w[2], w.x * w.y, w.z + W.az);
+  w = V3{nwx, nwy, nwz};
+  // world-frame linear velocity (old pose): third column of R(q) * thrust / m + gravity
+  v.x = fm(W.cxy, fm(q.x, q.z, q.w * q.y), v.x);
+  v.y = fm(W.cxy, fm(q.y, q.z, -(q.w * q.x)), v.y);
+  float r33 = fm(-2.0f, fm(q.x, q.x, q.y * q.y), 1.0f);
+  v.z = fm(W.cz, r33, v.z - P.dt_g);
+  // semi-implicit Euler: positions with the new velocities
+  p.x = fm(v.x, P.dt, p.x);
+  p.y = fm(v.y, P.dt, p.y);
+  p.z = fm(v.z, P.dt, p.z);
+  // q <- renormalise(q (x) [cos|h|, sinc|h| h]), h = w dt/2
   float hx = w.x * P.half_dt, hy = w.y * P.half_dt, hz = w.z * P.half_dt;
-  float s = (hx * hx + hy * hy) + hz * hz;
-  float c = horner7(P.cos_coef, s);
-  float k = horner7(P.sinc_coef, s);
+  float s = fm(hz, hz, fm(hy, hy, hx * hx));
+  float c = horner5(P.cos_coef, s);
+  float k = horner5(P.sinc_coef, s);
   Q4 n = quat_mul(q, Q4{c, k * hx, k * hy, k * hz});
-  float inv_n = 1.0f / sqrtf(((n.w * n.w + n.x * n.x) + n.y * n.y) + n.z * n.z);
+  float n2 = fm(n.z, n.z, fm(n.y, n.y, fm(n.x, n.x, n.w * n.w)));
+  float inv_n = fm(-0.5f, n2, 1.5f);
   q = Q4{n.w * inv_n, n.x * inv_n, n.y * inv_n, n.z * inv_n};
 }
 

@@ -8,7 +8,8 @@
 // traffic for CTBR_FIXED_YAW, ~1 kFLOP), so nothing here goes near the tensor cores.
 //
 // Arithmetic contract: this translation unit is compiled with -fmad=false and mirrors,
-// operation for operation, the fp32 restatement in oracle/env_oracle.py +
+// operation for operation (explicit fm() = fused, everything else separately rounded), the fp32
+// restatement in oracle/env_oracle.py +
 // oracle/drone_physics.py, so positions, rewards and reset masks are bit-identical to
 // the oracle (libm calls -- atan2/asin/exp/log/cos -- are within 2 ulp).
 //
@@ -29,11 +30,18 @@ using namespace ddqc;
 
 namespace {
 
-constexpr int kThreads = 256;
+#ifndef DDQC_ENV_THREADS
+#define DDQC_ENV_THREADS 128
+#endif
+#ifndef DDQC_ENV_MIN_BLOCKS
+#define DDQC_ENV_MIN_BLOCKS 8
+#endif
+constexpr int kThreads = DDQC_ENV_THREADS;
+constexpr int kMinBlocks = DDQC_ENV_MIN_BLOCKS;
 
 // ---- the fused step kernel -------------------------------------------------------------
 template <int ACT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O, DdqcEnvCtl* __restrict__ ctl,
                 const float* __restrict__ actions, const float* __restrict__ meas_override, const int n) {
   constexpr int A = (ACT == DDQC_ACT_CTBR_FIXED_YAW) ? 3 : 4;
@@ -109,7 +117,7 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
         for (int j = 0; j < 3; ++j) {
           float err = sp[j] - ms[j];
           integ[j] = integ[j] + err * P.step_dt;  // A6
-          float deriv = (err - prev[j]) / P.step_dt;
+          float deriv = (err - prev[j]) * P.inv_step_dt;
           prev[j] = err;
           c[j] = (P.pid_kp[j] * err + P.pid_ki[j] * integ[j]) + P.pid_kd[j] * deriv;
           S.pid_integral[j * n + i] = integ[j];
@@ -141,7 +149,10 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
 
     // ------------------------------------------------------------------ physics (A8)
     const V3 last_pos = p;
-    for (int sidx = 0; sidx < P.decimation; ++sidx) substep(P, p, q, v, w, rpm);
+    {
+      const Wrench W = rotor_wrench(P, rpm);  // zero-order hold: constant over the substeps
+      for (int sidx = 0; sidx < P.decimation; ++sidx) substep(P, W, p, q, v, w);
+    }
 
     // ------------------------------------------------------------------ buffers (A9-A12)
     ep_len += 1;
@@ -218,7 +229,7 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
 
     // ------------------------------------------------------------------ rewards (A19)
     float r_target = sumsq3(last_rel) - sumsq3(rel);
-    float r_close = (P.at_target_threshold_sq - sumsq3(rel)) / P.at_target_threshold_sq;
+    float r_close = (P.at_target_threshold_sq - sumsq3(rel)) * P.inv_at_target_threshold_sq;
     r_close = r_close < 0.0f ? 0.0f : r_close;
     float r_hover = (float)hover;
     float r_smooth;
@@ -234,10 +245,10 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
     float r_yaw = 0.0f;
     if (P.flags & DDQC_F_NEED_EULER) {
       float yaw = euler.z;
-      yaw = (yaw > 180.0f ? yaw - 360.0f : yaw) / 180.0f * 3.14159f;
+      yaw = (yaw > 180.0f ? yaw - 360.0f : yaw) * P.inv_180 * 3.14159f;
       r_yaw = expf(P.yaw_lambda * fabsf(yaw));
     }
-    float r_ang = sqrtf(sumsq3(V3{ang_b.x / 3.14159f, ang_b.y / 3.14159f, ang_b.z / 3.14159f}));
+    float r_ang = sqrtf(sumsq3(V3{ang_b.x * P.inv_pi_lit, ang_b.y * P.inv_pi_lit, ang_b.z * P.inv_pi_lit}));
     float r_crash = crash ? 1.0f : 0.0f;
 
     float rk[DDQC_NUM_REWARDS] = {r_target * P.rew_scale[0], r_close * P.rew_scale[1], r_hover * P.rew_scale[2],
@@ -295,7 +306,7 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
       V3 rel_f{cmd_new.x - p.x, cmd_new.y - p.y, cmd_new.z - p.z};
       V3 lrel_f{cmd_new.x - last_pos.x, cmd_new.y - last_pos.y, cmd_new.z - last_pos.z};
       float rt = (sumsq3(lrel_f) - sumsq3(rel_f)) * P.rew_scale[0];
-      float rc = (P.at_target_threshold_sq - sumsq3(rel_f)) / P.at_target_threshold_sq;
+      float rc = (P.at_target_threshold_sq - sumsq3(rel_f)) * P.inv_at_target_threshold_sq;
       rc = (rc < 0.0f ? 0.0f : rc) * P.rew_scale[1];
       float rw = 0.0f + rt;
       rw = rw + rc;

@@ -107,6 +107,7 @@ def make_env_params(
         P.act_span[j] = float(np.float32(hi[j]) - np.float32(lo[j]))
 
     P.step_dt = step_dt
+    P.inv_step_dt = float(np.float32(1.0) / np.float32(step_dt))
     if action_type != EnvActionType.ROTOR_RPMS:
         assert mixer is not None and rate_pid_gains is not None
         for j in range(3):
@@ -116,17 +117,20 @@ def make_env_params(
             P.mixer[j] = flat[j]
         P.inv_sqrt_kf = inv_sqrt_kf
 
+    # rigid-body constants: the double-precision expressions of oracle/drone_physics.PhysParams
     inertia = EnvDroneParams.INERTIA
-    P.dt, P.half_dt = dt, dt / 2.0
-    P.kf, P.km = EnvDroneParams.KF, EnvDroneParams.KM
-    P.inv_mass = 1.0 / EnvDroneParams.MASS
-    P.gravity = _GRAVITY
-    P.jxx, P.jyy, P.jzz = inertia["Jxx"], inertia["Jyy"], inertia["Jzz"]
-    P.inv_jxx, P.inv_jyy, P.inv_jzz = 1.0 / inertia["Jxx"], 1.0 / inertia["Jyy"], 1.0 / inertia["Jzz"]
+    jx, jy, jz = inertia["Jxx"], inertia["Jyy"], inertia["Jzz"]
+    mass = EnvDroneParams.MASS
+    P.dt, P.half_dt, P.dt_g = dt, dt / 2.0, dt * _GRAVITY
+    P.kf = EnvDroneParams.KF
+    P.dt_over_m, P.two_dt_over_m = dt / mass, 2.0 * dt / mass
+    P.k_w[0], P.k_w[1], P.k_w[2] = dt / jx, dt / jy, dt / jz
+    P.b_w[0], P.b_w[1], P.b_w[2] = dt * (jz - jy) / jx, dt * (jx - jz) / jy, dt * (jy - jx) / jz
     for r in range(4):
-        P.rotor_x[r], P.rotor_y[r] = _ROTOR_XY[r]
-        P.spin[r] = float(EnvDroneParams.ROTOR_SPIN_DIRECTIONS[r])
-    for k in range(7):
+        x, y = _ROTOR_XY[r]
+        P.arm_x[r], P.arm_y[r] = y, -x
+        P.km_spin[r] = EnvDroneParams.KM * float(EnvDroneParams.ROTOR_SPIN_DIRECTIONS[r])
+    for k in range(5):
         P.cos_coef[k] = (-1.0) ** k / math.factorial(2 * k)
         P.sinc_coef[k] = (-1.0) ** k / math.factorial(2 * k + 1)
 
@@ -149,6 +153,9 @@ def make_env_params(
         P.inv_init_quat[j] = iq[j] if j == 0 else -iq[j]
     P.at_target_threshold = env_cfg["at_target_threshold"]
     P.at_target_threshold_sq = env_cfg["at_target_threshold"] ** 2
+    P.inv_at_target_threshold_sq = float(np.float32(1.0) / np.float32(env_cfg["at_target_threshold"] ** 2))
+    P.inv_pi_lit = float(np.float32(1.0) / np.float32(3.14159))
+    P.inv_180 = float(np.float32(1.0) / np.float32(180.0))
     for j, key in enumerate(("pos_x_range", "pos_y_range", "pos_z_range")):
         lo_c, hi_c = command_cfg[key]
         P.cmd_lo[j] = lo_c

@@ -69,20 +69,27 @@ typedef struct DdqcEnvParams {
   float act_span[4];            /* fp32(action_bounds[:,1] - action_bounds[:,0]) */
   /* CTBR controller (controllers/ctbr/ctbr_controller.py:221-264) */
   float step_dt;                /* PID dt = dt*decimation                     hover_env.py:105-111 */
+  float inv_step_dt;            /* 1.0f / step_dt  (torch CUDA tensor/scalar division semantics) */
   float pid_kp[3], pid_ki[3], pid_kd[3];
   float mixer[16];              /* row-major pinv(A) @ diag(J,1), computed on the host with torch */
   float inv_sqrt_kf;
-  /* rigid body (restated Genesis substep) */
-  float dt, half_dt, kf, km, inv_mass, gravity;
-  float jxx, jyy, jzz, inv_jxx, inv_jyy, inv_jzz;
-  float rotor_x[4], rotor_y[4], spin[4];
-  float cos_coef[7], sinc_coef[7];
+  /* rigid body (restated Genesis substep; see DESIGN.md and oracle/drone_physics.py) */
+  float dt, half_dt;            /* sim dt, dt/2 */
+  float dt_g;                   /* dt * 9.81 */
+  float kf;                     /* thrust coefficient, N / RPM^2 */
+  float dt_over_m, two_dt_over_m;
+  float k_w[3];                 /* dt / J_ii */
+  float b_w[3];                 /* dt (J_kk - J_jj) / J_ii, (i,j,k) cyclic */
+  float arm_x[4], arm_y[4];     /* roll / pitch torque arm of rotor i:  y_i, -x_i */
+  float km_spin[4];             /* KM * spin_i */
+  float cos_coef[5], sinc_coef[5]; /* Taylor coefficients of cos(a), sin(a)/a in a^2 */
   /* noise (hover_env.py:430-434, 610-621) */
   float actuator_noise_std, min_rpm, max_rpm, obs_noise_std;
   /* termination thresholds (hover_env.py:481-520) */
   float term_pitch, term_roll, term_x, term_y, term_z, term_ground, term_ang_vel, term_lin_vel;
   float init_pos[3], init_quat[4], inv_init_quat[4];
-  float at_target_threshold, at_target_threshold_sq;
+  float at_target_threshold, at_target_threshold_sq, inv_at_target_threshold_sq;
+  float inv_pi_lit, inv_180;    /* 1.0f/3.14159f, 1.0f/180.0f             hover_env.py:847,852 */
   float cmd_lo[3], cmd_span[3]; /* command_cfg ranges: lower, fp32(upper-lower)   hover_env.py:328-337 */
   float obs_scale_pos, obs_scale_lin, obs_scale_ang;
   float rew_scale[DDQC_NUM_REWARDS]; /* reward_scales[k]*step_dt, dict order   hover_env.py:246-247 */

@@ -20,10 +20,17 @@ Pinning: `tests/test_oracle_reference_parity.py` runs the reference's own
 oracle against it (reset indices exact, floats to a few ulp); the frozen
 outputs live in `tests/golden/env_*.npz` (made by `oracle/make_golden.py`).
 
-All arithmetic is elementwise float32 in a fixed order (no BLAS, no reductions,
-no FMA), so the CUDA kernel -- compiled with -fmad=false -- reproduces it bit
-for bit; the only tolerance-level differences are the libm calls (atan2/asin for
-the Euler angles, exp for the yaw reward, log/cos for Gaussian noise).
+All arithmetic is elementwise float32 in a fixed order (no BLAS, no reductions;
+the env/controller code the reference owns is evaluated without FMA exactly as
+torch's elementwise kernels do, the restated Genesis part uses explicit fma()),
+so the CUDA kernel -- compiled with -fmad=false -- reproduces it bit for bit;
+the only tolerance-level differences are the libm calls (atan2/asin for the
+Euler angles, exp for the yaw reward, log/cos for Gaussian noise).
+
+Tensor / python-scalar divisions (`x / dt`, `x / 3.14159`, ...) follow torch's
+CUDA semantics -- the reference's default device -- i.e. x * (1.0f / s)
+(ATen div_true_kernel_cuda, cpu-scalar fast path); torch's CPU kernels divide.
+The two differ in the last bit only.
 """
 
 from __future__ import annotations
@@ -33,7 +40,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from drone_physics import PhysParams, quat_mul, rotate_by_quat, substep
+from drone_physics import PhysParams, quat_mul, rotate_by_quat, rotor_wrench, substep
 
 F32 = np.float32
 
@@ -323,7 +330,7 @@ class EnvOracle:
         sdt = F32(self.step_dt)
         err = self.body_rate_setpoints - self.base_ang_vel
         self.pid_integral = self.pid_integral + err * sdt
-        deriv = (err - self.pid_prev_error) / sdt
+        deriv = (err - self.pid_prev_error) * (F32(1.0) / sdt)
         self.pid_prev_error = err.copy()
         acc = (self.kp[None, :] * err + self.ki[None, :] * self.pid_integral) + self.kd[None, :] * deriv
         c = (acc[:, 0], acc[:, 1], acc[:, 2], y[:, 0])
@@ -349,8 +356,9 @@ class EnvOracle:
         self.last_rpm = rpm
 
         p, q, v, w = _cols(self.sim_pos), _cols(self.sim_quat), _cols(self.sim_vel), _cols(self.sim_ang)
+        wrench = rotor_wrench(self.P, _cols(rpm))
         for _ in range(self.decimation):
-            p, q, v, w = substep(self.P, np.sqrt, p, q, v, w, _cols(rpm))
+            p, q, v, w = substep(self.P, wrench, p, q, v, w)
         self.sim_pos, self.sim_quat = np.stack(p, 1), np.stack(q, 1)
         self.sim_vel, self.sim_ang = np.stack(v, 1), np.stack(w, 1)
 
@@ -429,7 +437,7 @@ class EnvOracle:
 
     def _reward_closeness(self):
         t2 = F32(self.at_target_threshold_square)
-        r = (t2 - self._sumsq(self.rel_pos)) / t2
+        r = (t2 - self._sumsq(self.rel_pos)) * (F32(1.0) / t2)
         return np.where(r < F32(0.0), F32(0.0), r)
 
     def _reward_hover_time(self):
@@ -440,11 +448,11 @@ class EnvOracle:
 
     def _reward_yaw(self):
         yaw = self.base_euler[:, 2]
-        yaw = np.where(yaw > F32(180.0), yaw - F32(360.0), yaw) / F32(180.0) * F32(3.14159)
+        yaw = np.where(yaw > F32(180.0), yaw - F32(360.0), yaw) * (F32(1.0) / F32(180.0)) * F32(3.14159)
         return np.exp(F32(self.yaw_lambda) * np.abs(yaw))
 
     def _reward_angular(self):
-        return np.sqrt(self._sumsq(self.base_ang_vel / F32(3.14159)))
+        return np.sqrt(self._sumsq(self.base_ang_vel * (F32(1.0) / F32(3.14159))))
 
     def _reward_crash(self):
         return self.crash_condition.astype(F32)

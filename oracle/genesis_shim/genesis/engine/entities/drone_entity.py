@@ -7,6 +7,7 @@ velocity (free-joint angular dofs, body frame).  `scene.step()` advances it with
 `hover_env.py:437-439`).
 """
 
+import numpy as np
 import torch
 
 import drone_physics as _phys
@@ -30,20 +31,19 @@ class DroneEntity(RigidEntity):
             raise ValueError("rpm must be non-negative")
         self.rpm = rpm.reshape(self.n_envs, 4).clone()
 
+    @staticmethod
+    def _np_cols(t):
+        a = t.numpy()
+        return tuple(a[:, j].copy() for j in range(a.shape[1]))
+
     def _step(self):
+        wrench = _phys.rotor_wrench(self.P, self._np_cols(self.rpm))
         p, q, v, w = _phys.substep(
-            self.P,
-            torch.sqrt,
-            tuple(self.pos.unbind(1)),
-            tuple(self.quat.unbind(1)),
-            tuple(self.vel.unbind(1)),
-            tuple(self.ang.unbind(1)),
-            tuple(self.rpm.unbind(1)),
+            self.P, wrench, self._np_cols(self.pos), self._np_cols(self.quat), self._np_cols(self.vel),
+            self._np_cols(self.ang),
         )
-        self.pos = torch.stack(p, 1)
-        self.quat = torch.stack(q, 1)
-        self.vel = torch.stack(v, 1)
-        self.ang = torch.stack(w, 1)
+        stack = lambda cols: torch.from_numpy(np.stack(cols, 1).astype(np.float32))  # noqa: E731
+        self.pos, self.quat, self.vel, self.ang = stack(p), stack(q), stack(v), stack(w)
         self.rpm = torch.zeros_like(self.rpm)  # external forces are cleared every step
 
     # --- getters (world frame) --------------------------------------------------
@@ -58,8 +58,8 @@ class DroneEntity(RigidEntity):
 
     def get_ang(self):
         # cd_ang of the base link = R(q) w_body
-        x, y, z = _phys.rotate_by_quat(*self.ang.unbind(1), *self.quat.unbind(1))
-        return torch.stack((x, y, z), 1)
+        cols = _phys.rotate_by_quat(*self._np_cols(self.ang), *self._np_cols(self.quat))
+        return torch.from_numpy(np.stack(cols, 1).astype(np.float32))
 
     # --- setters ----------------------------------------------------------------
     @staticmethod

@@ -3,6 +3,7 @@
 
 import math
 
+import numpy as np
 import torch
 
 import drone_physics as _phys
@@ -14,15 +15,23 @@ def inv_quat(quat):
     return out
 
 
+def _cols(t):
+    a = t.detach().cpu().numpy().astype(np.float32)
+    return tuple(np.ascontiguousarray(a[..., j]) for j in range(a.shape[-1]))
+
+
+def _stack(cols):
+    return torch.from_numpy(np.stack([np.asarray(c, dtype=np.float32) for c in cols], -1))
+
+
 def transform_by_quat(v, quat):
-    x, y, z = _phys.rotate_by_quat(*v.unbind(-1), *quat.unbind(-1))
-    return torch.stack((x, y, z), -1)
+    return _stack(_phys.rotate_by_quat(*_cols(v), *_cols(quat)))
 
 
 def transform_quat_by_quat(v, u):
     """Apply v first, then u:  u (x) v."""
-    w, x, y, z = _phys.quat_mul(*u.unbind(-1), *v.unbind(-1))
-    return torch.stack((w, x, y, z), -1)
+    v, u = torch.broadcast_tensors(v, u)
+    return _stack(_phys.quat_mul(*_cols(u), *_cols(v)))
 
 
 def quat_to_xyz(quat, rpy=False, degrees=False):
