@@ -65,7 +65,7 @@ ctbr_kernel(const float* __restrict__ meas, int64_t m_rs, int64_t m_cs, const fl
   for (int r = 0; r < 4; ++r) {
     float f = ((M.m[4 * r + 0] * c[0] + M.m[4 * r + 1] * c[1]) + M.m[4 * r + 2] * c[2]) + M.m[4 * r + 3] * c[3];
     f = f < 0.0f ? 0.0f : f;
-    rpm[i * 4 + r] = sqrtf(f) * inv_sqrt_kf;
+    rpm[i * 4 + r] = sqrt_nonneg(f) * inv_sqrt_kf;
   }
 }
 

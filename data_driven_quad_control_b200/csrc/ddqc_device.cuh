@@ -47,6 +47,16 @@ __device__ __forceinline__ float horner5(const float* c, float s) {
   return fm(acc, s, c[0]);
 }
 
+// sqrtf(x) for x >= +0, correctly rounded like sqrtf, but arranged so that the common inputs
+// never leave the inline MUFU.RSQ fast path: exact zeros (clamped rotor thrusts, reset envs) and
+// the practically unreachable range (0, 1e-30) would otherwise drag the whole warp through the
+// out-of-line special-case routine of sqrt.rn.f32.
+__device__ __forceinline__ float sqrt_nonneg(float x) {
+  float r = sqrtf(fmaxf(x, 1.0e-30f));
+  if (x < 1.0e-30f) r = (x == 0.0f) ? 0.0f : sqrtf(x);
+  return r;
+}
+
 __device__ __forceinline__ float clipf(float x, float lo, float hi) {
   return x < lo ? lo : (x > hi ? hi : x);  // NaN passes through, like torch.clip
 }

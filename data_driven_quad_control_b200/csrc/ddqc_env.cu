@@ -40,30 +40,34 @@ constexpr int kThreads = DDQC_ENV_THREADS;
 constexpr int kMinBlocks = DDQC_ENV_MIN_BLOCKS;
 
 // ---- the fused step kernel -------------------------------------------------------------
-template <int ACT>
+// LEAN = the throughput configuration: no Euler angles needed (thresholds >= 180 deg, yaw reward
+// scale 0), no actuator / observation noise, no materialised reference buffers, no measurement
+// override.  It is the same code with those branches compiled out (fewer registers, no spills).
+template <int ACT, bool LEAN>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O, DdqcEnvCtl* __restrict__ ctl,
                 const float* __restrict__ actions, const float* __restrict__ meas_override, const int n) {
   constexpr int A = (ACT == DDQC_ACT_CTBR_FIXED_YAW) ? 3 : 4;
   constexpr int NOBS = 13 + A;
   constexpr bool USES_CTBR = (ACT != DDQC_ACT_ROTOR_RPMS);
+  const bool need_euler = !LEAN && (P.flags & DDQC_F_NEED_EULER);
+  const float act_noise_std = LEAN ? 0.0f : P.actuator_noise_std;
+  const float obs_noise_std = LEAN ? 0.0f : P.obs_noise_std;
 
-  __shared__ float s_sums[8];
-  __shared__ unsigned int s_cnt[2];
-  __shared__ bool s_last;
-  if (threadIdx.x < 8) s_sums[threadIdx.x] = 0.0f;
-  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0u;
-  __syncthreads();
-
-  const int i = blockIdx.x * kThreads + threadIdx.x;
-  const bool live = i < n;
+  // Threads past the end (last CTA only) recompute env n-1 and skip every side effect, so the
+  // body is straight-line code and the warp-level reductions below need no special casing.
+  const int gid = blockIdx.x * kThreads + threadIdx.x;
+  const bool live = gid < n;
+  const int i = live ? gid : n - 1;
+  const int lane = threadIdx.x & 31;
+  const int copy = (blockIdx.x + (threadIdx.x >> 5)) % DDQC_STAT_COPIES;
   const uint64_t ev = ctl->rng_event;
   const bool pid_pending = ctl->pid_reset_pending != 0u;
 
   float rew_total = 0.0f;
   bool did_reset = false, did_timeout = false;
 
-  if (live) {
+  {
     // ------------------------------------------------------------------ load state
     V3 p{S.pos[i], S.pos[n + i], S.pos[2 * n + i]};
     Q4 q{S.quat[i], S.quat[n + i], S.quat[2 * n + i], S.quat[3 * n + i]};
@@ -101,7 +105,7 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
           }
         }
         V3 meas;
-        if (meas_override) {
+        if (!LEAN && meas_override) {
           meas = V3{meas_override[i], meas_override[n + i], meas_override[2 * n + i]};
         } else {  // A5: body rates as refreshed at the end of the previous step
           Q4 qc{q.w, -q.x, -q.y, -q.z};
@@ -120,8 +124,10 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
           float deriv = (err - prev[j]) * P.inv_step_dt;
           prev[j] = err;
           c[j] = (P.pid_kp[j] * err + P.pid_ki[j] * integ[j]) + P.pid_kd[j] * deriv;
-          S.pid_integral[j * n + i] = integ[j];
-          S.pid_prev_error[j * n + i] = prev[j];
+          if (live) {
+            S.pid_integral[j * n + i] = integ[j];
+            S.pid_prev_error[j * n + i] = prev[j];
+          }
         }
         c[3] = y[0];
 #pragma unroll
@@ -129,20 +135,20 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
           float f = ((P.mixer[4 * r + 0] * c[0] + P.mixer[4 * r + 1] * c[1]) + P.mixer[4 * r + 2] * c[2]) +
                     P.mixer[4 * r + 3] * c[3];
           f = f < 0.0f ? 0.0f : f;  // A7
-          rpm[r] = sqrtf(f) * P.inv_sqrt_kf;
+          rpm[r] = sqrt_nonneg(f) * P.inv_sqrt_kf;
         }
       } else {
 #pragma unroll
         for (int r = 0; r < 4; ++r) rpm[r] = y[r < A ? r : 0];
       }
     }
-    if (P.actuator_noise_std > 0.0f) {
+    if (act_noise_std > 0.0f) {
       float z[4];
       philox_normals<4>((uint32_t)i, ev, DDQC_STREAM_ACT_NOISE, P.seed, z);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) rpm[r] = fminf(fmaxf(rpm[r] + z[r] * P.actuator_noise_std, P.min_rpm), P.max_rpm);
+      for (int r = 0; r < 4; ++r) rpm[r] = fminf(fmaxf(rpm[r] + z[r] * act_noise_std, P.min_rpm), P.max_rpm);
     }
-    if (O.rpm) {
+    if (!LEAN && live && O.rpm) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) O.rpm[r * n + i] = rpm[r];
     }
@@ -159,7 +165,7 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
     V3 rel{cmd.x - p.x, cmd.y - p.y, cmd.z - p.z};
     V3 last_rel{cmd.x - last_pos.x, cmd.y - last_pos.y, cmd.z - last_pos.z};
     V3 euler{0.0f, 0.0f, 0.0f};
-    if (P.flags & DDQC_F_NEED_EULER) {
+    if (need_euler) {
       Q4 r = quat_mul(q, Q4{P.inv_init_quat[0], P.inv_init_quat[1], P.inv_init_quat[2], P.inv_init_quat[3]});
       const float rad2deg = 57.29577951308232f;
       euler.x = atan2f((r.w * r.x + r.y * r.z) * 2.0f, 1.0f - (r.x * r.x + r.y * r.y) * 2.0f) * rad2deg;
@@ -174,7 +180,7 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
     bool hover_resampled = false;
     V3 cmd_new = cmd;
     if (P.flags & DDQC_F_AUTO_TARGET) {
-      bool at_target = sqrtf(sumsq3(rel)) < P.at_target_threshold;
+      bool at_target = sqrt_nonneg(sumsq3(rel)) < P.at_target_threshold;
       bool fire;
       if (P.min_hover_steps > 0) {
         hover = at_target ? hover + 1 : 0;
@@ -195,13 +201,35 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
                  (fabsf(ang_b.x) > P.term_ang_vel) | (fabsf(ang_b.y) > P.term_ang_vel) |
                  (fabsf(ang_b.z) > P.term_ang_vel) | (fabsf(lin_b.x) > P.term_lin_vel) |
                  (fabsf(lin_b.y) > P.term_lin_vel) | (fabsf(lin_b.z) > P.term_lin_vel);
-    did_timeout = ep_len > P.max_episode_length;
-    did_reset = did_timeout | crash;
+    did_timeout = live & (ep_len > P.max_episode_length);
+    did_reset = live & (did_timeout | crash);
 
     float last_act_obs[A];
 #pragma unroll
     for (int j = 0; j < A; ++j) last_act_obs[j] = last_act[j];
     Q4 q_obs = q;
+
+  // A18: sum of episode_sums[k] over the envs that reset, reduced per warp without divergence --
+  // for every reset lane L its 7 sums are broadcast and lane k keeps the running total of term k;
+  // lanes 0..6 then issue ONE 7-address RED per warp (no shared memory, no CTA barrier).
+  const unsigned int rmask = __ballot_sync(0xffffffffu, did_reset);
+  if (rmask) {
+    float part = 0.0f;
+    for (unsigned int m = rmask; m; m &= m - 1) {
+      const int L = __ffs(m) - 1;
+#pragma unroll
+      for (int k = 0; k < DDQC_NUM_REWARDS; ++k) {
+        float vk = __shfl_sync(0xffffffffu, sums[k], L);
+        if (lane == k) part += vk;
+      }
+    }
+    if (lane < DDQC_NUM_REWARDS) atomicAdd(&ctl->acc_sums[copy][lane], part);
+    if (lane == 8) atomicAdd(&ctl->acc_reset[copy], (unsigned int)__popc(rmask));
+  }
+  if (did_reset) {
+#pragma unroll
+    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) sums[k] = 0.0f;
+  }
 
     if (did_reset) {  // reset_idx (hover_env.py:556-595)
       V3 ip{P.init_pos[0], P.init_pos[1], P.init_pos[2]};
@@ -218,11 +246,6 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
       for (int j = 0; j < A; ++j) last_act_obs[j] = 0.0f;
       ep_len = 0;
       hover = 0;
-#pragma unroll
-      for (int k = 0; k < DDQC_NUM_REWARDS; ++k) {  // A18
-        atomicAdd(&s_sums[k], sums[k]);
-        sums[k] = 0.0f;
-      }
       cmd_new = resample_command(P, (uint32_t)i, ev, DDQC_STREAM_RESET);
       hover_resampled = false;
     }
@@ -243,12 +266,12 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
       }
     }
     float r_yaw = 0.0f;
-    if (P.flags & DDQC_F_NEED_EULER) {
+    if (need_euler) {
       float yaw = euler.z;
       yaw = (yaw > 180.0f ? yaw - 360.0f : yaw) * P.inv_180 * 3.14159f;
       r_yaw = expf(P.yaw_lambda * fabsf(yaw));
     }
-    float r_ang = sqrtf(sumsq3(V3{ang_b.x * P.inv_pi_lit, ang_b.y * P.inv_pi_lit, ang_b.z * P.inv_pi_lit}));
+    float r_ang = sqrt_nonneg(sumsq3(V3{ang_b.x * P.inv_pi_lit, ang_b.y * P.inv_pi_lit, ang_b.z * P.inv_pi_lit}));
     float r_crash = crash ? 1.0f : 0.0f;
 
     float rk[DDQC_NUM_REWARDS] = {r_target * P.rew_scale[0], r_close * P.rew_scale[1], r_hover * P.rew_scale[2],
@@ -261,7 +284,7 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
       rew = rew + rk[k];
       sums[k] = sums[k] + rk[k];
     }
-    rew_total = rew;
+    rew_total = live ? rew : 0.0f;
 
     // ------------------------------------------------------------------ observations (A20)
     float obs[NOBS];
@@ -280,10 +303,10 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
     obs[12] = clipf(ang_b.z * P.obs_scale_ang, -1.0f, 1.0f);
 #pragma unroll
     for (int j = 0; j < A; ++j) obs[13 + j] = last_act_obs[j];
-    if (P.obs_noise_std > 0.0f) {
+    if (obs_noise_std > 0.0f) {
       float z[13];
       philox_normals<13>((uint32_t)i, ev, DDQC_STREAM_OBS_NOISE, P.seed, z);
-      const float s = P.obs_noise_std;
+      const float s = obs_noise_std;
       obs[0] = obs[0] + z[0] * s;
       obs[1] = obs[1] + z[1] * s;
       obs[2] = obs[2] + z[2] * s;
@@ -302,7 +325,7 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
     }
 
     // A15/A16 fix-up record: the values this env would have if some other env reset this step
-    if (hover_resampled) {
+    if (hover_resampled && live) {
       V3 rel_f{cmd_new.x - p.x, cmd_new.y - p.y, cmd_new.z - p.z};
       V3 lrel_f{cmd_new.x - last_pos.x, cmd_new.y - last_pos.y, cmd_new.z - last_pos.z};
       float rt = (sumsq3(lrel_f) - sumsq3(rel_f)) * P.rew_scale[0];
@@ -326,6 +349,7 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
     }
 
     // ------------------------------------------------------------------ store
+    if (live) {
     S.pos[i] = p.x;
     S.pos[n + i] = p.y;
     S.pos[2 * n + i] = p.z;
@@ -363,117 +387,109 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
     O.reset[i] = did_reset ? 1 : 0;
     O.time_outs[i] = did_timeout ? 1.0f : 0.0f;
 
-    if (O.base_lin_vel) {
+    if (!LEAN && O.base_lin_vel) {
       O.base_lin_vel[i] = lin_b.x;
       O.base_lin_vel[n + i] = lin_b.y;
       O.base_lin_vel[2 * n + i] = lin_b.z;
     }
-    if (O.base_ang_vel) {
+    if (!LEAN && O.base_ang_vel) {
       O.base_ang_vel[i] = ang_b.x;
       O.base_ang_vel[n + i] = ang_b.y;
       O.base_ang_vel[2 * n + i] = ang_b.z;
     }
-    if (O.rel_pos) {
+    if (!LEAN && O.rel_pos) {
       O.rel_pos[i] = rel.x;
       O.rel_pos[n + i] = rel.y;
       O.rel_pos[2 * n + i] = rel.z;
     }
-    if (O.last_rel_pos) {
+    if (!LEAN && O.last_rel_pos) {
       O.last_rel_pos[i] = last_rel.x;
       O.last_rel_pos[n + i] = last_rel.y;
       O.last_rel_pos[2 * n + i] = last_rel.z;
     }
-    if (O.base_euler) {
+    if (!LEAN && O.base_euler) {
       O.base_euler[i] = euler.x;
       O.base_euler[n + i] = euler.y;
       O.base_euler[2 * n + i] = euler.z;
     }
-    if (O.crash) O.crash[i] = crash ? 1 : 0;
-    if (O.last_base_pos) {
+    if (!LEAN && O.crash) O.crash[i] = crash ? 1 : 0;
+    if (!LEAN && O.last_base_pos) {
       O.last_base_pos[i] = did_reset ? P.init_pos[0] : last_pos.x;
       O.last_base_pos[n + i] = did_reset ? P.init_pos[1] : last_pos.y;
       O.last_base_pos[2 * n + i] = did_reset ? P.init_pos[2] : last_pos.z;
     }
+    }  // live
   }
 
   // -------------------------------------------------------------------- statistics
-  // warp-level: reset / timeout counts by ballot, reward total by shuffle tree
+  // time-out count by ballot, reward total by a shuffle tree; one RED per warp each
   {
-    unsigned int rmask = __ballot_sync(0xffffffffu, did_reset);
     unsigned int tmask = __ballot_sync(0xffffffffu, did_timeout);
     float r = rew_total;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-    if ((threadIdx.x & 31) == 0) {
-      if (rmask) atomicAdd(&s_cnt[0], (unsigned int)__popc(rmask));
-      if (tmask) atomicAdd(&s_cnt[1], (unsigned int)__popc(tmask));
-      atomicAdd(&s_sums[7], r);
-    }
-  }
-  __syncthreads();
-  const int copy = blockIdx.x % DDQC_STAT_COPIES;
-  if (threadIdx.x < 8) {
-    float val = s_sums[threadIdx.x];
-    if (val != 0.0f) atomicAdd(&ctl->acc_sums[copy][threadIdx.x], val);
-  } else if (threadIdx.x == 8) {
-    if (s_cnt[0]) atomicAdd(&ctl->acc_reset[copy], s_cnt[0]);
-  } else if (threadIdx.x == 9) {
-    if (s_cnt[1]) atomicAdd(&ctl->acc_timeout[copy], s_cnt[1]);
+    if (lane == 7) atomicAdd(&ctl->acc_sums[copy][7], r);
+    if (lane == 9 && tmask) atomicAdd(&ctl->acc_timeout[copy], (unsigned int)__popc(tmask));
   }
 
   // -------------------------------------------------------------------- last-CTA finalisation
-  __threadfence();
+  // bar.sync orders every warp's stores / REDs before thread 0's device-scope fence (cumulative),
+  // which releases them to whichever CTA draws the last ticket.  Only warp 0 stays for the ticket.
   __syncthreads();
+  if (threadIdx.x >= 32) return;
+  int is_last = 0;
   if (threadIdx.x == 0) {
-    unsigned int ticket = atomicAdd(&ctl->blocks_done, 1u);
-    s_last = (ticket == gridDim.x - 1);
+    __threadfence();
+    is_last = (atomicAdd(&ctl->blocks_done, 1u) == gridDim.x - 1) ? 1 : 0;
   }
-  __syncthreads();
-  if (!s_last) return;
+  is_last = __shfl_sync(0xffffffffu, is_last, 0);
+  if (!is_last) return;
   __threadfence();
 
-  __shared__ float f_sums[8];
-  __shared__ unsigned int f_cnt[2];
-  if (threadIdx.x < 8) {
-    float acc = 0.0f;
+  // warp 0 of the last CTA: fold the per-copy accumulators (lane k < 8: sums, 8: resets, 9: time-outs)
+  float f_acc = 0.0f;
+  unsigned int f_cnt_acc = 0u;
+  if (lane < 8) {
     for (int c = 0; c < DDQC_STAT_COPIES; ++c) {
-      acc += __ldcg(&ctl->acc_sums[c][threadIdx.x]);
-      ctl->acc_sums[c][threadIdx.x] = 0.0f;
+      f_acc += __ldcg(&ctl->acc_sums[c][lane]);
+      ctl->acc_sums[c][lane] = 0.0f;
     }
-    f_sums[threadIdx.x] = acc;
-  } else if (threadIdx.x < 10) {
-    unsigned int* src = (threadIdx.x == 8) ? ctl->acc_reset : ctl->acc_timeout;
-    unsigned int acc = 0;
+  } else if (lane < 10) {
+    unsigned int* src = (lane == 8) ? ctl->acc_reset : ctl->acc_timeout;
     for (int c = 0; c < DDQC_STAT_COPIES; ++c) {
-      acc += __ldcg(&src[c]);
+      f_cnt_acc += __ldcg(&src[c]);
       src[c] = 0u;
     }
-    f_cnt[threadIdx.x - 8] = acc;
   }
-  __syncthreads();
+  float f_sums[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f_sums[k] = __shfl_sync(0xffffffffu, f_acc, k);
+  unsigned int f_cnt[2];
+  f_cnt[0] = __shfl_sync(0xffffffffu, f_cnt_acc, 8);
+  f_cnt[1] = __shfl_sync(0xffffffffu, f_cnt_acc, 9);
   const unsigned int n_reset = f_cnt[0];
   const unsigned int n_fix = __ldcg(&ctl->fixup_count);
 
   // A16: some env reset this step -> envs that only resampled their target see fresh rel_pos
   if (n_reset > 0) {
-    for (unsigned int s = threadIdx.x; s < n_fix; s += kThreads) {
+    for (unsigned int s = lane; s < n_fix; s += 32) {
       int e = __ldcg(&O.fixup_idx[s]);
       const float* fv = O.fixup_val + (size_t)s * 8;
       O.rew[e] = __ldcg(&fv[0]);
       S.episode_sums[0 * n + e] = __ldcg(&fv[1]);
       S.episode_sums[1 * n + e] = __ldcg(&fv[2]);
       float o0 = __ldcg(&fv[3]), o1 = __ldcg(&fv[4]), o2 = __ldcg(&fv[5]);
-      if (P.obs_noise_std > 0.0f) {  // same noise words as the main pass
+      if (obs_noise_std > 0.0f) {  // same noise words as the main pass
         float z[13];
         philox_normals<13>((uint32_t)e, ev, DDQC_STREAM_OBS_NOISE, P.seed, z);
-        o0 = o0 + z[0] * P.obs_noise_std;
-        o1 = o1 + z[1] * P.obs_noise_std;
-        o2 = o2 + z[2] * P.obs_noise_std;
+        o0 = o0 + z[0] * obs_noise_std;
+        o1 = o1 + z[1] * obs_noise_std;
+        o2 = o2 + z[2] * obs_noise_std;
       }
       O.obs[(size_t)e * NOBS + 0] = o0;
       O.obs[(size_t)e * NOBS + 1] = o1;
       O.obs[(size_t)e * NOBS + 2] = o2;
-      if (O.rel_pos && O.last_rel_pos && O.last_base_pos) {
+      if (!LEAN && O.rel_pos && O.last_rel_pos && O.last_base_pos) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           float cm = __ldcg(&S.commands[c * n + e]);
@@ -484,7 +500,8 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
     }
   }
 
-  if (threadIdx.x == 0) {
+  __syncwarp();
+  if (lane == 0) {
     const uint32_t row = (ctl->ep_row + 1) % DDQC_EP_RING;
     const uint32_t prev_row = ctl->ep_row;
     for (int k = 0; k < DDQC_NUM_REWARDS; ++k) {
@@ -532,16 +549,27 @@ extern "C" int ddqc_env_step(const DdqcEnvParams* P, const DdqcEnvState* S, cons
   const int n = (int)n_env;
   dim3 grid((n + kThreads - 1) / kThreads), block(kThreads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool lean = !(P->flags & DDQC_F_NEED_EULER) && !(P->actuator_noise_std > 0.0f) && !(P->obs_noise_std > 0.0f) &&
+                    !meas_override && !O->base_lin_vel && !O->base_ang_vel && !O->rel_pos && !O->last_rel_pos &&
+                    !O->base_euler && !O->crash && !O->rpm && !O->last_base_pos;
+#define DDQC_LAUNCH(ACT)                                                                                      \
+  do {                                                                                                        \
+    if (lean)                                                                                                 \
+      env_step_kernel<ACT, true><<<grid, block, 0, st>>>(*P, *S, *O, ctl, actions, meas_override, n);         \
+    else                                                                                                      \
+      env_step_kernel<ACT, false><<<grid, block, 0, st>>>(*P, *S, *O, ctl, actions, meas_override, n);        \
+  } while (0)
   switch (P->action_type) {
     case DDQC_ACT_ROTOR_RPMS:
-      env_step_kernel<DDQC_ACT_ROTOR_RPMS><<<grid, block, 0, st>>>(*P, *S, *O, ctl, actions, meas_override, n);
+      DDQC_LAUNCH(DDQC_ACT_ROTOR_RPMS);
       break;
     case DDQC_ACT_CTBR:
-      env_step_kernel<DDQC_ACT_CTBR><<<grid, block, 0, st>>>(*P, *S, *O, ctl, actions, meas_override, n);
+      DDQC_LAUNCH(DDQC_ACT_CTBR);
       break;
     default:
-      env_step_kernel<DDQC_ACT_CTBR_FIXED_YAW><<<grid, block, 0, st>>>(*P, *S, *O, ctl, actions, meas_override, n);
+      DDQC_LAUNCH(DDQC_ACT_CTBR_FIXED_YAW);
       break;
   }
+#undef DDQC_LAUNCH
   return (int)cudaGetLastError();
 }

@@ -279,8 +279,10 @@ class HoverEnv:
         need_euler = (
             self._aux
             or yaw_scale != 0.0
-            or env_cfg["termination_if_roll_greater_than"] < 180.001
-            or env_cfg["termination_if_pitch_greater_than"] < 180.001
+            # |roll| <= fp32(pi)*fp32(180/pi), which rounds to exactly 180.0f, and |pitch| <= 90:
+            # with thresholds >= 180 the two predicates (hover_env.py:483-488) can never fire
+            or env_cfg["termination_if_roll_greater_than"] < 180
+            or env_cfg["termination_if_pitch_greater_than"] < 180
         )
         self._params = make_env_params(
             env_cfg, obs_cfg, self.reward_scales, reward_cfg["yaw_lambda"], command_cfg, action_type,
