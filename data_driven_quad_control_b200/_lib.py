@@ -222,8 +222,6 @@ def load():
         )
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
-        if name.startswith("ddqc_ddmpc") and not hasattr(lib, name):
-            continue  # TEMP: solver TU not written yet
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args

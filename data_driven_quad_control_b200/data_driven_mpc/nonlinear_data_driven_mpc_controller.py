@@ -1,0 +1,230 @@
+"""Batched nonlinear data-driven MPC controllers on the `ddqc_ddmpc_solve` CUDA kernel.
+
+The reference drives a third-party `direct_data_driven_mpc.NonlinearDataDrivenMPCController`
+(one CPU process per controller, cvxpy + OSQP per step).  This module keeps that controller's
+constructor keywords and step API -- as used by the reference at
+`data_driven_mpc/utilities/param_grid_search/controller_creation.py:91-112` (ctor),
+`.../controller_evaluation.py:361` (`update_and_solve_data_driven_mpc`), `:389-392`
+(`get_optimal_control_input_at_step`), `:416-422` (`get_du_value_at_step`,
+`store_input_output_measurement`) and `comparison/utilities/controller_workers/dd_mpc_worker.py:78`
+(`set_output_setpoint`) -- and adds a batched front: `BatchedNonlinearDataDrivenMPC` holds B
+controllers (leading dimension B on every tensor) and solves them in one launch.
+
+`NonlinearDataDrivenMPCController` is the single-controller, numpy-in / numpy-out drop-in.
+
+Supported configuration: the one every shipped reference config uses (`ext_out_incr_in=False`,
+`update_cost_threshold=None`), `alpha_reg_type` APPROXIMATED (0) or ZERO (2), block-diagonal
+Q / R with identical diagonal blocks (what `controller_creation.py:73-88` builds).  Anything
+else raises NotImplementedError / ValueError instead of silently solving a different problem.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from enum import Enum
+
+import numpy as np
+import torch
+
+from data_driven_quad_control_b200 import _lib
+
+
+class AlphaRegType(Enum):
+    APPROXIMATED = 0  # regularise w.r.t. an approximation of alpha_Lin^sr(D_t)
+    PREVIOUS = 1  # w.r.t. the previous optimal alpha
+    ZERO = 2  # w.r.t. zero
+
+
+def _block_diag_weights(M, blocks: int, dim: int, name: str) -> np.ndarray:
+    """Diagonal of the repeated block of kron(I_blocks, diag(w)); validates the structure."""
+    M = np.asarray(M, dtype=np.float64)
+    if M.shape != (blocks * dim, blocks * dim):
+        raise ValueError(f"{name} must have shape {(blocks * dim, blocks * dim)}, got {M.shape}")
+    w = np.diag(M)[:dim].copy()
+    if not np.array_equal(M, np.kron(np.eye(blocks), np.diag(w))):
+        raise NotImplementedError(f"{name} must be block diagonal with identical diagonal blocks: kron(I, diag(w))")
+    if (w <= 0).any():
+        raise ValueError(f"{name} weights must be positive")
+    return w
+
+
+class BatchedNonlinearDataDrivenMPC:
+    def __init__(
+        self,
+        n: int,
+        m: int,
+        p: int,
+        u,
+        y,
+        L: int,
+        Q,
+        R,
+        S,
+        y_r,
+        lamb_alpha: float,
+        lamb_sigma: float,
+        U,
+        Us,
+        alpha_reg_type: AlphaRegType | int = AlphaRegType.ZERO,
+        lamb_alpha_s: float | None = None,
+        lamb_sigma_s: float | None = None,
+        ext_out_incr_in: bool = False,
+        update_cost_threshold: float | None = None,
+        n_mpc_step: int = 1,
+        device: torch.device | str = "cuda",
+        solve_on_init: bool = True,
+        max_iter: int = 200,
+    ):
+        if ext_out_incr_in:
+            raise NotImplementedError("ext_out_incr_in=True (extended output / input increments) is not supported")
+        if update_cost_threshold:
+            raise NotImplementedError("update_cost_threshold is not supported (always None in the reference configs)")
+        art = AlphaRegType(alpha_reg_type) if not isinstance(alpha_reg_type, AlphaRegType) else alpha_reg_type
+        if art == AlphaRegType.PREVIOUS:
+            raise NotImplementedError("alpha_reg_type PREVIOUS is not supported by the condensed GPU solver yet")
+        if art == AlphaRegType.APPROXIMATED and (lamb_alpha_s is None or lamb_sigma_s is None):
+            raise ValueError("lamb_alpha_s and lamb_sigma_s are required for alpha_reg_type APPROXIMATED")
+        self._lib = _lib.load()
+        self.device = _lib.require_cuda(device)
+        dev = self.device
+        f64 = dict(dtype=torch.float64, device=dev)
+
+        u_t = torch.as_tensor(np.asarray(u) if not torch.is_tensor(u) else u).to(**f64)
+        y_t = torch.as_tensor(np.asarray(y) if not torch.is_tensor(y) else y).to(**f64)
+        if u_t.ndim != 3 or y_t.ndim != 3 or u_t.shape[:2] != y_t.shape[:2] or u_t.shape[2] != m or y_t.shape[2] != p:
+            raise ValueError("u must have shape (B, N, m) and y (B, N, p)")
+        self.B, self.N = int(u_t.shape[0]), int(u_t.shape[1])
+        self.n, self.m, self.p, self.L = int(n), int(m), int(p), int(L)
+        self.n_mpc_step = int(n_mpc_step)
+        if not 1 <= self.n_mpc_step <= self.L + 1:
+            raise ValueError("n_mpc_step out of range")
+        ell = self.L + self.n + 1
+        if self.N - ell + 1 < (m + p) * ell + 1:
+            # fewer Hankel columns than rows: the data cannot be persistently exciting of the needed order
+            raise ValueError(f"N = {self.N} is too short for L = {L}, n = {n}: need N >= {(m + p + 1) * ell}")
+        self.alpha_reg_type = art
+        self.u = u_t.contiguous().clone()
+        self.y = y_t.contiguous().clone()
+
+        cfg = _lib.MpcConfig()
+        cfg.n, cfg.m, cfg.p, cfg.L, cfg.N = self.n, self.m, self.p, self.L, self.N
+        cfg.alpha_reg_type = art.value
+        cfg.max_iter = int(max_iter)
+        qw = _block_diag_weights(Q, ell, p, "Q")
+        rw = _block_diag_weights(R, ell, m, "R")
+        sw = _block_diag_weights(S, 1, p, "S")
+        U = np.asarray(U, dtype=np.float64).reshape(m, 2)
+        Us = np.asarray(Us, dtype=np.float64).reshape(m, 2)
+        for i in range(p):
+            cfg.Q[i], cfg.S[i] = qw[i], sw[i]
+        for i in range(m):
+            cfg.R[i] = rw[i]
+            cfg.U_lo[i], cfg.U_hi[i] = U[i]
+            cfg.Us_lo[i], cfg.Us_hi[i] = Us[i]
+        cfg.lamb_alpha, cfg.lamb_sigma = float(lamb_alpha), float(lamb_sigma)
+        cfg.lamb_alpha_s = float(lamb_alpha_s) if lamb_alpha_s is not None else 1.0
+        cfg.lamb_sigma_s = float(lamb_sigma_s) if lamb_sigma_s is not None else 1.0
+        self._cfg = cfg
+        ws_bytes = self._lib.ddqc_ddmpc_workspace_bytes(C.byref(cfg), self.B)
+        if ws_bytes < 0:
+            raise ValueError("unsupported problem size for the GPU solver (see ddqc_ddmpc.cu limits)")
+        self._ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+
+        self.y_r = torch.zeros((self.B, p), **f64)
+        self.set_output_setpoint(y_r)
+        self.us = torch.zeros((self.B, m), **f64)  # last optimal equilibrium input
+        self.ys = torch.zeros((self.B, p), **f64)
+        self._us_prev = torch.zeros_like(self.us)
+        self._ys_prev = torch.zeros_like(self.ys)
+        self._have_prev = torch.zeros((self.B,), dtype=torch.int32, device=dev)
+        self.optimal_u = torch.zeros((self.B, self.L + 1, m), **f64)
+        self.status = torch.zeros((self.B,), dtype=torch.int32, device=dev)
+        self.iters = torch.zeros((self.B,), dtype=torch.int32, device=dev)
+        if solve_on_init:
+            self.update_and_solve_data_driven_mpc()
+
+    # ------------------------------------------------------------------ API
+    def set_output_setpoint(self, y_r) -> None:
+        t = torch.as_tensor(np.asarray(y_r) if not torch.is_tensor(y_r) else y_r).to(self.y_r)
+        if t.numel() == self.p:
+            t = t.reshape(1, self.p).expand(self.B, self.p)
+        self.y_r.copy_(t.reshape(self.B, self.p))
+
+    def update_and_solve_data_driven_mpc(self) -> None:
+        """One solve of every controller of the batch on its current (u, y) window."""
+        # the equilibrium of the previous solve parameterises alpha_sr (type APPROXIMATED)
+        self._us_prev.copy_(self.us)
+        self._ys_prev.copy_(self.ys)
+        rc = self._lib.ddqc_ddmpc_solve(
+            C.byref(self._cfg), self._ws.data_ptr(), self.u.data_ptr(), self.y.data_ptr(), self.y_r.data_ptr(),
+            self._us_prev.data_ptr(), self._ys_prev.data_ptr(), self._have_prev.data_ptr(),
+            self.optimal_u.data_ptr(), self.us.data_ptr(), self.ys.data_ptr(), self.status.data_ptr(),
+            self.iters.data_ptr(), self.B, _lib.stream_ptr(self.device),
+        )  # fmt: skip
+        _lib.check(rc, "ddqc_ddmpc_solve")
+        self._have_prev.fill_(1)
+
+    def get_optimal_control_input_at_step(self, n_step: int = 0) -> torch.Tensor:
+        if not 0 <= n_step < self.n_mpc_step:
+            raise ValueError("The specified step `n_step` must be within the range [0, n_mpc_step - 1].")
+        return self.optimal_u[:, n_step, :]
+
+    def get_du_value_at_step(self, n_step: int = 0):
+        return None  # only meaningful with ext_out_incr_in=True
+
+    def store_input_output_measurement(self, u_current, y_current, du_current=None) -> None:
+        u_c = torch.as_tensor(np.asarray(u_current) if not torch.is_tensor(u_current) else u_current)
+        y_c = torch.as_tensor(np.asarray(y_current) if not torch.is_tensor(y_current) else y_current)
+        u_c = u_c.to(device=self.device, dtype=torch.float64).reshape(self.B, self.m).contiguous()
+        y_c = y_c.to(device=self.device, dtype=torch.float64).reshape(self.B, self.p).contiguous()
+        rc = self._lib.ddqc_ddmpc_store(
+            C.byref(self._cfg), self.u.data_ptr(), self.y.data_ptr(), u_c.data_ptr(), y_c.data_ptr(), self.B,
+            _lib.stream_ptr(self.device),
+        )
+        _lib.check(rc, "ddqc_ddmpc_store")
+
+    def check_status(self) -> None:
+        """Raises if any controller of the batch failed (synchronises).  Mirrors the per-evaluation
+        FAILURE of the reference (controller_evaluation.py:178-215)."""
+        st = self.status.cpu()
+        if (st != 0).any():
+            bad = st.nonzero().flatten().tolist()
+            raise RuntimeError(f"DD-MPC solve failed for controllers {bad[:8]} (status {st[bad[0]].item()})")
+
+
+class NonlinearDataDrivenMPCController:
+    """Single-controller drop-in with the numpy interface of the third-party controller."""
+
+    def __init__(self, n, m, p, u, y, L, Q, R, S, y_r, lamb_alpha, lamb_sigma, U, Us, alpha_reg_type=AlphaRegType.ZERO,
+                 lamb_alpha_s=None, lamb_sigma_s=None, ext_out_incr_in=False, update_cost_threshold=None,
+                 n_mpc_step=1, device="cuda", solve_on_init=True):  # fmt: skip
+        u, y = np.asarray(u, dtype=np.float64), np.asarray(y, dtype=np.float64)
+        self._b = BatchedNonlinearDataDrivenMPC(
+            n, m, p, u[None], y[None], L, Q, R, S, np.asarray(y_r, dtype=np.float64).reshape(1, -1), lamb_alpha,
+            lamb_sigma, U, Us, alpha_reg_type, lamb_alpha_s, lamb_sigma_s, ext_out_incr_in, update_cost_threshold,
+            n_mpc_step, device, solve_on_init,
+        )  # fmt: skip
+        self.n, self.m, self.p, self.L, self.N = n, m, p, L, u.shape[0]
+        self.n_mpc_step = n_mpc_step
+        self.y_r = np.asarray(y_r, dtype=np.float64).reshape(-1, 1)
+        if solve_on_init:
+            self._b.check_status()
+
+    def set_output_setpoint(self, y_r) -> None:
+        self.y_r = np.asarray(y_r, dtype=np.float64).reshape(-1, 1)
+        self._b.set_output_setpoint(self.y_r.reshape(1, -1))
+
+    def update_and_solve_data_driven_mpc(self) -> None:
+        self._b.update_and_solve_data_driven_mpc()
+        self._b.check_status()
+
+    def get_optimal_control_input_at_step(self, n_step: int = 0) -> np.ndarray:
+        return self._b.get_optimal_control_input_at_step(n_step)[0].cpu().numpy()
+
+    def get_du_value_at_step(self, n_step: int = 0):
+        return None
+
+    def store_input_output_measurement(self, u_current, y_current, du_current=None) -> None:
+        self._b.store_input_output_measurement(
+            np.asarray(u_current, dtype=np.float64).reshape(1, -1), np.asarray(y_current, dtype=np.float64).reshape(1, -1)
+        )

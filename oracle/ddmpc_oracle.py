@@ -1,0 +1,473 @@
+"""TEST INFRASTRUCTURE ONLY (oracle) -- numpy float64 restatement of the nonlinear data-driven
+MPC controller the reference uses.  PARITY UNPINNED: the controller lives in the un-vendored
+third-party package `direct-data-driven-mpc @ git+https://github.com/pavelacamposp/
+direct-data-driven-mpc@94150cc` (reference `pyproject.toml:20`, solved there through `cvxpy`,
+unpinned, default QP solver OSQP); neither is under /root/reference nor installed, and no
+reference test pins a QP solution (`tests/data_driven_mpc_tests/test_dd_mpc_controller_eval.py:
+136-141` checks shapes / finiteness only).  What IS anchored on the reference:
+
+  * the constructor contract and weight matrices:
+      data_driven_mpc/utilities/param_grid_search/controller_creation.py:51-112
+  * the closed-loop call sequence (update_and_solve -> get_optimal_control_input_at_step ->
+    store_input_output_measurement) and the RMSE / early-stop metric:
+      data_driven_mpc/utilities/param_grid_search/controller_evaluation.py:345-450
+  * the parameter semantics: configs/data_driven_mpc/dd_mpc_controller_params.yaml:15-95
+  * the initial data collection procedure:
+      data_driven_mpc/utilities/drone_initial_data_collection.py:117-187
+
+The optimisation problem is the published scheme the package implements (J. Berberich,
+J. Koehler, M. A. Mueller, F. Allgoewer, "Linear Tracking MPC for Nonlinear Systems -- Part II:
+The Data-Driven Case", IEEE TAC 67(9), 2022, Problem (22)), with l = L+n+1, C = N-l+1:
+
+  min   sum_{k=-n..L} |ubar_k - u_s|_R^2 + |ybar_k - y_s|_Q^2 + |y_s - y_r|_S^2
+        + lamb_alpha |alpha - alpha_sr|^2 + lamb_sigma |sigma|^2
+  s.t.  [ubar; ybar + sigma; 1] = [H_l(u); H_l(y); 1^T] alpha
+        ubar_k = u_{t+k}, ybar_k = y_{t+k}                    k = -n..-1   (initial condition)
+        ubar_k = u_s,     ybar_k = y_s                        k = L-n..L   (terminal equality)
+        ubar_k in U (k = 0..L),  u_s in U_s
+
+alpha_reg_type 0 (APPROXIMATED): alpha_sr is the minimiser of lamb_alpha_s|a|^2 + lamb_sigma_s|s|^2
+s.t. [1 (x) u_s'; 1 (x) y_s' + s; 1] = [H_u; H_y; 1^T] a with (u_s', y_s') the previous optimal
+equilibrium (Remark 3 of the paper); on the very first solve, when no previous solution exists,
+alpha_sr = 0 (UNVERIFIED convention).  Type 1: previous optimal alpha.  Type 2: zero.
+
+The oracle solves the LITERAL problem (all of alpha, sigma, ubar, ybar, u_s, y_s as variables,
+693 of them at the default sizes) with a dense primal-dual interior-point method and certifies
+the result through its KKT residuals; the product solves an algebraically condensed form on the
+GPU, so agreement between the two is a genuine check.
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+APPROXIMATED, PREVIOUS, ZERO = 0, 1, 2
+
+
+def hankel(w: np.ndarray, ell: int) -> np.ndarray:
+    """Block-Hankel matrix of depth `ell` of a signal w (N, d): row block j, column c holds
+    w[j + c]; shape (d*ell, N-ell+1)."""
+    N, d = w.shape
+    C = N - ell + 1
+    H = np.empty((d * ell, C))
+    for j in range(ell):
+        H[j * d : (j + 1) * d, :] = w[j : j + C, :].T
+    return H
+
+
+@dataclass
+class MPCParams:
+    n: int
+    m: int
+    p: int
+    L: int
+    N: int
+    Q: np.ndarray  # (p,) diagonal output weights
+    R: np.ndarray  # (m,)
+    S: np.ndarray  # (p,)
+    lamb_alpha: float
+    lamb_sigma: float
+    U: np.ndarray  # (m, 2)
+    Us: np.ndarray  # (m, 2)
+    alpha_reg_type: int = ZERO
+    lamb_alpha_s: float | None = None
+    lamb_sigma_s: float | None = None
+
+    @property
+    def ell(self) -> int:
+        return self.L + self.n + 1
+
+    @property
+    def C(self) -> int:
+        return self.N - self.ell + 1
+
+    @staticmethod
+    def from_yaml_dict(d: dict, m: int = 3, p: int = 3) -> "MPCParams":
+        return MPCParams(
+            n=d["n"], m=m, p=p, L=d["L"], N=d["N"],
+            Q=np.array(d["Q_weights"], float), R=np.array(d["R_weights"], float), S=np.array(d["S_weights"], float),
+            lamb_alpha=float(d["lambda_alpha"]), lamb_sigma=float(d["lambda_sigma"]),
+            U=np.array(d["U"], float), Us=np.array(d["Us"], float), alpha_reg_type=int(d["alpha_reg_type"]),
+            lamb_alpha_s=d.get("lambda_alpha_s"), lamb_sigma_s=d.get("lambda_sigma_s"),
+        )  # fmt: skip
+
+
+# --------------------------------------------------------------------------------------------
+# literal QP assembly
+# --------------------------------------------------------------------------------------------
+def build_literal_qp(prm: MPCParams, u_win, y_win, y_r, alpha_sr):
+    """0.5 z'Pz + q'z,  A z = b,  G z <= h   with z = [alpha, sigma, ubar, ybar, u_s, y_s]."""
+    n, m, p, L, ell, C = prm.n, prm.m, prm.p, prm.L, prm.ell, prm.C
+    Hu, Hy = hankel(u_win, ell), hankel(y_win, ell)
+    o_a, o_s, o_u, o_y = 0, C, C + p * ell, C + p * ell + m * ell
+    o_us, o_ys = o_y + p * ell, o_y + p * ell + m
+    nz = o_ys + p
+    P = np.zeros((nz, nz))
+    q = np.zeros(nz)
+    # lamb_alpha |alpha - alpha_sr|^2
+    P[o_a : o_a + C, o_a : o_a + C] += 2 * prm.lamb_alpha * np.eye(C)
+    q[o_a : o_a + C] += -2 * prm.lamb_alpha * alpha_sr
+    # lamb_sigma |sigma|^2
+    P[o_s : o_s + p * ell, o_s : o_s + p * ell] += 2 * prm.lamb_sigma * np.eye(p * ell)
+    # sum_k |ubar_k - u_s|_R^2 ,  |ybar_k - y_s|_Q^2
+    for j in range(ell):
+        for i in range(m):
+            a, b, w = o_u + j * m + i, o_us + i, prm.R[i]
+            P[a, a] += 2 * w
+            P[b, b] += 2 * w
+            P[a, b] -= 2 * w
+            P[b, a] -= 2 * w
+        for i in range(p):
+            a, b, w = o_y + j * p + i, o_ys + i, prm.Q[i]
+            P[a, a] += 2 * w
+            P[b, b] += 2 * w
+            P[a, b] -= 2 * w
+            P[b, a] -= 2 * w
+    # |y_s - y_r|_S^2
+    for i in range(p):
+        P[o_ys + i, o_ys + i] += 2 * prm.S[i]
+        q[o_ys + i] += -2 * prm.S[i] * y_r[i]
+
+    rows, rhs = [], []
+
+    def eq(coefs, val):
+        r = np.zeros(nz)
+        for idx, c in coefs:
+            r[idx] += c
+        rows.append(r)
+        rhs.append(val)
+
+    for r_ in range(m * ell):  # H_u alpha - ubar = 0
+        row = np.zeros(nz)
+        row[o_a : o_a + C] = Hu[r_]
+        row[o_u + r_] = -1
+        rows.append(row)
+        rhs.append(0.0)
+    for r_ in range(p * ell):  # H_y alpha - ybar - sigma = 0
+        row = np.zeros(nz)
+        row[o_a : o_a + C] = Hy[r_]
+        row[o_y + r_] = -1
+        row[o_s + r_] = -1
+        rows.append(row)
+        rhs.append(0.0)
+    row = np.zeros(nz)
+    row[o_a : o_a + C] = 1
+    rows.append(row)
+    rhs.append(1.0)
+    u_past, y_past = u_win[-n:], y_win[-n:]
+    for j in range(n):  # initial condition
+        for i in range(m):
+            eq([(o_u + j * m + i, 1)], u_past[j, i])
+        for i in range(p):
+            eq([(o_y + j * p + i, 1)], y_past[j, i])
+    for j in range(L, ell):  # terminal equality (k = L-n..L)
+        for i in range(m):
+            eq([(o_u + j * m + i, 1), (o_us + i, -1)], 0.0)
+        for i in range(p):
+            eq([(o_y + j * p + i, 1), (o_ys + i, -1)], 0.0)
+    A, b = np.array(rows), np.array(rhs)
+
+    g_rows, g_rhs = [], []
+    for j in range(n, ell):  # ubar_k in U, k = 0..L
+        for i in range(m):
+            r1 = np.zeros(nz)
+            r1[o_u + j * m + i] = 1
+            g_rows.append(r1)
+            g_rhs.append(prm.U[i, 1])
+            g_rows.append(-r1)
+            g_rhs.append(-prm.U[i, 0])
+    for i in range(m):  # u_s in U_s
+        r1 = np.zeros(nz)
+        r1[o_us + i] = 1
+        g_rows.append(r1)
+        g_rhs.append(prm.Us[i, 1])
+        g_rows.append(-r1)
+        g_rhs.append(-prm.Us[i, 0])
+    G, h = np.array(g_rows), np.array(g_rhs)
+    offs = dict(alpha=o_a, sigma=o_s, ubar=o_u, ybar=o_y, us=o_us, ys=o_ys, nz=nz)
+    return P, q, A, b, G, h, offs
+
+
+# --------------------------------------------------------------------------------------------
+# dense primal-dual interior point (Mehrotra predictor-corrector) for a convex QP
+# --------------------------------------------------------------------------------------------
+def _refined_solve(K, rhs, iters=3):
+    """LU solve in float64 with residuals accumulated in extended precision."""
+    import scipy.linalg as sla
+
+    lu = sla.lu_factor(K)
+    x = sla.lu_solve(lu, rhs)
+    Kl = K.astype(np.longdouble)
+    for _ in range(iters):
+        r = (rhs.astype(np.longdouble) - Kl @ x.astype(np.longdouble)).astype(np.float64)
+        x = x + sla.lu_solve(lu, r)
+    return x
+
+
+def solve_qp_ipm(P, q, A, b, G, h, tol=1e-10, max_iter=80):
+    nz, ne, ni = P.shape[0], A.shape[0], G.shape[0]
+    # column scaling keeps the 1e9-weighted slack block and the O(1) blocks comparable
+    d = 1.0 / np.sqrt(np.maximum(np.diag(P), 1e-12))
+    Ps, qs, As, Gs = P * d[:, None] * d[None, :], q * d, A * d[None, :], G * d[None, :]
+    z = np.zeros(nz)
+    nu = np.zeros(ne)
+    s = np.maximum(h - Gs @ z, 1.0)
+    lam = np.ones(ni)
+    info = {"iters": 0, "converged": False}
+    for it in range(max_iter):
+        r_d = Ps @ z + qs + As.T @ nu + Gs.T @ lam
+        r_p = As @ z - b
+        r_g = Gs @ z + s - h
+        mu = float(s @ lam) / ni
+        res = max(np.abs(r_d).max() / (1 + np.abs(qs).max()), np.abs(r_p).max(), np.abs(r_g).max())
+        info["iters"] = it
+        info["residual"], info["mu"] = float(res), mu
+        if (res < tol and mu < tol) or (res < 1e-8 and mu < 1e-11):
+            info["converged"] = True
+            break
+        if mu < 1e-13:  # complementarity exhausted: further steps only degrade the KKT conditioning
+            info["converged"] = res < 1e-6
+            break
+        w = lam / s
+        K = np.zeros((nz + ne, nz + ne))
+        K[:nz, :nz] = Ps + Gs.T @ (w[:, None] * Gs)
+        K[:nz, nz:] = As.T
+        K[nz:, :nz] = As
+
+        def newton(r_c):
+            rhs = np.concatenate([-r_d - Gs.T @ (w * r_g - r_c / s), -r_p])
+            sol = _refined_solve(K, rhs, iters=2)
+            dz, dnu = sol[:nz], sol[nz:]
+            dlam = w * (Gs @ dz + r_g) - r_c / s
+            ds = -(r_c + s * dlam) / lam
+            return dz, dnu, dlam, ds
+
+        def step_len(v, dv):
+            neg = dv < 0
+            return min(1.0, float(np.min(-v[neg] / dv[neg]))) if neg.any() else 1.0
+
+        try:
+            dz, dnu, dlam, ds = newton(s * lam)  # affine scaling direction
+            if not (np.isfinite(dz).all() and np.isfinite(dlam).all()):
+                raise FloatingPointError
+        except (ValueError, FloatingPointError, np.linalg.LinAlgError):
+            # the barrier has driven lam/s beyond what float64 LU can factor: the iterate is as
+            # converged as this method gets; the caller certifies it through kkt_residuals()
+            info["converged"] = res < 1e-6 and mu < 1e-7
+            break
+        a_aff = min(step_len(s, ds), step_len(lam, dlam))
+        mu_aff = float((s + a_aff * ds) @ (lam + a_aff * dlam)) / ni
+        sig = (mu_aff / mu) ** 3
+        dz, dnu, dlam, ds = newton(s * lam + ds * dlam - sig * mu)
+        a = 0.99 * min(step_len(s, ds), step_len(lam, dlam))
+        z, nu, lam, s = z + a * dz, nu + a * dnu, lam + a * dlam, s + a * ds
+    return z * d, nu, lam, s, info
+
+
+def kkt_residuals(P, q, A, b, G, h, z, nu, lam):
+    """(stationarity, equality, inequality violation, complementarity, min multiplier): all ~0 at
+    the optimum of the convex QP -- a solver-independent certificate."""
+    # multipliers were computed for the column-scaled problem; stationarity is re-derived in the
+    # original scaling by least squares on the active set instead of trusting them
+    slack = h - G @ z
+    act = slack < 1e-7 * (1 + np.abs(h))
+    M = np.concatenate([A.T, G[act].T], axis=1)
+    g = P @ z + q
+    mult, *_ = np.linalg.lstsq(M, -g, rcond=None)
+    stat = np.abs(g + M @ mult).max() / (1 + np.abs(g).max())
+    lam_act = mult[A.shape[0] :]
+    return dict(
+        stationarity=float(stat),
+        equality=float(np.abs(A @ z - b).max()),
+        inequality=float(max(0.0, -slack.min())),
+        min_active_multiplier=float(lam_act.min()) if lam_act.size else 0.0,
+        n_active=int(act.sum()),
+    )
+
+
+def solve_alpha_sr(prm: MPCParams, u_win, y_win, us_prev, ys_prev):
+    """Equality-constrained QP of Remark 3 (see module docstring), sigma eliminated:
+    min lamb_alpha_s |a|^2 + lamb_sigma_s |H_y a - 1(x)y_s'|^2  s.t. H_u a = 1(x)u_s', 1'a = 1."""
+    ell, C = prm.ell, prm.C
+    Hu, Hy = hankel(u_win, ell), hankel(y_win, ell)
+    E = np.vstack([Hu, np.ones((1, C))])
+    e = np.concatenate([np.tile(us_prev, ell), [1.0]])
+    t = np.tile(ys_prev, ell)
+    la, ls = float(prm.lamb_alpha_s), float(prm.lamb_sigma_s)
+    K = np.zeros((C + E.shape[0], C + E.shape[0]))
+    K[:C, :C] = 2 * (la * np.eye(C) + ls * Hy.T @ Hy)
+    K[:C, C:] = E.T
+    K[C:, :C] = E
+    rhs = np.concatenate([2 * ls * Hy.T @ t, e])
+    sol = _refined_solve(K, rhs, iters=4)
+    return sol[:C]
+
+
+class NonlinearDDMPCOracle:
+    """Single-controller mirror of the third-party `NonlinearDataDrivenMPCController` API used by
+    the reference (ctor: controller_creation.py:91-112; methods: controller_evaluation.py:361-422)."""
+
+    def __init__(self, n, m, p, u, y, L, Q, R, S, y_r, lamb_alpha, lamb_sigma, U, Us, alpha_reg_type=ZERO,
+                 lamb_alpha_s=None, lamb_sigma_s=None, ext_out_incr_in=False, update_cost_threshold=None,
+                 n_mpc_step=1, solve_on_init=True):  # fmt: skip
+        if ext_out_incr_in or update_cost_threshold:
+            raise NotImplementedError("only the shipped configuration (both off) is restated")
+        u, y = np.array(u, float), np.array(y, float)
+        ell = L + n + 1
+        Q, R, S = np.asarray(Q, float), np.asarray(R, float), np.asarray(S, float)
+        self.prm = MPCParams(
+            n=n, m=m, p=p, L=L, N=u.shape[0], Q=np.diag(Q)[:p].copy(), R=np.diag(R)[:m].copy(), S=np.diag(S)[:p].copy(),
+            lamb_alpha=lamb_alpha, lamb_sigma=lamb_sigma, U=np.asarray(U, float), Us=np.asarray(Us, float),
+            alpha_reg_type=int(getattr(alpha_reg_type, "value", alpha_reg_type)),
+            lamb_alpha_s=lamb_alpha_s, lamb_sigma_s=lamb_sigma_s,
+        )  # fmt: skip
+        assert Q.shape == (p * ell, p * ell) and R.shape == (m * ell, m * ell) and S.shape == (p, p)
+        self.n, self.m, self.p, self.L, self.N = n, m, p, L, u.shape[0]
+        self.n_mpc_step = n_mpc_step
+        self.u, self.y = u.copy(), y.copy()
+        self.y_r = np.asarray(y_r, float).reshape(-1, 1)
+        self.us_prev = self.ys_prev = None
+        self.alpha_prev = None
+        self.optimal_u = None
+        self.last = {}
+        if solve_on_init:
+            self.update_and_solve_data_driven_mpc()
+
+    def set_output_setpoint(self, y_r):
+        self.y_r = np.asarray(y_r, float).reshape(-1, 1)
+
+    def alpha_sr(self):
+        prm = self.prm
+        if prm.alpha_reg_type == APPROXIMATED and self.us_prev is not None:
+            return solve_alpha_sr(prm, self.u, self.y, self.us_prev, self.ys_prev)
+        if prm.alpha_reg_type == PREVIOUS and self.alpha_prev is not None:
+            return self.alpha_prev
+        return np.zeros(prm.C)
+
+    def update_and_solve_data_driven_mpc(self):
+        prm = self.prm
+        a_sr = self.alpha_sr()
+        P, q, A, b, G, h, offs = build_literal_qp(prm, self.u, self.y, self.y_r.ravel(), a_sr)
+        z, nu, lam, s, info = solve_qp_ipm(P, q, A, b, G, h)
+        if not info["converged"]:
+            raise RuntimeError("oracle IPM did not converge")
+        ell = prm.ell
+        ubar = z[offs["ubar"] : offs["ubar"] + prm.m * ell].reshape(ell, prm.m)
+        self.optimal_u = ubar[prm.n :].copy()  # ubar_0 .. ubar_L
+        self.us_prev = z[offs["us"] : offs["us"] + prm.m].copy()
+        self.ys_prev = z[offs["ys"] : offs["ys"] + prm.p].copy()
+        self.alpha_prev = z[: prm.C].copy()
+        self.last = dict(z=z, offs=offs, info=info, qp=(P, q, A, b, G, h), mult=(nu, lam), alpha_sr=a_sr)
+
+    def get_optimal_control_input_at_step(self, n_step=0):
+        return self.optimal_u[n_step].copy()
+
+    def get_du_value_at_step(self, n_step=0):
+        return None
+
+    def store_input_output_measurement(self, u_current, y_current, du_current=None):
+        self.u = np.vstack([self.u[1:], np.asarray(u_current, float).reshape(1, -1)])
+        self.y = np.vstack([self.y[1:], np.asarray(y_current, float).reshape(1, -1)])
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic initial data: PID-stabilised hover + persistently exciting perturbation
+# (data_driven_mpc/utilities/drone_initial_data_collection.py:117-187 on the oracle env)
+# --------------------------------------------------------------------------------------------
+def collect_initial_data(seed: int, N: int = 350, hover_pos=(0.0, 0.0, 1.5), u_range=None, U=None,
+                         obs_noise_std: float = 1e-4, settle_steps: int = 150):  # fmt: skip
+    import copy
+
+    import torch  # mixer via the same torch.linalg.pinv call as the product's host code
+
+    import env_oracle as eo
+    from controllers_oracle import TrackingOracle
+
+    u_range = np.array([[-0.1, 0.1], [-0.5, 0.5], [-0.5, 0.5]]) if u_range is None else np.asarray(u_range, float)
+    U = np.array([[0.0, 0.52974], [-1.5708, 1.5708], [-1.5708, 1.5708]]) if U is None else np.asarray(U, float)
+    env_cfg = dict(
+        dt=0.01, decimation=4, simulate_action_latency=True, clip_actions=1.0, actuator_noise_std=0.0,
+        termination_if_roll_greater_than=180, termination_if_pitch_greater_than=180,
+        termination_if_close_to_ground=0.0, termination_if_x_greater_than=100.0,
+        termination_if_y_greater_than=100.0, termination_if_z_greater_than=10.0,
+        termination_if_ang_vel_greater_than=20, termination_if_lin_vel_greater_than=20,
+        base_init_pos=[0.0, 0.0, 1.0], base_init_quat=[1.0, 0.0, 0.0, 0.0], episode_length_s=100,
+        at_target_threshold=0.1, min_hover_time_s=0.5, resampling_time_s=3.0,
+    )  # fmt: skip
+    obs_cfg = dict(obs_scales=dict(rel_pos=1 / 3.0, lin_vel=1 / 3.0, ang_vel=1 / 3.14159), obs_noise_std=0.0)
+    rew = dict(yaw_lambda=-10.0, reward_scales=dict(target=10.0, closeness=1.5, hover_time=0.01, smooth=-0.01,
+                                                     yaw=0.0, angular=-2e-4, crash=-10.0))  # fmt: skip
+    cmd = dict(num_commands=3, pos_x_range=[-1.0, 1.0], pos_y_range=[-1.0, 1.0], pos_z_range=[1.0, 3.0])
+    mixer, isk = ctbr_mixer()
+    env = eo.EnvOracle(1, env_cfg, obs_cfg, copy.deepcopy(rew), cmd, action_type=eo.CTBR_FIXED_YAW,
+                       auto_target_updates=False, mixer=mixer, inv_sqrt_kf=isk, rng=eo.PhiloxRng(seed))  # fmt: skip
+    env.reset()
+    target = np.array([hover_pos], np.float32)
+    env.update_target_pos([0], target)
+    ctrl = TrackingOracle(0.027, [[2.0, 0.0, 2.2], [2.0, 0.0, 2.2], [18.0, 0.0, 6.0]], 5.0, 1, env.step_dt)
+    q_sp = np.array([[1.0, 0.0, 0.0, 0.0]], np.float32)
+    rng = np.random.default_rng(seed)
+    lo, span = env.act_lo.astype(np.float64), env.act_span.astype(np.float64)
+
+    def measure():
+        pos = env.base_pos.astype(np.float64)
+        if obs_noise_std > 0:
+            pos = pos + rng.standard_normal(pos.shape) * obs_noise_std / obs_cfg["obs_scales"]["rel_pos"]
+        return pos
+
+    def act(cmd_ctbr):
+        a = -1.0 + (cmd_ctbr - lo) * 2.0 / span
+        env.step(np.clip(a, -1, 1).astype(np.float32))
+
+    for _ in range(settle_steps):  # hover_at_target
+        c = ctrl.compute(measure().astype(np.float32), env.base_quat, target, q_sp)[:, :3].astype(np.float64)
+        act(c)
+    m = 3
+    u_N = np.hstack([rng.uniform(u_range[i, 0], u_range[i, 1], (N, 1)) for i in range(m)])
+    y_N = np.zeros((N, 3))
+    for k in range(N):
+        c = ctrl.compute(measure().astype(np.float32), env.base_quat, target, q_sp)[:, :3].astype(np.float64)
+        u_N[k] = np.clip(u_N[k] + c[0], U[:, 0], U[:, 1])
+        act(u_N[k : k + 1])
+        y_N[k] = measure()[0]
+    state = dict(env=env, ctrl=ctrl, rng=rng, measure=measure, act=act)
+    return u_N, y_N, state
+
+
+def ctbr_mixer():
+    """The CTBR mixer exactly as the reference builds it (ctbr_controller.py:131-219), fp32 torch CPU."""
+    import torch
+
+    f32 = dict(dtype=torch.float32)
+    KF, KM = torch.tensor(3.16e-10, **f32), torch.tensor(7.94e-12, **f32)
+    theta = torch.deg2rad(torch.tensor([45.0, 135.0, 225.0, 315.0], **f32))
+    spin = torch.tensor([-1, 1, -1, 1], dtype=torch.int)
+    A = torch.vstack([-torch.sin(theta) * 0.0397, -torch.cos(theta) * 0.0397, KM / KF * spin, torch.ones_like(theta)])
+    J = torch.eye(4, **f32)
+    J[0, 0], J[1, 1], J[2, 2] = 1.4e-5, 1.4e-5, 2.17e-5
+    mixer = torch.linalg.pinv(A) @ J
+    return mixer.numpy(), float(torch.rsqrt(KF))
+
+
+def default_params() -> MPCParams:
+    return MPCParams(
+        n=6, m=3, p=3, L=35, N=350, Q=np.array([10.0, 10, 10]), R=np.array([10.0, 1, 1]), S=np.array([1000.0] * 3),
+        lamb_alpha=50.0, lamb_sigma=1e9, U=np.array([[0.0, 0.52974], [-1.5708, 1.5708], [-1.5708, 1.5708]]),
+        Us=np.array([[0.001, 0.528], [-1.571, 1.570], [-1.571, 1.570]]), alpha_reg_type=APPROXIMATED,
+        lamb_alpha_s=1.0, lamb_sigma_s=1e7,
+    )  # fmt: skip
+
+
+def ctor_kwargs(prm: MPCParams, u, y, y_r):
+    """Keyword arguments exactly as controller_creation.py:73-112 builds them."""
+    ell = prm.ell
+    return dict(
+        n=prm.n, m=prm.m, p=prm.p, u=u, y=y, L=prm.L, Q=np.kron(np.eye(ell), np.diag(prm.Q)),
+        R=np.kron(np.eye(ell), np.diag(prm.R)), S=np.kron(np.eye(1), np.diag(prm.S)), y_r=np.asarray(y_r).reshape(-1, 1),
+        lamb_alpha=prm.lamb_alpha, lamb_sigma=prm.lamb_sigma, U=prm.U, Us=prm.Us, lamb_alpha_s=prm.lamb_alpha_s,
+        lamb_sigma_s=prm.lamb_sigma_s, alpha_reg_type=prm.alpha_reg_type, ext_out_incr_in=False,
+        update_cost_threshold=None, n_mpc_step=1,
+    )  # fmt: skip

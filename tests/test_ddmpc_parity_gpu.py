@@ -1,0 +1,149 @@
+"""GPU parity of the batched condensed DD-MPC solver against the literal-QP interior-point oracle."""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # north star: optimal inputs within 1e-4 of the reference solution (problem conditioning ~1e11 limits fp64 agreement to ~1e-6)
+
+
+def _small_params():
+    import ddmpc_oracle as mo
+
+    # tests/data_driven_mpc_tests/config/test_controller_params.yaml of the reference: N=40, n=2, L=5
+    prm = mo.default_params()
+    prm.n, prm.L, prm.N = 2, 5, 80
+    return prm
+
+
+class _Plant:
+    """Stable random linear system x+ = A x + B u, y = C x + noise (one per controller)."""
+
+    def __init__(self, rng, m, p):
+        self.A = np.diag(rng.uniform(0.6, 0.95, 6)) + 0.02 * rng.standard_normal((6, 6))
+        self.B = rng.standard_normal((6, m)) * 0.3
+        self.C = rng.standard_normal((p, 6)) * 0.5
+        self.x = np.zeros(6)
+        self.rng, self.p = rng, p
+
+    def step(self, u):
+        self.x = self.A @ self.x + self.B @ u
+        return self.C @ self.x + 1e-4 * self.rng.standard_normal(self.p)
+
+
+def _synthetic_windows(prm, seed, B, return_plants=False):
+    """Cheap persistently exciting data: stable random linear systems driven by bounded noise."""
+    rng = np.random.default_rng(seed)
+    us, ys, plants = [], [], []
+    for _ in range(B):
+        plant = _Plant(rng, prm.m, prm.p)
+        u = np.stack([rng.uniform(0.15, 0.4, prm.N), rng.uniform(-0.5, 0.5, prm.N), rng.uniform(-0.5, 0.5, prm.N)], 1)
+        y = np.stack([plant.step(u[k]) for k in range(prm.N)])
+        us.append(u)
+        ys.append(y)
+        plants.append(plant)
+    if return_plants:
+        return np.stack(us), np.stack(ys), plants
+    return np.stack(us), np.stack(ys)
+
+
+def _batched(prm, u, y, y_r, **kw):
+    import ddmpc_oracle as mo
+    from data_driven_quad_control_b200.data_driven_mpc.nonlinear_data_driven_mpc_controller import (
+        BatchedNonlinearDataDrivenMPC,
+    )
+
+    kwargs = mo.ctor_kwargs(prm, u, y, y_r[0])
+    kwargs["y_r"] = y_r
+    return BatchedNonlinearDataDrivenMPC(**kwargs, device="cuda", **kw)
+
+
+@pytest.mark.parametrize("alpha_reg_type", [0, 2])
+def test_small_batch_closed_loop_matches_oracle(build_lib, alpha_reg_type):
+    import ddmpc_oracle as mo
+
+    prm = _small_params()
+    prm.alpha_reg_type = alpha_reg_type
+    B, T = 6, 4
+    u, y, plants = _synthetic_windows(prm, 3, B, return_plants=True)
+    y_r = np.tile(np.array([[0.3, -0.2, 0.5]]), (B, 1)) + 0.1 * np.arange(B)[:, None]
+    gpu = _batched(prm, u, y, y_r, solve_on_init=False)
+    orcs = [mo.NonlinearDDMPCOracle(**mo.ctor_kwargs(prm, u[b], y[b], y_r[b]), solve_on_init=False) for b in range(B)]
+    for t in range(T):
+        gpu.update_and_solve_data_driven_mpc()
+        assert (gpu.status.cpu().numpy() == 0).all(), gpu.status
+        u0 = gpu.get_optimal_control_input_at_step(0).cpu().numpy()
+        upred = gpu.optimal_u.cpu().numpy()
+        y_new = np.stack([plants[b].step(u0[b]) for b in range(B)])  # closed loop on the true plants
+        for b, orc in enumerate(orcs):
+            orc.update_and_solve_data_driven_mpc()
+            np.testing.assert_allclose(upred[b], orc.optimal_u, rtol=0, atol=TOL)
+            np.testing.assert_allclose(gpu.us[b].cpu().numpy(), orc.us_prev, rtol=0, atol=TOL)
+            np.testing.assert_allclose(gpu.ys[b].cpu().numpy(), orc.ys_prev, rtol=0, atol=10 * TOL)
+            orc.store_input_output_measurement(u0[b], y_new[b])
+        gpu.store_input_output_measurement(torch.from_numpy(u0).cuda(), torch.from_numpy(y_new).cuda())
+        for b, orc in enumerate(orcs):  # rolling windows stay identical
+            assert np.array_equal(gpu.u[b].cpu().numpy(), orc.u) and np.array_equal(gpu.y[b].cpu().numpy(), orc.y)
+
+
+def test_default_size_matches_oracle_and_golden(build_lib):
+    """n=6, L=35, N=350 (693-variable QP) on PID-stabilised drone data (tests/golden/ddmpc_default.npz)."""
+    import os
+
+    import ddmpc_oracle as mo
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ddmpc_default.npz"))
+    prm = mo.default_params()
+    u, y, y_r = g["u"], g["y"], g["y_r"]
+    gpu = _batched(prm, u[None], y[None], y_r[None], solve_on_init=False)
+    for t in range(g["u_opt"].shape[0]):
+        gpu.update_and_solve_data_driven_mpc()
+        assert int(gpu.status[0]) == 0
+        np.testing.assert_allclose(gpu.optimal_u[0].cpu().numpy(), g["u_opt"][t], rtol=0, atol=TOL)
+        np.testing.assert_allclose(gpu.us[0].cpu().numpy(), g["us"][t], rtol=0, atol=TOL)
+        gpu.store_input_output_measurement(g["u_opt"][t][0][None], g["y_next"][t][None])
+    assert int(gpu.iters.max()) <= 20
+
+
+def test_single_controller_numpy_api(build_lib):
+    import ddmpc_oracle as mo
+    from data_driven_quad_control_b200.data_driven_mpc.nonlinear_data_driven_mpc_controller import (
+        NonlinearDataDrivenMPCController,
+    )
+
+    prm = _small_params()
+    u, y = _synthetic_windows(prm, 11, 1)
+    y_r = np.array([0.2, 0.1, 0.4])
+    ctrl = NonlinearDataDrivenMPCController(**mo.ctor_kwargs(prm, u[0], y[0], y_r))
+    orc = mo.NonlinearDDMPCOracle(**mo.ctor_kwargs(prm, u[0], y[0], y_r))
+    u0 = ctrl.get_optimal_control_input_at_step(n_step=0)
+    assert isinstance(u0, np.ndarray) and u0.shape == (3,)
+    np.testing.assert_allclose(u0, orc.get_optimal_control_input_at_step(0), rtol=0, atol=TOL)
+    assert ctrl.get_du_value_at_step(0) is None and ctrl.n == prm.n and ctrl.y_r.shape == (3, 1)
+    ctrl.set_output_setpoint(np.array([[0.0], [0.0], [0.1]]))
+    orc.set_output_setpoint(np.array([[0.0], [0.0], [0.1]]))
+    ctrl.store_input_output_measurement(u0, y[0, -1])
+    orc.store_input_output_measurement(u0, y[0, -1])
+    ctrl.update_and_solve_data_driven_mpc()
+    orc.update_and_solve_data_driven_mpc()
+    np.testing.assert_allclose(ctrl.get_optimal_control_input_at_step(0), orc.get_optimal_control_input_at_step(0), rtol=0, atol=TOL)
+    with pytest.raises(ValueError):
+        ctrl.get_optimal_control_input_at_step(n_step=1)
+
+
+def test_unsupported_modes_fail_loudly(build_lib):
+    import ddmpc_oracle as mo
+    from data_driven_quad_control_b200.data_driven_mpc.nonlinear_data_driven_mpc_controller import (
+        NonlinearDataDrivenMPCController,
+    )
+
+    prm = _small_params()
+    u, y = _synthetic_windows(prm, 1, 1)
+    kw = mo.ctor_kwargs(prm, u[0], y[0], np.zeros(3))
+    for bad in (dict(ext_out_incr_in=True), dict(update_cost_threshold=0.1), dict(alpha_reg_type=1)):
+        with pytest.raises(NotImplementedError):
+            NonlinearDataDrivenMPCController(**{**kw, **bad})
+    with pytest.raises(ValueError):
+        NonlinearDataDrivenMPCController(**{**kw, "u": u[0][:30], "y": y[0][:30]})
