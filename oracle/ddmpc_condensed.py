@@ -15,8 +15,8 @@ for fixed targets is a ridge regression in dual form,
     rho = E_B y_B + T [u_s; y_s] + tau - v_sr,   D0 = diag(lamb_alpha / w_i) (0 on hard rows),
 
 i.e. a strictly convex BOX-constrained QP in (L-n) m + m + p variables (93 at the default
-sizes) whose only constraints are simple bounds.  It is solved exactly by a primal active-set
-method.  alpha itself (309 numbers) is never formed.
+sizes) whose only constraints are simple bounds.  It is solved exactly by block principal
+pivoting on the active bounds.  alpha itself (309 numbers) is never formed.
 """
 
 from __future__ import annotations
@@ -67,46 +67,47 @@ def row_classes(prm: MPCParams):
     return w, np.array(B), T
 
 
-def box_qp_active_set(Hq, f, lo, hi, x0=None, max_iter=200, tol=1e-11):
-    """min 0.5 x'Hq x + f'x, lo <= x <= hi (Hq SPD) by a primal active-set method."""
+def box_qp_active_set(Hq, f, lo, hi, x0=None, max_iter=200):
+    """min 0.5 x'Hq x + f'x, lo <= x <= hi (Hq SPD): block principal pivoting in the space of the
+    active bounds, exactly as `box_qp_bpp` of ddqc_ddmpc.cu (W = Hq^-1 explicit; per pass
+    mu = W_AA^-1 (x0_A - b_A), x = x0 - W[:,A] mu; all infeasible indices exchanged at once, single
+    largest-index exchanges after three passes without progress)."""
     nx = len(f)
-    x = np.clip(np.zeros(nx) if x0 is None else x0, lo, hi)
-    at_lo = np.isfinite(lo) & (x <= lo)
-    at_hi = np.isfinite(hi) & (x >= hi)
+    W = np.linalg.inv(Hq)
+    W = 0.5 * (W + W.T)
+    xu = -W @ f
+    state = np.zeros(nx, int)
+    tol_x, tol_g = 1e-10, 1e-11 * max(1.0, np.abs(f).max())
+    best, patience = nx + 1, 3
     for it in range(max_iter):
-        free = ~(at_lo | at_hi)
-        g = Hq @ x + f
-        # Newton step on the free variables
-        d = np.zeros(nx)
-        if free.any():
-            d[free] = np.linalg.solve(Hq[np.ix_(free, free)], -g[free])
-        if np.abs(d).max() > tol * (1 + np.abs(x).max()):
-            # ratio test
-            t, blk, side = 1.0, -1, 0
-            for i in np.nonzero(free)[0]:
-                if d[i] > 0 and np.isfinite(hi[i]):
-                    ti = (hi[i] - x[i]) / d[i]
-                    if ti < t:
-                        t, blk, side = ti, i, 1
-                elif d[i] < 0 and np.isfinite(lo[i]):
-                    ti = (lo[i] - x[i]) / d[i]
-                    if ti < t:
-                        t, blk, side = ti, i, -1
-            x = x + t * d
-            if blk >= 0:
-                if side > 0:
-                    x[blk], at_hi[blk] = hi[blk], True
-                else:
-                    x[blk], at_lo[blk] = lo[blk], True
-                continue
-        # stationary on the current face: check multipliers
-        g = Hq @ x + f
-        viol = np.where(at_lo, -g, np.where(at_hi, g, -np.inf))  # >0 means the bound should be released
-        k = int(np.argmax(viol))
-        if viol[k] <= tol * (1 + np.abs(g).max()):
-            return x, it
-        at_lo[k] = at_hi[k] = False
-    raise RuntimeError("active set did not converge")
+        A = np.nonzero(state)[0]
+        bnd = np.where(state < 0, lo, hi)
+        x = xu.copy()
+        mu = np.zeros(0)
+        if len(A):
+            mu = np.linalg.solve(W[np.ix_(A, A)], xu[A] - bnd[A])
+            x = xu - W[:, A] @ mu
+            x[A] = bnd[A]
+        verdict = np.zeros(nx, int)
+        g_act = -mu
+        for a, i in enumerate(A):
+            if (state[i] < 0 and g_act[a] < -tol_g) or (state[i] > 0 and g_act[a] > tol_g):
+                verdict[i] = 2
+        free = state == 0
+        verdict[free & (x < lo - tol_x * (1 + np.abs(lo)))] = -1
+        verdict[free & (x > hi + tol_x * (1 + np.abs(hi)))] = 1
+        bad = np.nonzero(verdict)[0]
+        if len(bad) == 0:
+            return x, it + 1
+        if len(bad) < best:
+            best, patience, full = len(bad), 3, True
+        elif patience > 0:
+            patience, full = patience - 1, True
+        else:
+            full = False
+        for i in bad if full else bad[-1:]:
+            state[i] = 0 if verdict[i] == 2 else verdict[i]
+    raise RuntimeError("block principal pivoting did not converge")
 
 
 def solve_condensed(prm: MPCParams, u_win, y_win, y_r, us_prev=None, ys_prev=None, x0=None):

@@ -1,0 +1,181 @@
+"""CPU tests of the host side: C-ABI library loads and exports every declared symbol, struct
+layouts agree, parameter block values, config surface, sharding helpers, fail-loud behaviour."""
+
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(build_lib):
+    from data_driven_quad_control_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "ddqc.h")).read()
+    declared = set(re.findall(r"\b(ddqc_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(build_lib)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported by libddqc.so"
+    loaded = _lib.load()  # also checks the ctypes struct sizes against ddqc_struct_size()
+    assert loaded.ddqc_abi_version() == 1
+    assert loaded.ddqc_struct_size(99) == -1
+
+
+def test_argument_validation_without_gpu(build_lib):
+    """Entry points reject bad arguments before touching the device (no compute call is made)."""
+    from data_driven_quad_control_b200 import _lib
+
+    lib = _lib.load()
+    P, S, O = _lib.EnvParams(), _lib.EnvState(), _lib.EnvOut()
+    assert lib.ddqc_env_step(None, None, None, None, None, None, 16, None) == -1  # DDQC_E_NULL
+    assert lib.ddqc_env_step(ctypes.byref(P), ctypes.byref(S), ctypes.byref(O), None, None, None, 0, None) == -2
+    P.action_type, P.decimation = 7, 4
+    assert lib.ddqc_env_step(ctypes.byref(P), ctypes.byref(S), ctypes.byref(O), None, None, None, 16, None) == -4
+    cfg = _lib.MpcConfig()
+    cfg.n, cfg.m, cfg.p, cfg.L, cfg.N = 6, 3, 3, 35, 350
+    assert lib.ddqc_ddmpc_workspace_bytes(ctypes.byref(cfg), 4096) > 0
+    cfg.alpha_reg_type = 1
+    assert lib.ddqc_ddmpc_workspace_bytes(ctypes.byref(cfg), 4096) == -1
+    cfg.alpha_reg_type, cfg.N = 0, 4000  # H would have > 512 rows? no: rows fixed by l; C large is fine
+    assert lib.ddqc_ddmpc_workspace_bytes(ctypes.byref(cfg), 1) > 0
+    cfg.L = 100  # r = 6*107+1 > kMaxR
+    assert lib.ddqc_ddmpc_workspace_bytes(ctypes.byref(cfg), 1) == -1
+
+
+def test_env_params_block():
+    from data_driven_quad_control_b200.controllers.ctbr.ctbr_controller import build_ctbr_matrices
+    from data_driven_quad_control_b200.envs.hover_env import make_env_params
+    from data_driven_quad_control_b200.envs.hover_env_config import (
+        EnvActionBounds,
+        EnvActionType,
+        EnvDroneParams,
+        get_cfgs,
+    )
+
+    env_cfg, obs_cfg, rew_cfg, cmd_cfg = get_cfgs()
+    mats = build_ctbr_matrices(EnvDroneParams.get())
+    scales = {k: v * 0.04 for k, v in rew_cfg["reward_scales"].items()}
+    P = make_env_params(env_cfg, obs_cfg, scales, rew_cfg["yaw_lambda"], cmd_cfg, EnvActionType.CTBR_FIXED_YAW, True,
+                        False, 7, mixer=mats["mixer"], inv_sqrt_kf=float(mats["inv_sqrt_KF"]),
+                        rate_pid_gains=[[10.0, 0.0, 0.1]] * 3)  # fmt: skip
+    assert P.max_episode_length == 375 and P.min_hover_steps == 13 and P.decimation == 4
+    assert P.flags == 3  # latency | auto target, no Euler needed at 180 deg thresholds
+    assert abs(P.act_span[0] - 0.52974) < 1e-7 and P.act_lo[1] == -15.0 and P.act_span[2] == 30.0
+    assert abs(P.inv_sqrt_kf - 56254.395) < 0.01 and abs(P.inv_step_dt - 25.0) < 1e-6
+    np.testing.assert_allclose(list(P.mixer)[:4], [-1.2467909e-4, -1.2467905e-4, -2.1590723e-4, 0.24999937], rtol=2e-6)
+    assert abs(EnvDroneParams.WEIGHT - 0.26487) < 1e-9 and abs(EnvActionBounds.MAX_THRUST - 0.52974) < 1e-9
+    assert abs(EnvActionBounds.MIN_RPM - 2893.6858) < 1e-3 and abs(EnvActionBounds.MAX_RPM - 26043.1725) < 1e-3
+    # the restated rigid-body constants equal those of the oracle bit for bit
+    import drone_physics as dp
+
+    Q = dp.PhysParams.cf2x(0.01)
+    f32 = np.float32
+    assert f32(P.dt_g) == Q.dt_g and f32(P.two_dt_over_m) == Q.two_dt_over_m and f32(P.half_dt) == Q.half_dt
+    assert [f32(x) for x in P.k_w] == list(Q.k_w) and [f32(x) for x in P.b_w] == list(Q.b_w)
+    assert [f32(x) for x in P.arm_x] == list(Q.arm_x) and [f32(x) for x in P.km_spin] == list(Q.km_spin)
+    assert [f32(x) for x in P.cos_coef] == list(Q.cos_coef) and [f32(x) for x in P.sinc_coef] == list(Q.sinc_coef)
+    # Euler angles are needed as soon as a threshold can fire or the yaw reward counts
+    env_cfg["termination_if_roll_greater_than"] = 60
+    assert make_env_params(env_cfg, obs_cfg, scales, -10.0, cmd_cfg, EnvActionType.ROTOR_RPMS, False, True, 0).flags & 4
+
+
+def test_config_surface():
+    from data_driven_quad_control_b200.envs.hover_env_config import EnvActionType, EnvState, get_cfgs
+    from data_driven_quad_control_b200.learning.config.reward_config import get_reward_cfg_by_action_type
+
+    env_cfg, obs_cfg, rew_cfg, cmd_cfg = get_cfgs()
+    assert list(rew_cfg["reward_scales"]) == ["target", "closeness", "hover_time", "smooth", "yaw", "angular", "crash"]
+    assert EnvActionType.get_num_actions(EnvActionType.CTBR_FIXED_YAW) == 3
+    assert EnvActionType.get_num_obs(EnvActionType.CTBR) == 17
+    assert get_reward_cfg_by_action_type(EnvActionType.CTBR_FIXED_YAW)["reward_scales"]["yaw"] == 0.0
+    assert get_reward_cfg_by_action_type(EnvActionType.ROTOR_RPMS)["reward_scales"]["smooth"] == -1e-4
+    s = EnvState(*(torch.zeros(1, k) for k in (3, 4, 3, 3, 3)), torch.zeros(1, dtype=torch.int32), torch.zeros(1, 3))
+    assert s.to_cpu().base_pos.device.type == "cpu" and s.ctbr_controller_state is None
+
+
+@pytest.mark.reference
+def test_config_matches_reference():
+    import sys
+
+    sys.path.insert(0, "/root/reference/src")
+    from data_driven_quad_control.envs import hover_env_config as ref
+    from data_driven_quad_control.learning.config.reward_config import get_reward_cfg_by_action_type as ref_rew
+
+    from data_driven_quad_control_b200.envs import hover_env_config as ours
+    from data_driven_quad_control_b200.learning.config.reward_config import get_reward_cfg_by_action_type
+
+    assert ours.get_cfgs() == ref.get_cfgs()
+    for at in ours.EnvActionType:
+        assert get_reward_cfg_by_action_type(at) == ref_rew(ref.EnvActionType(at.value))
+        assert ours.EnvActionType.get_num_obs(at) == ref.EnvActionType.get_num_obs(ref.EnvActionType(at.value))
+    assert ours.EnvDroneParams.get() == ref.EnvDroneParams.get()
+    assert ours.EnvCTBRControllerConfig.get() == ref.EnvCTBRControllerConfig.get()
+    assert ours.EnvActionBounds.BASE_RPM == ref.EnvActionBounds.BASE_RPM
+
+
+def test_math_utils_known_answers():
+    """The known-answer vectors of the reference's tests/utility_tests/test_math_utils.py."""
+    from data_driven_quad_control_b200.utilities.math_utils import (
+        linear_interpolate,
+        quaternion_to_matrix,
+        yaw_from_quaternion,
+        yaw_to_quaternion,
+    )
+
+    x = torch.tensor([0.0, 0.5, 1.0])
+    torch.testing.assert_close(linear_interpolate(x, 0.0, 1.0, 10.0, 20.0), torch.tensor([10.0, 15.0, 20.0]))
+    r = linear_interpolate(torch.tensor([0.25, 2.5]), torch.tensor([0.0, 0.0]), torch.tensor([1.0, 5.0]),
+                           torch.tensor([100.0, 200.0]), torch.tensor([200.0, 500.0]))  # fmt: skip
+    torch.testing.assert_close(r, torch.tensor([125.0, 350.0]))
+    q = yaw_to_quaternion(torch.deg2rad(torch.tensor([0.0, 90.0])))
+    torch.testing.assert_close(q, torch.tensor([[1.0, 0, 0, 0], [0.7071, 0, 0, 0.7071]]), rtol=0, atol=1e-4)
+    R = quaternion_to_matrix(q)
+    expected = torch.tensor([[[1.0, 0, 0], [0, 1, 0], [0, 0, 1]], [[0.0, -1, 0], [1, 0, 0], [0, 0, 1]]])
+    torch.testing.assert_close(R, expected, rtol=0, atol=1e-6)
+    quats = torch.tensor([[0.7071, 0, 0, 0.7071], [0.9239, 0.3827, 0, 0], [0, 0, 0.3827, 0.9239], [0.0990, -0.2391, 0.3696, 0.8924]])
+    yaw = yaw_from_quaternion(quats)
+    exp = torch.deg2rad(torch.tensor([90.0, 0.0, 180.0, 180.0]))
+    torch.testing.assert_close(torch.sin(yaw), torch.sin(exp), rtol=0, atol=1e-4)
+    torch.testing.assert_close(torch.cos(yaw), torch.cos(exp), rtol=0, atol=1e-4)
+
+
+def test_no_cpu_fallback(build_lib):
+    """Without a CUDA device every product class refuses to construct (no silent CPU path)."""
+    from data_driven_quad_control_b200 import _lib
+    from data_driven_quad_control_b200.envs.hover_env import HoverEnv
+    from data_driven_quad_control_b200.envs.hover_env_config import EnvActionType, get_cfgs
+    from data_driven_quad_control_b200.utilities.vectorized_pid_controller import VectorizedPIDController
+
+    with pytest.raises(_lib.DdqcError):
+        HoverEnv(4, *get_cfgs(), device="cpu", action_type=EnvActionType.CTBR)
+    with pytest.raises(_lib.DdqcError):
+        VectorizedPIDController(torch.ones(3, 3), 4, 0.04, device="cpu")
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.DdqcError):
+            HoverEnv(4, *get_cfgs(), device="cuda", action_type=EnvActionType.CTBR)
+    with pytest.raises(NotImplementedError):
+        HoverEnv(4, *get_cfgs(), show_viewer=True)
+    with pytest.raises(ValueError):
+        VectorizedPIDController(torch.ones(3, 2), 4, 0.04)
+
+
+def test_sharding_helpers():
+    from data_driven_quad_control_b200.parallel import shard_range, shard_round_robin
+
+    for n, w in ((1 << 20, 8), (4096, 3), (5, 8), (900, 8)):
+        ranges = [shard_range(n, r, w) for r in range(w)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        sizes = [b - a for a, b in ranges]
+        assert max(sizes) - min(sizes) <= 1
+        rr = sorted(i for r in range(w) for i in shard_round_robin(n, r, w))
+        assert rr == list(range(n))
+    with pytest.raises(ValueError):
+        shard_range(10, 3, 2)
