@@ -35,11 +35,13 @@ ENV_BYTES_PER_STEP = {3: 357, 4: 373}  # algorithmic HBM bytes p
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--no-ddmpc", action="store_true", help="skip the DD-MPC leg")
+    ap.add_argument("--ddmpc-batch", type=int, default=4096)
+    ap.add_argument("--ddmpc-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--small", action="store_true", help="also time configs[1] (4096 envs, CUDA-graph replay)")
@@ -252,7 +254,188 @@ def run_b200(args) -> dict:
         },
         "rollout_stats": stats,
     }
+    if not args.no_ddmpc:
+        del env, actions
+        torch.cuda.empty_cache()
+        leg = run_ddmpc_leg(dev, args.ddmpc_batch, args.ddmpc_steps)
+        # controllers are sharded by index like the envs: aggregate solves/s is the sum over ranks
+        v = torch.tensor([leg["value"], leg["closed_loop_solves_per_s"]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(v)
+        leg["value"], leg["closed_loop_solves_per_s"] = float(v[0]), float(v[1])
+        leg["n_gpus"] = world
+        line["ddmpc"] = leg
+        line["gpu_launches"] = K + leg["gpu_launches"]
     return line if rank == 0 else {}
+
+
+# ------------------------------------------------------------------------------------------
+# DD-MPC leg (BASELINE configs[3]): batch of controllers, default parameters, Hankel data from
+# PID-stabilised drones with a persistently exciting perturbation, closed loop on the GPU env
+# ------------------------------------------------------------------------------------------
+MPC_DEFAULT = dict(n=6, N=350, L=35, Q=[10.0, 10, 10], R=[10.0, 1, 1], S=[1000.0] * 3, lamb_alpha=50.0, lamb_sigma=1e9,
+                   U=[[0.0, 0.52974], [-1.5708, 1.5708], [-1.5708, 1.5708]],
+                   Us=[[0.001, 0.528], [-1.571, 1.570], [-1.571, 1.570]],
+                   u_range=[[-0.1, 0.1], [-0.5, 0.5], [-0.5, 0.5]], lamb_alpha_s=1.0, lamb_sigma_s=1e7,
+                   init_hover_pos=[0.0, 0.0, 1.5], y_r=[1.0, 1.0, 2.5])  # fmt: skip
+
+
+def ddmpc_flops_per_solve(n=6, m=3, p=3, L=35, N=350) -> float:
+    """Floating-point operations of the condensed algorithm (ddqc_ddmpc.cu), counted from its loops:
+    Gram by sliding dot products, one r-dim Cholesky + one ry-dim tail Cholesky, nx+1 forward
+    substitutions, Z = X^T X, nx-dim inverse."""
+    ell = L + n + 1
+    C = N - ell + 1
+    ru, ry = m * ell + 1, p * ell
+    r = ru + ry
+    nx = (L - n) * m + m + p
+    gram = 2.0 * (m + p) ** 2 * (2 * ell - 1) * C
+    chol = r**3 / 3.0 + ry**3 / 3.0
+    subst = (nx + 1) * r * r
+    syrk = (nx + 1) * (nx + 2) / 2.0 * 2 * r
+    boxqp = 2.0 * nx**3
+    return gram + chol + subst + syrk + boxqp
+
+
+def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
+    import numpy as np
+    import torch
+
+    from data_driven_quad_control_b200.data_driven_mpc.nonlinear_data_driven_mpc_controller import (
+        AlphaRegType,
+        BatchedNonlinearDataDrivenMPC,
+    )
+    from data_driven_quad_control_b200.data_driven_mpc.utilities.drone_initial_data_collection import (
+        collect_initial_input_output_data_batched,
+    )
+    from data_driven_quad_control_b200.envs.hover_env import HoverEnv
+    from data_driven_quad_control_b200.envs.hover_env_config import EnvActionType, get_cfgs
+    from data_driven_quad_control_b200.learning.config.reward_config import get_reward_cfg_by_action_type
+    from data_driven_quad_control_b200.utilities.drone_tracking_controller import (
+        create_drone_tracking_controller,
+        hover_at_target,
+    )
+    from data_driven_quad_control_b200.utilities.math_utils import linear_interpolate
+
+    P = MPC_DEFAULT
+    env_cfg, obs_cfg, _, cmd_cfg = get_cfgs()
+    obs_cfg["obs_noise_std"] = 1e-4  # as data_driven_mpc/dd_mpc_controller_eval.py:151-168 of the reference
+    env_cfg.update(episode_length_s=100, termination_if_close_to_ground=0.0, termination_if_x_greater_than=100.0,
+                   termination_if_y_greater_than=100.0, termination_if_z_greater_than=10.0)  # fmt: skip
+    at = EnvActionType.CTBR_FIXED_YAW
+    env = HoverEnv(batch, env_cfg, obs_cfg, get_reward_cfg_by_action_type(at), cmd_cfg, device=dev, action_type=at,
+                   auto_target_updates=False, seed=77, materialize_buffers=True)  # fmt: skip
+    env.reset()
+    hover = torch.tensor(P["init_hover_pos"], device=dev).repeat(batch, 1)
+    yaw = torch.zeros(batch, device=dev)
+    env.update_target_pos(torch.arange(batch, device=dev), hover)
+    trk = create_drone_tracking_controller(env)
+    hover_at_target(env, trk, hover, yaw, min_at_target_steps=10, error_threshold=5e-2, max_steps=300)
+    gen = torch.Generator(device=dev).manual_seed(5)
+    t0 = time.perf_counter()
+    u_N, y_N = collect_initial_input_output_data_batched(
+        env, trk, hover, yaw, torch.tensor(P["U"]), torch.tensor(P["u_range"]), P["N"], gen
+    )
+    torch.cuda.synchronize()
+    t_collect = time.perf_counter() - t0
+    ell = P["L"] + P["n"] + 1
+    ctrl = BatchedNonlinearDataDrivenMPC(
+        n=P["n"], m=3, p=3, u=u_N, y=y_N, L=P["L"], Q=np.kron(np.eye(ell), np.diag(P["Q"])),
+        R=np.kron(np.eye(ell), np.diag(P["R"])), S=np.diag(P["S"]), y_r=np.array(P["y_r"]), lamb_alpha=P["lamb_alpha"],
+        lamb_sigma=P["lamb_sigma"], U=P["U"], Us=P["Us"], alpha_reg_type=AlphaRegType.APPROXIMATED,
+        lamb_alpha_s=P["lamb_alpha_s"], lamb_sigma_s=P["lamb_sigma_s"], device=dev, solve_on_init=False,
+    )  # fmt: skip
+    y_r = torch.tensor(P["y_r"], device=dev).repeat(batch, 1)
+    env.update_target_pos(torch.arange(batch, device=dev), y_r)
+    bounds = env.action_bounds
+    d0 = torch.linalg.norm(env.base_pos - y_r, dim=1)
+    ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(T + warm)]
+    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(T + warm)]
+    sq_err = torch.zeros(batch, device=dev, dtype=torch.float64)
+    iters = []
+    torch.cuda.synchronize()
+    t_loop0 = None
+    for t in range(T + warm):
+        if t == warm:
+            torch.cuda.synchronize()
+            t_loop0 = time.perf_counter()
+        ev_a[t].record()
+        ctrl.update_and_solve_data_driven_mpc()
+        ev_b[t].record()
+        u0 = ctrl.get_optimal_control_input_at_step(0)
+        action = linear_interpolate(x=u0.to(torch.float32), x_min=bounds[:, 0], x_max=bounds[:, 1], y_min=-1, y_max=1)
+        env.step(action)
+        y_k = env.get_pos()
+        ctrl.store_input_output_measurement(u0, y_k)
+        sq_err += ((y_k.to(torch.float64) - y_r) ** 2).sum(1)
+        iters.append(ctrl.iters.clone())
+    torch.cuda.synchronize()
+    t_loop = time.perf_counter() - t_loop0
+    solve_ms = sorted(ev_a[t].elapsed_time(ev_b[t]) for t in range(warm, T + warm))
+    med = solve_ms[len(solve_ms) // 2]
+    avg = sum(solve_ms) / len(solve_ms)
+    status = ctrl.status.cpu()
+    it_all = torch.stack(iters[warm:]).float()
+    dist_end = torch.linalg.norm(env.base_pos - y_r, dim=1)
+    flops = ddmpc_flops_per_solve()
+    return {
+        "metric": "DD-MPC QP solves/s",
+        "value": batch / (avg * 1e-3),
+        "unit": "solves/s",
+        "batch": batch,
+        "closed_loop_steps": T,
+        "ms_per_batch_solve_avg": avg,
+        "ms_per_batch_solve_median": med,
+        "closed_loop_solves_per_s": batch * T / t_loop,
+        "config": "n=6, L=35, N=350, m=p=3 (693-variable QP, 331 equalities, 111 box rows), alpha_reg_type=0, "
+        "data: PID-stabilised hover at [0,0,1.5] + uniform excitation, obs noise 1e-4, y_r=[1,1,2.5]",
+        "dtype": "f64",
+        "pivoting_passes_mean": float(it_all.mean()),
+        "pivoting_passes_max": float(it_all.max()),
+        "failed_controllers": int((status != 0).sum()),
+        "rmse_mean": float(torch.sqrt(sq_err / (T + warm)).mean()),
+        "dist_to_target_start_mean": float(d0.mean()),
+        "dist_to_target_end_mean": float(dist_end.mean()),
+        "data_collection_s": t_collect,
+        "flops_per_solve": flops,
+        "achieved_fp64_tflops": batch * flops / (avg * 1e-3) / 1e12,
+        "gpu_launches": T,
+    }
+
+
+def _cpu_mpc_worker(arg):
+    n_solves, seed = arg
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+
+    import ddmpc_oracle as mo
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ddmpc_default.npz"))
+    prm = mo.default_params()
+    ctrl = mo.NonlinearDDMPCOracle(**mo.ctor_kwargs(prm, g["u"], g["y"], g["y_r"]), solve_on_init=False)
+    t0 = time.perf_counter()
+    for k in range(n_solves):
+        ctrl.update_and_solve_data_driven_mpc()
+        ctrl.store_input_output_measurement(g["u_opt"][k % 3][0], g["y_next"][k % 3])
+    return time.perf_counter() - t0
+
+
+def cpu_ddmpc_baseline(n_solves: int = 3, procs: int | None = None) -> dict:
+    import multiprocessing as mp
+
+    procs = procs or os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    with mp.get_context("spawn").Pool(procs) as pool:
+        times = pool.map(_cpu_mpc_worker, [(n_solves, s) for s in range(procs)])
+    return {
+        "value": procs * n_solves / max(times),
+        "unit": "solves/s",
+        "cores": procs,
+        "kind": "port",
+        "sample": f"oracle/ddmpc_oracle.py (literal 693-variable QP, dense interior point, numpy/LAPACK; cvxpy+OSQP of "
+        f"the reference is not installable offline): {procs} processes x {n_solves} closed-loop solves, one controller "
+        "per process as the reference's grid search does",
+    }
 
 
 # ------------------------------------------------------------------------------------------
@@ -347,6 +530,9 @@ def main():
         line = run_b200(args)
         if line and not args.no_cpu_baseline and int(os.environ.get("WORLD_SIZE", "1")) == 1:
             line["cpu_baseline"] = cpu_env_baseline(2000)
+            if "ddmpc" in line:
+                line["ddmpc"]["cpu_baseline"] = cpu_ddmpc_baseline(3)
+                line["ddmpc"]["speedup_vs_cpu_baseline"] = line["ddmpc"]["value"] / line["ddmpc"]["cpu_baseline"]["value"]
     if line:
         print(json.dumps(line))
 

@@ -199,6 +199,7 @@ SIGNATURES = {
     "ddqc_ddmpc_workspace_bytes": (i64, [P(MpcConfig), i64]),
     "ddqc_ddmpc_solve": (C.c_int, [P(MpcConfig), vp] + [vp] * 11 + [i64, vp]),
     "ddqc_ddmpc_store": (C.c_int, [P(MpcConfig), vp, vp, vp, vp, i64, vp]),
+    "ddqc_ddmpc_debug_phase_buffer": (C.c_int, [vp]),
 }
 
 _STRUCTS = {0: EnvParams, 1: EnvCtl, 2: EnvState, 3: EnvOut, 4: MpcConfig}

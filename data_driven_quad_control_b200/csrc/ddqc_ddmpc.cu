@@ -436,7 +436,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, const doubl
                    const double* __restrict__ us_prev, const double* __restrict__ ys_prev,
                    const int32_t* __restrict__ have_prev, double* __restrict__ u_opt, double* __restrict__ us_opt,
                    double* __restrict__ ys_opt, int32_t* __restrict__ status, int32_t* __restrict__ iters,
-                   const int batch) {
+                   const int batch, long long* __restrict__ phase_clk) {
   extern __shared__ double smem[];
   const Dims d = make_dims(cfg);
   const int tid = threadIdx.x;
@@ -468,8 +468,18 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, const doubl
   const int row_one = m * ell;
   const int row_y0 = m * ell + 1;
 
+  long long t_prev = clock64();
+#define DDQC_PHASE(k)                                                  \
+  do {                                                                 \
+    if (phase_clk && tid == 0) {                                       \
+      const long long t_now = clock64();                               \
+      atomicAdd((unsigned long long*)&phase_clk[k], (unsigned long long)(t_now - t_prev)); \
+      t_prev = t_now;                                                  \
+    }                                                                  \
+  } while (0)
   for (int b = blockIdx.x; b < batch; b += gridDim.x) {
     if (tid == 0) s_flag = 0;
+    t_prev = clock64();
     // ---- stage the (u, y) window, signal-major ----
     const double* ub = u_win + (size_t)b * N * m;
     const double* yb = y_win + (size_t)b * N * p;
@@ -513,6 +523,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, const doubl
     }
     __syncthreads();
 
+    DDQC_PHASE(0);
     // ---- 2. shared factorisation of the hard block (columns [0, ru)) ----
     chol_blocked(Gm, d.ld, d.r, 0, d.ru, sD, sP, &s_flag);
     // trailing block [ru, r) now holds S0; copy it for the alpha_sr system
@@ -525,6 +536,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, const doubl
     }
     __syncthreads();
 
+    DDQC_PHASE(1);
     // ---- 3. v_sr = b_s - D_s (G + D_s)^-1 b_s ----
     for (int i = tid; i < d.r; i += kThreads) v_sr[i] = 0.0;
     if (use_sr) {
@@ -554,6 +566,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, const doubl
     }
     __syncthreads();
 
+    DDQC_PHASE(2);
     // ---- 4. tail factorisation with D0, right-hand sides, Z = X^T X ----
     for (int i = tid; i < d.ry; i += kThreads) {
       const int j = i / p, comp = i % p;
@@ -565,6 +578,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, const doubl
     __syncthreads();
     chol_blocked(Gm, d.ld, d.r, d.ru, d.r, sD, sP, &s_flag);
 
+    DDQC_PHASE(3);
     // K = [E_B | T] and c = tau - v_sr, column-major into X
     for (int e = tid; e < d.ldx * (d.nx + 1); e += kThreads) X[e] = 0.0;
     __syncthreads();
@@ -592,6 +606,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, const doubl
     forward_subst(Gm, d.ld, d.r, X, d.ldx, d.nx + 1);
     __syncthreads();
 
+    DDQC_PHASE(4);
     // Z = X^T X (nx+1 columns): Hq = 2 lamb_alpha Z[:nx,:nx] + structure, f = 2 lamb_alpha Z[:nx, nx] + ...
     double* sf = sv;
     double* slo = sv + kMaxNx;
@@ -661,6 +676,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, const doubl
     }
     __syncthreads();
 
+    DDQC_PHASE(5);
     // ---- 5. box QP: explicit inverse Hessian (CTA) + block principal pivoting on the active set (warp 0) ----
     {
       double fmax_abs = 0.0;
@@ -673,10 +689,11 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, const doubl
         sg[i] = acc;
       }
       __syncthreads();
+      DDQC_PHASE(6);
       if (tid < 32) {
         int it_w = 0, conv_w = 0;
         box_qp_bpp(sH, sF, sg, slo, shi, sx, srhs, tol_g, s_state, s_idx, s_verdict, d.nx,
-                   cfg.max_iter > 0 ? cfg.max_iter : 200, tid, &it_w, &conv_w, &s_flag);
+                   cfg.max_iter > 0 ? cfg.max_iter : 20000, tid, &it_w, &conv_w, &s_flag);
         if (tid == 0) {
           s_cnt[2] = it_w;
           s_cnt[3] = conv_w;
@@ -686,6 +703,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, const doubl
     }
     const int it = s_cnt[2], converged = s_cnt[3];
 
+    DDQC_PHASE(7);
     // ---- 6. outputs ----
     for (int e = tid; e < (L + 1) * m; e += kThreads) {
       const int k = e / m, comp = e % m;
@@ -745,6 +763,15 @@ size_t smem_bytes(const Dims& d) {
 
 }  // namespace
 
+static long long* g_phase_clk = nullptr;
+// Developer aid (not part of the reference-facing surface): device buffer of 8 cycle counters that the
+// solver accumulates per phase (Gram, hard-block Cholesky, alpha_sr, tail Cholesky, substitutions, Z,
+// inverse, pivoting).  Pass NULL to switch it off.
+extern "C" int ddqc_ddmpc_debug_phase_buffer(void* dev_ptr) {
+  g_phase_clk = static_cast<long long*>(dev_ptr);
+  return 0;
+}
+
 extern "C" int64_t ddqc_ddmpc_workspace_bytes(const DdqcMpcConfig* cfg, int64_t batch) {
   if (check_cfg(cfg) != 0 || batch < 0) return -1;
   const Dims d = make_dims(*cfg);
@@ -774,7 +801,7 @@ extern "C" int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg, void* ws, const double
   if (grid > kMaxSlots) grid = kMaxSlots;
   ddmpc_solve_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       *cfg, static_cast<double*>(ws), u_win, y_win, y_r, us_prev, ys_prev, have_prev, u_opt, us_opt, ys_opt, status,
-      iters, (int)batch);
+      iters, (int)batch, g_phase_clk);
   return (int)cudaGetLastError();
 }
 

@@ -73,7 +73,7 @@ class BatchedNonlinearDataDrivenMPC:
         n_mpc_step: int = 1,
         device: torch.device | str = "cuda",
         solve_on_init: bool = True,
-        max_iter: int = 200,
+        max_iter: int = 20000,
     ):
         if ext_out_incr_in:
             raise NotImplementedError("ext_out_incr_in=True (extended output / input increments) is not supported")

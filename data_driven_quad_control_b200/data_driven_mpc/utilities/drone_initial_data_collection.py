@@ -1,0 +1,58 @@
+"""Batched initial input-output data collection for data-driven MPC controllers.
+
+Vectorized counterpart of the reference's `collect_initial_input_output_data`
+(data_driven_mpc/utilities/drone_initial_data_collection.py:32-189): every drone of the env is
+stabilised at its target by the tracking controller while a persistently exciting perturbation,
+uniform in `u_range`, is added to its command; the applied (clipped) input and the measured
+position are recorded.  The reference collects for ONE env index with a numpy generator; here all
+`num_envs` drones collect at once (one data set per future controller), entirely on the device.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from data_driven_quad_control_b200.controllers.tracking.tracking_controller import DroneTrackingController
+from data_driven_quad_control_b200.controllers.tracking.tracking_controller_config import TrackingCtrlDroneState
+from data_driven_quad_control_b200.envs.hover_env import HoverEnv
+from data_driven_quad_control_b200.envs.hover_env_config import EnvActionType
+from data_driven_quad_control_b200.utilities.math_utils import linear_interpolate, yaw_to_quaternion
+
+
+def collect_initial_input_output_data_batched(
+    env: HoverEnv,
+    stabilizing_controller: DroneTrackingController,
+    target_pos: torch.Tensor,
+    target_yaw: torch.Tensor,
+    input_bounds: torch.Tensor,
+    u_range: torch.Tensor,
+    N: int,
+    generator: torch.Generator | None = None,
+) -> tuple[torch.Tensor, torch.Tensor]:
+    """Returns (u_N, y_N) with shapes (num_envs, N, m) and (num_envs, N, 3), float64.
+
+    `input_bounds` (m, 2) are the MPC input bounds U the applied input is clipped to, `u_range`
+    (m, 2) the range of the exciting perturbation (reference :117-160)."""
+    if env.action_type != EnvActionType.CTBR_FIXED_YAW and env.action_type != EnvActionType.CTBR:
+        raise ValueError("data collection needs a CTBR action type")
+    dev, B = env.device, env.num_envs
+    m = env.num_actions
+    bounds = env.action_bounds
+    lo = input_bounds[:, 0].to(dev, torch.float32)
+    hi = input_bounds[:, 1].to(dev, torch.float32)
+    ur = u_range.to(dev, torch.float32)
+    target = TrackingCtrlDroneState(X=target_pos, Q=yaw_to_quaternion(target_yaw))
+    current = TrackingCtrlDroneState(X=env.get_pos(), Q=env.get_quat())
+    pe = ur[:, 0] + (ur[:, 1] - ur[:, 0]) * torch.rand((N, B, m), device=dev, generator=generator)
+    u_N = torch.empty((B, N, m), dtype=torch.float64, device=dev)
+    y_N = torch.empty((B, N, 3), dtype=torch.float64, device=dev)
+    with torch.no_grad():
+        for k in range(N):
+            current.X, current.Q = env.get_pos(), env.get_quat()
+            cmd = stabilizing_controller.compute(state_setpoint=target, state_measurement=current)[:, :m]
+            u_k = torch.minimum(torch.maximum(cmd + pe[k], lo), hi)
+            action = linear_interpolate(x=u_k, x_min=bounds[:, 0], x_max=bounds[:, 1], y_min=-1, y_max=1)
+            env.step(torch.clamp(action, -1, 1))
+            u_N[:, k] = u_k
+            y_N[:, k] = env.get_pos()
+    return u_N, y_N

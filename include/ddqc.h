@@ -280,6 +280,9 @@ int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg_host, void* ws, const double* u_wi
 int ddqc_ddmpc_store(const DdqcMpcConfig* cfg_host, double* u_win, double* y_win,
                      const double* u_new, const double* y_new, int64_t batch, void* stream);
 
+/* Developer aid: device buffer of 8 int64 cycle counters accumulated per solver phase (NULL: off). */
+int ddqc_ddmpc_debug_phase_buffer(void* dev_ptr);
+
 /* library identification and layout self-check: sizeof of struct `which`
  * (0 DdqcEnvParams, 1 DdqcEnvCtl, 2 DdqcEnvState, 3 DdqcEnvOut, 4 DdqcMpcConfig), -1 otherwise. */
 int ddqc_abi_version(void);
