@@ -443,6 +443,7 @@ def cpu_ddmpc_baseline(n_solves: int = 3, procs: int | None = None) -> dict:
 # ------------------------------------------------------------------------------------------
 def _cpu_env_worker(arg):
     n_envs, steps, seed = arg
+    os.environ["DDQC_ORACLE_FAST_FMA"] = "1"  # timing only: no software FMA emulation
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import torch

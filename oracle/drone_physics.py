@@ -32,6 +32,7 @@ TwoSum error term, round-to-odd, then one rounding to float32).
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -55,8 +56,15 @@ COS_COEF = tuple((-1.0) ** k / math.factorial(2 * k) for k in range(N_TAYLOR))
 SINC_COEF = tuple((-1.0) ** k / math.factorial(2 * k + 1) for k in range(N_TAYLOR))
 
 
+# Timing-only switch (bench.py cpu_baseline): a CPU user would not emulate FMAs in software, so the
+# baseline run evaluates fma(a,b,c) as the two-rounding a*b+c.  Never set in the parity tests.
+FAST_FMA = os.environ.get("DDQC_ORACLE_FAST_FMA", "0") == "1"
+
+
 def fma(a, b, c):
     """Correctly rounded float32 fused multiply-add of float32 arrays / scalars."""
+    if FAST_FMA:
+        return np.asarray(a, dtype=F32) * np.asarray(b, dtype=F32) + np.asarray(c, dtype=F32)
     a64 = np.asarray(a, dtype=F32).astype(F64)
     b64 = np.asarray(b, dtype=F32).astype(F64)
     c64 = np.asarray(c, dtype=F32).astype(F64)

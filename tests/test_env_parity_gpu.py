@@ -212,3 +212,52 @@ def test_state_save_restore_matches_oracle(build_lib):
         env.step(torch.from_numpy(acts[t]).cuda())
         orc.step(acts[t])
         _compare_step(env, orc, t, yaw_tol=2e-6)
+
+
+@pytest.mark.parametrize("at_name", ["ROTOR_RPMS", "CTBR"])
+def test_configs0_hover_to_target_500_steps(build_lib, at_name):
+    """BASELINE configs[0]: single drone, SE(3) PID tracking controller (+ external CTBR controller
+    in RPM mode), 500 steps from the reset pose to [0,0,1.5] (examples/drone_tracking_controller_example.py
+    overrides).  The GPU stack (tracking kernel -> CTBR kernel -> fused env step) against the numpy
+    oracles driven by the same loop: positions within 1e-4 relative over the 500 steps."""
+    import controllers_oracle as co
+    import env_oracle as eo
+    from data_driven_quad_control_b200.controllers.ctbr.ctbr_controller import DroneCTBRController, build_ctbr_matrices
+    from data_driven_quad_control_b200.controllers.tracking.tracking_controller_config import TrackingCtrlDroneState
+    from data_driven_quad_control_b200.envs.hover_env_config import EnvCTBRControllerConfig, EnvDroneParams
+    from data_driven_quad_control_b200.utilities.drone_tracking_controller import (
+        create_drone_tracking_controller,
+        tracking_env_action,
+    )
+
+    over = dict(episode_length_s=100, termination_if_close_to_ground=0.0, termination_if_x_greater_than=10.0,
+                termination_if_y_greater_than=10.0, termination_if_z_greater_than=10.0)  # fmt: skip
+    env, orc = _make_pair(1, at_name, False, env_over=over)
+    env.reset()
+    orc.reset()
+    mats = build_ctbr_matrices(EnvDroneParams.get())
+    gains = EnvCTBRControllerConfig.get()["ctbr_controller_params"]["rate_pid_gains"]
+    trk = create_drone_tracking_controller(env)
+    o_trk = co.TrackingOracle(0.027, [[2.0, 0.0, 2.2], [2.0, 0.0, 2.2], [18.0, 0.0, 6.0]], 5.0, 1, orc.step_dt)
+    ctbr = o_ctbr = None
+    if at_name == "ROTOR_RPMS":
+        ctbr = DroneCTBRController(EnvDroneParams.get(), EnvCTBRControllerConfig.get(), env.step_dt, 1, env.device)
+        o_ctbr = co.CTBROracle(mats["mixer"].numpy(), float(mats["inv_sqrt_KF"]), gains, 1, orc.step_dt)
+    target = torch.tensor([[0.0, 0.0, 1.5]], device="cuda")
+    q_sp = torch.tensor([[1.0, 0.0, 0.0, 0.0]], device="cuda")
+    tgt = TrackingCtrlDroneState(X=target, Q=q_sp)
+    lo, span = orc.act_lo, orc.act_span
+    worst = 0.0
+    for t in range(500):
+        cur = TrackingCtrlDroneState(X=env.get_pos(), Q=env.get_quat())
+        env.step(tracking_env_action(env, trk, tgt, cur, ctbr))
+        cmd = o_trk.compute(orc.base_pos, orc.base_quat, target.cpu().numpy(), q_sp.cpu().numpy())
+        if o_ctbr is not None:
+            cmd = o_ctbr.compute(orc.base_ang_vel, cmd[:, 1:], cmd[:, 0])
+        # linear_interpolate(x, lo, hi, -1, 1) in torch's op order: y_min + (x - x_min) * (y_max - y_min) / (x_max - x_min)
+        orc.step((np.float32(-1.0) + (cmd - lo) * np.float32(2.0) / span).astype(np.float32))
+        p_gpu, p_orc = env.base_pos.cpu().numpy(), orc.base_pos
+        worst = max(worst, float(np.abs(p_gpu - p_orc).max() / max(1.0, np.abs(p_orc).max())))
+        assert not orc.reset_buf.any() and not env.reset_buf.any()
+    assert worst < 1e-4, worst
+    assert np.abs(env.base_pos.cpu().numpy() - np.array([[0.0, 0.0, 1.5]])).max() < 5e-3  # it got there
