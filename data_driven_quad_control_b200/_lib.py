@@ -197,7 +197,7 @@ SIGNATURES = {
         [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, vp, P(f32), f32, f32, f32, vp, i64, vp],
     ),
     "ddqc_ddmpc_workspace_bytes": (i64, [P(MpcConfig), i64]),
-    "ddqc_ddmpc_solve": (C.c_int, [P(MpcConfig), vp] + [vp] * 11 + [i64, vp]),
+    "ddqc_ddmpc_solve": (C.c_int, [P(MpcConfig), vp] + [vp] * 12 + [i64, vp]),
     "ddqc_ddmpc_store": (C.c_int, [P(MpcConfig), vp, vp, vp, vp, i64, vp]),
     "ddqc_ddmpc_debug_phase_buffer": (C.c_int, [vp]),
 }

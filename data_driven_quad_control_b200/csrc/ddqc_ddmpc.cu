@@ -6,22 +6,32 @@
 // ctor contract controller_creation.py:91-112): the Hankel-matrix QP over
 // (alpha, sigma, ubar, ybar, u_s, y_s) of Berberich et al. 2022 (Part II), Problem (22).
 //
-// One persistent CTA per controller slot.  Instead of the 693-variable QP the kernel solves the
-// algebraically equivalent condensed problem (derivation: DESIGN.md, numpy mirror:
-// oracle/ddmpc_condensed.py):
-//   1. G = H H^T, H = [H_u; 1^T; H_y] (r x C, r = (m+p)l + 1), built from the Hankel structure
-//      (2l-1 sliding dot products per signal pair + a diagonal recurrence) -- H is never stored;
-//   2. right-looking blocked Cholesky of the leading "hard" block (input rows + ones row), which
-//      the two regularised systems share, leaving the output-row Schur complement S0;
-//   3. alpha_sr enters only through v_sr = H alpha_sr = b_s - D_s (G + D_s)^-1 b_s
-//      (tail Cholesky of S0 + D_s, one right-hand side);
-//   4. tail Cholesky of S0 + D0, forward substitution X = L^-1 [K, c] for the nx+1 structured
-//      right-hand sides, Z = X^T X  ->  box-constrained QP in nx = (L-n) m + m + p variables;
-//   5. block principal pivoting on the box QP (exact; 1-5 small Cholesky solves in shared memory);
-//   6. ubar_0..ubar_L, u_s, y_s out.
-// Everything is fp64: cond(G) ~ 1e10-1e11 with lamb_sigma = 1e9 (measured), which rules out
-// fp32 / TF32 / BF16 tensor-core arithmetic for the factorisation; see DESIGN.md for the
-// tensor-core plan (FP64 DMMA for the trailing updates).
+// One persistent 512-thread CTA per SM pulls controllers from a work counter.  The 693-variable
+// QP is condensed (derivation: DESIGN.md section 4; numpy mirror: oracle/ddmpc_condensed.py) into
+// Schur complements of G + D, G = H H^T the Gram matrix of H = [H_u; 1^T; H_y], and solved as a
+// box-constrained QP in nx = (L-n) m + m + p variables.  Per controller:
+//
+//   0. Gram.  G is generated from the Hankel structure (one sliding dot product per signal pair
+//      and diagonal, then a two-term recurrence) and scattered, already permuted into the
+//      elimination order [R1 | R2 | R3 | aug], into an L2-resident workspace slot.
+//        R1 = past-input rows, ones row, terminal-input rows (hard, shared by both systems)
+//        R2 = output rows (soft: diagonal regularisation D differs between the two systems)
+//        R3 = predicted-input rows (the box-constrained decision variables y_B)
+//        aug = right-hand sides carried as extra rows: T_u (m), T_y (p), tau, b_s
+//   A. Eliminate R1 (left-looking blocked Cholesky of the panel in shared memory), then
+//      S1 = trailing - L L^T streamed through global memory once.  S1 is used twice:
+//   B. alpha_sr system: S1 + D_s, factor everything, forward substitution comes for free in the
+//      b_s row, blocked back-substitution gives z, e = D_s z on R2  (v_sr = b_s - e).
+//   C. main system: S1 + D_0, c-row = tau - b_s + e, eliminate R2 only; the Schur complement on
+//      [R3 | aug] is swept on R3 (Gauss-Jordan) which yields the box-QP Hessian and gradient.
+//   D. box QP: block principal pivoting in the space of the FREE variables, warm-started from
+//      the previous solve's active set (shifted one step); primal-dual interior point fallback
+//      followed by a pivoting polish when pivoting does not settle.
+//
+// The whole trailing matrix lives in shared memory (203 KB at the default sizes) in 8x8 blocks
+// (block-packed lower triangle, XOR-4 column swizzle inside a block) so that every FP64 tensor
+// core fragment (`mma.sync.m8n8k4.f64`, DMMA) is loaded without bank conflicts.  All Gram /
+// Schur contractions run on DMMA; fp64 is required (cond(G) ~ 1e10, D_0 entries of 5e-8).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -30,692 +40,956 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kNB = 32;        // Cholesky panel width
-constexpr int kMaxR = 512;     // max rows of H
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
 constexpr int kMaxNx = 128;    // max box-QP variables
 constexpr int kMaxSig = 8;     // max m, p
-constexpr int kMaxSlots = 296; // workspace slots (2 per SM)
+constexpr int kMaxSlots = 160; // workspace slots (>= SM count)
+constexpr int kNumPhases = 12;
+constexpr int kSmemLimit = 227 * 1024;
 
 struct Dims {
   int n, m, p, L, N, ell, C;
-  int ru;   // hard block: m*ell input rows + ones row
-  int ry;   // p*ell output rows
-  int r;    // ru + ry
-  int nB;   // (L-n)*m box rows
-  int nx;   // nB + m + p
-  int ld;   // leading dimension of the r x r workspace matrix
-  int ldx;  // leading dimension (rows) of X
+  int n1, n2, n3, na;        // class sizes (rows)
+  int n1p, n2p, n3p, nap;    // padded to multiples of 8
+  int nb1, nb2, nb3, nba;    // in 8x8 blocks
+  int nbt, nbA;              // trailing block rows, all block rows
+  int nx, nS, ldS, ldq;
+  int ga, gs;                // doubles: R1 panel (rect), trailing (block-packed lower)
 };
+
+__host__ __device__ inline int rup8(int v) { return (v + 7) & ~7; }
 
 __host__ __device__ inline Dims make_dims(const DdqcMpcConfig& c) {
   Dims d;
   d.n = c.n; d.m = c.m; d.p = c.p; d.L = c.L; d.N = c.N;
   d.ell = c.L + c.n + 1;
   d.C = c.N - d.ell + 1;
-  d.ru = c.m * d.ell + 1;
-  d.ry = c.p * d.ell;
-  d.r = d.ru + d.ry;
-  d.nB = (c.L - c.n) * c.m;
-  d.nx = d.nB + c.m + c.p;
-  d.ld = (d.r + 3) & ~3;
-  d.ldx = (d.r + 3) & ~3;
+  d.n1 = c.m * (2 * c.n + 1) + 1;
+  d.n2 = c.p * d.ell;
+  d.n3 = (c.L - c.n) * c.m;
+  d.na = c.m + c.p + 2;
+  d.n1p = rup8(d.n1); d.n2p = rup8(d.n2); d.n3p = rup8(d.n3); d.nap = rup8(d.na);
+  d.nb1 = d.n1p / 8; d.nb2 = d.n2p / 8; d.nb3 = d.n3p / 8; d.nba = d.nap / 8;
+  d.nbt = d.nb2 + d.nb3 + d.nba;
+  d.nbA = d.nb1 + d.nbt;
+  d.nx = d.n3 + c.m + c.p;
+  d.nS = d.nx + 1;
+  d.ldS = d.nS | 1;
+  d.ldq = d.nx | 1;
+  d.ga = d.nbA * d.nb1 * 64;
+  d.gs = d.nbt * (d.nbt + 1) / 2 * 64;
   return d;
 }
 
-__host__ __device__ inline size_t slot_doubles(const Dims& d) {
-  // G/L (r x ld) | S copy (ry x ld) | X (ldx x (nx+1), column-major) | vectors (8 x ld)
-  return (size_t)d.r * d.ld + (size_t)d.ry * d.ld + (size_t)d.ldx * (d.nx + 1) + (size_t)8 * d.ld;
+// extra shared-memory doubles behind the matrix region
+__host__ __device__ inline int extra_doubles(const Dims& d) { return 8 * d.nbt + d.n2p + 2 * (d.nS + 2) + 64; }
+
+__host__ __device__ inline int region_doubles(const Dims& d) {
+  int r = d.gs;
+  if (d.ga > r) r = d.ga;
+  const int win = (d.m + d.p) * d.N;
+  if (win > r) r = win;
+  // box-QP stage: S7 | Hq | 20 vectors ; the factor scratch aliases S7
+  const int qp = d.nS * d.ldS + d.nx * d.ldq + 20 * kMaxNx;
+  if (qp > r) r = qp;
+  return r;
 }
 
-// ---- small dense kernels on a lower-triangular matrix in global memory (row-major, ld) ------
+__host__ __device__ inline size_t slot_doubles(const Dims& d) { return (size_t)d.ga + d.gs; }
 
-// Unblocked Cholesky of the nb x nb diagonal block held in shared memory (row stride kNB+1),
-// executed by warp 0.  Returns false on a non-positive pivot.
-__device__ bool chol_diag_warp(double* sD, int nb, int lane) {
-  bool ok = true;
-  for (int j = 0; j < nb; ++j) {
-    double djj = sD[j * (kNB + 1) + j];
-    if (!(djj > 0.0)) ok = false;
-    double dj = sqrt(djj);
-    __syncwarp();
-    if (lane == j) sD[j * (kNB + 1) + j] = dj;
-    if (lane > j && lane < nb) sD[lane * (kNB + 1) + j] /= dj;
-    __syncwarp();
-    if (lane > j && lane < nb) {
-      double lij = sD[lane * (kNB + 1) + j];
-      for (int k = j + 1; k <= lane; ++k) sD[lane * (kNB + 1) + k] -= lij * sD[k * (kNB + 1) + j];
+// ---- 8x8 block layout ---------------------------------------------------------------------------
+// element (g, c) of a block sits at g*8 + (c ^ 4*((g>>1)&1)): every DMMA operand fragment (8 rows
+// x 4 consecutive columns) covers all 32 banks exactly twice and every accumulator fragment is a
+// contiguous 512-byte read of 16-byte pieces.
+__device__ __forceinline__ int eoff(int g, int c) { return g * 8 + (c ^ ((g & 2) << 1)); }
+__device__ __forceinline__ int tri(int I) { return I * (I + 1) / 2; }
+
+template <bool RECT>
+__device__ __forceinline__ int bidx(int I, int J, int nb1) {
+  return RECT ? I * nb1 + J : tri(I) + J;
+}
+
+__device__ __forceinline__ double ld_ab(const double* blk, int g, int t, int h) {
+  return blk[g * 8 + ((4 * h + t) ^ ((g & 2) << 1))];
+}
+__device__ __forceinline__ double2 ld_c(const double* blk, int g, int t) {
+  return *reinterpret_cast<const double2*>(blk + g * 8 + ((2 * t) ^ ((g & 2) << 1)));
+}
+__device__ __forceinline__ void st_c(double* blk, int g, int t, double2 v) {
+  *reinterpret_cast<double2*>(blk + g * 8 + ((2 * t) ^ ((g & 2) << 1))) = v;
+}
+// D(8x8) += A(8x4, row) * B(4x8, col): FP64 tensor core
+__device__ __forceinline__ void dmma(double2& c, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c.x), "+d"(c.y)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// sum_{J < Jn} L_IJ L_KJ^T for up to two row blocks I0, I1 sharing the K operand
+template <bool RECT>
+__device__ __forceinline__ void syrk_pair(const double* __restrict__ M, int nb1, int I0, int I1, bool two, int K, int Jn,
+                                          int g, int t, double2& s0, double2& s1) {
+  double2 a0 = {0.0, 0.0}, a1 = {0.0, 0.0}, b0 = {0.0, 0.0}, b1 = {0.0, 0.0};
+  const double* rK = M + (size_t)bidx<RECT>(K, 0, nb1) * 64;
+  const double* r0 = M + (size_t)bidx<RECT>(I0, 0, nb1) * 64;
+  const double* r1 = M + (size_t)bidx<RECT>(two ? I1 : I0, 0, nb1) * 64;
+  for (int J = 0; J < Jn; ++J) {
+    const double kb0 = ld_ab(rK + J * 64, g, t, 0), kb1 = ld_ab(rK + J * 64, g, t, 1);
+    const double x0 = ld_ab(r0 + J * 64, g, t, 0), x1 = ld_ab(r0 + J * 64, g, t, 1);
+    dmma(a0, x0, kb0);
+    dmma(a1, x1, kb1);
+    if (two) {
+      const double y0 = ld_ab(r1 + J * 64, g, t, 0), y1 = ld_ab(r1 + J * 64, g, t, 1);
+      dmma(b0, y0, kb0);
+      dmma(b1, y1, kb1);
     }
-    __syncwarp();
+  }
+  s0.x = a0.x + a1.x; s0.y = a0.y + a1.y;
+  s1.x = b0.x + b1.x; s1.y = b0.y + b1.y;
+}
+
+// Cholesky of one 8x8 block by one warp (lane i < 8 owns row i).  On exit the block holds L
+// strictly below the diagonal, 1/L_ii ON the diagonal and zeros above.
+__device__ __forceinline__ bool chol8_warp(double* blk, int lane) {
+  double a[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a[c] = (lane < 8 && c <= lane) ? blk[eoff(lane, c)] : 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    double dj = shfl_d(a[j], j);
+    if (!(dj > 0.0)) { ok = false; dj = 1.0; }
+    const double r = rsqrt(dj);
+    const double l = a[j] * r;
+    a[j] = (lane == j) ? r : l;
+#pragma unroll
+    for (int c = j + 1; c < 8; ++c) {
+      const double lc = shfl_d(l, c);
+      if (lane >= c) a[c] -= l * lc;
+    }
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) blk[eoff(lane, c)] = (c <= lane) ? a[c] : 0.0;
   }
   return ok;
 }
 
-// Right-looking blocked Cholesky of columns [c0, c1) of the n x n lower-triangular matrix A.
-// After the call columns [c0, c1) hold L and the trailing block [c1, n) x [c1, n) holds the Schur
-// complement.  sD: (kNB x (kNB+1)) doubles, sP: (n x kNB) doubles of shared memory.
-__device__ bool chol_blocked(double* __restrict__ A, int ld, int n, int c0, int c1, double* sD, double* sP,
-                             int* s_flag) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  for (int k0 = c0; k0 < c1; k0 += kNB) {
-    const int nb = min(kNB, c1 - k0);
-    // diagonal block -> shared memory
-    for (int e = tid; e < nb * nb; e += kThreads) {
-      int i = e / nb, j = e % nb;
-      sD[i * (kNB + 1) + j] = (j <= i) ? A[(size_t)(k0 + i) * ld + k0 + j] : 0.0;
+// X <- X L^-T for one 8x8 block held as an accumulator fragment (thread (g,t): X[g][2t], X[g][2t+1]);
+// Lr0 / Lr1 = rows 2t and 2t+1 of L, rinv = reciprocal diagonal.
+__device__ __forceinline__ void trsm8_frag(double2& v, const double (&Lr0)[8], const double (&Lr1)[8],
+                                           const double (&rinv)[8], int lane, int t) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const double cand = (c & 1) ? v.y : v.x;
+    const double xc = shfl_d(cand, (lane & ~3) | (c >> 1)) * rinv[c];
+    if ((c >> 1) == t) {
+      if (c & 1) v.y = xc; else v.x = xc;
     }
-    __syncthreads();
-    if (tid < 32) {
-      bool ok = chol_diag_warp(sD, nb, lane);
-      if (!ok && lane == 0) *s_flag = 1;
-    }
-    __syncthreads();
-    for (int e = tid; e < nb * nb; e += kThreads) {
-      int i = e / nb, j = e % nb;
-      if (j <= i) A[(size_t)(k0 + i) * ld + k0 + j] = sD[i * (kNB + 1) + j];
-    }
-    // panel: rows below the diagonal block, one thread per row (x kept in registers)
-    const int rows = n - (k0 + nb);
-    for (int rr = tid; rr < rows; rr += kThreads) {
-      const int i = k0 + nb + rr;
-      double x[kNB];
-#pragma unroll
-      for (int t = 0; t < kNB; ++t) x[t] = (t < nb) ? A[(size_t)i * ld + k0 + t] : 0.0;
-#pragma unroll
-      for (int t = 0; t < kNB; ++t) {
-        if (t < nb) {
-          double acc = x[t];
-#pragma unroll
-          for (int s = 0; s < t; ++s) acc -= x[s] * sD[t * (kNB + 1) + s];
-          x[t] = acc / sD[t * (kNB + 1) + t];
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < kNB; ++t) {
-        if (t < nb) {
-          A[(size_t)i * ld + k0 + t] = x[t];
-          sP[rr * kNB + t] = x[t];
-        }
-      }
-    }
-    __syncthreads();
-    // trailing update of the lower triangle: A[i][j] -= sum_t P[i][t] P[j][t], 4 x 4 tiles
-    const int tiles = (rows + 3) / 4;
-    const int ntile = tiles * (tiles + 1) / 2;
-    for (int tt = tid; tt < ntile; tt += kThreads) {
-      // unrank (ti >= tj) from tt
-      int ti = (int)((sqrt(8.0 * tt + 1.0) - 1.0) * 0.5);
-      while ((ti + 1) * (ti + 2) / 2 <= tt) ++ti;
-      while (ti * (ti + 1) / 2 > tt) --ti;
-      const int tj = tt - ti * (ti + 1) / 2;
-      double acc[4][4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-      const int i0 = ti * 4, j0 = tj * 4;
-      for (int t = 0; t < nb; ++t) {
-        double pi[4], pj[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          pi[a] = (i0 + a < rows) ? sP[(i0 + a) * kNB + t] : 0.0;
-          pj[a] = (j0 + a < rows) ? sP[(j0 + a) * kNB + t] : 0.0;
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] += pi[a] * pj[b];
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int i = i0 + a, j = j0 + b;
-          if (i < rows && j <= i) A[(size_t)(k0 + nb + i) * ld + k0 + nb + j] -= acc[a][b];
-        }
-    }
-    __syncthreads();
+    if (2 * t > c) v.x -= xc * Lr0[c];
+    if (2 * t + 1 > c) v.y -= xc * Lr1[c];
   }
-  return true;
 }
 
-// Blocked forward substitution L X = B for `ncol` right-hand sides stored column-major in X (ldx
-// rows), L lower-triangular n x n (row-major, ld).  Per row panel: a GEMM-shaped update with both
-// operands contiguous (row of L, column of X), then the nb x nb triangular solve, one thread per
-// column.
-__device__ void forward_subst(const double* __restrict__ Lm, int ld, int n, double* __restrict__ X, int ldx, int ncol) {
-  for (int k0 = 0; k0 < n; k0 += kNB) {
-    const int nb = min(kNB, n - k0);
-    if (k0 > 0) {
-      for (int e = threadIdx.x; e < nb * ncol; e += kThreads) {
-        const int i = k0 + e % nb, c = e / nb;
-        const double* Li = Lm + (size_t)i * ld;
-        const double* xc = X + (size_t)c * ldx;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int k = 0;
-        for (; k + 3 < k0; k += 4) {
-          a0 += Li[k] * xc[k];
-          a1 += Li[k + 1] * xc[k + 1];
-          a2 += Li[k + 2] * xc[k + 2];
-          a3 += Li[k + 3] * xc[k + 3];
+// Left-looking blocked Cholesky of block columns [0, ncols) of a matrix of `nrows` block rows held
+// in shared memory (RECT: nrows x nb1 rectangle; else block-packed lower triangle).  Block rows
+// >= ncols are carried along (they receive the triangular solve = forward substitution).
+template <bool RECT>
+__device__ void factor_columns(double* __restrict__ M, int nb1, int nrows, int ncols, int* s_flag) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  for (int K = 0; K < ncols; ++K) {
+    // (a) update block column K with everything to its left; warp 0 owns the diagonal block
+    if (warp == 0) {
+      double* blk = M + (size_t)bidx<RECT>(K, K, nb1) * 64;
+      double2 s0, s1;
+      syrk_pair<RECT>(M, nb1, K, K, false, K, K, g, t, s0, s1);
+      double2 cv = ld_c(blk, g, t);
+      cv.x -= s0.x; cv.y -= s0.y;
+      st_c(blk, g, t, cv);
+      __syncwarp();
+      if (!chol8_warp(blk, lane) && lane == 0) *s_flag = 1;
+    } else if (K > 0) {
+      for (int I = K + 1 + 2 * (warp - 1); I < nrows; I += 2 * (kWarps - 1)) {
+        const bool two = I + 1 < nrows;
+        double2 s0, s1;
+        syrk_pair<RECT>(M, nb1, I, I + 1, two, K, K, g, t, s0, s1);
+        double* b0 = M + (size_t)bidx<RECT>(I, K, nb1) * 64;
+        double2 cv = ld_c(b0, g, t);
+        cv.x -= s0.x; cv.y -= s0.y;
+        st_c(b0, g, t, cv);
+        if (two) {
+          double* b1 = M + (size_t)bidx<RECT>(I + 1, K, nb1) * 64;
+          double2 cw = ld_c(b1, g, t);
+          cw.x -= s1.x; cw.y -= s1.y;
+          st_c(b1, g, t, cw);
         }
-        for (; k < k0; ++k) a0 += Li[k] * xc[k];
-        X[(size_t)c * ldx + i] -= (a0 + a1) + (a2 + a3);
       }
-      __syncthreads();
     }
-    for (int c = threadIdx.x; c < ncol; c += kThreads) {
-      double* xc = X + (size_t)c * ldx + k0;
-      for (int t = 0; t < nb; ++t) {
-        const double* Lt = Lm + (size_t)(k0 + t) * ld + k0;
-        double acc = xc[t];
-        for (int q = 0; q < t; ++q) acc -= Lt[q] * xc[q];
-        xc[t] = acc / Lt[t];
+    __syncthreads();
+    // (c) triangular solve of the blocks below the diagonal
+    if (K + 1 + warp < nrows) {
+      const double* dk = M + (size_t)bidx<RECT>(K, K, nb1) * 64;
+      double Lr0[8], Lr1[8], rinv[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        Lr0[c] = dk[eoff(2 * t, c)];
+        Lr1[c] = dk[eoff(2 * t + 1, c)];
+        rinv[c] = dk[eoff(c, c)];
+      }
+      for (int I = K + 1 + warp; I < nrows; I += kWarps) {
+        double* b0 = M + (size_t)bidx<RECT>(I, K, nb1) * 64;
+        double2 v = ld_c(b0, g, t);
+        trsm8_frag(v, Lr0, Lr1, rinv, lane, t);
+        st_c(b0, g, t, v);
       }
     }
     __syncthreads();
   }
 }
 
-// Solve (L L^T) x = b in place for ONE right-hand side with warp 0, where L is the composite
-// factor [[L_uu, 0], [L_yu, L_t]]: rows < ru and the L_yu block live in A (ld), the tail factor L_t
-// (ry x ry) in T (ldt).  Forward: row-oriented warp dot products; backward: column-oriented axpys
-// over the (contiguous) rows of L.
-__device__ void warp_solve_composite(const double* __restrict__ A, int ld, const double* __restrict__ T, int ldt, int ru,
-                                     int r, double* __restrict__ x, int lane) {
-  for (int i = 0; i < r; ++i) {
-    const double* Li = (i < ru) ? A + (size_t)i * ld : A + (size_t)i * ld;
-    const int nlead = i < ru ? i : ru;
-    double acc = 0.0;
-    for (int k = lane; k < nlead; k += 32) acc += Li[k] * x[k];
-    if (i >= ru) {
-      const double* Ti = T + (size_t)(i - ru) * ldt;
-      for (int k = lane; k < i - ru; k += 32) acc += Ti[k] * x[ru + k];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    const double diag = (i < ru) ? A[(size_t)i * ld + i] : T[(size_t)(i - ru) * ldt + (i - ru)];
-    if (lane == 0) x[i] = (x[i] - acc) / diag;
-    __syncwarp();
-  }
-  for (int k = r - 1; k >= 0; --k) {
-    const double diag = (k < ru) ? A[(size_t)k * ld + k] : T[(size_t)(k - ru) * ldt + (k - ru)];
-    const double xk = x[k] / diag;
-    __syncwarp();
-    if (lane == 0) x[k] = xk;
-    // x_i -= L[k][i] * x_k for i < k  (row k of L)
-    const double* Lk = A + (size_t)k * ld;
-    const int nlead = k < ru ? k : ru;
-    for (int i = lane; i < nlead; i += 32) x[i] -= Lk[i] * xk;
-    if (k >= ru) {
-      const double* Tk = T + (size_t)(k - ru) * ldt;
-      for (int i = lane; i < k - ru; i += 32) x[ru + i] -= Tk[i] * xk;
-    }
-    __syncwarp();
+// Schur complement of the trailing block columns [c0, nrows): C_IK -= sum_{J < c0} L_IJ L_KJ^T
+__device__ void schur_trailing(double* __restrict__ M, int nrows, int c0) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int nrem = nrows - c0;
+  const int nblk = nrem * (nrem + 1) / 2;
+  for (int b = warp; b < nblk; b += kWarps) {
+    int i = (int)((sqrtf(8.0f * b + 1.0f) - 1.0f) * 0.5f);
+    while (tri(i + 1) <= b) ++i;
+    while (tri(i) > b) --i;
+    const int j = b - tri(i);
+    double2 s0, s1;
+    syrk_pair<false>(M, 0, c0 + i, 0, false, c0 + j, c0, g, t, s0, s1);
+    double* blk = M + (size_t)(tri(c0 + i) + c0 + j) * 64;
+    double2 cv = ld_c(blk, g, t);
+    cv.x -= s0.x; cv.y -= s0.y;
+    st_c(blk, g, t, cv);
   }
 }
 
-// ---- box-constrained strictly convex QP:  min 0.5 x'Hx + f'x,  lo <= x <= hi ------------------
-//
-// Stage 1 (whole CTA): W = H^-1 explicitly (Cholesky H = L L^T, L^-1, W = L^-T L^-1) and the
-// unconstrained minimiser x0 = -W f.  Stage 2 (warp 0): block principal pivoting carried out in
-// the space of the ACTIVE bounds only.  For an active set A with bound values b_A,
-//     mu = W_AA^-1 (x0_A - b_A),   x = x0 - W[:,A] mu,     gradient_A = -mu,
-// so a pass costs one |A| x |A| Cholesky (|A| is the handful of active bounds, not nx) plus an
-// nx x |A| product.  All infeasible indices are exchanged at once; after three passes without
-// progress the method switches to single exchanges of the largest infeasible index (Murty),
-// which terminate finitely for an SPD Hessian.
+// pointer to element (hi, lo), hi >= lo, of the block-packed lower-triangular matrix
+__device__ __forceinline__ double* elem_tri(double* M, int hi, int lo) {
+  return M + (size_t)(tri(hi >> 3) + (lo >> 3)) * 64 + eoff(hi & 7, lo & 7);
+}
 
-// H (nx x nx, row-major, full) -> W = H^-1 in place; Li is scratch (nx x nx).
-__device__ void spd_inverse_cta(double* H, double* Li, int nx, int* flag) {
+// ---- small dense helpers for the box QP (whole CTA, uniform control flow) --------------------------
+
+// Cholesky of the k x k lower triangle of F (ld) with DEFERRED column scaling: on exit
+// L_ij = F[i][j] * rs[j] (i > j), 1 / L_jj = rs[j].  One barrier per column.
+__device__ void chol_dense(double* __restrict__ F, int ld, int k, double* __restrict__ rs, int* s_flag) {
   const int tid = threadIdx.x;
-  for (int j = 0; j < nx; ++j) {
-    if (tid == 0) {
-      const double djj = H[j * nx + j];
-      if (!(djj > 0.0)) *flag = 1;
-      H[j * nx + j] = sqrt(djj);
-    }
+  for (int j = 0; j < k; ++j) {
     __syncthreads();
-    const double dj = H[j * nx + j];
-    for (int i = j + 1 + tid; i < nx; i += kThreads) H[i * nx + j] /= dj;
-    __syncthreads();
-    const int rem = nx - j - 1;
-    for (int e = tid; e < rem * rem; e += kThreads) {
-      const int i = j + 1 + e / rem, k = j + 1 + e % rem;
-      if (k <= i) H[i * nx + k] -= H[i * nx + j] * H[k * nx + j];
+    double dj = F[j * ld + j];
+    if (!(dj > 0.0)) {
+      if (tid == 0) *s_flag = 1;
+      dj = 1.0;
     }
-    __syncthreads();
-  }
-  // Li = L^-1 (lower triangular), one thread per column: L y = e_c
-  for (int c = tid; c < nx; c += kThreads) {
-    for (int i = 0; i < c; ++i) Li[i * nx + c] = 0.0;
-    for (int i = c; i < nx; ++i) {
-      double acc = (i == c) ? 1.0 : 0.0;
-      for (int k = c; k < i; ++k) acc -= H[i * nx + k] * Li[k * nx + c];
-      Li[i * nx + c] = acc / H[i * nx + i];
+    const double inv = 1.0 / dj;
+    if (tid == 0) rs[j] = rsqrt(dj);
+    const int w = k - 1 - j;
+    for (int e = tid; e < w * w; e += kThreads) {
+      const int i = j + 1 + e / w, c = j + 1 + e % w;
+      if (c <= i) F[i * ld + c] -= F[i * ld + j] * F[c * ld + j] * inv;
     }
-  }
-  __syncthreads();
-  // W = Li^T Li
-  for (int e = tid; e < nx * nx; e += kThreads) {
-    const int i = e / nx, k = e % nx;
-    if (k > i) continue;
-    double acc = 0.0;
-    for (int t = i; t < nx; ++t) acc += Li[t * nx + i] * Li[t * nx + k];
-    H[i * nx + k] = acc;
-  }
-  __syncthreads();
-  for (int e = tid; e < nx * nx; e += kThreads) {
-    const int i = e / nx, k = e % nx;
-    if (k > i) H[i * nx + k] = H[k * nx + i];
   }
   __syncthreads();
 }
 
-// Stage 2, one warp.  W: nx x nx inverse Hessian; x0: unconstrained minimiser; F: scratch for the
-// active block (nx x nx); state[i] in {0 free, -1 at lo, +1 at hi}; idx / verdict: int scratch.
-__device__ void box_qp_bpp(const double* W, double* F, const double* x0, const double* lo, const double* hi, double* x,
-                           double* mu, double tol_g, int* state, int* idx, int* verdict, int nx, int max_iter,
-                           int lane, int* iters, int* converged, int* flag) {
-  const double tol_x = 1e-10;
-  int ninf_best = nx + 1, patience = 3;
-  *converged = 0;
-  int it = 0;
-  for (; it < max_iter; ++it) {
-    // ordered list of active indices
-    int na = 0;
-    for (int base = 0; base < nx; base += 32) {
-      const int i = base + lane;
-      const bool ac = i < nx && state[i] != 0;
-      const unsigned mk = __ballot_sync(0xffffffffu, ac);
-      if (ac) idx[na + __popc(mk & ((1u << lane) - 1u))] = i;
-      na += __popc(mk);
-    }
+// solve (L L^T) x = b in place (b in `x`), factor from chol_dense; executed by warp 0 only
+__device__ void solve_dense_warp(const double* __restrict__ F, int ld, int k, const double* __restrict__ rs,
+                                 double* __restrict__ x, int lane) {
+  for (int j = 0; j < k; ++j) {  // forward, column oriented
     __syncwarp();
-    // F = W_AA (lower), mu = x0_A - b_A
-    for (int e = lane; e < na * na; e += 32) {
-      const int a = e / na, c = e % na;
-      if (c <= a) F[a * nx + c] = W[idx[a] * nx + idx[c]];
-    }
-    for (int a = lane; a < na; a += 32) {
-      const int i = idx[a];
-      mu[a] = x0[i] - (state[i] < 0 ? lo[i] : hi[i]);
-    }
+    const double yj = x[j] * rs[j];
+    const double cj = yj * rs[j];
+    for (int i = j + 1 + lane; i < k; i += 32) x[i] -= F[i * ld + j] * cj;
     __syncwarp();
-    for (int j = 0; j < na; ++j) {  // Cholesky of the active block
-      const double djj = F[j * nx + j];
-      if (!(djj > 0.0) && lane == 0) *flag = 1;
-      const double dj = sqrt(djj);
-      __syncwarp();
-      if (lane == 0) F[j * nx + j] = dj;
-      for (int i = j + 1 + lane; i < na; i += 32) F[i * nx + j] /= dj;
-      __syncwarp();
-      for (int i = j + 1 + lane; i < na; i += 32) {
-        const double lij = F[i * nx + j];
-        for (int k = j + 1; k <= i; ++k) F[i * nx + k] -= lij * F[k * nx + j];
-      }
-      __syncwarp();
-    }
-    for (int i = 0; i < na; ++i) {  // forward
-      double acc = 0.0;
-      for (int k = lane; k < i; k += 32) acc += F[i * nx + k] * mu[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) mu[i] = (mu[i] - acc) / F[i * nx + i];
-      __syncwarp();
-    }
-    for (int i = na - 1; i >= 0; --i) {  // backward
-      double acc = 0.0;
-      for (int k = i + 1 + lane; k < na; k += 32) acc += F[k * nx + i] * mu[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) mu[i] = (mu[i] - acc) / F[i * nx + i];
-      __syncwarp();
-    }
-    // x = x0 - W[:,A] mu ; active entries sit exactly on their bounds
-    for (int i = lane; i < nx; i += 32) {
-      double acc = x0[i];
-      for (int a = 0; a < na; ++a) acc -= W[i * nx + idx[a]] * mu[a];
-      x[i] = state[i] < 0 ? lo[i] : (state[i] > 0 ? hi[i] : acc);
-    }
-    __syncwarp();
-    // verdicts.  gradient_i = -mu_a: at a lower bound it must be >= 0, at an upper bound <= 0.
-    for (int i = lane; i < nx; i += 32) verdict[i] = 0;
-    __syncwarp();
-    for (int a = lane; a < na; a += 32) {
-      const int i = idx[a];
-      const double gi = -mu[a];
-      if ((state[i] < 0 && gi < -tol_g) || (state[i] > 0 && gi > tol_g)) verdict[i] = 2;
-    }
-    for (int i = lane; i < nx; i += 32) {
-      if (state[i] == 0) {
-        if (x[i] < lo[i] - tol_x * (1.0 + fabs(lo[i]))) verdict[i] = -1;
-        else if (x[i] > hi[i] + tol_x * (1.0 + fabs(hi[i]))) verdict[i] = 1;
-      }
-    }
-    __syncwarp();
-    int ninf = 0, last = -1;
-    for (int base = 0; base < nx; base += 32) {
-      const int i = base + lane;
-      const unsigned mk = __ballot_sync(0xffffffffu, i < nx && verdict[i] != 0);
-      ninf += __popc(mk);
-      if (mk) last = base + 31 - __clz(mk);
-    }
-    if (ninf == 0) {
-      *converged = 1;
-      ++it;
-      break;
-    }
-    bool full;
-    if (ninf < ninf_best) {
-      ninf_best = ninf;
-      patience = 3;
-      full = true;
-    } else if (patience > 0) {
-      --patience;
-      full = true;
-    } else {
-      full = false;
-    }
-    for (int i = lane; i < nx; i += 32) {
-      if (!full && i != last) continue;
-      const int v = verdict[i];
-      if (v == -1) state[i] = -1;
-      else if (v == 1) state[i] = 1;
-      else if (v == 2) state[i] = 0;
-    }
-    __syncwarp();
+    if (lane == 0) x[j] = yj;
   }
-  *iters = it;
+  for (int j = k - 1; j >= 0; --j) {  // backward: x_j = y_j / L_jj, y_i -= L_ji x_j (row j of L)
+    __syncwarp();
+    const double xj = x[j] * rs[j];
+    for (int i = lane; i < j; i += 32) x[i] -= F[j * ld + i] * rs[i] * xj;
+    __syncwarp();
+    if (lane == 0) x[j] = xj;
+  }
+  __syncwarp();
+}
+
+// out = Hq x + f, 4 threads per row
+__device__ void matvec_sym(const double* __restrict__ Hq, int ld, int nx, const double* __restrict__ x,
+                           const double* __restrict__ f, double* __restrict__ out) {
+  const int tid = threadIdx.x, row = tid >> 2, part = tid & 3;
+  double acc = 0.0;
+  if (row < nx)
+    for (int j = part; j < nx; j += 4) acc += Hq[row * ld + j] * x[j];
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (row < nx && part == 0) out[row] = acc + f[row];
+}
+
+enum { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
+// block-wide reduction; every thread passes a value and receives the result (two barriers)
+__device__ double block_reduce(double v, int op, double* s_red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = op == RED_SUM ? v + w : (op == RED_MAX ? fmax(v, w) : fmin(v, w));
+  }
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  double r = s_red[0];
+  for (int w = 1; w < kWarps; ++w) r = op == RED_SUM ? r + s_red[w] : (op == RED_MAX ? fmax(r, s_red[w]) : fmin(r, s_red[w]));
+  return r;
+}
+
+struct QpWork {
+  const double* Hq; int ldq; int nx;
+  double* F; int ldf;          // factor scratch (>= nx x nx)
+  double *f, *lo, *hi, *x, *g, *rhs, *rs;
+  double *sl, *su, *zl, *zu, *dx, *dzl, *dzu, *rd, *dg;
+  double* s_red;
+  int *state, *idx, *verdict, *s_flag;
+};
+
+// One pass of block principal pivoting in the free space.  Returns the number of infeasible
+// indices (0 = optimal) and the largest infeasible index through `last`.
+__device__ int bpp_pass(const QpWork& q, double tol_g, int* last) {
+  const int tid = threadIdx.x, lane = tid & 31, nx = q.nx;
+  // x at the bounds of the active set, free list
+  if (tid < nx) {
+    const int st = q.state[tid];
+    q.x[tid] = st < 0 ? q.lo[tid] : (st > 0 ? q.hi[tid] : 0.0);
+  }
+  if (tid < 32) {
+    int nf = 0;
+    for (int base = 0; base < nx; base += 32) {
+      const int i = base + lane;
+      const bool fr = i < nx && q.state[i] == 0;
+      const unsigned mk = __ballot_sync(0xffffffffu, fr);
+      if (fr) q.idx[nf + __popc(mk & ((1u << lane) - 1u))] = i;
+      nf += __popc(mk);
+    }
+    if (lane == 0) q.idx[kMaxNx] = nf;
+  }
+  __syncthreads();
+  const int kf = q.idx[kMaxNx];
+  matvec_sym(q.Hq, q.ldq, nx, q.x, q.f, q.g);
+  for (int e = tid; e < kf * kf; e += kThreads) {
+    const int a = e / kf, c = e % kf;
+    if (c <= a) q.F[a * q.ldf + c] = q.Hq[q.idx[a] * q.ldq + q.idx[c]];
+  }
+  __syncthreads();
+  if (tid < kf) q.rhs[tid] = -q.g[q.idx[tid]];
+  chol_dense(q.F, q.ldf, kf, q.rs, q.s_flag);
+  if (tid < 32) solve_dense_warp(q.F, q.ldf, kf, q.rs, q.rhs, lane);
+  __syncthreads();
+  if (tid < kf) q.x[q.idx[tid]] = q.rhs[tid];
+  __syncthreads();
+  matvec_sym(q.Hq, q.ldq, nx, q.x, q.f, q.g);
+  __syncthreads();
+  const double tol_x = 1e-10;
+  int v = 0;
+  if (tid < nx) {
+    const int st = q.state[tid];
+    const double gi = q.g[tid], xi = q.x[tid];
+    if (st < 0 && gi < -tol_g) v = 2;
+    else if (st > 0 && gi > tol_g) v = 2;
+    else if (st == 0) {
+      if (xi < q.lo[tid] - tol_x * (1.0 + fabs(q.lo[tid]))) v = -1;
+      else if (xi > q.hi[tid] + tol_x * (1.0 + fabs(q.hi[tid]))) v = 1;
+    }
+    q.verdict[tid] = v;
+  }
+  const int ninf = __syncthreads_count(v != 0);
+  const double lastd = block_reduce(v != 0 ? (double)tid : -1.0, RED_MAX, q.s_red);
+  *last = (int)lastd;
+  return ninf;
+}
+
+// pivoting driver; returns 1 when converged.  `passes` accumulates the number of passes.
+__device__ int bpp_solve(const QpWork& q, double tol_g, int max_pass, int* passes) {
+  const int tid = threadIdx.x, nx = q.nx;
+  int best = nx + 1, patience = 3;
+  for (int it = 0; it < max_pass; ++it) {
+    int last;
+    const int ninf = bpp_pass(q, tol_g, &last);
+    ++*passes;
+    if (ninf == 0) return 1;
+    bool full;
+    if (ninf < best) { best = ninf; patience = 3; full = true; }
+    else if (patience > 0) { --patience; full = true; }
+    else full = false;
+    if (tid < nx && (full || tid == last)) {
+      const int v = q.verdict[tid];
+      if (v == -1) q.state[tid] = -1;
+      else if (v == 1) q.state[tid] = 1;
+      else if (v == 2) q.state[tid] = 0;
+    }
+    __syncthreads();
+  }
+  return 0;
+}
+
+// Mehrotra predictor-corrector interior point method for the box QP.  Leaves x in q.x and an
+// active-set estimate in q.state.  Returns iterations + 1 (negated when the cap was reached).
+__device__ int ipm_solve(const QpWork& q, int max_it) {
+  const int tid = threadIdx.x, lane = tid & 31, nx = q.nx;
+  const bool act = tid < nx;
+  const bool il = act && isfinite(q.lo[act ? tid : 0]);
+  const bool iu = act && isfinite(q.hi[act ? tid : 0]);
+  const double lo = il ? q.lo[tid] : 0.0, hi = iu ? q.hi[tid] : 0.0;
+  double x = 0.0, sl = 1.0, su = 1.0, zl = 0.0, zu = 0.0;
+  if (act) {
+    x = (il && iu) ? 0.5 * (lo + hi) : (il ? lo + 1.0 : (iu ? hi - 1.0 : 0.0));
+    if (il) sl = x - lo;
+    if (iu) su = hi - x;
+    q.x[tid] = x;
+  }
+  __syncthreads();
+  matvec_sym(q.Hq, q.ldq, nx, q.x, q.f, q.g);
+  __syncthreads();
+  const double sc = fmax(1.0, block_reduce(act ? fabs(q.g[tid]) : 0.0, RED_MAX, q.s_red));
+  if (il) zl = sc;
+  if (iu) zu = sc;
+  const double nc = block_reduce((il ? 1.0 : 0.0) + (iu ? 1.0 : 0.0), RED_SUM, q.s_red);
+  int it = 0;
+  bool done = false;
+  for (; it < max_it; ++it) {
+    if (act) q.x[tid] = x;
+    __syncthreads();
+    matvec_sym(q.Hq, q.ldq, nx, q.x, q.f, q.g);
+    __syncthreads();
+    const double gi = act ? q.g[tid] : 0.0;
+    const double rd = gi - zl + zu;
+    const double mu = block_reduce((il ? sl * zl : 0.0) + (iu ? su * zu : 0.0), RED_SUM, q.s_red) / nc;
+    const double rdmax = block_reduce(fabs(rd), RED_MAX, q.s_red);
+    if (rdmax < 1e-9 * sc && mu < 1e-12 * sc) { done = true; break; }
+    // F = Hq + diag(zl/sl + zu/su)
+    const double dg = (il ? zl / sl : 0.0) + (iu ? zu / su : 0.0);
+    if (act) q.dg[tid] = dg;
+    __syncthreads();
+    for (int e = tid; e < nx * nx; e += kThreads) {
+      const int a = e / nx, c = e % nx;
+      if (c <= a) q.F[a * q.ldf + c] = q.Hq[a * q.ldq + c] + (a == c ? q.dg[a] : 0.0);
+    }
+    if (act) q.rhs[tid] = -gi;  // affine right-hand side
+    chol_dense(q.F, q.ldf, nx, q.rs, q.s_flag);
+    if (tid < 32) solve_dense_warp(q.F, q.ldf, nx, q.rs, q.rhs, lane);
+    __syncthreads();
+    const double dxa = act ? q.rhs[tid] : 0.0;
+    const double dzla = il ? (-sl * zl - zl * dxa) / sl : 0.0;
+    const double dzua = iu ? (-su * zu + zu * dxa) / su : 0.0;
+    double a1 = 1.0;
+    if (il && dxa < 0.0) a1 = fmin(a1, -sl / dxa);
+    if (iu && dxa > 0.0) a1 = fmin(a1, su / dxa);
+    if (il && dzla < 0.0) a1 = fmin(a1, -zl / dzla);
+    if (iu && dzua < 0.0) a1 = fmin(a1, -zu / dzua);
+    const double aa = block_reduce(a1, RED_MIN, q.s_red);
+    const double mu_aff =
+        block_reduce((il ? (sl + aa * dxa) * (zl + aa * dzla) : 0.0) + (iu ? (su - aa * dxa) * (zu + aa * dzua) : 0.0),
+                     RED_SUM, q.s_red) / nc;
+    const double rat = mu_aff / mu;
+    const double sig = rat * rat * rat;
+    const double rcl = sig * mu - dxa * dzla, rcu = sig * mu + dxa * dzua;
+    if (act) q.rhs[tid] = -rd + (il ? (rcl - sl * zl) / sl : 0.0) - (iu ? (rcu - su * zu) / su : 0.0);
+    __syncthreads();
+    if (tid < 32) solve_dense_warp(q.F, q.ldf, nx, q.rs, q.rhs, lane);
+    __syncthreads();
+    const double dx = act ? q.rhs[tid] : 0.0;
+    const double dzl = il ? (rcl - sl * zl - zl * dx) / sl : 0.0;
+    const double dzu = iu ? (rcu - su * zu + zu * dx) / su : 0.0;
+    double a2 = 1.0;
+    if (il && dx < 0.0) a2 = fmin(a2, -sl / dx);
+    if (iu && dx > 0.0) a2 = fmin(a2, su / dx);
+    if (il && dzl < 0.0) a2 = fmin(a2, -zl / dzl);
+    if (iu && dzu < 0.0) a2 = fmin(a2, -zu / dzu);
+    double al = block_reduce(a2, RED_MIN, q.s_red);
+    if (al < 1.0) al *= 0.995;
+    x += al * dx;
+    if (il) { sl += al * dx; zl += al * dzl; }
+    if (iu) { su -= al * dx; zu += al * dzu; }
+  }
+  if (act) {
+    q.x[tid] = x;
+    q.state[tid] = (il && zl > sl) ? -1 : ((iu && zu > su) ? 1 : 0);
+  }
+  __syncthreads();
+  return done ? (it + 1) : -(it + 1);
+}
+
+// ---- Gram generation -------------------------------------------------------------------------------
+// position of Hankel row (signal a, block row j) in the elimination order [R1 | R2 | R3 | aug]
+__device__ __forceinline__ int pos_of(const Dims& d, int a, int j) {
+  if (a < d.m) {
+    if (j < d.n) return j * d.m + a;
+    if (j >= d.L) return d.n * d.m + 1 + (j - d.L) * d.m + a;
+    return d.n1p + d.n2p + (j - d.n) * d.m + a;
+  }
+  return d.n1p + j * d.p + (a - d.m);
+}
+
+// write element (P, Q) of the permuted, padded Gram matrix into the workspace slot (GA panel or
+// GS trailing), mirroring inside diagonal blocks so that every block is fully defined
+__device__ __forceinline__ void put_sym(const Dims& d, double* __restrict__ GA, double* __restrict__ GS, int P, int Q,
+                                        double v) {
+  const int hi = P > Q ? P : Q, lo = P > Q ? Q : P;
+  if (lo < d.n1p) {
+    double* blk = GA + (size_t)((hi >> 3) * d.nb1 + (lo >> 3)) * 64;
+    blk[eoff(hi & 7, lo & 7)] = v;
+    if ((hi >> 3) == (lo >> 3)) blk[eoff(lo & 7, hi & 7)] = v;
+  } else {
+    const int h = hi - d.n1p, l = lo - d.n1p;
+    double* blk = GS + (size_t)(tri(h >> 3) + (l >> 3)) * 64;
+    blk[eoff(h & 7, l & 7)] = v;
+    if ((h >> 3) == (l >> 3)) blk[eoff(l & 7, h & 7)] = v;
+  }
 }
 
 // ---- the solver ----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1)
-ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, const double* __restrict__ u_win,
-                   const double* __restrict__ y_win, const double* __restrict__ y_r,
-                   const double* __restrict__ us_prev, const double* __restrict__ ys_prev,
-                   const int32_t* __restrict__ have_prev, double* __restrict__ u_opt, double* __restrict__ us_opt,
+ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __restrict__ work_counter,
+                   const double* __restrict__ u_win, const double* __restrict__ y_win,
+                   const double* __restrict__ y_r, const double* __restrict__ us_prev,
+                   const double* __restrict__ ys_prev, const int32_t* __restrict__ have_prev,
+                   int8_t* __restrict__ act_state, double* __restrict__ u_opt, double* __restrict__ us_opt,
                    double* __restrict__ ys_opt, int32_t* __restrict__ status, int32_t* __restrict__ iters,
                    const int batch, long long* __restrict__ phase_clk) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const Dims d = make_dims(cfg);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int m = d.m, p = d.p, ell = d.ell, C = d.C, N = d.N, n = d.n, L = d.L;
   const int nsig = m + p;
 
-  // shared memory carve-up
-  double* sW = smem;                              // windows, signal-major: nsig x N
-  double* sD = sW + (size_t)nsig * N;             // kNB x (kNB+1)
-  double* sv = sD + kNB * (kNB + 1);              // vectors: f, lo, hi, x, g, rhs (6 x kMaxNx)
-  double* sP = sv + 6 * kMaxNx;                   // Cholesky panel: r x kNB ...
-  double* sH = sP;                                // ... aliased later by the box-QP Hessian nx x nx
-  double* sF = sH + (size_t)d.nx * d.nx;          // and the factor of its free block
+  double* sM = smem;                       // matrix region (aliased by window / panel / QP data)
+  double* sx = smem + region_doubles(d);   // extras
+  double* s_yv = sx;                       // 8*nbt : back-substitution vector
+  double* s_e = s_yv + 8 * d.nbt;          // n2p   : e = D_s z on R2
+  double* s_vec = s_e + d.n2p;             // 2*(nS+2) : sweep pivot-column double buffer
+  double* s_red = s_vec + 2 * (d.nS + 2);  // 64
   __shared__ int s_flag;
+  __shared__ int s_next;
   __shared__ int s_state[kMaxNx];
-  __shared__ int s_idx[kMaxNx];
+  __shared__ int s_idx[kMaxNx + 1];
   __shared__ int s_verdict[kMaxNx];
-  __shared__ int s_cnt[4];
 
   double* slot = ws + (size_t)blockIdx.x * slot_doubles(d);
-  double* Gm = slot;                              // r x ld
-  double* S2 = Gm + (size_t)d.r * d.ld;           // ry x ld  (Schur complement copy for alpha_sr)
-  double* X = S2 + (size_t)d.ry * d.ld;           // ldx x (nx+1), column-major
-  double* vec = X + (size_t)d.ldx * (d.nx + 1);   // 8 x ld scratch vectors
-  double* v_sr = vec;                             // r
-  double* cs = vec + d.ld;                        // r
-
-  // row index helpers (row order: input rows j*m+i | ones row | output rows)
-  const int row_one = m * ell;
-  const int row_y0 = m * ell + 1;
+  double* GA = slot;
+  double* GS = slot + d.ga;
 
   long long t_prev = clock64();
-#define DDQC_PHASE(k)                                                  \
-  do {                                                                 \
-    if (phase_clk && tid == 0) {                                       \
-      const long long t_now = clock64();                               \
+#define DDQC_PHASE(k)                                                                      \
+  do {                                                                                     \
+    if (phase_clk && tid == 0) {                                                           \
+      const long long t_now = clock64();                                                   \
       atomicAdd((unsigned long long*)&phase_clk[k], (unsigned long long)(t_now - t_prev)); \
-      t_prev = t_now;                                                  \
-    }                                                                  \
+      t_prev = t_now;                                                                      \
+    }                                                                                      \
   } while (0)
-  for (int b = blockIdx.x; b < batch; b += gridDim.x) {
-    if (tid == 0) s_flag = 0;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      s_next = atomicAdd(work_counter, 1);
+      s_flag = 0;
+    }
+    __syncthreads();
+    const int b = s_next;
+    if (b >= batch) break;
     t_prev = clock64();
-    // ---- stage the (u, y) window, signal-major ----
+    const bool use_sr = (cfg.alpha_reg_type == 0) && have_prev[b] != 0;
     const double* ub = u_win + (size_t)b * N * m;
     const double* yb = y_win + (size_t)b * N * p;
+
+    // ---- 0. stage the (u, y) window signal-major; Gram -> workspace slot -------------------------
+    double* sW = sM;
     for (int e = tid; e < N * m; e += kThreads) sW[(e % m) * N + e / m] = ub[e];
     for (int e = tid; e < N * p; e += kThreads) sW[(m + e % p) * N + e / p] = yb[e];
-    __syncthreads();
-
-    // ---- 1. Hankel Gram, lower triangle of G ----
-    // G[(j,a),(k,b)] = sum_c w_a[j+c] w_b[k+c]; one task per (a, b, diagonal delta = j-k in (-ell, ell))
+    // aug block rows and pad rows: explicit zeros first
     {
+      const int r0 = d.nb1 + d.nb2 + d.nb3;  // first aug block row (all-rows numbering)
+      double2* za = reinterpret_cast<double2*>(GA + (size_t)r0 * d.nb1 * 64);
+      for (int e = tid; e < d.nba * d.nb1 * 32; e += kThreads) za[e] = make_double2(0.0, 0.0);
+      const int tb = d.nb2 + d.nb3;
+      double2* zs = reinterpret_cast<double2*>(GS + (size_t)tri(tb) * 64);
+      const int cnt = (tri(d.nbt) - tri(tb)) * 32;
+      for (int e = tid; e < cnt; e += kThreads) zs[e] = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    {
+      // pad rows (identity) of the three classes
+      const int npad = (d.n1p - d.n1) + (d.n2p - d.n2) + (d.n3p - d.n3);
+      const int ntot = d.n1p + d.n2p + d.n3p + d.nap;
+      for (int e = tid; e < npad * ntot; e += kThreads) {
+        int k = e / ntot;
+        const int q = e % ntot;
+        int P;
+        if (k < d.n1p - d.n1) P = d.n1 + k;
+        else if ((k -= d.n1p - d.n1) < d.n2p - d.n2) P = d.n1p + d.n2 + k;
+        else P = d.n1p + d.n2p + d.n3 + (k - (d.n2p - d.n2));
+        put_sym(d, GA, GS, P, q, P == q ? 1.0 : 0.0);
+      }
+      // G[(j,a),(k,b)] = sum_c w_a[j+c] w_b[k+c]: one task per unordered signal pair and diagonal
       const int ndiag = 2 * ell - 1;
       const int ntask = nsig * nsig * ndiag;
-      for (int t = tid; t < ntask; t += kThreads) {
-        const int a = t / (nsig * ndiag), bsig = (t / ndiag) % nsig, dl = t % ndiag - (ell - 1);
+      for (int tk = tid; tk < ntask; tk += kThreads) {
+        const int a = tk / (nsig * ndiag), bs = (tk / ndiag) % nsig, dl = tk % ndiag - (ell - 1);
+        if (a > bs || (a == bs && dl < 0)) continue;
         int j = dl > 0 ? dl : 0, k = dl > 0 ? 0 : -dl;
         const double* wa = sW + a * N;
-        const double* wb = sW + bsig * N;
-        double f = 0.0;
-        for (int c = 0; c < C; ++c) f += wa[j + c] * wb[k + c];
-        for (; j < ell && k < ell; ++j, ++k) {
-          const int ra = (a < m) ? j * m + a : row_y0 + j * p + (a - m);
-          const int rb = (bsig < m) ? k * m + bsig : row_y0 + k * p + (bsig - m);
-          if (rb <= ra) Gm[(size_t)ra * d.ld + rb] = f;
+        const double* wb = sW + bs * N;
+        double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
+        int c = 0;
+        for (; c + 3 < C; c += 4) {
+          f0 += wa[j + c] * wb[k + c];
+          f1 += wa[j + c + 1] * wb[k + c + 1];
+          f2 += wa[j + c + 2] * wb[k + c + 2];
+          f3 += wa[j + c + 3] * wb[k + c + 3];
+        }
+        for (; c < C; ++c) f0 += wa[j + c] * wb[k + c];
+        double f = (f0 + f1) + (f2 + f3);
+        for (;; ++j, ++k) {
+          put_sym(d, GA, GS, pos_of(d, a, j), pos_of(d, bs, k), f);
           if (j + 1 >= ell || k + 1 >= ell) break;
-          f += wa[j + C] * wb[k + C] - wa[j] * wb[k];  // j + C <= N - 1 here
+          f += wa[j + C] * wb[k + C] - wa[j] * wb[k];
         }
       }
-      // ones row: sliding sums, and G[one][one] = C
-      for (int t = tid; t < nsig; t += kThreads) {
-        const double* wa = sW + t * N;
+      // ones row: sliding sums, G[one][one] = C
+      const int Pone = n * m;
+      for (int a = tid; a < nsig; a += kThreads) {
+        const double* wa = sW + a * N;
         double f = 0.0;
         for (int c = 0; c < C; ++c) f += wa[c];
         for (int j = 0; j < ell; ++j) {
-          const int ra = (t < m) ? j * m + t : row_y0 + j * p + (t - m);
-          if (ra > row_one) Gm[(size_t)ra * d.ld + row_one] = f;
-          else Gm[(size_t)row_one * d.ld + ra] = f;
+          put_sym(d, GA, GS, pos_of(d, a, j), Pone, f);
           if (j + 1 < ell) f += wa[j + C] - wa[j];
         }
       }
-      if (tid == 0) Gm[(size_t)row_one * d.ld + row_one] = (double)C;
+      if (tid == 0) put_sym(d, GA, GS, Pone, Pone, (double)C);
+      // aug rows: T_u (m), T_y (p), tau, b_s
+      const int Pa = d.n1p + d.n2p + d.n3p;
+      for (int e = tid; e < nsig * ell; e += kThreads) {
+        const int a = e / ell, j = e % ell;
+        const int P = pos_of(d, a, j);
+        if (a < m) {
+          if (j >= L) put_sym(d, GA, GS, Pa + a, P, 1.0);
+          if (j < n) put_sym(d, GA, GS, Pa + nsig, P, ub[(size_t)(N - n + j) * m + a]);
+          if (use_sr) put_sym(d, GA, GS, Pa + nsig + 1, P, us_prev[(size_t)b * m + a]);
+        } else {
+          if (j >= n) put_sym(d, GA, GS, Pa + a, P, 1.0);
+          if (j < n) put_sym(d, GA, GS, Pa + nsig, P, yb[(size_t)(N - n + j) * p + (a - m)]);
+          if (use_sr) put_sym(d, GA, GS, Pa + nsig + 1, P, ys_prev[(size_t)b * p + (a - m)]);
+        }
+      }
+      if (tid == 0) {
+        put_sym(d, GA, GS, Pa + nsig, Pone, 1.0);
+        if (use_sr) put_sym(d, GA, GS, Pa + nsig + 1, Pone, 1.0);
+      }
     }
     __syncthreads();
-
     DDQC_PHASE(0);
-    // ---- 2. shared factorisation of the hard block (columns [0, ru)) ----
-    chol_blocked(Gm, d.ld, d.r, 0, d.ru, sD, sP, &s_flag);
-    // trailing block [ru, r) now holds S0; copy it for the alpha_sr system
-    const bool use_sr = (cfg.alpha_reg_type == 0) && have_prev && have_prev[b] != 0;
-    if (use_sr) {
-      for (int e = tid; e < d.ry * d.ry; e += kThreads) {
-        int i = e / d.ry, j = e % d.ry;
-        if (j <= i) S2[(size_t)i * d.ld + j] = Gm[(size_t)(d.ru + i) * d.ld + d.ru + j];
-      }
+
+    // ---- A. eliminate R1: panel in shared memory, S1 = trailing - L L^T through global ------------
+    {
+      const double2* src = reinterpret_cast<const double2*>(GA);
+      double2* dst = reinterpret_cast<double2*>(sM);
+#pragma unroll 4
+      for (int e = tid; e < d.ga / 2; e += kThreads) dst[e] = src[e];
     }
     __syncthreads();
-
+    factor_columns<true>(sM, d.nb1, d.nbA, d.nb1, &s_flag);
     DDQC_PHASE(1);
-    // ---- 3. v_sr = b_s - D_s (G + D_s)^-1 b_s ----
-    for (int i = tid; i < d.r; i += kThreads) v_sr[i] = 0.0;
-    if (use_sr) {
-      const double ds = cfg.lamb_alpha_s / cfg.lamb_sigma_s;
-      for (int i = tid; i < d.ry; i += kThreads) S2[(size_t)i * d.ld + i] += ds;
-      __syncthreads();
-      // S2 is a ry x ry matrix of its own (offset 0)
-      chol_blocked(S2, d.ld, d.ry, 0, d.ry, sD, sP, &s_flag);
-      // b_s
-      for (int i = tid; i < d.r; i += kThreads) {
-        double v;
-        if (i < row_one) v = us_prev[(size_t)b * m + i % m];
-        else if (i == row_one) v = 1.0;
-        else v = ys_prev[(size_t)b * p + (i - row_y0) % p];
-        cs[i] = v;
-      }
-      __syncthreads();
-      if (tid < 32) warp_solve_composite(Gm, d.ld, S2, d.ld, d.ru, d.r, cs, tid);
-      __syncthreads();
-      for (int i = tid; i < d.r; i += kThreads) {
-        double bs;
-        if (i < row_one) bs = us_prev[(size_t)b * m + i % m];
-        else if (i == row_one) bs = 1.0;
-        else bs = ys_prev[(size_t)b * p + (i - row_y0) % p];
-        v_sr[i] = (i >= row_y0) ? bs - ds * cs[i] : bs;
-      }
-    }
-    __syncthreads();
-
-    DDQC_PHASE(2);
-    // ---- 4. tail factorisation with D0, right-hand sides, Z = X^T X ----
-    for (int i = tid; i < d.ry; i += kThreads) {
-      const int j = i / p, comp = i % p;
-      double w;
-      if (j < n || j >= L) w = cfg.lamb_sigma;
-      else w = cfg.Q[comp] * cfg.lamb_sigma / (cfg.Q[comp] + cfg.lamb_sigma);
-      Gm[(size_t)(d.ru + i) * d.ld + d.ru + i] += cfg.lamb_alpha / w;
-    }
-    __syncthreads();
-    chol_blocked(Gm, d.ld, d.r, d.ru, d.r, sD, sP, &s_flag);
-
-    DDQC_PHASE(3);
-    // K = [E_B | T] and c = tau - v_sr, column-major into X
-    for (int e = tid; e < d.ldx * (d.nx + 1); e += kThreads) X[e] = 0.0;
-    __syncthreads();
-    for (int c = tid; c < d.nx + 1; c += kThreads) {
-      double* x = X + (size_t)c * d.ldx;
-      if (c < d.nB) {
-        x[n * m + c] = 1.0;  // box row of predicted input (j = n + c / m, component c % m)
-      } else if (c < d.nB + m) {
-        const int comp = c - d.nB;
-        for (int j = L; j < ell; ++j) x[j * m + comp] = 1.0;  // terminal input rows = u_s
-      } else if (c < d.nx) {
-        const int comp = c - d.nB - m;
-        for (int j = n; j < ell; ++j) x[row_y0 + j * p + comp] = 1.0;  // free + terminal output rows target y_s
-      } else {
-        for (int i = 0; i < d.r; ++i) {
-          double tau = 0.0;
-          if (i < n * m) tau = ub[(size_t)(N - n) * m + i];  // past inputs
-          else if (i == row_one) tau = 1.0;
-          else if (i >= row_y0 && i < row_y0 + n * p) tau = yb[(size_t)(N - n) * p + (i - row_y0)];
-          x[i] = tau - v_sr[i];
+    {
+      const int nblk = tri(d.nbt);
+      for (int bb = warp; bb < nblk; bb += 2 * kWarps) {
+        const int b2 = bb + kWarps;
+        const bool two = b2 < nblk;
+        int i0 = (int)((sqrtf(8.0f * bb + 1.0f) - 1.0f) * 0.5f);
+        while (tri(i0 + 1) <= bb) ++i0;
+        while (tri(i0) > bb) --i0;
+        const int j0 = bb - tri(i0);
+        int i1 = i0, j1 = j0;
+        if (two) {
+          i1 = (int)((sqrtf(8.0f * b2 + 1.0f) - 1.0f) * 0.5f);
+          while (tri(i1 + 1) <= b2) ++i1;
+          while (tri(i1) > b2) --i1;
+          j1 = b2 - tri(i1);
+        }
+        double2 c0 = ld_c(GS + (size_t)bb * 64, g, t);
+        double2 c1 = two ? ld_c(GS + (size_t)b2 * 64, g, t) : make_double2(0.0, 0.0);
+        double2 a0 = {0.0, 0.0}, a1 = {0.0, 0.0};
+        const double* pi0 = sM + (size_t)(d.nb1 + i0) * d.nb1 * 64;
+        const double* pj0 = sM + (size_t)(d.nb1 + j0) * d.nb1 * 64;
+        const double* pi1 = sM + (size_t)(d.nb1 + i1) * d.nb1 * 64;
+        const double* pj1 = sM + (size_t)(d.nb1 + j1) * d.nb1 * 64;
+        for (int J = 0; J < d.nb1; ++J) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            dmma(a0, ld_ab(pi0 + J * 64, g, t, h), ld_ab(pj0 + J * 64, g, t, h));
+            if (two) dmma(a1, ld_ab(pi1 + J * 64, g, t, h), ld_ab(pj1 + J * 64, g, t, h));
+          }
+        }
+        c0.x -= a0.x; c0.y -= a0.y;
+        st_c(GS + (size_t)bb * 64, g, t, c0);
+        if (two) {
+          c1.x -= a1.x; c1.y -= a1.y;
+          st_c(GS + (size_t)b2 * 64, g, t, c1);
         }
       }
     }
     __syncthreads();
-    forward_subst(Gm, d.ld, d.r, X, d.ldx, d.nx + 1);
-    __syncthreads();
+    DDQC_PHASE(2);
 
-    DDQC_PHASE(4);
-    // Z = X^T X (nx+1 columns): Hq = 2 lamb_alpha Z[:nx,:nx] + structure, f = 2 lamb_alpha Z[:nx, nx] + ...
-    double* sf = sv;
-    double* slo = sv + kMaxNx;
-    double* shi = sv + 2 * kMaxNx;
-    double* sx = sv + 3 * kMaxNx;
-    double* sg = sv + 4 * kMaxNx;
-    double* srhs = sv + 5 * kMaxNx;
+    // ---- B. alpha_sr:  e = D_s (S1 + D_s)^-1 b_s restricted to R2 -----------------------------------
+    const int ncol_all = d.nb2 + d.nb3;
+    const int aug_t = nsig, aug_b = nsig + 1;                 // aug indices of tau and b_s
+    const int Paug = d.n2p + d.n3p;                           // trailing position of the first aug row
+    if (use_sr) {
+      const double ds = cfg.lamb_alpha_s / cfg.lamb_sigma_s;
+      {
+        const double2* src = reinterpret_cast<const double2*>(GS);
+        double2* dst = reinterpret_cast<double2*>(sM);
+#pragma unroll 4
+        for (int e = tid; e < d.gs / 2; e += kThreads) dst[e] = src[e];
+      }
+      __syncthreads();
+      for (int q = tid; q < d.n2; q += kThreads) *elem_tri(sM, q, q) += ds;
+      __syncthreads();
+      factor_columns<false>(sM, 0, d.nbt, ncol_all, &s_flag);
+      DDQC_PHASE(3);
+      // y = L^-1 b_s sits in the b_s row; z = L^-T y by blocked back-substitution
+      for (int q = tid; q < 8 * ncol_all; q += kThreads) s_yv[q] = *elem_tri(sM, Paug + aug_b, q);
+      __syncthreads();
+      for (int K = ncol_all - 1; K >= 0; --K) {
+        if (warp == 0) {
+          const double* dk = sM + (size_t)(tri(K) + K) * 64;
+          double val = lane < 8 ? s_yv[8 * K + lane] : 0.0;
+#pragma unroll
+          for (int gg = 7; gg >= 0; --gg) {
+            const double zg = shfl_d(val, gg) * dk[eoff(gg, gg)];
+            if (lane == gg) val = zg;
+            if (lane < gg) val -= dk[eoff(gg, lane)] * zg;
+          }
+          if (lane < 8) s_yv[8 * K + lane] = val;
+        }
+        __syncthreads();
+        if (tid < 8 * K) {
+          const int J = tid >> 3, c = tid & 7;
+          const double* blk = sM + (size_t)(tri(K) + J) * 64;
+          double acc = s_yv[tid];
+#pragma unroll
+          for (int gg = 0; gg < 8; ++gg) acc -= blk[eoff(gg, c)] * s_yv[8 * K + gg];
+          s_yv[tid] = acc;
+        }
+        __syncthreads();
+      }
+      for (int q = tid; q < d.n2p; q += kThreads) s_e[q] = q < d.n2 ? ds * s_yv[q] : 0.0;
+      __syncthreads();
+      DDQC_PHASE(4);
+    }
+
+    // ---- C. main system: S1 + D_0, c = tau - b_s + e, eliminate R2, Schur on [R3 | aug] --------------
     {
-      const int nc = d.nx + 1;
-      for (int e = tid; e < d.nx * nc; e += kThreads) {
-        const int a = e / nc, c = e % nc;
-        if (c < d.nx && c > a) continue;  // lower triangle + the rhs column
-        const double* xa = X + (size_t)a * d.ldx;
-        const double* xc = X + (size_t)c * d.ldx;
-        double acc = 0.0;
-        for (int i = 0; i < d.r; ++i) acc += xa[i] * xc[i];
-        acc *= 2.0 * cfg.lamb_alpha;
-        if (c < d.nx) {
-          sH[a * d.nx + c] = acc;
-          sH[c * d.nx + a] = acc;
+      const double2* src = reinterpret_cast<const double2*>(GS);
+      double2* dst = reinterpret_cast<double2*>(sM);
+#pragma unroll 4
+      for (int e = tid; e < d.gs / 2; e += kThreads) dst[e] = src[e];
+    }
+    __syncthreads();
+    for (int q = tid; q < d.n2; q += kThreads) {
+      const int j = q / p, comp = q % p;
+      const double w = (j < n || j >= L) ? cfg.lamb_sigma : cfg.Q[comp] * cfg.lamb_sigma / (cfg.Q[comp] + cfg.lamb_sigma);
+      *elem_tri(sM, q, q) += cfg.lamb_alpha / w;
+    }
+    if (use_sr) {
+      for (int q = tid; q < 8 * ncol_all; q += kThreads) {
+        double* ct = elem_tri(sM, Paug + aug_t, q);
+        *ct = *ct - *elem_tri(sM, Paug + aug_b, q) + (q < d.n2 ? s_e[q] : 0.0);
+      }
+      if (tid < aug_t) {
+        double* ct = elem_tri(sM, Paug + aug_t, Paug + tid);
+        *ct -= *elem_tri(sM, Paug + aug_b, Paug + tid);
+      }
+      if (tid == 0) {
+        double* ctt = elem_tri(sM, Paug + aug_t, Paug + aug_t);
+        *ctt += -2.0 * *elem_tri(sM, Paug + aug_b, Paug + aug_t) + *elem_tri(sM, Paug + aug_b, Paug + aug_b);
+      }
+    }
+    __syncthreads();
+    factor_columns<false>(sM, 0, d.nbt, d.nb2, &s_flag);
+    schur_trailing(sM, d.nbt, d.nb2);
+    __syncthreads();
+    DDQC_PHASE(5);
+
+    // ---- sweep: S7 (dense, lower) <- Schur complement on [R3 (n3) | T_u, T_y, c] ---------------------
+    const int nS = d.nS, ldS = d.ldS, nx = d.nx, ldq = d.ldq;
+    double* S7 = sM;
+    {
+      double tmp = 0.0;
+      // the source blocks start at (tri(nb2) + nb2) * 64 >= nS * ldS (checked on the host), so the
+      // copy cannot overwrite a block that is still to be read
+      for (int e = tid; e < nS * nS; e += kThreads) {
+        const int i = e / nS, k = e % nS;
+        if (k > i) continue;
+        const int Pi = i < d.n3 ? d.n2p + i : Paug + (i - d.n3);
+        const int Pk = k < d.n3 ? d.n2p + k : Paug + (k - d.n3);
+        tmp = *elem_tri(sM, Pi, Pk);
+        S7[i * ldS + k] = tmp;
+      }
+    }
+    __syncthreads();
+    {
+      // Gauss-Jordan sweep of pivots 0..n3-1 on the lower triangle; the pivot column of the next step
+      // is double-buffered in s_vec so that one barrier per pivot suffices
+      const int W = nS + 1, R = (nS + 1) / 2;
+      double* vb0 = s_vec;
+      double* vb1 = s_vec + nS + 2;
+      for (int i = tid; i < nS; i += kThreads) vb0[i] = S7[i * ldS + 0];
+      __syncthreads();
+      for (int j = 0; j < d.n3; ++j) {
+        const double* vc = (j & 1) ? vb1 : vb0;
+        double* vn = (j & 1) ? vb0 : vb1;
+        const double inv = 1.0 / vc[j];
+        for (int e = tid; e < R * W; e += kThreads) {
+          const int rr = e / W, cc = e % W;
+          int i, k;
+          if (cc <= rr) { i = rr; k = cc; }
+          else { i = nS - 1 - rr; k = cc - rr - 1; if (i == rr) continue; }
+          double v;
+          if (i == j) v = (k == j) ? -inv : vc[k] * inv;
+          else if (k == j) v = vc[i] * inv;
+          else v = S7[i * ldS + k] - vc[i] * vc[k] * inv;
+          S7[i * ldS + k] = v;
+          if (k == j + 1) vn[i] = v;
+          if (i == j + 1) vn[k] = v;
+        }
+        __syncthreads();
+      }
+    }
+    DDQC_PHASE(6);
+
+    // ---- box QP assembly: Hq = 2 lamb_alpha Z + structure, f ----------------------------------------
+    double* Hq = sM + nS * ldS;
+    double* qv = Hq + nx * ldq;  // 20 vectors of kMaxNx
+    QpWork q;
+    q.Hq = Hq; q.ldq = ldq; q.nx = nx;
+    q.F = sM; q.ldf = ldS;
+    q.f = qv; q.lo = qv + kMaxNx; q.hi = qv + 2 * kMaxNx; q.x = qv + 3 * kMaxNx; q.g = qv + 4 * kMaxNx;
+    q.rhs = qv + 5 * kMaxNx; q.rs = qv + 6 * kMaxNx; q.sl = qv + 7 * kMaxNx; q.su = qv + 8 * kMaxNx;
+    q.zl = qv + 9 * kMaxNx; q.zu = qv + 10 * kMaxNx; q.dx = qv + 11 * kMaxNx; q.dzl = qv + 12 * kMaxNx;
+    q.dzu = qv + 13 * kMaxNx; q.rd = qv + 14 * kMaxNx; q.dg = qv + 15 * kMaxNx;
+    q.s_red = s_red; q.state = s_state; q.idx = s_idx; q.verdict = s_verdict; q.s_flag = &s_flag;
+    {
+      const double la2 = 2.0 * cfg.lamb_alpha;
+      for (int e = tid; e < nS * nx; e += kThreads) {
+        const int i = e / nx, k = e % nx;  // i in [0, nS), k in [0, nx)
+        if (k > i) continue;
+        const double sw = S7[i * ldS + k];
+        const bool iB = i < d.n3, kB = k < d.n3;
+        const double z = (iB == kB) ? -sw : sw;
+        if (i < nx) {
+          Hq[i * ldq + k] = la2 * z;
+          Hq[k * ldq + i] = la2 * z;
         } else {
-          sf[a] = acc;
+          q.f[k] = la2 * z;
         }
       }
     }
     __syncthreads();
     if (tid == 0) {
-      // structured part of the box-QP objective
-      for (int bi = 0; bi < d.nB; ++bi) {
+      const int nB = d.n3;
+      for (int bi = 0; bi < nB; ++bi) {
         const int comp = bi % m;
         const double w2 = 2.0 * cfg.R[comp];
-        sH[bi * d.nx + bi] += w2;
-        sH[bi * d.nx + d.nB + comp] -= w2;
-        sH[(d.nB + comp) * d.nx + bi] -= w2;
-        sH[(d.nB + comp) * d.nx + d.nB + comp] += w2;
+        Hq[bi * ldq + bi] += w2;
+        Hq[bi * ldq + nB + comp] -= w2;
+        Hq[(nB + comp) * ldq + bi] -= w2;
+        Hq[(nB + comp) * ldq + nB + comp] += w2;
       }
       for (int i = 0; i < m; ++i) {
         double su = 0.0;
         for (int j = 0; j < n; ++j) su += ub[(size_t)(N - n + j) * m + i];
-        sH[(d.nB + i) * d.nx + d.nB + i] += 2.0 * n * cfg.R[i];
-        sf[d.nB + i] += -2.0 * cfg.R[i] * su;
+        Hq[(nB + i) * ldq + nB + i] += 2.0 * n * cfg.R[i];
+        q.f[nB + i] += -2.0 * cfg.R[i] * su;
       }
       for (int i = 0; i < p; ++i) {
         double sy = 0.0;
         for (int j = 0; j < n; ++j) sy += yb[(size_t)(N - n + j) * p + i];
-        const int q = d.nB + m + i;
-        sH[q * d.nx + q] += 2.0 * (n * cfg.Q[i] + cfg.S[i]);
-        sf[q] += -2.0 * (cfg.Q[i] * sy + cfg.S[i] * y_r[(size_t)b * p + i]);
+        const int qq = nB + m + i;
+        Hq[qq * ldq + qq] += 2.0 * (n * cfg.Q[i] + cfg.S[i]);
+        q.f[qq] += -2.0 * (cfg.Q[i] * sy + cfg.S[i] * y_r[(size_t)b * p + i]);
       }
     }
-    for (int i = tid; i < d.nx; i += kThreads) {
+    const bool warm = act_state != nullptr && have_prev[b] != 0;
+    if (tid < nx) {
       double lo, hi;
-      if (i < d.nB) {
-        lo = cfg.U_lo[i % m];
-        hi = cfg.U_hi[i % m];
-      } else if (i < d.nB + m) {
-        const int comp = i - d.nB;
+      if (tid < d.n3) {
+        lo = cfg.U_lo[tid % m];
+        hi = cfg.U_hi[tid % m];
+      } else if (tid < d.n3 + m) {
+        const int comp = tid - d.n3;
         lo = fmax(cfg.U_lo[comp], cfg.Us_lo[comp]);
         hi = fmin(cfg.U_hi[comp], cfg.Us_hi[comp]);
       } else {
         lo = -INFINITY;
         hi = INFINITY;
       }
-      slo[i] = lo;
-      shi[i] = hi;
-      s_state[i] = 0;
+      q.lo[tid] = lo;
+      q.hi[tid] = hi;
+      int st = 0;
+      if (warm) {
+        // receding horizon: predicted input k of this solve was input k+1 of the previous one
+        const int8_t* as = act_state + (size_t)b * nx;
+        if (tid < d.n3) st = tid + m < d.n3 ? as[tid + m] : as[tid];
+        else st = as[tid];
+        if ((st < 0 && !isfinite(lo)) || (st > 0 && !isfinite(hi))) st = 0;
+      }
+      s_state[tid] = st;
     }
     __syncthreads();
-
-    DDQC_PHASE(5);
-    // ---- 5. box QP: explicit inverse Hessian (CTA) + block principal pivoting on the active set (warp 0) ----
-    {
-      double fmax_abs = 0.0;
-      for (int i = 0; i < d.nx; ++i) fmax_abs = fmax(fmax_abs, fabs(sf[i]));
-      const double tol_g = 1e-11 * fmax(1.0, fmax_abs);
-      spd_inverse_cta(sH, sF, d.nx, &s_flag);
-      for (int i = tid; i < d.nx; i += kThreads) {  // x0 = -W f
-        double acc = 0.0;
-        for (int k = 0; k < d.nx; ++k) acc -= sH[i * d.nx + k] * sf[k];
-        sg[i] = acc;
-      }
-      __syncthreads();
-      DDQC_PHASE(6);
-      if (tid < 32) {
-        int it_w = 0, conv_w = 0;
-        box_qp_bpp(sH, sF, sg, slo, shi, sx, srhs, tol_g, s_state, s_idx, s_verdict, d.nx,
-                   cfg.max_iter > 0 ? cfg.max_iter : 20000, tid, &it_w, &conv_w, &s_flag);
-        if (tid == 0) {
-          s_cnt[2] = it_w;
-          s_cnt[3] = conv_w;
-        }
-      }
-      __syncthreads();
-    }
-    const int it = s_cnt[2], converged = s_cnt[3];
-
     DDQC_PHASE(7);
-    // ---- 6. outputs ----
+
+    // ---- D. box QP ------------------------------------------------------------------------------------
+    int passes = 0, ipm_it = 0, converged;
+    {
+      const double fmax_abs = block_reduce(tid < nx ? fabs(q.f[tid]) : 0.0, RED_MAX, s_red);
+      const double tol_g = 1e-11 * fmax(1.0, fmax_abs);
+      const int cap = cfg.max_iter > 0 ? cfg.max_iter : 12;
+      converged = bpp_solve(q, tol_g, warm ? cap : (cap < 8 ? cap : 8), &passes);
+      DDQC_PHASE(8);
+      if (!converged) {
+        ipm_it = ipm_solve(q, 60);
+        // keep the interior-point iterate in case the polish does not settle
+        if (tid < nx) q.dx[tid] = q.x[tid];
+        __syncthreads();
+        converged = bpp_solve(q, tol_g, 6, &passes);
+        if (!converged) {
+          if (tid < nx) q.x[tid] = q.dx[tid];
+          converged = ipm_it > 0;
+          __syncthreads();
+        }
+        ipm_it = (ipm_it < 0 ? -ipm_it : ipm_it) - 1;
+        DDQC_PHASE(9);
+      }
+    }
+
+    // ---- outputs ----------------------------------------------------------------------------------------
     for (int e = tid; e < (L + 1) * m; e += kThreads) {
       const int k = e / m, comp = e % m;
-      u_opt[(size_t)b * (L + 1) * m + e] = (k < L - n) ? sx[k * m + comp] : sx[d.nB + comp];
+      u_opt[(size_t)b * (L + 1) * m + e] = (k < L - n) ? q.x[k * m + comp] : q.x[d.n3 + comp];
     }
-    for (int i = tid; i < m; i += kThreads) us_opt[(size_t)b * m + i] = sx[d.nB + i];
-    for (int i = tid; i < p; i += kThreads) ys_opt[(size_t)b * p + i] = sx[d.nB + m + i];
+    for (int i = tid; i < m; i += kThreads) us_opt[(size_t)b * m + i] = q.x[d.n3 + i];
+    for (int i = tid; i < p; i += kThreads) ys_opt[(size_t)b * p + i] = q.x[d.n3 + m + i];
+    if (act_state != nullptr && tid < nx) act_state[(size_t)b * nx + tid] = (int8_t)s_state[tid];
     if (tid == 0) {
       status[b] = s_flag ? 2 : (converged ? 0 : 1);
-      iters[b] = it;
+      iters[b] = passes + (ipm_it << 16);
     }
-    __syncthreads();
+    DDQC_PHASE(10);
   }
 }
 
@@ -746,27 +1020,25 @@ __global__ void ddmpc_store_kernel(const int N, const int m, const int p, double
   if (threadIdx.x < p) yb[(size_t)(N - 1) * p + threadIdx.x] = y_new[(size_t)b * p + threadIdx.x];
 }
 
+size_t smem_bytes(const Dims& d) { return (size_t)(region_doubles(d) + extra_doubles(d)) * sizeof(double); }
+
 int check_cfg(const DdqcMpcConfig* c) {
   if (!c) return DDQC_E_NULL;
   if (c->m < 1 || c->p < 1 || c->m > kMaxSig || c->p > kMaxSig || c->n < 1 || c->L <= c->n) return DDQC_E_SHAPE;
   const Dims d = make_dims(*c);
-  if (d.C < 1 || d.r > kMaxR || d.nx > kMaxNx) return DDQC_E_SHAPE;
+  if (d.C < 1 || d.nx > kMaxNx) return DDQC_E_SHAPE;
+  if (smem_bytes(d) + 2048 > (size_t)kSmemLimit) return DDQC_E_SHAPE;
+  // the dense copy of the final Schur complement must not overlap the blocks it is read from
+  if (d.nS * d.ldS > (d.nb2 * (d.nb2 + 1) / 2 + d.nb2) * 64) return DDQC_E_SHAPE;
   if (c->alpha_reg_type != 0 && c->alpha_reg_type != 2) return DDQC_E_CONFIG;
   return 0;
-}
-
-size_t smem_bytes(const Dims& d) {
-  const size_t panel = (size_t)d.r * kNB, boxqp = 2 * (size_t)d.nx * d.nx;
-  size_t dbl = (size_t)(d.m + d.p) * d.N + kNB * (kNB + 1) + 6 * kMaxNx + (panel > boxqp ? panel : boxqp);
-  return dbl * sizeof(double);
 }
 
 }  // namespace
 
 static long long* g_phase_clk = nullptr;
-// Developer aid (not part of the reference-facing surface): device buffer of 8 cycle counters that the
-// solver accumulates per phase (Gram, hard-block Cholesky, alpha_sr, tail Cholesky, substitutions, Z,
-// inverse, pivoting).  Pass NULL to switch it off.
+// Developer aid (not part of the reference-facing surface): device buffer of 12 cycle counters that the
+// solver accumulates per phase.  Pass NULL to switch it off.
 extern "C" int ddqc_ddmpc_debug_phase_buffer(void* dev_ptr) {
   g_phase_clk = static_cast<long long*>(dev_ptr);
   return 0;
@@ -776,22 +1048,22 @@ extern "C" int64_t ddqc_ddmpc_workspace_bytes(const DdqcMpcConfig* cfg, int64_t 
   if (check_cfg(cfg) != 0 || batch < 0) return -1;
   const Dims d = make_dims(*cfg);
   const int64_t slots = batch < kMaxSlots ? batch : kMaxSlots;
-  return (int64_t)(slot_doubles(d) * sizeof(double)) * (slots > 0 ? slots : 1);
+  return 256 + (int64_t)(slot_doubles(d) * sizeof(double)) * (slots > 0 ? slots : 1);
 }
 
 extern "C" int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg, void* ws, const double* u_win, const double* y_win,
                                 const double* y_r, const double* us_prev, const double* ys_prev,
-                                const int32_t* have_prev, double* u_opt, double* us_opt, double* ys_opt,
-                                int32_t* status, int32_t* iters, int64_t batch, void* stream) {
+                                const int32_t* have_prev, int8_t* act_state, double* u_opt, double* us_opt,
+                                double* ys_opt, int32_t* status, int32_t* iters, int64_t batch, void* stream) {
   int rc = check_cfg(cfg);
   if (rc) return rc;
-  if (!ws || !u_win || !y_win || !y_r || !u_opt || !us_opt || !ys_opt || !status || !iters) return DDQC_E_NULL;
-  if (cfg->alpha_reg_type == 0 && (!us_prev || !ys_prev || !have_prev)) return DDQC_E_NULL;
+  if (!ws || !u_win || !y_win || !y_r || !u_opt || !us_opt || !ys_opt || !status || !iters || !have_prev)
+    return DDQC_E_NULL;
+  if (cfg->alpha_reg_type == 0 && (!us_prev || !ys_prev)) return DDQC_E_NULL;
   if (batch < 0) return DDQC_E_SHAPE;
   if (batch == 0) return 0;
   const Dims d = make_dims(*cfg);
   const size_t smem = smem_bytes(d);
-  if (smem > 227 * 1024) return DDQC_E_SHAPE;
   cudaError_t e = cudaFuncSetAttribute(ddmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   int dev = 0, sms = 148;
@@ -799,9 +1071,14 @@ extern "C" int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg, void* ws, const double
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = (int)(batch < sms ? batch : sms);
   if (grid > kMaxSlots) grid = kMaxSlots;
-  ddmpc_solve_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      *cfg, static_cast<double*>(ws), u_win, y_win, y_r, us_prev, ys_prev, have_prev, u_opt, us_opt, ys_opt, status,
-      iters, (int)batch, g_phase_clk);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // layout of ws: [work counter, 256 B][slot 0][slot 1]...
+  e = cudaMemsetAsync(ws, 0, 256, st);
+  if (e != cudaSuccess) return (int)e;
+  double* slots = reinterpret_cast<double*>(static_cast<char*>(ws) + 256);
+  ddmpc_solve_kernel<<<grid, kThreads, smem, st>>>(*cfg, slots, static_cast<int*>(ws), u_win, y_win, y_r, us_prev,
+                                                   ys_prev, have_prev, act_state, u_opt, us_opt, ys_opt, status, iters,
+                                                   (int)batch, g_phase_clk);
   return (int)cudaGetLastError();
 }
 

@@ -73,7 +73,8 @@ class BatchedNonlinearDataDrivenMPC:
         n_mpc_step: int = 1,
         device: torch.device | str = "cuda",
         solve_on_init: bool = True,
-        max_iter: int = 20000,
+        max_iter: int = 12,
+        warm_start: bool = True,
     ):
         if ext_out_incr_in:
             raise NotImplementedError("ext_out_incr_in=True (extended output / input increments) is not supported")
@@ -140,6 +141,9 @@ class BatchedNonlinearDataDrivenMPC:
         self.optimal_u = torch.zeros((self.B, self.L + 1, m), **f64)
         self.status = torch.zeros((self.B,), dtype=torch.int32, device=dev)
         self.iters = torch.zeros((self.B,), dtype=torch.int32, device=dev)
+        # active set of the condensed box QP, carried between solves as the warm start
+        self.nx = (self.L - self.n) * m + m + p
+        self._act_state = torch.zeros((self.B, self.nx), dtype=torch.int8, device=dev) if warm_start else None
         if solve_on_init:
             self.update_and_solve_data_driven_mpc()
 
@@ -158,11 +162,21 @@ class BatchedNonlinearDataDrivenMPC:
         rc = self._lib.ddqc_ddmpc_solve(
             C.byref(self._cfg), self._ws.data_ptr(), self.u.data_ptr(), self.y.data_ptr(), self.y_r.data_ptr(),
             self._us_prev.data_ptr(), self._ys_prev.data_ptr(), self._have_prev.data_ptr(),
-            self.optimal_u.data_ptr(), self.us.data_ptr(), self.ys.data_ptr(), self.status.data_ptr(),
+            self._act_state.data_ptr() if self._act_state is not None else None, self.optimal_u.data_ptr(), self.us.data_ptr(), self.ys.data_ptr(), self.status.data_ptr(),
             self.iters.data_ptr(), self.B, _lib.stream_ptr(self.device),
         )  # fmt: skip
         _lib.check(rc, "ddqc_ddmpc_solve")
         self._have_prev.fill_(1)
+
+    @property
+    def pivoting_passes(self) -> torch.Tensor:
+        """Pivoting passes of the last solve (per controller)."""
+        return self.iters & 0xFFFF
+
+    @property
+    def ipm_iterations(self) -> torch.Tensor:
+        """Interior-point iterations of the last solve (0 unless the pivoting fell back)."""
+        return self.iters >> 16
 
     def get_optimal_control_input_at_step(self, n_step: int = 0) -> torch.Tensor:
         if not 0 <= n_step < self.n_mpc_step:

@@ -252,7 +252,7 @@ int ddqc_tracking_compute(const float* pos, int64_t p_rs, int64_t p_cs,
 typedef struct DdqcMpcConfig {
   int32_t n, m, p, L, N;        /* estimated order, inputs, outputs, horizon, window length */
   int32_t alpha_reg_type;       /* 0 approximated, 1 previous, 2 zero */
-  int32_t max_iter;             /* active-set iteration cap */
+  int32_t max_iter;             /* pivoting passes before the interior-point fallback (<=0: 12) */
   int32_t pad0;
   double Q[8], R[8], S[8];      /* diagonal weights (first p / m / p entries) */
   double lamb_alpha, lamb_sigma, lamb_alpha_s, lamb_sigma_s;
@@ -266,21 +266,26 @@ int64_t ddqc_ddmpc_workspace_bytes(const DdqcMpcConfig* cfg_host, int64_t batch)
  *  u_win [B][N][m], y_win [B][N][p] : rolling input/output windows (float64)
  *  y_r   [B][p]                      : output setpoints
  *  us_prev, ys_prev [B][m],[B][p]    : previous optimal equilibrium (alpha_reg_type 0);
- *  have_prev [B] int32               : 0 -> alpha_sr = 0 (first solve)
+ *  have_prev [B] int32               : 0 -> alpha_sr = 0 and cold active set (first solve)
+ *  act_state [B][nx] int8 (or NULL)  : active set of the box QP (-1 lower, 0 free, +1 upper),
+ *                                      nx = (L-n) m + m + p; read as the warm start (shifted one
+ *                                      step) when have_prev != 0, always written
  *  u_opt [B][L+1][m]                 : optimal predicted inputs ubar_0..ubar_L
  *  us_opt [B][m], ys_opt [B][p]      : optimal equilibrium
- *  status [B] int32 (0 ok, 1 iteration cap, 2 factorisation breakdown), iters [B] int32 */
+ *  status [B] int32 (0 ok, 1 not converged, 2 factorisation breakdown)
+ *  iters [B] int32 = pivoting passes + (interior-point iterations << 16)
+ *  ws: ddqc_ddmpc_workspace_bytes() bytes, 256-byte aligned; its first 256 bytes are the work counter */
 int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg_host, void* ws, const double* u_win,
                      const double* y_win, const double* y_r, const double* us_prev,
-                     const double* ys_prev, const int32_t* have_prev, double* u_opt,
-                     double* us_opt, double* ys_opt, int32_t* status, int32_t* iters,
+                     const double* ys_prev, const int32_t* have_prev, int8_t* act_state,
+                     double* u_opt, double* us_opt, double* ys_opt, int32_t* status, int32_t* iters,
                      int64_t batch, void* stream);
 
 /* store_input_output_measurement for a batch: shift each window one sample and append. */
 int ddqc_ddmpc_store(const DdqcMpcConfig* cfg_host, double* u_win, double* y_win,
                      const double* u_new, const double* y_new, int64_t batch, void* stream);
 
-/* Developer aid: device buffer of 8 int64 cycle counters accumulated per solver phase (NULL: off). */
+/* Developer aid: device buffer of 12 int64 cycle counters accumulated per solver phase (NULL: off). */
 int ddqc_ddmpc_debug_phase_buffer(void* dev_ptr);
 
 /* library identification and layout self-check: sizeof of struct `which`

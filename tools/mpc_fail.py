@@ -1,6 +1,6 @@
 """Developer probe: dump DD-MPC problems whose pivoting hit the iteration cap."""
 import os, sys
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import numpy as np, torch
 import bench
 from data_driven_quad_control_b200.data_driven_mpc import nonlinear_data_driven_mpc_controller as mod

@@ -1,6 +1,6 @@
 """Developer probe: DD-MPC solver phase timing at default sizes."""
 import os, sys, json, time
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import numpy as np, torch
 from data_driven_quad_control_b200 import _lib
 from data_driven_quad_control_b200.data_driven_mpc.nonlinear_data_driven_mpc_controller import BatchedNonlinearDataDrivenMPC
@@ -13,16 +13,16 @@ y = np.repeat(g["y"][None], B, 0) + 1e-4 * rng.standard_normal((B, 350, 3))
 P = bench.MPC_DEFAULT; ell = 42
 ctrl = BatchedNonlinearDataDrivenMPC(n=6, m=3, p=3, u=u, y=y, L=35, Q=np.kron(np.eye(ell), np.diag(P["Q"])), R=np.kron(np.eye(ell), np.diag(P["R"])), S=np.diag(P["S"]), y_r=np.array(P["y_r"]), lamb_alpha=50.0, lamb_sigma=1e9, U=P["U"], Us=P["Us"], alpha_reg_type=0, lamb_alpha_s=1.0, lamb_sigma_s=1e7, solve_on_init=False)
 lib = _lib.load()
-clk = torch.zeros(8, dtype=torch.int64, device="cuda")
+clk = torch.zeros(12, dtype=torch.int64, device="cuda")
 ctrl.update_and_solve_data_driven_mpc(); torch.cuda.synchronize()
 lib.ddqc_ddmpc_debug_phase_buffer(clk.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); ctrl.update_and_solve_data_driven_mpc(); e1.record(); torch.cuda.synchronize()
 lib.ddqc_ddmpc_debug_phase_buffer(None)
 ms = e0.elapsed_time(e1)
-names = ["gram", "chol_hard", "alpha_sr", "chol_tail", "subst", "Z", "inverse", "pivot"]
+names = ["gram", "A_factor", "A_update", "B_factor", "B_backsub", "C_factor_schur", "sweep", "qp_assemble", "pivoting", "ipm_polish", "out", "-"]
 c = clk.cpu().numpy().astype(float)
 print(json.dumps({"B": B, "ms": ms, "solves_per_s": B / ms * 1e3, "us_per_solve_per_cta": ms * 1e3 * min(B, 148) / B,
                   "phase_pct": {n: round(100 * v / c.sum(), 1) for n, v in zip(names, c)},
                   "phase_kcycles_per_solve": {n: round(v / B / 1e3, 1) for n, v in zip(names, c)},
-                  "iters_mean": float(ctrl.iters.float().mean()), "status_bad": int((ctrl.status != 0).sum())}))
+                  "passes_mean": float(ctrl.pivoting_passes.float().mean()), "ipm_frac": float((ctrl.ipm_iterations > 0).float().mean()), "status_bad": int((ctrl.status != 0).sum())}))
