@@ -40,13 +40,16 @@
 
 namespace {
 
-constexpr int kThreads = 512;
+#ifndef DDQC_MPC_THREADS
+#define DDQC_MPC_THREADS 512
+#endif
+constexpr int kThreads = DDQC_MPC_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxNx = 128;    // max box-QP variables
 constexpr int kMaxSig = 8;     // max m, p
 constexpr int kMaxSlots = 160; // workspace slots (>= SM count)
-constexpr int kNumPhases = 12;
 constexpr int kSmemLimit = 227 * 1024;
+constexpr int kMaxPos = 1024;  // max (m + p) * ell
 
 struct Dims {
   int n, m, p, L, N, ell, C;
@@ -75,7 +78,7 @@ __host__ __device__ inline Dims make_dims(const DdqcMpcConfig& c) {
   d.nbA = d.nb1 + d.nbt;
   d.nx = d.n3 + c.m + c.p;
   d.nS = d.nx + 1;
-  d.ldS = d.nS | 1;
+  d.ldS = (d.nS + 1) & ~1;  // even: rows are accessed as double2
   d.ldq = d.nx | 1;
   d.ga = d.nbA * d.nb1 * 64;
   d.gs = d.nbt * (d.nbt + 1) / 2 * 64;
@@ -83,17 +86,17 @@ __host__ __device__ inline Dims make_dims(const DdqcMpcConfig& c) {
 }
 
 // extra shared-memory doubles behind the matrix region
-__host__ __device__ inline int extra_doubles(const Dims& d) { return 8 * d.nbt + d.n2p + 2 * (d.nS + 2) + 64; }
+__host__ __device__ inline int extra_doubles(const Dims& d) { return 8 * d.nbt + d.n2p + 2 * (d.nS + 22) + 64; }
 
 __host__ __device__ inline int region_doubles(const Dims& d) {
   int r = d.gs;
   if (d.ga > r) r = d.ga;
-  const int win = (d.m + d.p) * d.N;
+  const int win = (d.m + d.p) * d.N + d.ell * (d.m + d.p) * 8 * ((d.m + d.p + 8) / 8);
   if (win > r) r = win;
   // box-QP stage: S7 | Hq | 20 vectors ; the factor scratch aliases S7
   const int qp = d.nS * d.ldS + d.nx * d.ldq + 20 * kMaxNx;
   if (qp > r) r = qp;
-  return r;
+  return (r + 1) & ~1;  // keep everything behind the region 16-byte aligned
 }
 
 __host__ __device__ inline size_t slot_doubles(const Dims& d) { return (size_t)d.ga + d.gs; }
@@ -150,100 +153,203 @@ __device__ __forceinline__ void syrk_pair(const double* __restrict__ M, int nb1,
   s1.x = b0.x + b1.x; s1.y = b0.y + b1.y;
 }
 
-// Cholesky of one 8x8 block by one warp (lane i < 8 owns row i).  On exit the block holds L
-// strictly below the diagonal, 1/L_ii ON the diagonal and zeros above.
+// Cholesky of one 8x8 block by one warp.  Lane l holds M[l>>3][l&7] and M[(l>>3)+4][l&7]; the pivot
+// loop is ROLLED on purpose: this code sits on the critical path of every block column and an
+// unrolled version (hundreds of straight-line instructions executed by a single warp) spends most
+// of its time in instruction-cache misses.  On exit the block holds L strictly below the diagonal
+// and 1/L_ii ON the diagonal; the strict upper triangle is left as it was.
+#define LT(i, c) a[(i) * ((i) + 1) / 2 + (c)]
 __device__ __forceinline__ bool chol8_warp(double* blk, int lane) {
-  double a[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) a[c] = (lane < 8 && c <= lane) ? blk[eoff(lane, c)] : 0.0;
+  const int r0 = lane >> 3, c = lane & 7;
+  double A = blk[eoff(r0, c)], B = blk[eoff(r0 + 4, c)];
   bool ok = true;
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < 8; ++j) {
-    double dj = shfl_d(a[j], j);
+    double dj = shfl_d(j < 4 ? A : B, ((j & 3) << 3) | j);
     if (!(dj > 0.0)) { ok = false; dj = 1.0; }
     const double r = rsqrt(dj);
-    const double l = a[j] * r;
-    a[j] = (lane == j) ? r : l;
-#pragma unroll
-    for (int c = j + 1; c < 8; ++c) {
-      const double lc = shfl_d(l, c);
-      if (lane >= c) a[c] -= l * lc;
+    if (c == j) {
+      A = (r0 == j) ? r : A * r;
+      B = (r0 + 4 == j) ? r : B * r;
+    }
+    const double x1 = shfl_d(A, (r0 << 3) | j), x2 = shfl_d(B, (r0 << 3) | j);
+    const double y1 = shfl_d(A, ((c & 3) << 3) | j), y2 = shfl_d(B, ((c & 3) << 3) | j);
+    const double lc = c < 4 ? y1 : y2;
+    if (c > j) {
+      if (r0 >= c) A -= x1 * lc;
+      if (r0 + 4 >= c) B -= x2 * lc;
     }
   }
-  if (lane < 8) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) blk[eoff(lane, c)] = (c <= lane) ? a[c] : 0.0;
-  }
+  if (r0 >= c) blk[eoff(r0, c)] = A;
+  if (r0 + 4 >= c) blk[eoff(r0 + 4, c)] = B;
   return ok;
 }
 
-// X <- X L^-T for one 8x8 block held as an accumulator fragment (thread (g,t): X[g][2t], X[g][2t+1]);
-// Lr0 / Lr1 = rows 2t and 2t+1 of L, rinv = reciprocal diagonal.
-__device__ __forceinline__ void trsm8_frag(double2& v, const double (&Lr0)[8], const double (&Lr1)[8],
-                                           const double (&rinv)[8], int lane, int t) {
+// load the factor of a diagonal block (36 values, broadcast reads) into registers
+__device__ __forceinline__ void load_diag(const double* dk, double (&a)[36]) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const double cand = (c & 1) ? v.y : v.x;
-    const double xc = shfl_d(cand, (lane & ~3) | (c >> 1)) * rinv[c];
-    if ((c >> 1) == t) {
-      if (c & 1) v.y = xc; else v.x = xc;
-    }
-    if (2 * t > c) v.x -= xc * Lr0[c];
-    if (2 * t + 1 > c) v.y -= xc * Lr1[c];
-  }
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c <= i; ++c) LT(i, c) = dk[eoff(i, c)];
 }
 
-// Left-looking blocked Cholesky of block columns [0, ncols) of a matrix of `nrows` block rows held
-// in shared memory (RECT: nrows x nb1 rectangle; else block-packed lower triangle).  Block rows
-// >= ncols are carried along (they receive the triangular solve = forward substitution).
+// X <- X L^-T for one 8x8 block held as an accumulator fragment (thread (g,t): X[g][2t], X[g][2t+1]).
+// The four lanes of a quad all-gather their row (6 shuffles off the dependency chain), solve it
+// redundantly in registers and keep their own two entries.
+__device__ __forceinline__ void trsm8_frag(double2& v, const double (&a)[36], int t) {
+  const bool o1 = t & 1, o2 = t & 2;
+  const double p0 = __shfl_xor_sync(0xffffffffu, v.x, 1), p1 = __shfl_xor_sync(0xffffffffu, v.y, 1);
+  double q[4];
+  q[0] = o1 ? p0 : v.x; q[1] = o1 ? p1 : v.y; q[2] = o1 ? v.x : p0; q[3] = o1 ? v.y : p1;
+  double x[8];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const double pe = __shfl_xor_sync(0xffffffffu, q[e], 2);
+    x[e] = o2 ? pe : q[e];
+    x[4 + e] = o2 ? q[e] : pe;
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    double acc = x[c];
+#pragma unroll
+    for (int k = 0; k < c; ++k) acc -= x[k] * LT(c, k);
+    x[c] = acc * LT(c, c);
+  }
+  const double e0 = o1 ? x[2] : x[0], e1 = o1 ? x[3] : x[1], e2 = o1 ? x[6] : x[4], e3 = o1 ? x[7] : x[5];
+  v.x = o2 ? e2 : e0;
+  v.y = o2 ? e3 : e1;
+}
+
+#ifdef DDQC_PROF_FACTOR
+__device__ long long* g_fprof = nullptr;
+#define FPROF(k)                                                                            \
+  do {                                                                                      \
+    if (g_fprof && lane == 0 && warp < 2) {                                                 \
+      const long long tn = clock64();                                                       \
+      atomicAdd((unsigned long long*)&g_fprof[12 + warp * 6 + (k)], (unsigned long long)(tn - tp)); \
+      tp = tn;                                                                              \
+    }                                                                                       \
+  } while (0)
+#else
+#define FPROF(k)
+#endif
+
 template <bool RECT>
 __device__ void factor_columns(double* __restrict__ M, int nb1, int nrows, int ncols, int* s_flag) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+#ifdef DDQC_PROF_FACTOR
+  long long tp = clock64();
+#endif
   for (int K = 0; K < ncols; ++K) {
-    // (a) update block column K with everything to its left; warp 0 owns the diagonal block
     if (warp == 0) {
-      double* blk = M + (size_t)bidx<RECT>(K, K, nb1) * 64;
-      double2 s0, s1;
-      syrk_pair<RECT>(M, nb1, K, K, false, K, K, g, t, s0, s1);
-      double2 cv = ld_c(blk, g, t);
-      cv.x -= s0.x; cv.y -= s0.y;
-      st_c(blk, g, t, cv);
-      __syncwarp();
-      if (!chol8_warp(blk, lane) && lane == 0) *s_flag = 1;
-    } else if (K > 0) {
-      for (int I = K + 1 + 2 * (warp - 1); I < nrows; I += 2 * (kWarps - 1)) {
+      if (!chol8_warp(M + (size_t)bidx<RECT>(K, K, nb1) * 64, lane) && lane == 0) *s_flag = 1;
+    } else if ((warp & 3) != 0 && K > 0 && K + 1 < ncols) {
+      // warps 4, 8, 12 share warp 0's SM sub-partition (and its FP64 pipe): they stay idle here so that
+      // the diagonal-block chain is not queued behind 16-cycle DMMA issues
+      const int bw = (warp >> 2) * 3 + (warp & 3) - 1;
+      for (int I = K + 1 + 2 * bw; I < nrows; I += 2 * (kWarps - kWarps / 4)) {
         const bool two = I + 1 < nrows;
         double2 s0, s1;
-        syrk_pair<RECT>(M, nb1, I, I + 1, two, K, K, g, t, s0, s1);
-        double* b0 = M + (size_t)bidx<RECT>(I, K, nb1) * 64;
+        syrk_pair<RECT>(M, nb1, I, I + 1, two, K + 1, K, g, t, s0, s1);
+        double* b0 = M + (size_t)bidx<RECT>(I, K + 1, nb1) * 64;
         double2 cv = ld_c(b0, g, t);
         cv.x -= s0.x; cv.y -= s0.y;
         st_c(b0, g, t, cv);
         if (two) {
-          double* b1 = M + (size_t)bidx<RECT>(I + 1, K, nb1) * 64;
+          double* b1 = M + (size_t)bidx<RECT>(I + 1, K + 1, nb1) * 64;
           double2 cw = ld_c(b1, g, t);
           cw.x -= s1.x; cw.y -= s1.y;
           st_c(b1, g, t, cw);
         }
       }
     }
+    FPROF(0);
     __syncthreads();
-    // (c) triangular solve of the blocks below the diagonal
+    FPROF(1);
     if (K + 1 + warp < nrows) {
-      const double* dk = M + (size_t)bidx<RECT>(K, K, nb1) * 64;
-      double Lr0[8], Lr1[8], rinv[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        Lr0[c] = dk[eoff(2 * t, c)];
-        Lr1[c] = dk[eoff(2 * t + 1, c)];
-        rinv[c] = dk[eoff(c, c)];
-      }
+      double a[36];
+      load_diag(M + (size_t)bidx<RECT>(K, K, nb1) * 64, a);
       for (int I = K + 1 + warp; I < nrows; I += kWarps) {
         double* b0 = M + (size_t)bidx<RECT>(I, K, nb1) * 64;
         double2 v = ld_c(b0, g, t);
-        trsm8_frag(v, Lr0, Lr1, rinv, lane, t);
+        trsm8_frag(v, a, t);
         st_c(b0, g, t, v);
       }
+    }
+    FPROF(2);
+    __syncthreads();
+    FPROF(3);
+    if (K + 1 < ncols) {
+      const double* rk = M + (size_t)bidx<RECT>(K + 1, K, nb1) * 64;
+      const double kb0 = ld_ab(rk, g, t, 0), kb1 = ld_ab(rk, g, t, 1);
+      for (int I = K + 1 + warp; I < nrows; I += kWarps) {
+        const double* li = M + (size_t)bidx<RECT>(I, K, nb1) * 64;
+        double* b0 = M + (size_t)bidx<RECT>(I, K + 1, nb1) * 64;
+        double2 acc = {0.0, 0.0}, cv = ld_c(b0, g, t);
+        dmma(acc, ld_ab(li, g, t, 0), kb0);
+        dmma(acc, ld_ab(li, g, t, 1), kb1);
+        cv.x -= acc.x; cv.y -= acc.y;
+        st_c(b0, g, t, cv);
+      }
+      // no barrier: warp 0 wrote the next diagonal block itself, and step 1 of the next column only
+      // reads block columns <= K (complete) and writes block column K+2
+    }
+    FPROF(4);
+  }
+  __syncthreads();
+}
+
+// L y' = y (in place) for the leading ncols block columns of a factored block-packed matrix
+__device__ void fwdsub_blocked(const double* __restrict__ M, int ncols, double* __restrict__ y) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int K = 0; K < ncols; ++K) {
+    if (warp == 0) {
+      const double* dk = M + (size_t)(tri(K) + K) * 64;
+      double val = lane < 8 ? y[8 * K + lane] : 0.0;
+#pragma unroll
+      for (int gg = 0; gg < 8; ++gg) {
+        const double zg = shfl_d(val, gg) * dk[eoff(gg, gg)];
+        if (lane == gg) val = zg;
+        if (lane > gg && lane < 8) val -= dk[eoff(lane, gg)] * zg;
+      }
+      if (lane < 8) y[8 * K + lane] = val;
+    }
+    __syncthreads();
+    if (tid < 8 * (ncols - K - 1)) {
+      const int I = K + 1 + (tid >> 3), gr = tid & 7;
+      const double* blk = M + (size_t)(tri(I) + K) * 64;
+      double acc = y[8 * I + gr];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc -= blk[eoff(gr, c)] * y[8 * K + c];
+      y[8 * I + gr] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// L^T z = y (in place)
+__device__ void backsub_blocked(const double* __restrict__ M, int ncols, double* __restrict__ y) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int K = ncols - 1; K >= 0; --K) {
+    if (warp == 0) {
+      const double* dk = M + (size_t)(tri(K) + K) * 64;
+      double val = lane < 8 ? y[8 * K + lane] : 0.0;
+#pragma unroll
+      for (int gg = 7; gg >= 0; --gg) {
+        const double zg = shfl_d(val, gg) * dk[eoff(gg, gg)];
+        if (lane == gg) val = zg;
+        if (lane < gg) val -= dk[eoff(gg, lane)] * zg;
+      }
+      if (lane < 8) y[8 * K + lane] = val;
+    }
+    __syncthreads();
+    if (tid < 8 * K) {
+      const int J = tid >> 3, c = tid & 7;
+      const double* blk = M + (size_t)(tri(K) + J) * 64;
+      double acc = y[tid];
+#pragma unroll
+      for (int gg = 0; gg < 8; ++gg) acc -= blk[eoff(gg, c)] * y[8 * K + gg];
+      y[tid] = acc;
     }
     __syncthreads();
   }
@@ -275,59 +381,19 @@ __device__ __forceinline__ double* elem_tri(double* M, int hi, int lo) {
 
 // ---- small dense helpers for the box QP (whole CTA, uniform control flow) --------------------------
 
-// Cholesky of the k x k lower triangle of F (ld) with DEFERRED column scaling: on exit
-// L_ij = F[i][j] * rs[j] (i > j), 1 / L_jj = rs[j].  One barrier per column.
-__device__ void chol_dense(double* __restrict__ F, int ld, int k, double* __restrict__ rs, int* s_flag) {
-  const int tid = threadIdx.x;
-  for (int j = 0; j < k; ++j) {
-    __syncthreads();
-    double dj = F[j * ld + j];
-    if (!(dj > 0.0)) {
-      if (tid == 0) *s_flag = 1;
-      dj = 1.0;
-    }
-    const double inv = 1.0 / dj;
-    if (tid == 0) rs[j] = rsqrt(dj);
-    const int w = k - 1 - j;
-    for (int e = tid; e < w * w; e += kThreads) {
-      const int i = j + 1 + e / w, c = j + 1 + e % w;
-      if (c <= i) F[i * ld + c] -= F[i * ld + j] * F[c * ld + j] * inv;
-    }
-  }
-  __syncthreads();
-}
-
-// solve (L L^T) x = b in place (b in `x`), factor from chol_dense; executed by warp 0 only
-__device__ void solve_dense_warp(const double* __restrict__ F, int ld, int k, const double* __restrict__ rs,
-                                 double* __restrict__ x, int lane) {
-  for (int j = 0; j < k; ++j) {  // forward, column oriented
-    __syncwarp();
-    const double yj = x[j] * rs[j];
-    const double cj = yj * rs[j];
-    for (int i = j + 1 + lane; i < k; i += 32) x[i] -= F[i * ld + j] * cj;
-    __syncwarp();
-    if (lane == 0) x[j] = yj;
-  }
-  for (int j = k - 1; j >= 0; --j) {  // backward: x_j = y_j / L_jj, y_i -= L_ji x_j (row j of L)
-    __syncwarp();
-    const double xj = x[j] * rs[j];
-    for (int i = lane; i < j; i += 32) x[i] -= F[j * ld + i] * rs[i] * xj;
-    __syncwarp();
-    if (lane == 0) x[j] = xj;
-  }
-  __syncwarp();
-}
-
 // out = Hq x + f, 4 threads per row
 __device__ void matvec_sym(const double* __restrict__ Hq, int ld, int nx, const double* __restrict__ x,
                            const double* __restrict__ f, double* __restrict__ out) {
-  const int tid = threadIdx.x, row = tid >> 2, part = tid & 3;
-  double acc = 0.0;
-  if (row < nx)
-    for (int j = part; j < nx; j += 4) acc += Hq[row * ld + j] * x[j];
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  if (row < nx && part == 0) out[row] = acc + f[row];
+  const int tid = threadIdx.x, part = tid & 3;
+  for (int r0 = 0; r0 < nx; r0 += kThreads / 4) {
+    const int row = r0 + (tid >> 2);
+    double acc = 0.0;
+    if (row < nx)
+      for (int j = part; j < nx; j += 4) acc += Hq[row * ld + j] * x[j];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (row < nx && part == 0) out[row] = acc + f[row];
+  }
 }
 
 enum { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
@@ -356,6 +422,33 @@ struct QpWork {
   int *state, *idx, *verdict, *s_flag;
 };
 
+// Gather the principal submatrix Hq[idx, idx] (idx = q.idx when `use_idx`, identity otherwise) plus an
+// optional diagonal into block-packed storage at q.F (padded with identity rows to a multiple of 8)
+// and factor it on the tensor cores.
+__device__ void qp_factor(const QpWork& q, int k, bool use_idx, const double* diag) {
+  const int tid = threadIdx.x;
+  const int nbq = (k + 7) >> 3, kp = nbq * 8;
+  double2* z = reinterpret_cast<double2*>(q.F);
+  for (int e = tid; e < tri(nbq) * 32; e += kThreads) z[e] = make_double2(0.0, 0.0);
+  __syncthreads();
+  for (int a = tid >> 5; a < kp; a += kWarps) {
+    const int ia = a < k ? (use_idx ? q.idx[a] : a) : 0;
+    for (int c = tid & 31; c <= a; c += 32) {
+      double v;
+      if (a < k) {
+        const int ic = use_idx ? q.idx[c] : c;
+        v = q.Hq[ia * q.ldq + ic];
+        if (a == c && diag) v += diag[a];
+      } else {
+        v = a == c ? 1.0 : 0.0;
+      }
+      *elem_tri(q.F, a, c) = v;
+    }
+  }
+  __syncthreads();
+  factor_columns<false>(q.F, 0, nbq, nbq, q.s_flag);
+}
+
 // One pass of block principal pivoting in the free space.  Returns the number of infeasible
 // indices (0 = optimal) and the largest infeasible index through `last`.
 __device__ int bpp_pass(const QpWork& q, double tol_g, int* last) {
@@ -379,15 +472,11 @@ __device__ int bpp_pass(const QpWork& q, double tol_g, int* last) {
   __syncthreads();
   const int kf = q.idx[kMaxNx];
   matvec_sym(q.Hq, q.ldq, nx, q.x, q.f, q.g);
-  for (int e = tid; e < kf * kf; e += kThreads) {
-    const int a = e / kf, c = e % kf;
-    if (c <= a) q.F[a * q.ldf + c] = q.Hq[q.idx[a] * q.ldq + q.idx[c]];
-  }
+  qp_factor(q, kf, true, nullptr);
+  if (tid < 8 * ((kf + 7) >> 3)) q.rhs[tid] = tid < kf ? -q.g[q.idx[tid]] : 0.0;
   __syncthreads();
-  if (tid < kf) q.rhs[tid] = -q.g[q.idx[tid]];
-  chol_dense(q.F, q.ldf, kf, q.rs, q.s_flag);
-  if (tid < 32) solve_dense_warp(q.F, q.ldf, kf, q.rs, q.rhs, lane);
-  __syncthreads();
+  fwdsub_blocked(q.F, (kf + 7) >> 3, q.rhs);
+  backsub_blocked(q.F, (kf + 7) >> 3, q.rhs);
   if (tid < kf) q.x[q.idx[tid]] = q.rhs[tid];
   __syncthreads();
   matvec_sym(q.Hq, q.ldq, nx, q.x, q.f, q.g);
@@ -473,14 +562,12 @@ __device__ int ipm_solve(const QpWork& q, int max_it) {
     const double dg = (il ? zl / sl : 0.0) + (iu ? zu / su : 0.0);
     if (act) q.dg[tid] = dg;
     __syncthreads();
-    for (int e = tid; e < nx * nx; e += kThreads) {
-      const int a = e / nx, c = e % nx;
-      if (c <= a) q.F[a * q.ldf + c] = q.Hq[a * q.ldq + c] + (a == c ? q.dg[a] : 0.0);
-    }
-    if (act) q.rhs[tid] = -gi;  // affine right-hand side
-    chol_dense(q.F, q.ldf, nx, q.rs, q.s_flag);
-    if (tid < 32) solve_dense_warp(q.F, q.ldf, nx, q.rs, q.rhs, lane);
+    qp_factor(q, nx, false, q.dg);
+    const int nbq = (nx + 7) >> 3;
+    if (tid < 8 * nbq) q.rhs[tid] = act ? -gi : 0.0;  // affine right-hand side
     __syncthreads();
+    fwdsub_blocked(q.F, nbq, q.rhs);
+    backsub_blocked(q.F, nbq, q.rhs);
     const double dxa = act ? q.rhs[tid] : 0.0;
     const double dzla = il ? (-sl * zl - zl * dxa) / sl : 0.0;
     const double dzua = iu ? (-su * zu + zu * dxa) / su : 0.0;
@@ -496,10 +583,10 @@ __device__ int ipm_solve(const QpWork& q, int max_it) {
     const double rat = mu_aff / mu;
     const double sig = rat * rat * rat;
     const double rcl = sig * mu - dxa * dzla, rcu = sig * mu + dxa * dzua;
-    if (act) q.rhs[tid] = -rd + (il ? (rcl - sl * zl) / sl : 0.0) - (iu ? (rcu - su * zu) / su : 0.0);
+    if (tid < 8 * nbq) q.rhs[tid] = act ? -rd + (il ? (rcl - sl * zl) / sl : 0.0) - (iu ? (rcu - su * zu) / su : 0.0) : 0.0;
     __syncthreads();
-    if (tid < 32) solve_dense_warp(q.F, q.ldf, nx, q.rs, q.rhs, lane);
-    __syncthreads();
+    fwdsub_blocked(q.F, nbq, q.rhs);
+    backsub_blocked(q.F, nbq, q.rhs);
     const double dx = act ? q.rhs[tid] : 0.0;
     const double dzl = il ? (rcl - sl * zl - zl * dx) / sl : 0.0;
     const double dzu = iu ? (rcu - su * zu + zu * dx) / su : 0.0;
@@ -520,6 +607,83 @@ __device__ int ipm_solve(const QpWork& q, int max_it) {
   }
   __syncthreads();
   return done ? (it + 1) : -(it + 1);
+}
+
+// ---- Gauss-Jordan sweep of the leading `npiv` pivots of a symmetric matrix (lower triangle) -------------
+// Sweeping pivot j is the symmetric rank-1 update  A <- A - p p^T / d - 2 e_j e_j^T  with
+// p = A[:, j] - e_j, d = A[j][j]: the same update for every entry; the constant -2 on the swept
+// diagonal entries commutes with the later updates and is applied once at the end.
+// Thread t owns CH consecutive entries of one row of the lower triangle and keeps them in REGISTERS
+// for the whole sweep (the matrix is read once and written once: the phase is otherwise bound by
+// shared-memory bandwidth); per pivot it reads p[row] and its CH-chunk of p.  The owners of row /
+// column j+1 publish the next p into a double buffer, so one barrier per pivot suffices.
+__host__ __device__ inline int sweep_threads(int nS, int ch) {
+  int tot = 0;
+  for (int i = 0; i < nS; ++i) tot += (i + ch) / ch;
+  return tot;
+}
+
+template <int CH>
+__device__ void sweep_lower(double* __restrict__ S, int ld, int nS, int npiv, double* __restrict__ vbuf) {
+  const int tid = threadIdx.x;
+  // thread -> (row, k0): rows in order, ceil((row + 1) / CH) threads each
+  int row = -1, k0 = 0;
+  {
+    int t = tid;
+    // rows r with (r + CH) / CH == c threads: r in [CH (c-1), CH c - 1]; closed form by groups of CH rows
+    for (int c = 1; row < 0; ++c) {
+      const int r_lo = CH * (c - 1), r_hi = min(CH * c - 1, nS - 1);
+      if (r_lo >= nS) break;
+      const int cnt = (r_hi - r_lo + 1) * c;
+      if (t < cnt) { row = r_lo + t / c; k0 = (t % c) * CH; }
+      else t -= cnt;
+    }
+  }
+  const bool own = row >= 0;
+  const int vstride = ((nS + CH + 1) & ~1);
+  double* vb0 = vbuf;
+  double* vb1 = vbuf + vstride;
+  double val[CH];
+#pragma unroll
+  for (int e = 0; e < CH; ++e) val[e] = (own && k0 + e <= row) ? S[row * ld + k0 + e] : 0.0;
+  for (int i = tid; i < vstride; i += kThreads) {
+    vb0[i] = i < nS ? S[i * ld] - (i == 0 ? 1.0 : 0.0) : 0.0;
+    vb1[i] = 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < npiv; ++j) {
+    const double* vc = (j & 1) ? vb1 : vb0;
+    double* vn = (j & 1) ? vb0 : vb1;
+    if (own) {
+      const double pi = vc[row] * (-1.0 / (vc[j] + 1.0));
+      const double2* pk = reinterpret_cast<const double2*>(vc + k0);
+#pragma unroll
+      for (int e = 0; e < CH; e += 2) {
+        const double2 pv = pk[e >> 1];
+        val[e] = fma(pi, pv.x, val[e]);
+        val[e + 1] = fma(pi, pv.y, val[e + 1]);
+      }
+      if (row == j + 1) {
+#pragma unroll
+        for (int e = 0; e < CH; ++e)
+          if (k0 + e <= row) vn[k0 + e] = (k0 + e == row) ? val[e] - 1.0 : val[e];
+      } else if (row > j + 1) {
+        const int en = j + 1 - k0;
+        if ((unsigned)en < (unsigned)CH) {
+#pragma unroll
+          for (int e = 0; e < CH; ++e)
+            if (e == en) vn[row] = val[e];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (own) {
+#pragma unroll
+    for (int e = 0; e < CH; ++e)
+      if (k0 + e <= row) S[row * ld + k0 + e] = val[e] - ((k0 + e == row && row < npiv) ? 2.0 : 0.0);
+  }
+  __syncthreads();
 }
 
 // ---- Gram generation -------------------------------------------------------------------------------
@@ -570,16 +734,19 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
   double* s_yv = sx;                       // 8*nbt : back-substitution vector
   double* s_e = s_yv + 8 * d.nbt;          // n2p   : e = D_s z on R2
   double* s_vec = s_e + d.n2p;             // 2*(nS+2) : sweep pivot-column double buffer
-  double* s_red = s_vec + 2 * (d.nS + 2);  // 64
+  double* s_red = s_vec + 2 * (d.nS + 22);  // 64
   __shared__ int s_flag;
   __shared__ int s_next;
   __shared__ int s_state[kMaxNx];
   __shared__ int s_idx[kMaxNx + 1];
   __shared__ int s_verdict[kMaxNx];
+  __shared__ short s_ppos[kMaxPos];  // Hankel row (signal a, block row j) -> position in the elimination order
 
   double* slot = ws + (size_t)blockIdx.x * slot_doubles(d);
   double* GA = slot;
   double* GS = slot + d.ga;
+
+  for (int e = tid; e < nsig * ell; e += kThreads) s_ppos[e] = (short)pos_of(d, e / ell, e % ell);
 
   long long t_prev = clock64();
 #define DDQC_PHASE(k)                                                                      \
@@ -607,6 +774,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
 
     // ---- 0. stage the (u, y) window signal-major; Gram -> workspace slot -------------------------
     double* sW = sM;
+    double* sT = sM + nsig * N;  // first block column of G, (ell*nsig) x ldT
     for (int e = tid; e < N * m; e += kThreads) sW[(e % m) * N + e / m] = ub[e];
     for (int e = tid; e < N * p; e += kThreads) sW[(m + e % p) * N + e / p] = yb[e];
     // aug block rows and pad rows: explicit zeros first
@@ -633,43 +801,81 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
         else P = d.n1p + d.n2p + d.n3 + (k - (d.n2p - d.n2));
         put_sym(d, GA, GS, P, q, P == q ? 1.0 : 0.0);
       }
-      // G[(j,a),(k,b)] = sum_c w_a[j+c] w_b[k+c]: one task per unordered signal pair and diagonal
-      const int ndiag = 2 * ell - 1;
-      const int ntask = nsig * nsig * ndiag;
-      for (int tk = tid; tk < ntask; tk += kThreads) {
-        const int a = tk / (nsig * ndiag), bs = (tk / ndiag) % nsig, dl = tk % ndiag - (ell - 1);
-        if (a > bs || (a == bs && dl < 0)) continue;
-        int j = dl > 0 ? dl : 0, k = dl > 0 ? 0 : -dl;
-        const double* wa = sW + a * N;
-        const double* wb = sW + bs * N;
-        double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
-        int c = 0;
-        for (; c + 3 < C; c += 4) {
-          f0 += wa[j + c] * wb[k + c];
-          f1 += wa[j + c + 1] * wb[k + c + 1];
-          f2 += wa[j + c + 2] * wb[k + c + 2];
-          f3 += wa[j + c + 3] * wb[k + c + 3];
+      // First block column of G on the tensor cores:  T[(j,a)][b] = sum_c w_a[j+c] w_b[c]  (b = nsig
+      // is the all-ones signal), i.e. [Hankel rows] x [first block row]^T, K = C.  Operands are read
+      // straight from the window, H is never materialised.
+      {
+        const int nrho = ell * nsig, nrb = (nrho + 7) >> 3, ncb = (nsig + 1 + 7) >> 3, ldT = ncb * 8;
+        for (int task = warp; task < nrb * ncb; task += kWarps) {
+          const int rb = task / ncb, cb = task % ncb;
+          const int rho = rb * 8 + g;
+          const bool av = rho < nrho;
+          const double* wa = sW + (av ? (rho % nsig) * N + rho / nsig : 0);
+          const int bsig = cb * 8 + g;
+          const bool bv = bsig < nsig, bone = bsig == nsig;
+          const double* wb = sW + (bv ? bsig * N : 0);
+          double2 acc0 = {0.0, 0.0}, acc1 = {0.0, 0.0};
+          for (int c0 = 0; c0 < C; c0 += 8) {
+            const int ca = c0 + t, cbb = c0 + 4 + t;
+            const double a0 = (av && ca < C) ? wa[ca] : 0.0;
+            const double b0 = ca < C ? (bv ? wb[ca] : (bone ? 1.0 : 0.0)) : 0.0;
+            const double a1 = (av && cbb < C) ? wa[cbb] : 0.0;
+            const double b1 = cbb < C ? (bv ? wb[cbb] : (bone ? 1.0 : 0.0)) : 0.0;
+            dmma(acc0, a0, b0);
+            dmma(acc1, a1, b1);
+          }
+          if (av) {
+            sT[rho * ldT + cb * 8 + 2 * t] = acc0.x + acc1.x;
+            sT[rho * ldT + cb * 8 + 2 * t + 1] = acc0.y + acc1.y;
+          }
         }
-        for (; c < C; ++c) f0 += wa[j + c] * wb[k + c];
-        double f = (f0 + f1) + (f2 + f3);
-        for (;; ++j, ++k) {
-          put_sym(d, GA, GS, pos_of(d, a, j), pos_of(d, bs, k), f);
-          if (j + 1 >= ell || k + 1 >= ell) break;
-          f += wa[j + C] * wb[k + C] - wa[j] * wb[k];
+        __syncthreads();
+        // every other entry follows from the Hankel structure by a two-term recurrence along the
+        // block diagonals.  A task walks two diagonals whose lengths add up to ~ell, so all tasks
+        // cost the same: (a < b, u): delta = u and delta = u - ell;  (a == a, u): delta = u and ell-1-u.
+        const int nlt = nsig * (nsig - 1) / 2, half = (ell + 1) / 2;
+        const int ntask = nlt * ell + nsig * half;
+        for (int tk = tid; tk < ntask; tk += kThreads) {
+          int a, bs, u, d0, d1;
+          if (tk < nlt * ell) {
+            int pi = tk / ell;
+            u = tk % ell;
+            a = 0;
+            while (pi >= nsig - 1 - a) { pi -= nsig - 1 - a; ++a; }
+            bs = a + 1 + pi;
+            d0 = u;
+            d1 = u - ell;  // invalid (-ell) for u == 0
+          } else {
+            const int r2 = tk - nlt * ell;
+            a = bs = r2 / half;
+            u = r2 % half;
+            d0 = u;
+            d1 = ell - 1 - u;
+            if (d1 == d0) d1 = -ell;
+          }
+          const double* wa = sW + a * N;
+          const double* wb = sW + bs * N;
+          const short* pa = s_ppos + a * ell;
+          const short* pb = s_ppos + bs * ell;
+#pragma unroll 1
+          for (int rep = 0; rep < 2; ++rep) {
+            const int dl = rep ? d1 : d0;
+            if (dl <= -ell) continue;
+            int j = dl > 0 ? dl : 0, k = dl > 0 ? 0 : -dl;
+            double f = dl >= 0 ? sT[(dl * nsig + a) * ldT + bs] : sT[(-dl * nsig + bs) * ldT + a];
+            for (;; ++j, ++k) {
+              put_sym(d, GA, GS, pa[j], pb[k], f);
+              if (j + 1 >= ell || k + 1 >= ell) break;
+              f += wa[j + C] * wb[k + C] - wa[j] * wb[k];
+            }
+          }
         }
+        // ones row: G[(j,a), one] = sum_c w_a[j+c] = T[(j,a)][nsig];  G[one][one] = C
+        const int Pone = n * m;
+        for (int e = tid; e < nrho; e += kThreads) put_sym(d, GA, GS, s_ppos[(e % nsig) * ell + e / nsig], Pone, sT[e * ldT + nsig]);
+        if (tid == 0) put_sym(d, GA, GS, Pone, Pone, (double)C);
       }
-      // ones row: sliding sums, G[one][one] = C
       const int Pone = n * m;
-      for (int a = tid; a < nsig; a += kThreads) {
-        const double* wa = sW + a * N;
-        double f = 0.0;
-        for (int c = 0; c < C; ++c) f += wa[c];
-        for (int j = 0; j < ell; ++j) {
-          put_sym(d, GA, GS, pos_of(d, a, j), Pone, f);
-          if (j + 1 < ell) f += wa[j + C] - wa[j];
-        }
-      }
-      if (tid == 0) put_sym(d, GA, GS, Pone, Pone, (double)C);
       // aug rows: T_u (m), T_y (p), tau, b_s
       const int Pa = d.n1p + d.n2p + d.n3p;
       for (int e = tid; e < nsig * ell; e += kThreads) {
@@ -764,29 +970,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       // y = L^-1 b_s sits in the b_s row; z = L^-T y by blocked back-substitution
       for (int q = tid; q < 8 * ncol_all; q += kThreads) s_yv[q] = *elem_tri(sM, Paug + aug_b, q);
       __syncthreads();
-      for (int K = ncol_all - 1; K >= 0; --K) {
-        if (warp == 0) {
-          const double* dk = sM + (size_t)(tri(K) + K) * 64;
-          double val = lane < 8 ? s_yv[8 * K + lane] : 0.0;
-#pragma unroll
-          for (int gg = 7; gg >= 0; --gg) {
-            const double zg = shfl_d(val, gg) * dk[eoff(gg, gg)];
-            if (lane == gg) val = zg;
-            if (lane < gg) val -= dk[eoff(gg, lane)] * zg;
-          }
-          if (lane < 8) s_yv[8 * K + lane] = val;
-        }
-        __syncthreads();
-        if (tid < 8 * K) {
-          const int J = tid >> 3, c = tid & 7;
-          const double* blk = sM + (size_t)(tri(K) + J) * 64;
-          double acc = s_yv[tid];
-#pragma unroll
-          for (int gg = 0; gg < 8; ++gg) acc -= blk[eoff(gg, c)] * s_yv[8 * K + gg];
-          s_yv[tid] = acc;
-        }
-        __syncthreads();
-      }
+      backsub_blocked(sM, ncol_all, s_yv);
       for (int q = tid; q < d.n2p; q += kThreads) s_e[q] = q < d.n2 ? ds * s_yv[q] : 0.0;
       __syncthreads();
       DDQC_PHASE(4);
@@ -829,47 +1013,19 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     const int nS = d.nS, ldS = d.ldS, nx = d.nx, ldq = d.ldq;
     double* S7 = sM;
     {
-      double tmp = 0.0;
       // the source blocks start at (tri(nb2) + nb2) * 64 >= nS * ldS (checked on the host), so the
-      // copy cannot overwrite a block that is still to be read
+      // copy cannot overwrite a block that is still to be read.  Full symmetric storage.
       for (int e = tid; e < nS * nS; e += kThreads) {
         const int i = e / nS, k = e % nS;
-        if (k > i) continue;
-        const int Pi = i < d.n3 ? d.n2p + i : Paug + (i - d.n3);
-        const int Pk = k < d.n3 ? d.n2p + k : Paug + (k - d.n3);
-        tmp = *elem_tri(sM, Pi, Pk);
-        S7[i * ldS + k] = tmp;
+        const int hi = i > k ? i : k, lo = i > k ? k : i;
+        const int Pi = hi < d.n3 ? d.n2p + hi : Paug + (hi - d.n3);
+        const int Pk = lo < d.n3 ? d.n2p + lo : Paug + (lo - d.n3);
+        S7[i * ldS + k] = *elem_tri(sM, Pi, Pk);
       }
     }
     __syncthreads();
-    {
-      // Gauss-Jordan sweep of pivots 0..n3-1 on the lower triangle; the pivot column of the next step
-      // is double-buffered in s_vec so that one barrier per pivot suffices
-      const int W = nS + 1, R = (nS + 1) / 2;
-      double* vb0 = s_vec;
-      double* vb1 = s_vec + nS + 2;
-      for (int i = tid; i < nS; i += kThreads) vb0[i] = S7[i * ldS + 0];
-      __syncthreads();
-      for (int j = 0; j < d.n3; ++j) {
-        const double* vc = (j & 1) ? vb1 : vb0;
-        double* vn = (j & 1) ? vb0 : vb1;
-        const double inv = 1.0 / vc[j];
-        for (int e = tid; e < R * W; e += kThreads) {
-          const int rr = e / W, cc = e % W;
-          int i, k;
-          if (cc <= rr) { i = rr; k = cc; }
-          else { i = nS - 1 - rr; k = cc - rr - 1; if (i == rr) continue; }
-          double v;
-          if (i == j) v = (k == j) ? -inv : vc[k] * inv;
-          else if (k == j) v = vc[i] * inv;
-          else v = S7[i * ldS + k] - vc[i] * vc[k] * inv;
-          S7[i * ldS + k] = v;
-          if (k == j + 1) vn[i] = v;
-          if (i == j + 1) vn[k] = v;
-        }
-        __syncthreads();
-      }
-    }
+    if (sweep_threads(nS, 10) <= kThreads) sweep_lower<10>(S7, ldS, nS, d.n3, s_vec);
+    else sweep_lower<20>(S7, ldS, nS, d.n3, s_vec);
     DDQC_PHASE(6);
 
     // ---- box QP assembly: Hq = 2 lamb_alpha Z + structure, f ----------------------------------------
@@ -1026,8 +1182,9 @@ int check_cfg(const DdqcMpcConfig* c) {
   if (!c) return DDQC_E_NULL;
   if (c->m < 1 || c->p < 1 || c->m > kMaxSig || c->p > kMaxSig || c->n < 1 || c->L <= c->n) return DDQC_E_SHAPE;
   const Dims d = make_dims(*c);
-  if (d.C < 1 || d.nx > kMaxNx) return DDQC_E_SHAPE;
-  if (smem_bytes(d) + 2048 > (size_t)kSmemLimit) return DDQC_E_SHAPE;
+  if (d.C < 1 || d.nx > kMaxNx || (d.m + d.p) * d.ell > kMaxPos) return DDQC_E_SHAPE;
+  if (sweep_threads(d.nS, 20) > kThreads) return DDQC_E_SHAPE;
+  if (smem_bytes(d) + 4608 > (size_t)kSmemLimit) return DDQC_E_SHAPE;
   // the dense copy of the final Schur complement must not overlap the blocks it is read from
   if (d.nS * d.ldS > (d.nb2 * (d.nb2 + 1) / 2 + d.nb2) * 64) return DDQC_E_SHAPE;
   if (c->alpha_reg_type != 0 && c->alpha_reg_type != 2) return DDQC_E_CONFIG;
@@ -1041,6 +1198,9 @@ static long long* g_phase_clk = nullptr;
 // solver accumulates per phase.  Pass NULL to switch it off.
 extern "C" int ddqc_ddmpc_debug_phase_buffer(void* dev_ptr) {
   g_phase_clk = static_cast<long long*>(dev_ptr);
+#ifdef DDQC_PROF_FACTOR
+  cudaMemcpyToSymbol(g_fprof, &g_phase_clk, sizeof(void*));
+#endif
   return 0;
 }
 
