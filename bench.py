@@ -368,14 +368,16 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
         y_k = env.get_pos()
         ctrl.store_input_output_measurement(u0, y_k)
         sq_err += ((y_k.to(torch.float64) - y_r) ** 2).sum(1)
-        iters.append(ctrl.iters.clone())
+        iters.append(ctrl.iters.clone())  # passes + (interior-point iterations << 16)
     torch.cuda.synchronize()
     t_loop = time.perf_counter() - t_loop0
     solve_ms = sorted(ev_a[t].elapsed_time(ev_b[t]) for t in range(warm, T + warm))
     med = solve_ms[len(solve_ms) // 2]
     avg = sum(solve_ms) / len(solve_ms)
     status = ctrl.status.cpu()
-    it_all = torch.stack(iters[warm:]).float()
+    it_raw = torch.stack(iters[warm:])
+    it_all = (it_raw & 0xFFFF).float()
+    ipm_all = (it_raw >> 16).float()
     dist_end = torch.linalg.norm(env.base_pos - y_r, dim=1)
     flops = ddmpc_flops_per_solve()
     return {
@@ -392,6 +394,8 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
         "dtype": "f64",
         "pivoting_passes_mean": float(it_all.mean()),
         "pivoting_passes_max": float(it_all.max()),
+        "ipm_fallback_fraction": float((ipm_all > 0).float().mean()),
+        "ipm_iterations_mean_when_used": float(ipm_all[ipm_all > 0].mean()) if bool((ipm_all > 0).any()) else 0.0,
         "failed_controllers": int((status != 0).sum()),
         "rmse_mean": float(torch.sqrt(sq_err / (T + warm)).mean()),
         "dist_to_target_start_mean": float(d0.mean()),

@@ -163,22 +163,29 @@ __device__ __forceinline__ bool chol8_warp(double* blk, int lane) {
   const int r0 = lane >> 3, c = lane & 7;
   double A = blk[eoff(r0, c)], B = blk[eoff(r0 + 4, c)];
   bool ok = true;
+  double dj = shfl_d(A, 0);
+  // One shuffle round per pivot: the column-j entries every lane needs, plus the two values that give
+  // the NEXT pivot (d_{j+1} = a_{j+1,j+1} - l_{j+1,j}^2), so the chain is rsqrt -> scale -> shuffle -> fma.
+  // Branch-free on purpose (selects, masked multipliers): a divergent `if` costs more than the arithmetic.
 #pragma unroll 1
   for (int j = 0; j < 8; ++j) {
-    double dj = shfl_d(j < 4 ? A : B, ((j & 3) << 3) | j);
-    if (!(dj > 0.0)) { ok = false; dj = 1.0; }
+    ok = ok && (dj > 0.0);
+    dj = dj > 0.0 ? dj : 1.0;
     const double r = rsqrt(dj);
-    if (c == j) {
-      A = (r0 == j) ? r : A * r;
-      B = (r0 + 4 == j) ? r : B * r;
-    }
+    const bool cj = c == j;
+    A = cj ? ((r0 == j) ? r : A * r) : A;
+    B = cj ? ((r0 + 4 == j) ? r : B * r) : B;
+    const int jn = (j + 1) & 7, ln = (jn & 3) << 3;
     const double x1 = shfl_d(A, (r0 << 3) | j), x2 = shfl_d(B, (r0 << 3) | j);
     const double y1 = shfl_d(A, ((c & 3) << 3) | j), y2 = shfl_d(B, ((c & 3) << 3) | j);
+    const double sn = jn < 4 ? A : B;
+    const double ln_j = shfl_d(sn, ln | j);    // l_{j+1,j}
+    const double dn = shfl_d(sn, ln | jn);     // a_{j+1,j+1} before this pivot's update
     const double lc = c < 4 ? y1 : y2;
-    if (c > j) {
-      if (r0 >= c) A -= x1 * lc;
-      if (r0 + 4 >= c) B -= x2 * lc;
-    }
+    const double ma = (c > j && r0 >= c) ? lc : 0.0, mb = (c > j && r0 + 4 >= c) ? lc : 0.0;
+    A = fma(-x1, ma, A);
+    B = fma(-x2, mb, B);
+    dj = fma(-ln_j, ln_j, dn);
   }
   if (r0 >= c) blk[eoff(r0, c)] = A;
   if (r0 + 4 >= c) blk[eoff(r0 + 4, c)] = B;
@@ -187,10 +194,15 @@ __device__ __forceinline__ bool chol8_warp(double* blk, int lane) {
 
 // load the factor of a diagonal block (36 values, broadcast reads) into registers
 __device__ __forceinline__ void load_diag(const double* dk, double (&a)[36]) {
+  // 16-byte broadcast reads (the XOR-4 swizzle keeps even/odd column pairs adjacent)
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int c = 0; c <= i; ++c) LT(i, c) = dk[eoff(i, c)];
+    for (int c = 0; c <= i; c += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(dk + eoff(i, c));
+      LT(i, c) = v.x;
+      if (c + 1 <= i) LT(i, c + 1) = v.y;
+    }
 }
 
 // X <- X L^-T for one 8x8 block held as an accumulator fragment (thread (g,t): X[g][2t], X[g][2t+1]).
@@ -307,10 +319,10 @@ __device__ void fwdsub_blocked(const double* __restrict__ M, int ncols, double* 
       const double* dk = M + (size_t)(tri(K) + K) * 64;
       double val = lane < 8 ? y[8 * K + lane] : 0.0;
 #pragma unroll
-      for (int gg = 0; gg < 8; ++gg) {
+      for (int gg = 0; gg < 8; ++gg) {  // branch-free: selects and masked multipliers
         const double zg = shfl_d(val, gg) * dk[eoff(gg, gg)];
-        if (lane == gg) val = zg;
-        if (lane > gg && lane < 8) val -= dk[eoff(lane, gg)] * zg;
+        const double lg = (lane > gg && lane < 8) ? dk[eoff(lane & 7, gg)] : 0.0;
+        val = (lane == gg) ? zg : fma(-lg, zg, val);
       }
       if (lane < 8) y[8 * K + lane] = val;
     }
@@ -335,10 +347,10 @@ __device__ void backsub_blocked(const double* __restrict__ M, int ncols, double*
       const double* dk = M + (size_t)(tri(K) + K) * 64;
       double val = lane < 8 ? y[8 * K + lane] : 0.0;
 #pragma unroll
-      for (int gg = 7; gg >= 0; --gg) {
+      for (int gg = 7; gg >= 0; --gg) {  // branch-free: selects and masked multipliers
         const double zg = shfl_d(val, gg) * dk[eoff(gg, gg)];
-        if (lane == gg) val = zg;
-        if (lane < gg) val -= dk[eoff(gg, lane)] * zg;
+        const double lg = (lane < gg) ? dk[eoff(gg, lane & 7)] : 0.0;
+        val = (lane == gg) ? zg : fma(-lg, zg, val);
       }
       if (lane < 8) y[8 * K + lane] = val;
     }
