@@ -280,21 +280,28 @@ MPC_DEFAULT = dict(n=6, N=350, L=35, Q=[10.0, 10, 10], R=[10.0, 1, 1], S=[1000.0
                    init_hover_pos=[0.0, 0.0, 1.5], y_r=[1.0, 1.0, 2.5])  # fmt: skip
 
 
-def ddmpc_flops_per_solve(n=6, m=3, p=3, L=35, N=350) -> float:
-    """Floating-point operations of the condensed algorithm (ddqc_ddmpc.cu), counted from its loops:
-    Gram by sliding dot products, one r-dim Cholesky + one ry-dim tail Cholesky, nx+1 forward
-    substitutions, Z = X^T X, nx-dim inverse."""
+def ddmpc_flops_per_solve(n=6, m=3, p=3, L=35, N=350, passes=1.0) -> float:
+    """Algorithmic floating-point operations of one solve of the condensed algorithm (ddqc_ddmpc.cu,
+    DESIGN.md section 4), counted from its loops with symmetric halves counted once:
+    Gram first block column (dense) + diagonal recurrences; elimination of R1 on the augmented matrix;
+    full factorisation of S1 + D_s (alpha_sr); elimination of R2 of S1 + D_0; Gauss-Jordan sweep of R3;
+    `passes` free-space factorisations of the nx-dim box QP."""
     ell = L + n + 1
     C = N - ell + 1
-    ru, ry = m * ell + 1, p * ell
-    r = ru + ry
-    nx = (L - n) * m + m + p
-    gram = 2.0 * (m + p) ** 2 * (2 * ell - 1) * C
-    chol = r**3 / 3.0 + ry**3 / 3.0
-    subst = (nx + 1) * r * r
-    syrk = (nx + 1) * (nx + 2) / 2.0 * 2 * r
-    boxqp = 2.0 * nx**3
-    return gram + chol + subst + syrk + boxqp
+    nsig = m + p
+    n1, n2, n3, na = m * (2 * n + 1) + 1, p * ell, (L - n) * m, nsig + 2
+    nx = n3 + nsig
+
+    def elim(rows, cols):  # eliminate `cols` leading columns of a symmetric `rows` x `rows` matrix
+        return sum((rows - k) ** 2 for k in range(cols))
+
+    gram = 2.0 * (nsig * ell) * (nsig + 1) * C + 4.0 * (nsig * ell + 1) ** 2 / 2
+    phase_a = elim(n1 + n2 + n3 + na, n1)
+    phase_b = elim(n2 + n3 + 1, n2 + n3) + 2.0 * (n2 + n3) ** 2
+    phase_c = elim(n2 + n3 + na - 1, n2)
+    sweep = n3 * (nx + 1) ** 2
+    boxqp = passes * (nx**3 / 3.0 + 4.0 * nx * nx)
+    return gram + phase_a + phase_b + phase_c + sweep + boxqp
 
 
 def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
@@ -379,7 +386,8 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
     it_all = (it_raw & 0xFFFF).float()
     ipm_all = (it_raw >> 16).float()
     dist_end = torch.linalg.norm(env.base_pos - y_r, dim=1)
-    flops = ddmpc_flops_per_solve()
+    flops = ddmpc_flops_per_solve(passes=float(it_all.mean()))
+    fp64_peak = 37.1  # TFLOP/s: DMMA m8n8k4 / DFMA, measured on this pool's B200 by tools/ubench_fp64.cu
     return {
         "metric": "DD-MPC QP solves/s",
         "value": batch / (avg * 1e-3),
@@ -403,6 +411,13 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
         "data_collection_s": t_collect,
         "flops_per_solve": flops,
         "achieved_fp64_tflops": batch * flops / (avg * 1e-3) / 1e12,
+        "roofline": {
+            "bound": "tensor", "kernel": "ddmpc_solve_kernel", "achieved": batch * flops / (avg * 1e-3) / 1e12,
+            "peak": fp64_peak, "unit": "TFLOP/s", "frac": batch * flops / (avg * 1e-3) / 1e12 / fp64_peak,
+            "peak_source": "FP64 tensor (DMMA m8n8k4) = FP64 FMA pipe, 64 FMA/clk/SM, measured 37.1 TFLOP/s with "
+            "tools/ubench_fp64.cu (MEASURED_PEAKS.json carries no fp64 figure)",
+            "flops_per_solve": flops, "traffic": None,
+        },
         "gpu_launches": T,
     }
 

@@ -1188,6 +1188,71 @@ __global__ void ddmpc_store_kernel(const int N, const int m, const int p, double
   if (threadIdx.x < p) yb[(size_t)(N - 1) * p + threadIdx.x] = y_new[(size_t)b * p + threadIdx.x];
 }
 
+// ---- closed-loop evaluation helpers (controller_evaluation.py:345-450 of the reference, batched) ----
+
+// env action (normalised to [-1, 1], fp32) from the optimal input of step `n_step`:
+// linear_interpolate(u, lo, hi, -1, 1) = -1 + (u - lo) * 2 / (hi - lo)   (math_utils.py:13-20 order)
+__global__ void ddmpc_action_kernel(const double* __restrict__ u_opt, const int Lp1, const int m, const int n_step,
+                                    const float* __restrict__ bounds /* [m][2] */, float* __restrict__ action,
+                                    double* __restrict__ u_applied, const int batch) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= batch * m) return;
+  const int b = e / m, i = e % m;
+  const double u = u_opt[((size_t)b * Lp1 + n_step) * m + i];
+  const float lo = bounds[2 * i], hi = bounds[2 * i + 1];
+  const float uf = (float)u;
+  action[e] = -1.0f + (uf - lo) * 2.0f / (hi - lo);
+  u_applied[e] = u;
+}
+
+// store_input_output_measurement + tracking-error bookkeeping in one launch (one CTA per controller):
+// shifts the windows, appends (u_applied, y), accumulates |y - y_r|^2 and raises the early-stop flag
+// when |y - y_r| - d0 > max_inc (controller_evaluation.py:424-447).  Controllers that already stopped
+// (fail_step >= 0) keep their windows and sums frozen, like an aborted evaluation.
+__global__ void ddmpc_post_step_kernel(const int N, const int m, const int p, double* __restrict__ u_win,
+                                       double* __restrict__ y_win, const double* __restrict__ u_new,
+                                       const float* __restrict__ y_meas, const long long y_rs, const long long y_cs,
+                                       const double* __restrict__ y_r, const double* __restrict__ d0,
+                                       const double max_inc, double* __restrict__ sq_sum, int32_t* __restrict__ n_acc,
+                                       int32_t* __restrict__ fail_step, double* __restrict__ y_log, const int step,
+                                       const int batch) {
+  const int b = blockIdx.x;
+  if (b >= batch) return;
+  if (fail_step[b] >= 0) return;  // uniform per CTA
+  double* ub = u_win + (size_t)b * N * m;
+  double* yb = y_win + (size_t)b * N * p;
+  for (int base = 0; base < (N - 1) * m; base += blockDim.x) {
+    const int e = base + threadIdx.x;
+    double v = (e < (N - 1) * m) ? ub[e + m] : 0.0;
+    __syncthreads();
+    if (e < (N - 1) * m) ub[e] = v;
+    __syncthreads();
+  }
+  for (int base = 0; base < (N - 1) * p; base += blockDim.x) {
+    const int e = base + threadIdx.x;
+    double v = (e < (N - 1) * p) ? yb[e + p] : 0.0;
+    __syncthreads();
+    if (e < (N - 1) * p) yb[e] = v;
+    __syncthreads();
+  }
+  if (threadIdx.x < m) ub[(size_t)(N - 1) * m + threadIdx.x] = u_new[(size_t)b * m + threadIdx.x];
+  if (threadIdx.x < p) {
+    const double y = (double)y_meas[(long long)b * y_rs + threadIdx.x * y_cs];
+    yb[(size_t)(N - 1) * p + threadIdx.x] = y;
+    if (y_log) y_log[((size_t)step * batch + b) * p + threadIdx.x] = y;
+  }
+  if (threadIdx.x == 0) {
+    double sq = 0.0;
+    for (int i = 0; i < p; ++i) {
+      const double e = (double)y_meas[(long long)b * y_rs + i * y_cs] - y_r[(size_t)b * p + i];
+      sq += e * e;
+    }
+    sq_sum[b] += sq;
+    n_acc[b] += 1;
+    if (max_inc >= 0.0 && sqrt(sq) - d0[b] > max_inc) fail_step[b] = step;
+  }
+}
+
 size_t smem_bytes(const Dims& d) { return (size_t)(region_doubles(d) + extra_doubles(d)) * sizeof(double); }
 
 int check_cfg(const DdqcMpcConfig* c) {
@@ -1262,5 +1327,33 @@ extern "C" int ddqc_ddmpc_store(const DdqcMpcConfig* cfg, double* u_win, double*
   if (batch <= 0) return batch == 0 ? 0 : DDQC_E_SHAPE;
   ddmpc_store_kernel<<<(unsigned)batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(cfg->N, cfg->m, cfg->p, u_win, y_win,
                                                                                     u_new, y_new, (int)batch);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ddqc_ddmpc_action(const DdqcMpcConfig* cfg, const double* u_opt, int32_t n_step, const float* bounds,
+                                 float* action, double* u_applied, int64_t batch, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (!u_opt || !bounds || !action || !u_applied) return DDQC_E_NULL;
+  if (n_step < 0 || n_step > cfg->L || batch < 0) return DDQC_E_SHAPE;
+  if (batch == 0) return 0;
+  const int tot = (int)batch * cfg->m;
+  ddmpc_action_kernel<<<(tot + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      u_opt, cfg->L + 1, cfg->m, n_step, bounds, action, u_applied, (int)batch);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ddqc_ddmpc_post_step(const DdqcMpcConfig* cfg, double* u_win, double* y_win, const double* u_applied,
+                                    const float* y_meas, int64_t y_rs, int64_t y_cs, const double* y_r,
+                                    const double* d0, double max_inc, double* sq_sum, int32_t* n_acc,
+                                    int32_t* fail_step, double* y_log, int32_t step, int64_t batch, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (!u_win || !y_win || !u_applied || !y_meas || !y_r || !d0 || !sq_sum || !n_acc || !fail_step) return DDQC_E_NULL;
+  if (batch < 0 || step < 0) return DDQC_E_SHAPE;
+  if (batch == 0) return 0;
+  ddmpc_post_step_kernel<<<(unsigned)batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      cfg->N, cfg->m, cfg->p, u_win, y_win, u_applied, y_meas, (long long)y_rs, (long long)y_cs, y_r, d0, max_inc,
+      sq_sum, n_acc, fail_step, y_log, step, (int)batch);
   return (int)cudaGetLastError();
 }

@@ -285,6 +285,26 @@ int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg_host, void* ws, const double* u_wi
 int ddqc_ddmpc_store(const DdqcMpcConfig* cfg_host, double* u_win, double* y_win,
                      const double* u_new, const double* y_new, int64_t batch, void* stream);
 
+/* Closed-loop evaluation of a batch of controllers without host round trips
+ * (sim_nonlinear_dd_mpc_control_loop_parallel, data_driven_mpc/utilities/param_grid_search/
+ * controller_evaluation.py:345-450):
+ *  ddqc_ddmpc_action    : env action in [-1,1] (fp32, [B][m]) from ubar_{n_step} via
+ *                         linear_interpolate (utilities/math_utils.py:13-20) over `bounds` [m][2];
+ *                         also copies the applied input (physical units, float64) to u_applied [B][m]
+ *  ddqc_ddmpc_post_step : store_input_output_measurement(u_applied, y_meas) (:416-422) fused with the
+ *                         tracking-error bookkeeping: sq_sum[b] += |y - y_r|^2, n_acc[b] += 1 and
+ *                         fail_step[b] = step when |y - y_r| - d0[b] > max_inc (:424-447; max_inc < 0
+ *                         disables the check).  Controllers with fail_step[b] >= 0 are frozen.
+ *                         y_meas is fp32 with strides (y_rs, y_cs) in elements; y_log (or NULL) is
+ *                         [steps][B][p] float64.  RMSE = sqrt(sq_sum / num_steps) (:449-450). */
+int ddqc_ddmpc_action(const DdqcMpcConfig* cfg_host, const double* u_opt, int32_t n_step,
+                      const float* bounds, float* action, double* u_applied, int64_t batch, void* stream);
+int ddqc_ddmpc_post_step(const DdqcMpcConfig* cfg_host, double* u_win, double* y_win,
+                         const double* u_applied, const float* y_meas, int64_t y_rs, int64_t y_cs,
+                         const double* y_r, const double* d0, double max_inc, double* sq_sum,
+                         int32_t* n_acc, int32_t* fail_step, double* y_log, int32_t step,
+                         int64_t batch, void* stream);
+
 /* Developer aid: device buffer of 12 int64 cycle counters accumulated per solver phase (NULL: off). */
 int ddqc_ddmpc_debug_phase_buffer(void* dev_ptr);
 

@@ -160,3 +160,173 @@ def solve_condensed(prm: MPCParams, u_win, y_win, y_r, us_prev=None, ys_prev=Non
     u_s, y_s = x[nB : nB + m], x[nB + m :]
     u_pred = np.vstack([x[:nB].reshape(L - n, m), np.tile(u_s, (n + 1, 1))])  # ubar_0..ubar_L
     return dict(u_opt=u_pred, us=u_s, ys=y_s, x=x, iters=iters, Hq=Hq, f=f, lo=lo, hi=hi, v_sr=v_sr)
+
+
+# =============================================================================================
+# v2: the elimination order the CUDA solver uses since round 1b (ddqc_ddmpc.cu, phases A-D)
+# =============================================================================================
+# Rows are ordered [R1 | R2 | R3 | aug]: R1 = past inputs, ones row, terminal inputs (hard, shared by
+# both regularised systems), R2 = output rows (soft), R3 = predicted-input rows (the box-constrained
+# decision variables), aug = right-hand sides carried as extra rows (T_u, T_y, tau, b_s).  Eliminating
+# R1 then R2 leaves the Schur complement on [R3 | aug]; a Gauss-Jordan sweep on R3 yields
+#   Z = K^T (G + D0)^-1 K   for K = [E_B | T | c],
+# i.e. exactly the Hessian / gradient blocks `solve_condensed` obtains from 94 forward substitutions.
+# The box QP is solved by block principal pivoting in the space of the FREE variables (warm-startable)
+# with a Mehrotra interior-point fallback followed by a pivoting polish.
+def perm_rows(prm):
+    n,m,p,L,ell=prm.n,prm.m,prm.p,prm.L,prm.ell
+    # canonical rows (as in hankel_gram): u rows j*m+i | y rows m*ell+j*p+i | ones (last)
+    r=(m+p)*ell+1
+    R1=[j*m+i for j in range(n) for i in range(m)]+[r-1]+[j*m+i for j in range(L,ell) for i in range(m)]
+    R2=[m*ell+j*p+i for j in range(ell) for i in range(p)]
+    R3=[j*m+i for j in range(n,L) for i in range(m)]
+    return np.array(R1),np.array(R2),np.array(R3)
+
+def chol_partial(A, k):
+    """eliminate first k columns of symmetric A (right-looking); return Schur complement of trailing"""
+    A=A.copy()
+    L11=np.linalg.cholesky(A[:k,:k])
+    L21=np.linalg.solve(L11, A[:k,k:]).T
+    return A[k:,k:]-L21@L21.T, L11, L21
+
+def sweep(S,k):
+    S=S.copy()
+    for j in range(k):
+        d=S[j,j]; col=S[:,j].copy()
+        S-=np.outer(col,col)/d
+        S[:,j]=col/d; S[j,:]=col/d; S[j,j]=-1.0/d
+    return S
+
+def box_qp_free(Hq,f,lo,hi,state0=None,max_pass=15):
+    nx=len(f); state=np.zeros(nx,int) if state0 is None else state0.copy()
+    # sanitize: infinite bounds cannot be active
+    state[(state<0)&~np.isfinite(lo)]=0; state[(state>0)&~np.isfinite(hi)]=0
+    tol_x=1e-10; tol_g=1e-11*max(1.0,np.abs(f).max())
+    best,patience=nx+1,3
+    for it in range(max_pass):
+        F=np.nonzero(state==0)[0]; A=np.nonzero(state)[0]
+        x=np.where(state<0,lo,np.where(state>0,hi,0.0))
+        x=np.where(state==0,0.0,x)
+        rhs=-(f[F]+Hq[np.ix_(F,A)]@x[A])
+        if len(F): x[F]=np.linalg.solve(Hq[np.ix_(F,F)],rhs)
+        g=Hq@x+f
+        verdict=np.zeros(nx,int)
+        verdict[(state<0)&(g<-tol_g)]=2; verdict[(state>0)&(g>tol_g)]=2
+        fr=state==0
+        verdict[fr&(x<lo-tol_x*(1+np.abs(lo)))]=-1
+        verdict[fr&(x>hi+tol_x*(1+np.abs(hi)))]=1
+        bad=np.nonzero(verdict)[0]
+        if len(bad)==0: return x,state,it+1,True
+        if len(bad)<best: best,patience,full=len(bad),3,True
+        elif patience>0: patience-=1; full=True
+        else: full=False
+        for i in (bad if full else bad[-1:]): state[i]=0 if verdict[i]==2 else verdict[i]
+    return x,state,max_pass,False
+
+def box_qp_ipm(Hq,f,lo,hi,max_iter=60,tol=1e-10):
+    nx=len(f)
+    il=np.isfinite(lo); iu=np.isfinite(hi)
+    # start: midpoint (or 0 for free vars)
+    x=np.where(il&iu,0.5*(np.where(il,lo,0)+np.where(iu,hi,0)),0.0)
+    sl=np.where(il,x-lo,1.0); su=np.where(iu,hi-x,1.0)
+    zl=np.where(il,1.0,0.0); zu=np.where(iu,1.0,0.0)
+    # scale duals to problem
+    g=Hq@x+f; sc=max(1.0,np.abs(g).max()); zl*=sc; zu*=sc
+    nc=il.sum()+iu.sum()
+    for it in range(max_iter):
+        g=Hq@x+f
+        rd=g-zl+zu                    # dual residual
+        mu=(sl[il]@zl[il]+su[iu]@zu[iu])/nc
+        if np.abs(rd).max()<tol*sc and mu<tol*sc*1e-2: break
+        dl=np.where(il,zl/sl,0.0); du=np.where(iu,zu/su,0.0)
+        Lc=np.linalg.cholesky(Hq+np.diag(dl+du))
+        def solve(rcl,rcu):
+            # complementarity residual targets: sl*zl + sl*dzl + zl*dsl = rcl ; dsl=dx, dsu=-dx
+            rhs=-rd+np.where(il,(rcl-sl*zl)/sl,0.0)-np.where(iu,(rcu-su*zu)/su,0.0)
+            dx=np.linalg.solve(Lc.T,np.linalg.solve(Lc,rhs))
+            dzl=np.where(il,(rcl-sl*zl-zl*dx)/sl,0.0); dzu=np.where(iu,(rcu-su*zu+zu*dx)/su,0.0)
+            return dx,dzl,dzu
+        def maxstep(dx,dzl,dzu):
+            a=1.0
+            for v,dv,msk in ((sl,dx,il),(su,-dx,iu),(zl,dzl,il),(zu,dzu,iu)):
+                neg=msk&(dv<0)
+                if neg.any(): a=min(a,(-v[neg]/dv[neg]).min())
+            return a
+        dxa,dzla,dzua=solve(np.zeros(nx),np.zeros(nx))
+        aa=maxstep(dxa,dzla,dzua)
+        mu_aff=(((sl+aa*dxa)*(zl+aa*dzla))[il].sum()+((su-aa*dxa)*(zu+aa*dzua))[iu].sum())/nc
+        sig=(mu_aff/mu)**3
+        rcl=sig*mu-dxa*dzla; rcu=sig*mu+dxa*dzua
+        dx,dzl,dzu=solve(rcl,rcu)
+        a=min(1.0,0.995*maxstep(dx,dzl,dzu)) if maxstep(dx,dzl,dzu)<1 else 1.0
+        x=x+a*dx; sl=np.where(il,sl+a*dx,1.0); su=np.where(iu,su-a*dx,1.0); zl=zl+a*dzl; zu=zu+a*dzu
+    state=np.zeros(nx,int); state[il&(zl>sl)]=-1; state[iu&(zu>su)]=1
+    return x,state,it
+
+def solve_condensed_v2(prm,u_win,y_win,y_r,us_prev=None,ys_prev=None,state0=None):
+    n,m,p,L,ell=prm.n,prm.m,prm.p,prm.L,prm.ell
+    G,_=hankel_gram(u_win,y_win,ell)
+    r=G.shape[0]
+    R1,R2,R3=perm_rows(prm)
+    n1,n2,n3=len(R1),len(R2),len(R3)
+    w,B,T=row_classes(prm)
+    assert (B==R3).all()
+    tau=np.zeros(r); tau[:n*m]=u_win[-n:].ravel(); tau[m*ell:m*ell+n*p]=y_win[-n:].ravel(); tau[-1]=1.0
+    use_sr=prm.alpha_reg_type==APPROXIMATED and us_prev is not None
+    bs=np.concatenate([np.tile(us_prev,ell),np.tile(ys_prev,ell),[1.0]]) if use_sr else np.zeros(r)
+    # augmented matrix in order [R1 | R2 | R3 | aug(T_u, T_y, tau, bs)]
+    order=np.concatenate([R1,R2,R3])
+    K=np.concatenate([T,tau[:,None],bs[:,None]],axis=1)  # r x 8
+    na=K.shape[1]
+    A=np.zeros((r+na,r+na)); A[:r,:r]=G[np.ix_(order,order)]; A[r:,:r]=K[order].T; A[:r,r:]=K[order]
+    # phase A: eliminate R1
+    S40,_,_=chol_partial(A,n1)      # order [R2 | R3 | aug8]
+    nt=S40.shape[0]
+    e_row=np.zeros(n2)
+    if use_sr:
+        ds=prm.lamb_alpha_s/prm.lamb_sigma_s
+        # phase B: order [R3 | R2 | bs]
+        idx=np.concatenate([np.arange(n2,n2+n3),np.arange(n2),[nt-1]])
+        Sb=S40[np.ix_(idx,idx)].copy()
+        Sb[np.arange(n3,n3+n2),np.arange(n3,n3+n2)]+=ds
+        Lb=np.linalg.cholesky(Sb[:-1,:-1])
+        yv=np.linalg.solve(Lb,Sb[:-1,-1])
+        Lyy=Lb[n3:,n3:]
+        zy=np.linalg.solve(Lyy.T,yv[n3:])
+        e_row=ds*zy
+    # phase C: order [R2 | R3 | T_u,T_y,tau,bs,e]
+    Sc=np.zeros((nt+1,nt+1)); Sc[:nt,:nt]=S40
+    Sc[nt,:n2]=e_row; Sc[:n2,nt]=e_row
+    D0=prm.lamb_alpha/w[R2]
+    Sc[np.arange(n2),np.arange(n2)]+=D0
+    S,_,_=chol_partial(Sc,n2)       # (n3 + 9)
+    # combine aug: c = tau - bs + e
+    nB=n3
+    Cm=np.zeros((nB+9,nB+7)); Cm[:nB,:nB]=np.eye(nB)
+    for k in range(6): Cm[nB+k,nB+k]=1
+    Cm[nB+6,nB+6]=1; Cm[nB+7,nB+6]=-1; Cm[nB+8,nB+6]=1
+    S7=Cm.T@S@Cm
+    Z=-sweep(S7,nB); Z[:nB,nB:]*=-1; Z[nB:,:nB]*=-1
+    nx=nB+m+p
+    Hq=2*prm.lamb_alpha*Z[:nx,:nx]; f=2*prm.lamb_alpha*Z[:nx,nx]
+    u_past,y_past=u_win[-n:],y_win[-n:]
+    for b_idx,row in enumerate(B):
+        i=row%m
+        Hq[b_idx,b_idx]+=2*prm.R[i]; Hq[b_idx,nB+i]-=2*prm.R[i]; Hq[nB+i,b_idx]-=2*prm.R[i]; Hq[nB+i,nB+i]+=2*prm.R[i]
+    for i in range(m):
+        Hq[nB+i,nB+i]+=2*n*prm.R[i]; f[nB+i]+=-2*prm.R[i]*u_past[:,i].sum()
+    for i in range(p):
+        Hq[nB+m+i,nB+m+i]+=2*(n*prm.Q[i]+prm.S[i]); f[nB+m+i]+=-2*(prm.Q[i]*y_past[:,i].sum()+prm.S[i]*y_r[i])
+    lo=np.concatenate([np.tile(prm.U[:,0],L-n),np.maximum(prm.U[:,0],prm.Us[:,0]),np.full(p,-np.inf)])
+    hi=np.concatenate([np.tile(prm.U[:,1],L-n),np.minimum(prm.U[:,1],prm.Us[:,1]),np.full(p,np.inf)])
+    x,state,it,ok=box_qp_free(Hq,f,lo,hi,state0)
+    info=dict(passes=it,ipm=0)
+    if not ok:
+        xi,st,iti=box_qp_ipm(Hq,f,lo,hi)
+        x2,state2,it2,ok2=box_qp_free(Hq,f,lo,hi,st,max_pass=5)
+        info.update(ipm=iti,polish=it2,polish_ok=ok2,ipm_err=np.abs(x2-xi).max())
+        x,state=(x2,state2) if ok2 else (xi,st)
+    u_s, y_s = x[nB:nB+m], x[nB+m:]
+    u_pred = np.vstack([x[:nB].reshape(L-n, m), np.tile(u_s, (n+1, 1))])  # ubar_0..ubar_L
+    return dict(x=x,state=state,Hq=Hq,f=f,info=info,u_opt=u_pred,us=u_s,ys=y_s)
+

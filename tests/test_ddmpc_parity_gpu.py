@@ -104,7 +104,7 @@ def test_default_size_matches_oracle_and_golden(build_lib):
         np.testing.assert_allclose(gpu.optimal_u[0].cpu().numpy(), g["u_opt"][t], rtol=0, atol=TOL)
         np.testing.assert_allclose(gpu.us[0].cpu().numpy(), g["us"][t], rtol=0, atol=TOL)
         gpu.store_input_output_measurement(g["u_opt"][t][0][None], g["y_next"][t][None])
-    assert int(gpu.iters.max()) <= 20
+    assert int(gpu.pivoting_passes.max()) <= 20 and int(gpu.ipm_iterations.max()) == 0
 
 
 def test_single_controller_numpy_api(build_lib):
@@ -147,3 +147,47 @@ def test_unsupported_modes_fail_loudly(build_lib):
             NonlinearDataDrivenMPCController(**{**kw, **bad})
     with pytest.raises(ValueError):
         NonlinearDataDrivenMPCController(**{**kw, "u": u[0][:30], "y": y[0][:30]})
+
+
+def test_hard_cases_fall_back_to_interior_point_and_match_oracle(build_lib):
+    """Saved default-size windows with 50-94 active bounds on which pivoting from a cold start cycles:
+    every controller must converge (status 0) through the interior-point fallback + polish and match the
+    literal-QP oracle solutions of the fixture."""
+    import os
+
+    import ddmpc_oracle as mo
+
+    h = np.load(os.path.join(os.path.dirname(__file__), "golden", "ddmpc_hard_cases.npz"))
+    B = h["u"].shape[0]
+    prm = mo.default_params()
+    gpu = _batched(prm, h["u"], h["y"], np.tile(h["y_r"], (B, 1)), solve_on_init=False, warm_start=False)
+    gpu.us.copy_(torch.from_numpy(h["us_prev"]))
+    gpu.ys.copy_(torch.from_numpy(h["ys_prev"]))
+    gpu._have_prev.fill_(1)
+    gpu.update_and_solve_data_driven_mpc()
+    assert (gpu.status.cpu().numpy() == 0).all(), gpu.status
+    assert int((gpu.ipm_iterations > 0).sum()) >= B // 2  # the fallback path is really exercised
+    np.testing.assert_allclose(gpu.optimal_u.cpu().numpy(), h["u_opt"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(gpu.us.cpu().numpy(), h["us"], rtol=0, atol=TOL)
+
+
+def test_warm_start_does_not_change_the_solution(build_lib):
+    """The carried active set only seeds the pivoting: warm- and cold-started controllers must return the
+    same optimum at every closed-loop step."""
+    prm = _small_params()
+    prm.alpha_reg_type = 0
+    B, T = 5, 6
+    u, y, plants = _synthetic_windows(prm, 17, B, return_plants=True)
+    y_r = np.tile(np.array([[0.4, -0.3, 0.6]]), (B, 1))
+    warm = _batched(prm, u, y, y_r, solve_on_init=False, warm_start=True)
+    cold = _batched(prm, u, y, y_r, solve_on_init=False, warm_start=False)
+    for t in range(T):
+        warm.update_and_solve_data_driven_mpc()
+        cold.update_and_solve_data_driven_mpc()
+        assert (warm.status.cpu().numpy() == 0).all() and (cold.status.cpu().numpy() == 0).all()
+        np.testing.assert_allclose(warm.optimal_u.cpu().numpy(), cold.optimal_u.cpu().numpy(), rtol=0, atol=1e-9)
+        u0 = warm.get_optimal_control_input_at_step(0).cpu().numpy()
+        y_new = np.stack([plants[b].step(u0[b]) for b in range(B)])
+        for c in (warm, cold):
+            c.store_input_output_measurement(torch.from_numpy(u0).cuda(), torch.from_numpy(y_new).cuda())
+    assert int(warm.pivoting_passes.max()) <= int(cold.pivoting_passes.max()) + 2

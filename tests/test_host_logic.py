@@ -179,3 +179,39 @@ def test_sharding_helpers():
         assert rr == list(range(n))
     with pytest.raises(ValueError):
         shard_range(10, 3, 2)
+
+
+def test_closed_loop_oracle_rmse_and_early_stop():
+    """oracle/ddmpc_eval_oracle.py follows controller_evaluation.py:345-450: RMSE = sqrt(mean_t sum (y - y_r)^2),
+    early stop when |y - y_r| - d0 > max increment, n inputs applied per solve with n_n_mpc_step."""
+    import ddmpc_eval_oracle as eo
+
+    class Mock:  # same surface as the reference's tests/mocks.py:133-158
+        n, m = 2, 1
+        optimal_u = None
+
+        def __init__(self):
+            self.y_r = np.array([[1.0], [0.0]])
+            self.solves, self.stored = 0, []
+
+        def update_and_solve_data_driven_mpc(self):
+            self.solves += 1
+            self.optimal_u = np.array([[0.5], [0.25]])
+
+        def get_optimal_control_input_at_step(self, n_step=0):
+            return self.optimal_u[n_step]
+
+        def get_du_value_at_step(self, n_step=0):
+            return None
+
+        def store_input_output_measurement(self, u_current, y_current, du_current):
+            self.stored.append((float(u_current[0]), tuple(y_current)))
+
+    ys = iter([np.array([0.0, 0.0]), np.array([0.5, 0.0]), np.array([1.0, 1.0]), np.array([1.0, 0.0])])
+    c = Mock()
+    rmse, u_sys, y_sys = eo.sim_control_loop(c, lambda u: next(ys), 4, 1.0, None, n_n_mpc_step=True)
+    assert c.solves == 2 and [s[0] for s in c.stored] == [0.5, 0.25, 0.5, 0.25]
+    assert rmse == pytest.approx(np.sqrt((1.0 + 0.25 + 1.0 + 0.0) / 4))
+    ys = iter([np.array([0.0, 0.0]), np.array([-1.0, 0.0])])
+    with pytest.raises(eo.MovedAway):
+        eo.sim_control_loop(Mock(), lambda u: next(ys), 4, 1.0, 0.5)
