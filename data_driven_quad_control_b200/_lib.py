@@ -202,6 +202,7 @@ SIGNATURES = {
     "ddqc_ddmpc_action": (C.c_int, [P(MpcConfig), vp, C.c_int32, vp, vp, vp, i64, vp]),
     "ddqc_ddmpc_post_step": (C.c_int, [P(MpcConfig), vp, vp, vp, vp, i64, i64, vp, vp, C.c_double, vp, vp, vp, vp, C.c_int32, i64, vp]),
     "ddqc_ddmpc_debug_phase_buffer": (C.c_int, [vp]),
+    "ddqc_policy_mlp_forward": (C.c_int, [vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp]),
 }
 
 _STRUCTS = {0: EnvParams, 1: EnvCtl, 2: EnvState, 3: EnvOut, 4: MpcConfig}

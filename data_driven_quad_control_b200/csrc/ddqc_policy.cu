@@ -1,0 +1,327 @@
+// ddqc_policy.cu -- fused policy-MLP forward (16 -> 128 -> 128 -> A, tanh) on the 5th-generation
+// tensor cores (tcgen05.mma, accumulators in TMEM) for sm_100a.
+//
+// Replaces the actor forward of the reference's rollouts: rsl_rl `ActorCritic.act_inference`
+// = nn.Sequential(Linear(16,128), Tanh, Linear(128,128), Tanh, Linear(128,A)) with the shape of
+// models/demo_ctbr_fixed_yaw/model_1500.pt (learning/config/hover_ppo_config.py:33-38), called once
+// per env step on the (N, 16) observation buffer `HoverEnv.step` returns.  With cuBLAS the two
+// 128-wide hidden activations make a round trip through HBM (1 KB per env-step, 3x the 357 B of
+// the env step itself); here an observation tile goes obs -> smem -> TMEM -> registers -> smem
+// -> TMEM -> registers -> action without leaving the SM.
+//
+// Structure: persistent CTAs (one per SM), two independent 128-thread warpgroups per CTA, each
+// walking its own stream of 128-env tiles so that one warpgroup's epilogue (TMEM -> registers,
+// bias + tanh, bf16 split, shared-memory stores) overlaps the other's tensor-core work:
+//   1. thread r loads observation row r (64 B), splits it into bf16 hi + lo and stores both in the
+//      canonical K-major no-swizzle UMMA layout (8 x 16 B core matrices);
+//   2. one elected thread issues D1[128x128] = A1 W1^T as three bf16 products
+//      (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM) and commits to an mbarrier;
+//   3. every thread reads its TMEM lane (tcgen05.ld 32x32b.x32), adds the bias, applies tanh, splits
+//      to bf16 hi/lo and writes the layer-2 operand tile;
+//   4. D2 = A2 W2^T (8 K-steps x 3 products), same commit / wait;
+//   5. bias + tanh, then the A-wide output layer (A <= 8, 384 FMAs per env) on the CUDA cores
+//      straight from the registers; 12-byte action rows are stored coalesced.
+// The hi/lo split (two bf16 = 16 mantissa bits per operand, cross term lo*lo dropped, ~1e-5 relative
+// per product) keeps the actions within 1e-4 of an fp32 forward (measured 3.2e-5 on the demo
+// checkpoint); precision = 1 runs the single hi*hi product (plain bf16 accuracy, one third of the
+// tensor-core work).  A three-term split would be fp32-exact but needs 324 KB of operand tiles.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ddqc.h"
+
+namespace {
+
+constexpr int kIn = 16, kHid = 128, kMaxOut = 8, kTileM = 128;
+constexpr int kWgThreads = 128, kThreads = 2 * kWgThreads;
+
+// shared-memory map (bytes)
+constexpr uint32_t kW2Hi = 0, kW2Lo = 32768, kW1Hi = 65536, kW1Lo = 69632;
+constexpr uint32_t kWgBase = 73728, kWgStride = 73728;  // per warpgroup: A2 hi | A2 lo | A1 hi | A1 lo
+constexpr uint32_t kA2Hi = 0, kA2Lo = 32768, kA1Hi = 65536, kA1Lo = 69632;
+constexpr uint32_t kParams = kWgBase + 2 * kWgStride;   // fp32: W3 [8][128] | b1 | b2 | b3
+constexpr uint32_t kW3 = kParams, kB1 = kW3 + kMaxOut * kHid * 4, kB2 = kB1 + kHid * 4, kB3 = kB2 + kHid * 4;
+constexpr uint32_t kBar = kB3 + 64;                     // 2 mbarriers (8 B each) + TMEM base pointer
+constexpr uint32_t kSmemBytes = kBar + 32;
+
+// K-major, no swizzle: element (r, k) of an [rows x K] bf16 operand; core matrix = 8 rows x 16 bytes
+__device__ __forceinline__ uint32_t core_off(int r, int k, int kchunks) {
+  return (uint32_t)((r >> 3) * (kchunks * 128) + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2);
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start >> 4 in [0,14), leading byte offset
+// >> 4 in [16,30) (distance of the two 16-byte K chunks of one MMA), stride byte offset >> 4 in [32,46)
+// (distance of consecutive 8-row groups), version 1 in [46,48), layout type 0 = no swizzle in [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D = F32 (1 << 4), A = B = BF16 (1 << 7,
+// 1 << 10), both K-major, N >> 3 in [17,23), M >> 4 in [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kHid >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, %1;" ::"r"(wg + 1), "n"(kWgThreads) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// x = hi + lo with hi, lo bf16 (16 mantissa bits together)
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// 8 consecutive K elements -> one 16-byte chunk of the hi operand and one of the lo operand
+__device__ __forceinline__ void store_chunk(uint8_t* smem, uint32_t off_hi, uint32_t off_lo, const float (&x)[8]) {
+  __nv_bfloat16 h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_bf16(x[i], h[i], l[i]);
+  *reinterpret_cast<uint4*>(smem + off_hi) = *reinterpret_cast<const uint4*>(h);
+  *reinterpret_cast<uint4*>(smem + off_lo) = *reinterpret_cast<const uint4*>(l);
+}
+
+// tanh(x) = (e - 1) / (e + 1), e = exp(2x); absolute error ~1e-7 (ex2.approx + approximate division)
+__device__ __forceinline__ float tanh_acc(float x) {
+  const float xc = fminf(fmaxf(x, -15.0f), 15.0f);
+  const float e = __expf(2.0f * xc);
+  return __fdividef(e - 1.0f, e + 1.0f);
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float* __restrict__ W1,
+                  const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
+                  const float* __restrict__ W3, const float* __restrict__ b3, const int n_out,
+                  float* __restrict__ actions) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, wg = tid >> 7, wtid = tid & 127, warp = tid >> 5;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kBar + 16);
+
+  // ---- one-time setup: weights -> bf16 hi/lo operand tiles, fp32 parameters, barriers, TMEM ----
+  for (int e = tid; e < kHid * kHid / 8; e += kThreads) {  // W2[n][k]: 8 consecutive k per thread
+    const int nn = e / (kHid / 8), k0 = (e % (kHid / 8)) * 8;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = W2[nn * kHid + k0 + i];
+    const uint32_t off = core_off(nn, k0, kHid / 8);
+    store_chunk(smem, kW2Hi + off, kW2Lo + off, x);
+  }
+  for (int e = tid; e < kHid * kIn / 8; e += kThreads) {
+    const int nn = e / (kIn / 8), k0 = (e % (kIn / 8)) * 8;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = W1[nn * kIn + k0 + i];
+    const uint32_t off = core_off(nn, k0, kIn / 8);
+    store_chunk(smem, kW1Hi + off, kW1Lo + off, x);
+  }
+  float* sW3 = reinterpret_cast<float*>(smem + kW3);
+  float* sB1 = reinterpret_cast<float*>(smem + kB1);
+  float* sB2 = reinterpret_cast<float*>(smem + kB2);
+  float* sB3 = reinterpret_cast<float*>(smem + kB3);
+  for (int e = tid; e < kMaxOut * kHid; e += kThreads) sW3[e] = e < n_out * kHid ? W3[e] : 0.0f;
+  for (int e = tid; e < kHid; e += kThreads) {
+    sB1[e] = b1[e];
+    sB2[e] = b2[e];
+  }
+  if (tid < kMaxOut) sB3[tid] = tid < n_out ? b3[tid] : 0.0f;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbase + kBar));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbase + kBar + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kBar + 16), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t d1 = tmem_base + wg * 256, d2 = d1 + 128;          // accumulator columns of this warpgroup
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;     // this warp's 32-lane slice of TMEM
+  const uint32_t mbar = sbase + kBar + 8 * wg;
+  uint8_t* wgs = smem + kWgBase + wg * kWgStride;
+  const uint32_t wga = sbase + kWgBase + wg * kWgStride;
+  uint32_t phase = 0;
+
+  const long long n_tiles = (n + kTileM - 1) / kTileM;
+  for (long long tile = (long long)blockIdx.x * 2 + wg; tile < n_tiles; tile += (long long)gridDim.x * 2) {
+    const long long row = tile * kTileM + wtid;
+    const bool valid = row < n;
+    // ---- 1. observation row -> layer-1 operand tile ----
+    {
+      float x[16];
+      const float4* src = reinterpret_cast<const float4*>(obs + (valid ? row : 0) * kIn);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = x[8 * c + i];
+        const uint32_t off = core_off(wtid, 8 * c, kIn / 8);
+        store_chunk(wgs, kA1Hi + off, kA1Lo + off, y);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    wg_sync(wg);
+    // ---- 2. D1 = A1 W1^T ----
+    if (wtid == 0) {
+      tc_fence_after();
+      const uint64_t ah = make_desc(wga + kA1Hi, 128, (kIn / 8) * 128), al = make_desc(wga + kA1Lo, 128, (kIn / 8) * 128);
+      const uint64_t bh = make_desc(sbase + kW1Hi, 128, (kIn / 8) * 128), bl = make_desc(sbase + kW1Lo, 128, (kIn / 8) * 128);
+      umma_bf16(d1, ah, bh, 0);
+      if (SPLIT) {
+        umma_bf16(d1, al, bh, 1);
+        umma_bf16(d1, ah, bl, 1);
+      }
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- 3. h1 = tanh(D1 + b1) -> layer-2 operand tile ----
+#pragma unroll 1
+    for (int cb = 0; cb < 4; ++cb) {
+      float v[32];
+      tmem_ld32(d1 + lane_addr + cb * 32, v);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = tanh_acc(v[8 * c + i] + sB1[cb * 32 + 8 * c + i]);
+        const uint32_t off = core_off(wtid, cb * 32 + 8 * c, kHid / 8);
+        store_chunk(wgs, kA2Hi + off, kA2Lo + off, y);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    wg_sync(wg);
+    // ---- 4. D2 = A2 W2^T ----
+    if (wtid == 0) {
+      tc_fence_after();
+#pragma unroll 1
+      for (int ks = 0; ks < kHid / 16; ++ks) {
+        const uint32_t ko = ks * 256;  // two 16-byte K chunks per MMA
+        const uint64_t ah = make_desc(wga + kA2Hi + ko, 128, (kHid / 8) * 128), al = make_desc(wga + kA2Lo + ko, 128, (kHid / 8) * 128);
+        const uint64_t bh = make_desc(sbase + kW2Hi + ko, 128, (kHid / 8) * 128), bl = make_desc(sbase + kW2Lo + ko, 128, (kHid / 8) * 128);
+        umma_bf16(d2, ah, bh, ks > 0);
+        if (SPLIT) {
+          umma_bf16(d2, al, bh, 1);
+          umma_bf16(d2, ah, bl, 1);
+        }
+      }
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- 5. h2 = tanh(D2 + b2); action = h2 W3^T + b3 on the CUDA cores ----
+    float out[kMaxOut];
+#pragma unroll
+    for (int j = 0; j < kMaxOut; ++j) out[j] = 0.0f;
+#pragma unroll 1
+    for (int cb = 0; cb < 4; ++cb) {
+      float v[32];
+      tmem_ld32(d2 + lane_addr + cb * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = tanh_acc(v[i] + sB2[cb * 32 + i]);
+#pragma unroll
+      for (int j = 0; j < kMaxOut; ++j) {
+        if (j < n_out) {  // uniform
+          const float4* w = reinterpret_cast<const float4*>(sW3 + j * kHid + cb * 32);
+          float acc = out[j];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 ww = w[q];
+            acc = fmaf(v[4 * q], ww.x, acc);
+            acc = fmaf(v[4 * q + 1], ww.y, acc);
+            acc = fmaf(v[4 * q + 2], ww.z, acc);
+            acc = fmaf(v[4 * q + 3], ww.w, acc);
+          }
+          out[j] = acc;
+        }
+      }
+    }
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < kMaxOut; ++j)
+        if (j < n_out) actions[row * n_out + j] = out[j] + sB3[j];
+    }
+    tc_fence_before();  // the TMEM reads above are ordered before the next tile's MMAs (via the next wg_sync)
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}
+
+}  // namespace
+
+extern "C" int ddqc_policy_mlp_forward(const float* obs, int64_t n, int32_t n_in, int32_t n_hidden, int32_t n_out,
+                                       const float* W1, const float* b1, const float* W2, const float* b2,
+                                       const float* W3, const float* b3, int32_t precision, float* actions,
+                                       void* stream) {
+  if (!obs || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !actions) return DDQC_E_NULL;
+  if (n_in != kIn || n_hidden != kHid || n_out < 1 || n_out > kMaxOut || n < 0) return DDQC_E_SHAPE;
+  if (precision != 0 && precision != 1) return DDQC_E_CONFIG;
+  if ((reinterpret_cast<uintptr_t>(obs) & 15) != 0) return DDQC_E_ALIGN;
+  if (n == 0) return 0;
+  auto kern = precision == 0 ? policy_mlp_kernel<true> : policy_mlp_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (e != cudaSuccess) return (int)e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long n_tiles = (n + kTileM - 1) / kTileM;
+  const int grid = (int)((n_tiles + 1) / 2 < sms ? (n_tiles + 1) / 2 : sms);
+  kern<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(obs, (long long)n, W1, b1, W2, b2, W3, b3, n_out,
+                                                                         actions);
+  return (int)cudaGetLastError();
+}
