@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--no-ddmpc", action="store_true", help="skip the DD-MPC leg")
+    ap.add_argument("--no-policy", action="store_true", help="skip the policy-rollout leg (BASELINE configs[2])")
     ap.add_argument("--ddmpc-batch", type=int, default=4096)
     ap.add_argument("--ddmpc-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -250,10 +251,23 @@ def run_b200(args) -> dict:
             "bytes_per_env_step": ENV_BYTES_PER_STEP[A],
             "avg_launch_ms": avg_ms,
             "median_launch_ms": med_ms,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2**20 envs (130.1 + 163.1 MB), from
+            # profiles/r1d_env_step_ncu_full.csv; below the algorithmic 374 MB because part of the written state is
+            # still in L2 at kernel end and is re-read from there by the next launch
+            "traffic": 293.2e6 * (N / float(1 << 20)) if N == 1 << 20 else None,
+            "traffic_source": "profiles/r1d_env_step_ncu_full.csv",
         },
         "rollout_stats": stats,
     }
+    if not args.no_policy:
+        leg = run_policy_leg(env, dev, N, steps=100, warm=10)
+        v = torch.tensor([leg["value"], leg["policy_forward_env_per_s"]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(v)
+        leg["value"], leg["policy_forward_env_per_s"] = float(v[0]), float(v[1])
+        leg["n_gpus"] = world
+        line["policy_rollout"] = leg
+        line["gpu_launches"] += leg["gpu_launches"]
     if not args.no_ddmpc:
         del env, actions
         torch.cuda.empty_cache()
@@ -265,8 +279,64 @@ def run_b200(args) -> dict:
         leg["value"], leg["closed_loop_solves_per_s"] = float(v[0]), float(v[1])
         leg["n_gpus"] = world
         line["ddmpc"] = leg
-        line["gpu_launches"] = K + leg["gpu_launches"]
+        line["gpu_launches"] += leg["gpu_launches"]
     return line if rank == 0 else {}
+
+
+# ------------------------------------------------------------------------------------------
+# policy-rollout leg (BASELINE configs[2]): random-init demo_ctbr_fixed_yaw-sized actor drives the env
+# ------------------------------------------------------------------------------------------
+def run_policy_leg(env, dev, N: int, steps: int = 100, warm: int = 10) -> dict:
+    import torch
+
+    from data_driven_quad_control_b200.learning.policy import FusedActorMLP
+
+    pol = FusedActorMLP.random_init(num_actions=env.num_actions, seed=0, device=dev, precision="bf16x2")
+    obs, _ = env.get_observations()
+    for _ in range(warm):
+        obs, *_ = env.step(pol.act_inference(obs))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        obs, *_ = env.step(pol.act_inference(obs))
+    e1.record()
+    torch.cuda.synchronize()
+    ms_roll = e0.elapsed_time(e1) / steps
+    e0.record()
+    for _ in range(steps):
+        pol.act_inference(obs)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_pol = e0.elapsed_time(e1) / steps
+    # tensor-core work of the kernel as executed: three bf16 products per layer-1/2 contraction
+    flops_tc = N * 3 * 2.0 * (16 * 128 + 128 * 128)
+    flops_alg = N * 2.0 * (16 * 128 + 128 * 128 + 128 * env.num_actions)
+    peak = 1384.2
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            peak = float(json.load(fh).get("bf16_tflops_sustained", peak))
+    return {
+        "metric": "env-steps/s including the policy forward (obs -> actor MLP -> env.step, all on the device)",
+        "value": N / (ms_roll * 1e-3),
+        "unit": "env-steps/s",
+        "envs_per_gpu": N,
+        "steps": steps,
+        "ms_per_step": ms_roll,
+        "policy": "random-init actor 16-128-128-%d, tanh (shape of models/demo_ctbr_fixed_yaw/model_1500.pt), torch.manual_seed(0)" % env.num_actions,
+        "policy_precision": "bf16 hi/lo split products on tcgen05, fp32 accumulation in TMEM (actions within 1e-4 of fp32)",
+        "policy_forward_ms": ms_pol,
+        "policy_forward_env_per_s": N / (ms_pol * 1e-3),
+        "roofline": {
+            "bound": "tensor", "kernel": "policy_mlp_kernel<split>", "achieved": flops_tc / (ms_pol * 1e-3) / 1e12,
+            "peak": peak, "unit": "TFLOP/s", "frac": flops_tc / (ms_pol * 1e-3) / 1e12 / peak,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained",
+            "algorithmic_tflops": flops_alg / (ms_pol * 1e-3) / 1e12,
+            "traffic": 69.6e6 if N == 1 << 20 else None, "traffic_source": "profiles/r1a_policy_mlp_ncu_full.csv (67.2 MB read = the obs tile, 2.4 MB written)",
+        },
+        "gpu_launches": 3 * steps,
+    }
 
 
 # ------------------------------------------------------------------------------------------
@@ -416,7 +486,8 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
             "peak": fp64_peak, "unit": "TFLOP/s", "frac": batch * flops / (avg * 1e-3) / 1e12 / fp64_peak,
             "peak_source": "FP64 tensor (DMMA m8n8k4) = FP64 FMA pipe, 64 FMA/clk/SM, measured 37.1 TFLOP/s with "
             "tools/ubench_fp64.cu (MEASURED_PEAKS.json carries no fp64 figure)",
-            "flops_per_solve": flops, "traffic": None,
+            "flops_per_solve": flops, "traffic": 123.9e6 if batch == 4096 else None,
+            "traffic_source": "profiles/r1b_ddmpc_solve_ncu_full.csv (DRAM bytes per launch of 4096 solves; the workspace slots stay in L2)",
         },
         "gpu_launches": T,
     }
