@@ -280,6 +280,9 @@ def run_b200(args) -> dict:
         leg["n_gpus"] = world
         line["ddmpc"] = leg
         line["gpu_launches"] += leg["gpu_launches"]
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return line if rank == 0 else {}
 
 
