@@ -205,6 +205,35 @@ __device__ __forceinline__ void load_diag(const double* dk, double (&a)[36]) {
     }
 }
 
+// Cholesky of one 8x8 block with every lane factoring the whole block redundantly in registers: no
+// shuffles and no shared-memory traffic on the 8-pivot dependency chain (rsqrt -> scale -> fma), no
+// divergent code.  The factor stays in `a` (the caller solves its own block against it straight from
+// registers) and is published to shared memory by identical 16-byte stores from all lanes.
+__device__ __forceinline__ bool chol8_regs(double* blk, double (&a)[36]) {
+  load_diag(blk, a);
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    double dj = LT(j, j);
+    ok = ok && (dj > 0.0);
+    dj = dj > 0.0 ? dj : 1.0;
+    const double r = rsqrt(dj);
+    LT(j, j) = r;
+#pragma unroll
+    for (int i = j + 1; i < 8; ++i) LT(i, j) *= r;
+#pragma unroll
+    for (int c = j + 1; c < 8; ++c)
+#pragma unroll
+      for (int i = c; i < 8; ++i) LT(i, c) = fma(-LT(i, j), LT(c, j), LT(i, c));
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c <= i; c += 2)
+      *reinterpret_cast<double2*>(blk + eoff(i, c)) = make_double2(LT(i, c), c + 1 <= i ? LT(i, c + 1) : 0.0);
+  return ok;
+}
+
 // X <- X L^-T for one 8x8 block held as an accumulator fragment (thread (g,t): X[g][2t], X[g][2t+1]).
 // The four lanes of a quad all-gather their row (6 shuffles off the dependency chain), solve it
 // redundantly in registers and keep their own two entries.
@@ -232,6 +261,22 @@ __device__ __forceinline__ void trsm8_frag(double2& v, const double (&a)[36], in
   v.y = o2 ? e3 : e1;
 }
 
+// Left-looking blocked Cholesky of block columns [0, ncols) of a matrix of `nrows` block rows held
+// in shared memory (RECT: nrows x nb1 rectangle; else block-packed lower triangle).  Block rows
+// >= ncols are carried along (they receive the triangular solve = forward substitution).
+//
+// The dependency chain of a Cholesky factorisation runs through the diagonal blocks:
+//   factor (K,K) -> solve block (K+1,K) -> rank-8 update of (K+1,K+1) -> factor (K+1,K+1) -> ...
+// Warp 0 owns exactly that chain and never waits for the bulk of the work; warps 1..15 own
+// everything else and run one barrier behind it.  Per block column K:
+//   warp 0 : factor (K,K) | barrier A | solve (K+1,K) | arrive B | update (K+1,K+1) with column K
+//   bulk   : update column K+1 with columns < K (the tensor-core bulk, overlaps warp 0's factor)
+//            | barrier A | solve (I,K), I >= K+2 | wait B | update (I,K+1), I >= K+2 with column K
+// Barrier A is a full 512-thread barrier (publishes the diagonal factor); B is asymmetric: warp 0 only
+// arrives (it has nothing to wait for), the bulk warps synchronise on it.
+__device__ __forceinline__ void bar_sync_named(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive_named(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
+
 #ifdef DDQC_PROF_FACTOR
 __device__ long long* g_fprof = nullptr;
 #define FPROF(k)                                                                            \
@@ -249,64 +294,93 @@ __device__ long long* g_fprof = nullptr;
 template <bool RECT>
 __device__ void factor_columns(double* __restrict__ M, int nb1, int nrows, int ncols, int* s_flag) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  constexpr int kBulk = kWarps - 1;
+  __syncthreads();
 #ifdef DDQC_PROF_FACTOR
   long long tp = clock64();
 #endif
   for (int K = 0; K < ncols; ++K) {
     if (warp == 0) {
-      if (!chol8_warp(M + (size_t)bidx<RECT>(K, K, nb1) * 64, lane) && lane == 0) *s_flag = 1;
-    } else if ((warp & 3) != 0 && K > 0 && K + 1 < ncols) {
-      // warps 4, 8, 12 share warp 0's SM sub-partition (and its FP64 pipe): they stay idle here so that
-      // the diagonal-block chain is not queued behind 16-cycle DMMA issues
-      const int bw = (warp >> 2) * 3 + (warp & 3) - 1;
-      for (int I = K + 1 + 2 * bw; I < nrows; I += 2 * (kWarps - kWarps / 4)) {
-        const bool two = I + 1 < nrows;
-        double2 s0, s1;
-        syrk_pair<RECT>(M, nb1, I, I + 1, two, K + 1, K, g, t, s0, s1);
-        double* b0 = M + (size_t)bidx<RECT>(I, K + 1, nb1) * 64;
-        double2 cv = ld_c(b0, g, t);
-        cv.x -= s0.x; cv.y -= s0.y;
-        st_c(b0, g, t, cv);
-        if (two) {
-          double* b1 = M + (size_t)bidx<RECT>(I + 1, K + 1, nb1) * 64;
-          double2 cw = ld_c(b1, g, t);
-          cw.x -= s1.x; cw.y -= s1.y;
-          st_c(b1, g, t, cw);
-        }
-      }
-    }
-    FPROF(0);
-    __syncthreads();
-    FPROF(1);
-    if (K + 1 + warp < nrows) {
+      double* dk = M + (size_t)bidx<RECT>(K, K, nb1) * 64;
       double a[36];
-      load_diag(M + (size_t)bidx<RECT>(K, K, nb1) * 64, a);
-      for (int I = K + 1 + warp; I < nrows; I += kWarps) {
-        double* b0 = M + (size_t)bidx<RECT>(I, K, nb1) * 64;
+      if (!chol8_regs(dk, a) && lane == 0) *s_flag = 1;
+      FPROF(0);
+      bar_sync_named(1);
+      FPROF(1);
+      if (K + 1 < nrows) {
+        double* b0 = M + (size_t)bidx<RECT>(K + 1, K, nb1) * 64;
         double2 v = ld_c(b0, g, t);
         trsm8_frag(v, a, t);
         st_c(b0, g, t, v);
+        __syncwarp();
       }
-    }
-    FPROF(2);
-    __syncthreads();
-    FPROF(3);
-    if (K + 1 < ncols) {
-      const double* rk = M + (size_t)bidx<RECT>(K + 1, K, nb1) * 64;
-      const double kb0 = ld_ab(rk, g, t, 0), kb1 = ld_ab(rk, g, t, 1);
-      for (int I = K + 1 + warp; I < nrows; I += kWarps) {
-        const double* li = M + (size_t)bidx<RECT>(I, K, nb1) * 64;
-        double* b0 = M + (size_t)bidx<RECT>(I, K + 1, nb1) * 64;
-        double2 acc = {0.0, 0.0}, cv = ld_c(b0, g, t);
-        dmma(acc, ld_ab(li, g, t, 0), kb0);
-        dmma(acc, ld_ab(li, g, t, 1), kb1);
+      FPROF(2);
+      bar_arrive_named(2);
+      if (K + 1 < ncols) {
+        const double* rk = M + (size_t)bidx<RECT>(K + 1, K, nb1) * 64;
+        double* dn = M + (size_t)bidx<RECT>(K + 1, K + 1, nb1) * 64;
+        const double x0 = ld_ab(rk, g, t, 0), x1 = ld_ab(rk, g, t, 1);
+        double2 acc = {0.0, 0.0}, cv = ld_c(dn, g, t);
+        dmma(acc, x0, x0);
+        dmma(acc, x1, x1);
         cv.x -= acc.x; cv.y -= acc.y;
-        st_c(b0, g, t, cv);
+        st_c(dn, g, t, cv);
+        __syncwarp();
       }
-      // no barrier: warp 0 wrote the next diagonal block itself, and step 1 of the next column only
-      // reads block columns <= K (complete) and writes block column K+2
+      FPROF(3);
+    } else {
+      const int bw = warp - 1;
+      // warps 4, 8, 12 share warp 0's SM sub-partition and its FP64 pipe: they sit out the tensor-core
+      // bulk so that the diagonal-block chain is not queued behind 16-cycle DMMA issues
+      if (K > 0 && K + 1 < ncols && (warp & 3) != 0) {
+        const int bw12 = (warp >> 2) * 3 + (warp & 3) - 1;
+        for (int I = K + 1 + 2 * bw12; I < nrows; I += 2 * (kWarps - kWarps / 4)) {
+          const bool two = I + 1 < nrows;
+          double2 s0, s1;
+          syrk_pair<RECT>(M, nb1, I, I + 1, two, K + 1, K, g, t, s0, s1);
+          double* b0 = M + (size_t)bidx<RECT>(I, K + 1, nb1) * 64;
+          double2 cv = ld_c(b0, g, t);
+          cv.x -= s0.x; cv.y -= s0.y;
+          st_c(b0, g, t, cv);
+          if (two) {
+            double* b1 = M + (size_t)bidx<RECT>(I + 1, K + 1, nb1) * 64;
+            double2 cw = ld_c(b1, g, t);
+            cw.x -= s1.x; cw.y -= s1.y;
+            st_c(b1, g, t, cw);
+          }
+        }
+      }
+      FPROF(0);
+      bar_sync_named(1);
+      FPROF(1);
+      if (K + 2 + bw < nrows) {
+        double a[36];
+        load_diag(M + (size_t)bidx<RECT>(K, K, nb1) * 64, a);
+        for (int I = K + 2 + bw; I < nrows; I += kBulk) {
+          double* b0 = M + (size_t)bidx<RECT>(I, K, nb1) * 64;
+          double2 v = ld_c(b0, g, t);
+          trsm8_frag(v, a, t);
+          st_c(b0, g, t, v);
+        }
+      }
+      FPROF(2);
+      bar_sync_named(2);
+      FPROF(3);
+      if (K + 1 < ncols && K + 2 + bw < nrows) {
+        const double* rk = M + (size_t)bidx<RECT>(K + 1, K, nb1) * 64;
+        const double kb0 = ld_ab(rk, g, t, 0), kb1 = ld_ab(rk, g, t, 1);
+        for (int I = K + 2 + bw; I < nrows; I += kBulk) {
+          const double* li = M + (size_t)bidx<RECT>(I, K, nb1) * 64;
+          double* b0 = M + (size_t)bidx<RECT>(I, K + 1, nb1) * 64;
+          double2 acc = {0.0, 0.0}, cv = ld_c(b0, g, t);
+          dmma(acc, ld_ab(li, g, t, 0), kb0);
+          dmma(acc, ld_ab(li, g, t, 1), kb1);
+          cv.x -= acc.x; cv.y -= acc.y;
+          st_c(b0, g, t, cv);
+        }
+      }
+      FPROF(4);
     }
-    FPROF(4);
   }
   __syncthreads();
 }
@@ -1278,6 +1352,7 @@ extern "C" int ddqc_ddmpc_debug_phase_buffer(void* dev_ptr) {
 #ifdef DDQC_PROF_FACTOR
   cudaMemcpyToSymbol(g_fprof, &g_phase_clk, sizeof(void*));
 #endif
+
   return 0;
 }
 

@@ -120,13 +120,14 @@ __global__ void __launch_bounds__(512, 1) k_test(double* out, long long* cyc, in
       if (mode == 34) chol8_var<2>(sm + (it & 7) * 64, lane);
       if (mode == 35) chol8_var<3>(sm + (it & 7) * 64, lane);
       if (mode == 8) { chol8_redundant(sm + (it & 7) * 64, lane); }
+      if (mode == 9 || mode == 13) { double aa[36]; chol8_regs(sm + (it & 7) * 64, aa); acc_out += aa[35]; }
       if (mode == 16) { chol8_redundant_fast(sm + (it & 7) * 64, lane); }
       if (mode == 2 || mode == 6) { double a[36]; load_diag(sm + (it & 7) * 64, a); double2 v = ld_c(sm + 512 + (it & 7) * 64, g, t); trsm8_frag(v, a, t); st_c(sm + 512 + (it & 7) * 64, g, t, v); }
       // restore a positive diagonal so that repeated factorisation stays finite
       if (lane < 8) sm[(it & 7) * 64 + eoff(lane, lane)] = 10.0 + lane;
       __syncwarp();
     }
-  } else if (mode == 5 || mode == 6) {
+  } else if (mode == 5 || mode == 6 || (mode == 13 && (warp & 3) != 0)) {
     double2 s0 = {0, 0}, s1 = {0, 0};
     for (int it = 0; it < iters * 4; ++it) {
       double2 a, b;
@@ -144,9 +145,9 @@ int main() {
   double* out; long long* cyc; cudaMalloc(&out, 8192); cudaMalloc(&cyc, 8);
   cudaFuncSetAttribute(k_test, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 64 * 8);
   const int iters = 2000; long long h;
-  for (int mode : {99, 35, 33, 34, 1, 8, 2}) {
+  for (int mode : {99, 1, 9, 13, 2}) {
     k_test<<<1, 512, 64 * 64 * 8>>>(out, cyc, mode, iters);
     cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
-    printf("mode %2d (1 chol8; 32 same copy; 33 no rsqrt; 34 no shuffles; 35 neither; 2 trsm) %.0f cycles/call   (%s)\n", mode, (double)h / iters, cudaGetErrorString(cudaGetLastError()));
+    printf("mode %2d (99 empty; 1 chol8 shuffle; 9 chol8 registers; 13 registers + DMMA on the other 3 sub-partitions; 2 trsm) %.0f cycles/call   (%s)\n", mode, (double)h / iters, cudaGetErrorString(cudaGetLastError()));
   }
 }
