@@ -40,10 +40,20 @@ def _setup(B, n_mpc_step=1, seed=3):
     env.update_target_pos(torch.arange(B, device=dev), hover)
     trk = create_drone_tracking_controller(env)
     hover_at_target(env, trk, hover, yaw, min_at_target_steps=10, error_threshold=5e-2, max_steps=300)
-    gen = torch.Generator(device=dev).manual_seed(seed)
+    u_range = np.array([[-0.1, 0.1], [-0.5, 0.5], [-0.5, 0.5]])
     u_N, y_N = collect_initial_input_output_data_batched(
-        env, trk, hover, yaw, torch.tensor(prm.U), torch.tensor([[-0.1, 0.1], [-0.5, 0.5], [-0.5, 0.5]]), prm.N, gen
+        env, trk, hover, yaw, torch.tensor(prm.U), torch.tensor(u_range), prm.N,
+        np_randoms=[np.random.default_rng(seed + b) for b in range(B)],  # the reference's numpy stream, one per env
     )
+    # excitation = the reference's draws; applied input = clip(stabilising command (fp32) + excitation, U)
+    for b in range(B):
+        rng = np.random.default_rng(seed + b)
+        pe = np.hstack([rng.uniform(u_range[i, 0], u_range[i, 1], (prm.N, 1)) for i in range(3)])
+        u_b = u_N[b].cpu().numpy()
+        assert (u_b >= prm.U[:, 0] - 1e-15).all() and (u_b <= prm.U[:, 1] + 1e-15).all()
+        inside = (u_b > prm.U[:, 0]) & (u_b < prm.U[:, 1])
+        cmd = (u_b - pe)[inside]
+        assert np.abs(cmd - cmd.astype(np.float32)).max() < 1e-9  # what is left is the fp32 controller command
     y_r = np.tile(np.array([[0.3, 0.2, 1.8]]), (B, 1)) + 0.05 * np.arange(B)[:, None]
     kw = mo.ctor_kwargs(prm, u_N[0].cpu().numpy(), y_N[0].cpu().numpy(), y_r[0])
     kw.update(u=u_N, y=y_N, y_r=y_r, n_mpc_step=n_mpc_step)

@@ -215,3 +215,20 @@ def test_closed_loop_oracle_rmse_and_early_stop():
     ys = iter([np.array([0.0, 0.0]), np.array([-1.0, 0.0])])
     with pytest.raises(eo.MovedAway):
         eo.sim_control_loop(Mock(), lambda u: next(ys), 4, 1.0, 0.5)
+
+
+def test_persistently_exciting_inputs_follow_the_reference_numpy_stream():
+    """Same numpy calls in the same order as drone_initial_data_collection.py:117-127 of the reference, so the
+    excitation and the generator state afterwards are identical to a single-env reference collection."""
+    from data_driven_quad_control_b200.data_driven_mpc.utilities.drone_initial_data_collection import (
+        persistently_exciting_inputs,
+    )
+
+    u_range = np.array([[-0.1, 0.1], [-0.5, 0.5], [-0.5, 0.5]])
+    N, m, p, eps_max = 50, 3, 3, 0.002
+    pe, w = persistently_exciting_inputs([np.random.default_rng(s) for s in (0, 7)], u_range, N, m, p, eps_max)
+    for b, seed in enumerate((0, 7)):
+        rng = np.random.default_rng(seed)
+        u_ref = np.hstack([rng.uniform(u_range[i, 0], u_range[i, 1], (N, 1)) for i in range(m)])  # reference :117-122
+        w_ref = eps_max * rng.uniform(-1.0, 1.0, (N, p))  # reference :125-127
+        assert np.array_equal(pe[b], u_ref) and np.array_equal(w[b], w_ref)
