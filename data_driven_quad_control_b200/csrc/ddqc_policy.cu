@@ -19,7 +19,7 @@
 //   3. every thread reads its TMEM lane (tcgen05.ld 32x32b.x32), adds the bias, applies tanh, splits
 //      to bf16 hi/lo and writes the layer-2 operand tile;
 //   4. D2 = A2 W2^T (8 K-steps x 3 products), same commit / wait;
-//   5. bias + tanh, then the A-wide output layer (A <= 8, 384 FMAs per env) on the CUDA cores
+//   5. bias + tanh, then the A-wide output layer (A <= 4, 384 FMAs per env) on the CUDA cores
 //      straight from the registers; 12-byte action rows are stored coalesced.
 // The hi/lo split (two bf16 = 16 mantissa bits per operand, cross term lo*lo dropped, ~1e-5 relative
 // per product) keeps the actions within 1e-4 of an fp32 forward (measured 3.2e-5 on the demo
@@ -33,16 +33,17 @@
 
 namespace {
 
-constexpr int kIn = 16, kHid = 128, kMaxOut = 8, kTileM = 128;
-constexpr int kWgThreads = 128, kThreads = 2 * kWgThreads;
+constexpr int kIn = 16, kHid = 128, kMaxOut = 4, kTileM = 128;
+constexpr int kWgThreads = 256, kThreads = 2 * kWgThreads;  // per warpgroup: 2 threads per env row (one per column half)
 
 // shared-memory map (bytes)
 constexpr uint32_t kW2Hi = 0, kW2Lo = 32768, kW1Hi = 65536, kW1Lo = 69632;
 constexpr uint32_t kWgBase = 73728, kWgStride = 73728;  // per warpgroup: A2 hi | A2 lo | A1 hi | A1 lo
 constexpr uint32_t kA2Hi = 0, kA2Lo = 32768, kA1Hi = 65536, kA1Lo = 69632;
-constexpr uint32_t kParams = kWgBase + 2 * kWgStride;   // fp32: W3 [8][128] | b1 | b2 | b3
+constexpr uint32_t kParams = kWgBase + 2 * kWgStride;   // fp32: W3 [4][128] | b1 | b2 | b3 | output partials 2 x [128][4]
 constexpr uint32_t kW3 = kParams, kB1 = kW3 + kMaxOut * kHid * 4, kB2 = kB1 + kHid * 4, kB3 = kB2 + kHid * 4;
-constexpr uint32_t kBar = kB3 + 64;                     // 2 mbarriers (8 B each) + TMEM base pointer
+constexpr uint32_t kPart = kB3 + 64, kPartStride = kTileM * kMaxOut * 4;
+constexpr uint32_t kBar = kPart + 2 * kPartStride;      // 2 mbarriers (8 B each) + TMEM base pointer
 constexpr uint32_t kSmemBytes = kBar + 32;
 
 // K-major, no swizzle: element (r, k) of an [rows x K] bf16 operand; core matrix = 8 rows x 16 bytes
@@ -105,26 +106,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// x = hi + lo with hi, lo bf16 (16 mantissa bits together)
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+// x = hi + lo with hi, lo bf16 (16 mantissa bits together); two values per conversion instruction
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);  // .x = a in the low half
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // 8 consecutive K elements -> one 16-byte chunk of the hi operand and one of the lo operand
 __device__ __forceinline__ void store_chunk(uint8_t* smem, uint32_t off_hi, uint32_t off_lo, const float (&x)[8]) {
-  __nv_bfloat16 h[8], l[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) split_bf16(x[i], h[i], l[i]);
-  *reinterpret_cast<uint4*>(smem + off_hi) = *reinterpret_cast<const uint4*>(h);
-  *reinterpret_cast<uint4*>(smem + off_lo) = *reinterpret_cast<const uint4*>(l);
+  uint4 h, l;
+  split_pair(x[0], x[1], h.x, l.x);
+  split_pair(x[2], x[3], h.y, l.y);
+  split_pair(x[4], x[5], h.z, l.z);
+  split_pair(x[6], x[7], h.w, l.w);
+  *reinterpret_cast<uint4*>(smem + off_hi) = h;
+  *reinterpret_cast<uint4*>(smem + off_lo) = l;
 }
 
-// tanh(x) = (e - 1) / (e + 1), e = exp(2x); absolute error ~1e-7 (ex2.approx + approximate division)
+// tanh(x) = 1 - 2 / (1 + exp(2x)): ex2.approx + rcp.approx, absolute error ~1e-7; saturates cleanly
+// (exp -> inf gives 1, exp -> 0 gives -1), so no clamp is needed
 __device__ __forceinline__ float tanh_acc(float x) {
-  const float xc = fminf(fmaxf(x, -15.0f), 15.0f);
-  const float e = __expf(2.0f * xc);
-  return __fdividef(e - 1.0f, e + 1.0f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return fmaf(-2.0f, r, 1.0f);
 }
 
 template <bool SPLIT>
@@ -134,7 +142,8 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
                   const float* __restrict__ W3, const float* __restrict__ b3, const int n_out,
                   float* __restrict__ actions) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, wg = tid >> 7, wtid = tid & 127, warp = tid >> 5;
+  const int tid = threadIdx.x, wg = tid >> 8, wtid = tid & 255, warp = tid >> 5;
+  const int row = wtid & 127, half = wtid >> 7;  // env row of the tile / column half this thread owns
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kBar + 16);
 
@@ -180,33 +189,26 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t d1 = tmem_base + wg * 256, d2 = d1 + 128;          // accumulator columns of this warpgroup
-  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;     // this warp's 32-lane slice of TMEM
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;     // this warp's 32-lane slice of TMEM (= row / 32)
   const uint32_t mbar = sbase + kBar + 8 * wg;
   uint8_t* wgs = smem + kWgBase + wg * kWgStride;
   const uint32_t wga = sbase + kWgBase + wg * kWgStride;
+  float* part = reinterpret_cast<float*>(smem + kPart + wg * kPartStride);
   uint32_t phase = 0;
 
   const long long n_tiles = (n + kTileM - 1) / kTileM;
   for (long long tile = (long long)blockIdx.x * 2 + wg; tile < n_tiles; tile += (long long)gridDim.x * 2) {
-    const long long row = tile * kTileM + wtid;
-    const bool valid = row < n;
-    // ---- 1. observation row -> layer-1 operand tile ----
+    const long long grow = tile * kTileM + row;
+    const bool valid = grow < n;
+    // ---- 1. observation row -> layer-1 operand tile (each thread one 8-element K chunk) ----
     {
-      float x[16];
-      const float4* src = reinterpret_cast<const float4*>(obs + (valid ? row : 0) * kIn);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 v = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
-      }
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float y[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = x[8 * c + i];
-        const uint32_t off = core_off(wtid, 8 * c, kIn / 8);
-        store_chunk(wgs, kA1Hi + off, kA1Lo + off, y);
-      }
+      float y[8];
+      const float4* src = reinterpret_cast<const float4*>(obs + (valid ? grow : 0) * kIn + 8 * half);
+      const float4 v0 = valid ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 v1 = valid ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      y[0] = v0.x; y[1] = v0.y; y[2] = v0.z; y[3] = v0.w; y[4] = v1.x; y[5] = v1.y; y[6] = v1.z; y[7] = v1.w;
+      const uint32_t off = core_off(row, 8 * half, kIn / 8);
+      store_chunk(wgs, kA1Hi + off, kA1Lo + off, y);
     }
     fence_async_smem();
     tc_fence_before();
@@ -226,17 +228,21 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
     mbar_wait(mbar, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- 3. h1 = tanh(D1 + b1) -> layer-2 operand tile ----
+    // ---- 3. h1 = tanh(D1 + b1) -> layer-2 operand tile (this thread: 64 of the row's 128 columns) ----
 #pragma unroll 1
-    for (int cb = 0; cb < 4; ++cb) {
+    for (int cb = 0; cb < 2; ++cb) {
+      const int c0 = half * 64 + cb * 32;
       float v[32];
-      tmem_ld32(d1 + lane_addr + cb * 32, v);
+      tmem_ld32(d1 + lane_addr + c0, v);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
+        const float4 ba = *reinterpret_cast<const float4*>(sB1 + c0 + 8 * c), bb = *reinterpret_cast<const float4*>(sB1 + c0 + 8 * c + 4);
         float y[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = tanh_acc(v[8 * c + i] + sB1[cb * 32 + 8 * c + i]);
-        const uint32_t off = core_off(wtid, cb * 32 + 8 * c, kHid / 8);
+        y[0] = tanh_acc(v[8 * c] + ba.x); y[1] = tanh_acc(v[8 * c + 1] + ba.y);
+        y[2] = tanh_acc(v[8 * c + 2] + ba.z); y[3] = tanh_acc(v[8 * c + 3] + ba.w);
+        y[4] = tanh_acc(v[8 * c + 4] + bb.x); y[5] = tanh_acc(v[8 * c + 5] + bb.y);
+        y[6] = tanh_acc(v[8 * c + 6] + bb.z); y[7] = tanh_acc(v[8 * c + 7] + bb.w);
+        const uint32_t off = core_off(row, c0 + 8 * c, kHid / 8);
         store_chunk(wgs, kA2Hi + off, kA2Lo + off, y);
       }
     }
@@ -262,20 +268,27 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
     mbar_wait(mbar, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- 5. h2 = tanh(D2 + b2); action = h2 W3^T + b3 on the CUDA cores ----
+    // ---- 5. h2 = tanh(D2 + b2); action = h2 W3^T + b3 on the CUDA cores (partial over this column half) ----
     float out[kMaxOut];
 #pragma unroll
     for (int j = 0; j < kMaxOut; ++j) out[j] = 0.0f;
 #pragma unroll 1
-    for (int cb = 0; cb < 4; ++cb) {
+    for (int cb = 0; cb < 2; ++cb) {
+      const int c0 = half * 64 + cb * 32;
       float v[32];
-      tmem_ld32(d2 + lane_addr + cb * 32, v);
+      tmem_ld32(d2 + lane_addr + c0, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = tanh_acc(v[i] + sB2[cb * 32 + i]);
+      for (int q = 0; q < 8; ++q) {
+        const float4 bq = *reinterpret_cast<const float4*>(sB2 + c0 + 4 * q);
+        v[4 * q] = tanh_acc(v[4 * q] + bq.x);
+        v[4 * q + 1] = tanh_acc(v[4 * q + 1] + bq.y);
+        v[4 * q + 2] = tanh_acc(v[4 * q + 2] + bq.z);
+        v[4 * q + 3] = tanh_acc(v[4 * q + 3] + bq.w);
+      }
 #pragma unroll
       for (int j = 0; j < kMaxOut; ++j) {
         if (j < n_out) {  // uniform
-          const float4* w = reinterpret_cast<const float4*>(sW3 + j * kHid + cb * 32);
+          const float4* w = reinterpret_cast<const float4*>(sW3 + j * kHid + c0);
           float acc = out[j];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -289,12 +302,16 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
         }
       }
     }
-    if (valid) {
+    tc_fence_before();  // the TMEM reads above are ordered before the next tile's MMAs (via the next wg_sync)
+    if (half == 1) *reinterpret_cast<float4*>(part + row * kMaxOut) = make_float4(out[0], out[1], out[2], out[3]);
+    wg_sync(wg);
+    if (half == 0 && valid) {
+      const float4 o = *reinterpret_cast<const float4*>(part + row * kMaxOut);
+      const float po[kMaxOut] = {o.x, o.y, o.z, o.w};
 #pragma unroll
       for (int j = 0; j < kMaxOut; ++j)
-        if (j < n_out) actions[row * n_out + j] = out[j] + sB3[j];
+        if (j < n_out) actions[grow * n_out + j] = (out[j] + po[j]) + sB3[j];
     }
-    tc_fence_before();  // the TMEM reads above are ordered before the next tile's MMAs (via the next wg_sync)
   }
 
   tc_fence_before();

@@ -32,8 +32,8 @@ class FusedActorMLP:
         self.num_obs, self.hidden, self.num_actions = self.W1.shape[1], self.W1.shape[0], self.W3.shape[0]
         if self.W2.shape != (self.hidden, self.hidden) or self.W3.shape[1] != self.hidden:
             raise ValueError("inconsistent actor weight shapes")
-        if (self.num_obs, self.hidden) != (16, 128) or not 1 <= self.num_actions <= 8:
-            raise NotImplementedError("the fused kernel supports the shipped actor shape 16 -> 128 -> 128 -> A (A <= 8) only")
+        if (self.num_obs, self.hidden) != (16, 128) or not 1 <= self.num_actions <= 4:
+            raise NotImplementedError("the fused kernel supports the shipped actor shape 16 -> 128 -> 128 -> A (A <= 4) only")
         self._out: torch.Tensor | None = None
 
     @classmethod

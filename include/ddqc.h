@@ -314,7 +314,7 @@ int ddqc_ddmpc_debug_phase_buffer(void* dev_ptr);
  * models/demo_ctbr_fixed_yaw/model_1500.pt: actor.{0,2,4}.{weight,bias}).  Weights are PyTorch
  * Linear weights, [out][in] row-major fp32; obs [n][16] row-major fp32 (16-byte aligned); actions
  * [n][n_out] fp32.  precision 0: bf16 hi/lo split products (within 1e-4 of the fp32 forward); 1: single bf16
- * product.  Only n_in = 16, n_hidden = 128, n_out <= 8 is supported (DDQC_E_SHAPE otherwise).
+ * product.  Only n_in = 16, n_hidden = 128, n_out <= 4 is supported (DDQC_E_SHAPE otherwise).
  * --------------------------------------------------------------------------------- */
 int ddqc_policy_mlp_forward(const float* obs, int64_t n, int32_t n_in, int32_t n_hidden, int32_t n_out,
                             const float* W1, const float* b1, const float* W2, const float* b2,
