@@ -88,13 +88,19 @@ __host__ __device__ inline Dims make_dims(const DdqcMpcConfig& c) {
 // extra shared-memory doubles behind the matrix region
 __host__ __device__ inline int extra_doubles(const Dims& d) { return 8 * d.nbt + d.n2p + 2 * (d.nS + 22) + 64; }
 
+// S7 (dense, nS x ldS) and the block-packed factor of the free block (up to nx variables) share one area
+__host__ __device__ inline int qp_scratch_doubles(const Dims& d) {
+  const int nbq = (d.nx + 7) >> 3, fblk = nbq * (nbq + 1) / 2 * 64, s7 = d.nS * d.ldS;
+  return ((fblk > s7 ? fblk : s7) + 1) & ~1;
+}
+
 __host__ __device__ inline int region_doubles(const Dims& d) {
   int r = d.gs;
   if (d.ga > r) r = d.ga;
   const int win = (d.m + d.p) * d.N + d.ell * (d.m + d.p) * 8 * ((d.m + d.p + 8) / 8);
   if (win > r) r = win;
-  // box-QP stage: S7 | Hq | 20 vectors ; the factor scratch aliases S7
-  const int qp = d.nS * d.ldS + d.nx * d.ldq + 20 * kMaxNx;
+  // box-QP stage: S7 | Hq | 20 vectors ; the block-packed factor scratch aliases S7
+  const int qp = qp_scratch_doubles(d) + d.nx * d.ldq + 20 * kMaxNx;
   if (qp > r) r = qp;
   return (r + 1) & ~1;  // keep everything behind the region 16-byte aligned
 }
@@ -806,7 +812,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
                    const double* __restrict__ u_win, const double* __restrict__ y_win,
                    const double* __restrict__ y_r, const double* __restrict__ us_prev,
                    const double* __restrict__ ys_prev, const int32_t* __restrict__ have_prev,
-                   int8_t* __restrict__ act_state, double* __restrict__ u_opt, double* __restrict__ us_opt,
+                   const double* __restrict__ lamb, int8_t* __restrict__ act_state, double* __restrict__ u_opt, double* __restrict__ us_opt,
                    double* __restrict__ ys_opt, int32_t* __restrict__ status, int32_t* __restrict__ iters,
                    const int batch, long long* __restrict__ phase_clk) {
   extern __shared__ __align__(16) double smem[];
@@ -855,6 +861,9 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     if (b >= batch) break;
     t_prev = clock64();
     const bool use_sr = (cfg.alpha_reg_type == 0) && have_prev[b] != 0;
+    // regularisation weights: per controller when `lamb` is given (grid search over lambda), else from the config
+    const double lam_a = lamb ? lamb[4 * (size_t)b] : cfg.lamb_alpha, lam_s = lamb ? lamb[4 * (size_t)b + 1] : cfg.lamb_sigma;
+    const double lam_as = lamb ? lamb[4 * (size_t)b + 2] : cfg.lamb_alpha_s, lam_ss = lamb ? lamb[4 * (size_t)b + 3] : cfg.lamb_sigma_s;
     const double* ub = u_win + (size_t)b * N * m;
     const double* yb = y_win + (size_t)b * N * p;
 
@@ -1041,7 +1050,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     const int aug_t = nsig, aug_b = nsig + 1;                 // aug indices of tau and b_s
     const int Paug = d.n2p + d.n3p;                           // trailing position of the first aug row
     if (use_sr) {
-      const double ds = cfg.lamb_alpha_s / cfg.lamb_sigma_s;
+      const double ds = lam_as / lam_ss;
       {
         const double2* src = reinterpret_cast<const double2*>(GS);
         double2* dst = reinterpret_cast<double2*>(sM);
@@ -1072,8 +1081,8 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     __syncthreads();
     for (int q = tid; q < d.n2; q += kThreads) {
       const int j = q / p, comp = q % p;
-      const double w = (j < n || j >= L) ? cfg.lamb_sigma : cfg.Q[comp] * cfg.lamb_sigma / (cfg.Q[comp] + cfg.lamb_sigma);
-      *elem_tri(sM, q, q) += cfg.lamb_alpha / w;
+      const double w = (j < n || j >= L) ? lam_s : cfg.Q[comp] * lam_s / (cfg.Q[comp] + lam_s);
+      *elem_tri(sM, q, q) += lam_a / w;
     }
     if (use_sr) {
       for (int q = tid; q < 8 * ncol_all; q += kThreads) {
@@ -1115,7 +1124,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     DDQC_PHASE(6);
 
     // ---- box QP assembly: Hq = 2 lamb_alpha Z + structure, f ----------------------------------------
-    double* Hq = sM + nS * ldS;
+    double* Hq = sM + qp_scratch_doubles(d);
     double* qv = Hq + nx * ldq;  // 20 vectors of kMaxNx
     QpWork q;
     q.Hq = Hq; q.ldq = ldq; q.nx = nx;
@@ -1126,7 +1135,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     q.dzu = qv + 13 * kMaxNx; q.rd = qv + 14 * kMaxNx; q.dg = qv + 15 * kMaxNx;
     q.s_red = s_red; q.state = s_state; q.idx = s_idx; q.verdict = s_verdict; q.s_flag = &s_flag;
     {
-      const double la2 = 2.0 * cfg.lamb_alpha;
+      const double la2 = 2.0 * lam_a;
       for (int e = tid; e < nS * nx; e += kThreads) {
         const int i = e / nx, k = e % nx;  // i in [0, nS), k in [0, nx)
         if (k > i) continue;
@@ -1365,7 +1374,8 @@ extern "C" int64_t ddqc_ddmpc_workspace_bytes(const DdqcMpcConfig* cfg, int64_t 
 
 extern "C" int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg, void* ws, const double* u_win, const double* y_win,
                                 const double* y_r, const double* us_prev, const double* ys_prev,
-                                const int32_t* have_prev, int8_t* act_state, double* u_opt, double* us_opt,
+                                const int32_t* have_prev, const double* lamb, int8_t* act_state, double* u_opt,
+                                double* us_opt,
                                 double* ys_opt, int32_t* status, int32_t* iters, int64_t batch, void* stream) {
   int rc = check_cfg(cfg);
   if (rc) return rc;
@@ -1389,8 +1399,8 @@ extern "C" int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg, void* ws, const double
   if (e != cudaSuccess) return (int)e;
   double* slots = reinterpret_cast<double*>(static_cast<char*>(ws) + 256);
   ddmpc_solve_kernel<<<grid, kThreads, smem, st>>>(*cfg, slots, static_cast<int*>(ws), u_win, y_win, y_r, us_prev,
-                                                   ys_prev, have_prev, act_state, u_opt, us_opt, ys_opt, status, iters,
-                                                   (int)batch, g_phase_clk);
+                                                   ys_prev, have_prev, lamb, act_state, u_opt, us_opt, ys_opt, status,
+                                                   iters, (int)batch, g_phase_clk);
   return (int)cudaGetLastError();
 }
 

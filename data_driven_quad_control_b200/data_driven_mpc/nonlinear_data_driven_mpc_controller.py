@@ -122,9 +122,21 @@ class BatchedNonlinearDataDrivenMPC:
             cfg.R[i] = rw[i]
             cfg.U_lo[i], cfg.U_hi[i] = U[i]
             cfg.Us_lo[i], cfg.Us_hi[i] = Us[i]
-        cfg.lamb_alpha, cfg.lamb_sigma = float(lamb_alpha), float(lamb_sigma)
-        cfg.lamb_alpha_s = float(lamb_alpha_s) if lamb_alpha_s is not None else 1.0
-        cfg.lamb_sigma_s = float(lamb_sigma_s) if lamb_sigma_s is not None else 1.0
+        # regularisation weights: scalars (one value for the batch) or (B,) arrays (one per controller)
+        lam = [lamb_alpha, lamb_sigma, 1.0 if lamb_alpha_s is None else lamb_alpha_s, 1.0 if lamb_sigma_s is None else lamb_sigma_s]
+        per_ctrl = any(np.ndim(v) > 0 or torch.is_tensor(v) for v in lam)
+        if per_ctrl:
+            cols = [torch.as_tensor(np.asarray(v.cpu()) if torch.is_tensor(v) else np.asarray(v), dtype=torch.float64).reshape(-1) for v in lam]
+            cols = [c.expand(self.B) if c.numel() == 1 else c for c in cols]
+            if any(c.numel() != self.B for c in cols):
+                raise ValueError("per-controller regularisation weights must have one entry per controller")
+            self._lamb = torch.stack(cols, dim=1).to(dev).contiguous()
+            if not bool((self._lamb > 0).all()):
+                raise ValueError("regularisation weights must be positive")
+            lam = [float(c[0]) for c in cols]
+        else:
+            self._lamb = None
+        cfg.lamb_alpha, cfg.lamb_sigma, cfg.lamb_alpha_s, cfg.lamb_sigma_s = (float(v) for v in lam)
         self._cfg = cfg
         ws_bytes = self._lib.ddqc_ddmpc_workspace_bytes(C.byref(cfg), self.B)
         if ws_bytes < 0:
@@ -162,7 +174,7 @@ class BatchedNonlinearDataDrivenMPC:
         rc = self._lib.ddqc_ddmpc_solve(
             C.byref(self._cfg), self._ws.data_ptr(), self.u.data_ptr(), self.y.data_ptr(), self.y_r.data_ptr(),
             self._us_prev.data_ptr(), self._ys_prev.data_ptr(), self._have_prev.data_ptr(),
-            self._act_state.data_ptr() if self._act_state is not None else None, self.optimal_u.data_ptr(), self.us.data_ptr(), self.ys.data_ptr(), self.status.data_ptr(),
+            self._lamb.data_ptr() if self._lamb is not None else None, self._act_state.data_ptr() if self._act_state is not None else None, self.optimal_u.data_ptr(), self.us.data_ptr(), self.ys.data_ptr(), self.status.data_ptr(),
             self.iters.data_ptr(), self.B, _lib.stream_ptr(self.device),
         )  # fmt: skip
         _lib.check(rc, "ddqc_ddmpc_solve")

@@ -21,6 +21,13 @@ def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def rank_world() -> tuple[int, int]:
+    """(rank, world size) of the current process group; (0, 1) without one."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 def shard_round_robin(n_total: int, rank: int, world: int) -> list[int]:
     """Indices owned by `rank` under round-robin assignment (used for grid-search combinations,
     whose cost depends on the (n, L) shape bucket, to balance the buckets over ranks)."""

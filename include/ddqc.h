@@ -267,6 +267,9 @@ int64_t ddqc_ddmpc_workspace_bytes(const DdqcMpcConfig* cfg_host, int64_t batch)
  *  y_r   [B][p]                      : output setpoints
  *  us_prev, ys_prev [B][m],[B][p]    : previous optimal equilibrium (alpha_reg_type 0);
  *  have_prev [B] int32               : 0 -> alpha_sr = 0 and cold active set (first solve)
+ *  lamb [B][4] (or NULL)            : per-controller (lamb_alpha, lamb_sigma, lamb_alpha_s, lamb_sigma_s)
+ *                                      overriding the config values (grid search over the regularisation
+ *                                      weights, configs/data_driven_mpc/dd_mpc_grid_search_params.yaml:92-111)
  *  act_state [B][nx] int8 (or NULL)  : active set of the box QP (-1 lower, 0 free, +1 upper),
  *                                      nx = (L-n) m + m + p; read as the warm start (shifted one
  *                                      step) when have_prev != 0, always written
@@ -277,7 +280,8 @@ int64_t ddqc_ddmpc_workspace_bytes(const DdqcMpcConfig* cfg_host, int64_t batch)
  *  ws: ddqc_ddmpc_workspace_bytes() bytes, 256-byte aligned; its first 256 bytes are the work counter */
 int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg_host, void* ws, const double* u_win,
                      const double* y_win, const double* y_r, const double* us_prev,
-                     const double* ys_prev, const int32_t* have_prev, int8_t* act_state,
+                     const double* ys_prev, const int32_t* have_prev, const double* lamb,
+                     int8_t* act_state,
                      double* u_opt, double* us_opt, double* ys_opt, int32_t* status, int32_t* iters,
                      int64_t batch, void* stream);
 

@@ -191,3 +191,25 @@ def test_warm_start_does_not_change_the_solution(build_lib):
         for c in (warm, cold):
             c.store_input_output_measurement(torch.from_numpy(u0).cuda(), torch.from_numpy(y_new).cuda())
     assert int(warm.pivoting_passes.max()) <= int(cold.pivoting_passes.max()) + 2
+
+
+@pytest.mark.parametrize("n,L,N", [(2, 6, 80), (2, 7, 90), (3, 6, 100), (3, 9, 130), (4, 10, 160)])
+def test_other_problem_shapes_match_oracle(build_lib, n, L, N):
+    """Shapes with different paddings of the row classes (R2 / R3 not multiples of 8, C a multiple of 8, odd l, a
+    box-QP factor larger than the dense Schur copy): the grid search sweeps n and L."""
+    import ddmpc_oracle as mo
+
+    prm = mo.default_params()
+    prm.n, prm.L, prm.N, prm.alpha_reg_type = n, L, N, 0
+    u, y = _synthetic_windows(prm, 3, 2)
+    y_r = np.tile(np.array([[0.3, -0.2, 0.5]]), (2, 1))
+    gpu = _batched(prm, u, y, y_r, solve_on_init=False)
+    orcs = [mo.NonlinearDDMPCOracle(**mo.ctor_kwargs(prm, u[b], y[b], y_r[b]), solve_on_init=False) for b in range(2)]
+    for t in range(2):
+        gpu.update_and_solve_data_driven_mpc()
+        assert (gpu.status.cpu().numpy() == 0).all()
+        for b, orc in enumerate(orcs):
+            orc.update_and_solve_data_driven_mpc()
+            np.testing.assert_allclose(gpu.optimal_u[b].cpu().numpy(), orc.optimal_u, rtol=0, atol=TOL)
+            orc.store_input_output_measurement(orc.optimal_u[0], y[b, -1])
+        gpu.store_input_output_measurement(torch.from_numpy(np.stack([o.u[-1] for o in orcs])).cuda(), torch.from_numpy(y[:, -1].copy()).cuda())

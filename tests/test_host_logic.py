@@ -232,3 +232,27 @@ def test_persistently_exciting_inputs_follow_the_reference_numpy_stream():
         u_ref = np.hstack([rng.uniform(u_range[i, 0], u_range[i, 1], (N, 1)) for i in range(m)])  # reference :117-122
         w_ref = eps_max * rng.uniform(-1.0, 1.0, (N, p))  # reference :125-127
         assert np.array_equal(pe[b], u_ref) and np.array_equal(w[b], w_ref)
+
+
+def test_grid_search_bookkeeping_follows_the_reference_worker():
+    """aggregate_combination == the sequential bookkeeping of parallel_worker.py:117-210 + controller_evaluation.py:
+    120-228 (entries in order, setpoints in order, stop at the first failure, nanmean of per-entry means)."""
+    from data_driven_quad_control_b200.data_driven_mpc.utilities.param_grid_search.batched_grid_search import aggregate_combination
+    from data_driven_quad_control_b200.data_driven_mpc.utilities.param_grid_search.param_grid_search_config import (
+        CtrlEvalStatus, DDMPCCombinationParams, DDMPCParameterGrid, combinations_from_grid,
+    )  # fmt: skip
+
+    comb = DDMPCCombinationParams(350, 6, 35, 50.0, 1e9, 1.0, 1e7)
+    rmse = np.array([[0.2, 0.4, 0.6], [0.1, 0.3, 0.5]])
+    status, res = aggregate_combination(comb, rmse, np.zeros((2, 3), bool))
+    assert status == CtrlEvalStatus.SUCCESS and list(res)[:7] == list(comb._fields)
+    assert res["average_RMSE"] == pytest.approx(np.mean([0.4, 0.3]))
+    failed = np.array([[False, False, False], [False, True, False]])  # second entry fails on its second setpoint
+    status, res = aggregate_combination(comb, rmse, failed)
+    assert status == CtrlEvalStatus.FAILURE and list(res)[0] == "n_successful_runs" and res["n_successful_runs"] == 4
+    assert res["average_RMSE"] == pytest.approx(np.mean([0.4, 0.1]))  # entry 2 averaged over its one completed run
+    status, res = aggregate_combination(comb, rmse, np.array([[True, False, False], [False, False, False]]))
+    assert res["n_successful_runs"] == 0 and np.isnan(res["average_RMSE"])  # nothing completed: NaN, later entries not run
+    grid = DDMPCParameterGrid([350], [4, 6], [30, 35], [1e1, 5e1], [1e5], [1e-3], [1e3, 1e5])
+    combos = combinations_from_grid(grid)
+    assert len(combos) == 16 and combos[0] == (350, 4, 30, 1e1, 1e5, 1e-3, 1e3) and combos[1].lamb_sigma_s == 1e5 and combos[2].lamb_alpha == 5e1
