@@ -197,7 +197,7 @@ SIGNATURES = {
         [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, vp, P(f32), f32, f32, f32, vp, i64, vp],
     ),
     "ddqc_ddmpc_workspace_bytes": (i64, [P(MpcConfig), i64]),
-    "ddqc_ddmpc_solve": (C.c_int, [P(MpcConfig), vp] + [vp] * 13 + [i64, vp]),
+    "ddqc_ddmpc_solve": (C.c_int, [P(MpcConfig), vp] + [vp] * 11 + [i64, vp]),
     "ddqc_ddmpc_store": (C.c_int, [P(MpcConfig), vp, vp, vp, vp, i64, vp]),
     "ddqc_ddmpc_action": (C.c_int, [P(MpcConfig), vp, C.c_int32, vp, vp, vp, i64, vp]),
     "ddqc_ddmpc_post_step": (C.c_int, [P(MpcConfig), vp, vp, vp, vp, i64, i64, vp, vp, C.c_double, vp, vp, vp, vp, C.c_int32, i64, vp]),

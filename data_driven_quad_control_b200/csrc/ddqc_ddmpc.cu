@@ -58,7 +58,7 @@ struct Dims {
   int nb1, nb2, nb3, nba;    // in 8x8 blocks
   int nbt, nbA;              // trailing block rows, all block rows
   int nx, nS, ldS, ldq;
-  int ga, gs;                // doubles: R1 panel (rect), trailing (block-packed lower)
+  int ga, gs, gsg;           // doubles: R1 panel (rect), trailing in shared memory / in the workspace (block-packed lower)
 };
 
 __host__ __device__ inline int rup8(int v) { return (v + 7) & ~7; }
@@ -71,22 +71,23 @@ __host__ __device__ inline Dims make_dims(const DdqcMpcConfig& c) {
   d.n1 = c.m * (2 * c.n + 1) + 1;
   d.n2 = c.p * d.ell;
   d.n3 = (c.L - c.n) * c.m;
-  d.na = c.m + c.p + 2;
+  d.na = c.m + c.p + 2;  // aug group 0: A_u, A_y, e_one, tau (group 1: T_u, T_y); each fits one block row
   d.n1p = rup8(d.n1); d.n2p = rup8(d.n2); d.n3p = rup8(d.n3); d.nap = rup8(d.na);
   d.nb1 = d.n1p / 8; d.nb2 = d.n2p / 8; d.nb3 = d.n3p / 8; d.nba = d.nap / 8;
-  d.nbt = d.nb2 + d.nb3 + d.nba;
-  d.nbA = d.nb1 + d.nbt;
+  d.nbt = d.nb2 + d.nb3 + 1;      // block rows held in shared memory (matrix + ONE aug block row)
+  d.nbA = d.nb1 + d.nbt + 1;      // block rows of the R1 panel (both aug block rows)
   d.nx = d.n3 + c.m + c.p;
   d.nS = d.nx + 1;
   d.ldS = (d.nS + 1) & ~1;  // even: rows are accessed as double2
   d.ldq = d.nx | 1;
   d.ga = d.nbA * d.nb1 * 64;
   d.gs = d.nbt * (d.nbt + 1) / 2 * 64;
+  d.gsg = (d.nbt + 1) * (d.nbt + 2) / 2 * 64;
   return d;
 }
 
 // extra shared-memory doubles behind the matrix region
-__host__ __device__ inline int extra_doubles(const Dims& d) { return 8 * d.nbt + d.n2p + 2 * (d.nS + 22) + 64; }
+__host__ __device__ inline int extra_doubles(const Dims& d) { return 8 * d.nbt + d.n2p + 2 * (d.nS + 22) + 64 + 8; }
 
 // S7 (dense, nS x ldS) and the block-packed factor of the free block (up to nx variables) share one area
 __host__ __device__ inline int qp_scratch_doubles(const Dims& d) {
@@ -105,7 +106,7 @@ __host__ __device__ inline int region_doubles(const Dims& d) {
   return (r + 1) & ~1;  // keep everything behind the region 16-byte aligned
 }
 
-__host__ __device__ inline size_t slot_doubles(const Dims& d) { return (size_t)d.ga + d.gs; }
+__host__ __device__ inline size_t slot_doubles(const Dims& d) { return (size_t)d.ga + d.gsg; }
 
 // ---- 8x8 block layout ---------------------------------------------------------------------------
 // element (g, c) of a block sits at g*8 + (c ^ 4*((g>>1)&1)): every DMMA operand fragment (8 rows
@@ -705,6 +706,8 @@ __device__ int ipm_solve(const QpWork& q, int max_it) {
 // Sweeping pivot j is the symmetric rank-1 update  A <- A - p p^T / d - 2 e_j e_j^T  with
 // p = A[:, j] - e_j, d = A[j][j]: the same update for every entry; the constant -2 on the swept
 // diagonal entries commutes with the later updates and is applied once at the end.
+// The source is read through `load(i, k)` (i >= k) once, before the first barrier, and the result is written
+// to the dense matrix S afterwards, so S may alias the source storage.
 // Thread t owns CH consecutive entries of one row of the lower triangle and keeps them in REGISTERS
 // for the whole sweep (the matrix is read once and written once: the phase is otherwise bound by
 // shared-memory bandwidth); per pivot it reads p[row] and its CH-chunk of p.  The owners of row /
@@ -715,8 +718,8 @@ __host__ __device__ inline int sweep_threads(int nS, int ch) {
   return tot;
 }
 
-template <int CH>
-__device__ void sweep_lower(double* __restrict__ S, int ld, int nS, int npiv, double* __restrict__ vbuf) {
+template <int CH, class Load>
+__device__ void sweep_lower(double* __restrict__ S, int ld, int nS, int npiv, double* __restrict__ vbuf, Load load) {
   const int tid = threadIdx.x;
   // thread -> (row, k0): rows in order, ceil((row + 1) / CH) threads each
   int row = -1, k0 = 0;
@@ -737,9 +740,9 @@ __device__ void sweep_lower(double* __restrict__ S, int ld, int nS, int npiv, do
   double* vb1 = vbuf + vstride;
   double val[CH];
 #pragma unroll
-  for (int e = 0; e < CH; ++e) val[e] = (own && k0 + e <= row) ? S[row * ld + k0 + e] : 0.0;
+  for (int e = 0; e < CH; ++e) val[e] = (own && k0 + e <= row) ? load(row, k0 + e) : 0.0;
   for (int i = tid; i < vstride; i += kThreads) {
-    vb0[i] = i < nS ? S[i * ld] - (i == 0 ? 1.0 : 0.0) : 0.0;
+    vb0[i] = i < nS ? load(i, 0) - (i == 0 ? 1.0 : 0.0) : 0.0;
     vb1[i] = 0.0;
   }
   __syncthreads();
@@ -778,6 +781,57 @@ __device__ void sweep_lower(double* __restrict__ S, int ld, int nS, int npiv, do
   __syncthreads();
 }
 
+// ---- tiny box QP (<= 6 variables) by one thread: min 0.5 x'Hx + f'x, lo <= x <= hi, H SPD -------------
+// block principal pivoting with Gaussian elimination on the free block; used for the optimal reachable
+// equilibrium (u_sr, y_sr) of the alpha_sr system.
+__device__ bool small_box_qp(const double* H, const double* f, const double* lo, const double* hi, int nv, double* x) {
+  int st[6] = {0, 0, 0, 0, 0, 0};
+  for (int pass = 0; pass < 64; ++pass) {
+    double A[6][7];
+    int idx[6], k = 0;
+    for (int i = 0; i < nv; ++i) {
+      x[i] = st[i] < 0 ? lo[i] : (st[i] > 0 ? hi[i] : 0.0);
+      if (st[i] == 0) idx[k++] = i;
+    }
+    for (int a = 0; a < k; ++a) {
+      double r = -f[idx[a]];
+      for (int j = 0; j < nv; ++j)
+        if (st[j] != 0) r -= H[idx[a] * 6 + j] * x[j];
+      for (int c = 0; c < k; ++c) A[a][c] = H[idx[a] * 6 + idx[c]];
+      A[a][k] = r;
+    }
+    for (int c = 0; c < k; ++c) {  // Gaussian elimination with partial pivoting
+      int pr = c;
+      for (int a = c + 1; a < k; ++a)
+        if (fabs(A[a][c]) > fabs(A[pr][c])) pr = a;
+      if (!(fabs(A[pr][c]) > 0.0)) return false;
+      for (int j = c; j <= k; ++j) { const double t = A[c][j]; A[c][j] = A[pr][j]; A[pr][j] = t; }
+      for (int a = c + 1; a < k; ++a) {
+        const double fct = A[a][c] / A[c][c];
+        for (int j = c; j <= k; ++j) A[a][j] -= fct * A[c][j];
+      }
+    }
+    for (int a = k - 1; a >= 0; --a) {
+      double v = A[a][k];
+      for (int c = a + 1; c < k; ++c) v -= A[a][c] * x[idx[c]];
+      x[idx[a]] = v / A[a][a];
+    }
+    bool changed = false;
+    for (int i = 0; i < nv; ++i) {
+      if (st[i] == 0) {
+        if (x[i] < lo[i]) { st[i] = -1; changed = true; }
+        else if (x[i] > hi[i]) { st[i] = 1; changed = true; }
+      } else {
+        double gi = f[i];
+        for (int j = 0; j < nv; ++j) gi += H[i * 6 + j] * x[j];
+        if ((st[i] < 0 && gi < 0.0) || (st[i] > 0 && gi > 0.0)) { st[i] = 0; changed = true; }
+      }
+    }
+    if (!changed) return true;
+  }
+  return false;
+}
+
 // ---- Gram generation -------------------------------------------------------------------------------
 // position of Hankel row (signal a, block row j) in the elimination order [R1 | R2 | R3 | aug]
 __device__ __forceinline__ int pos_of(const Dims& d, int a, int j) {
@@ -810,8 +864,7 @@ __device__ __forceinline__ void put_sym(const Dims& d, double* __restrict__ GA, 
 __global__ void __launch_bounds__(kThreads, 1)
 ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __restrict__ work_counter,
                    const double* __restrict__ u_win, const double* __restrict__ y_win,
-                   const double* __restrict__ y_r, const double* __restrict__ us_prev,
-                   const double* __restrict__ ys_prev, const int32_t* __restrict__ have_prev,
+                   const double* __restrict__ y_r, const int32_t* __restrict__ have_prev,
                    const double* __restrict__ lamb, int8_t* __restrict__ act_state, double* __restrict__ u_opt, double* __restrict__ us_opt,
                    double* __restrict__ ys_opt, int32_t* __restrict__ status, int32_t* __restrict__ iters,
                    const int batch, long long* __restrict__ phase_clk) {
@@ -827,6 +880,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
   double* s_e = s_yv + 8 * d.nbt;          // n2p   : e = D_s z on R2
   double* s_vec = s_e + d.n2p;             // 2*(nS+2) : sweep pivot-column double buffer
   double* s_red = s_vec + 2 * (d.nS + 22);  // 64
+  double* s_coef = s_red + 64;              // 8: rho = sum_a coef[a] * (aug group 0 row a)
   __shared__ int s_flag;
   __shared__ int s_next;
   __shared__ int s_state[kMaxNx];
@@ -860,7 +914,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     const int b = s_next;
     if (b >= batch) break;
     t_prev = clock64();
-    const bool use_sr = (cfg.alpha_reg_type == 0) && have_prev[b] != 0;
+    const bool use_sr = cfg.alpha_reg_type == 0;
     // regularisation weights: per controller when `lamb` is given (grid search over lambda), else from the config
     const double lam_a = lamb ? lamb[4 * (size_t)b] : cfg.lamb_alpha, lam_s = lamb ? lamb[4 * (size_t)b + 1] : cfg.lamb_sigma;
     const double lam_as = lamb ? lamb[4 * (size_t)b + 2] : cfg.lamb_alpha_s, lam_ss = lamb ? lamb[4 * (size_t)b + 3] : cfg.lamb_sigma_s;
@@ -876,17 +930,17 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     {
       const int r0 = d.nb1 + d.nb2 + d.nb3;  // first aug block row (all-rows numbering)
       double2* za = reinterpret_cast<double2*>(GA + (size_t)r0 * d.nb1 * 64);
-      for (int e = tid; e < d.nba * d.nb1 * 32; e += kThreads) za[e] = make_double2(0.0, 0.0);
+      for (int e = tid; e < 2 * d.nb1 * 32; e += kThreads) za[e] = make_double2(0.0, 0.0);
       const int tb = d.nb2 + d.nb3;
       double2* zs = reinterpret_cast<double2*>(GS + (size_t)tri(tb) * 64);
-      const int cnt = (tri(d.nbt) - tri(tb)) * 32;
+      const int cnt = (tri(tb + 2) - tri(tb)) * 32;
       for (int e = tid; e < cnt; e += kThreads) zs[e] = make_double2(0.0, 0.0);
     }
     __syncthreads();
     {
       // pad rows (identity) of the three classes
       const int npad = (d.n1p - d.n1) + (d.n2p - d.n2) + (d.n3p - d.n3);
-      const int ntot = d.n1p + d.n2p + d.n3p + d.nap;
+      const int ntot = d.n1p + d.n2p + d.n3p + 16;
       for (int e = tid; e < npad * ntot; e += kThreads) {
         int k = e / ntot;
         const int q = e % ntot;
@@ -971,24 +1025,24 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
         if (tid == 0) put_sym(d, GA, GS, Pone, Pone, (double)C);
       }
       const int Pone = n * m;
-      // aug rows: T_u (m), T_y (p), tau, b_s
-      const int Pa = d.n1p + d.n2p + d.n3p;
+      // aug rows.  group 0 (block row tb): A_u (m: ones on ALL input rows of a component), A_y (p), e_one, tau;
+      //            group 1 (block row tb + 1): T_u (m: ones on the terminal input rows), T_y (p: free + terminal outputs)
+      const int Pa0 = d.n1p + d.n2p + d.n3p, Pa1 = Pa0 + 8;
       for (int e = tid; e < nsig * ell; e += kThreads) {
         const int a = e / ell, j = e % ell;
         const int P = pos_of(d, a, j);
+        put_sym(d, GA, GS, Pa0 + a, P, 1.0);
         if (a < m) {
-          if (j >= L) put_sym(d, GA, GS, Pa + a, P, 1.0);
-          if (j < n) put_sym(d, GA, GS, Pa + nsig, P, ub[(size_t)(N - n + j) * m + a]);
-          if (use_sr) put_sym(d, GA, GS, Pa + nsig + 1, P, us_prev[(size_t)b * m + a]);
+          if (j >= L) put_sym(d, GA, GS, Pa1 + a, P, 1.0);
+          if (j < n) put_sym(d, GA, GS, Pa0 + nsig + 1, P, ub[(size_t)(N - n + j) * m + a]);
         } else {
-          if (j >= n) put_sym(d, GA, GS, Pa + a, P, 1.0);
-          if (j < n) put_sym(d, GA, GS, Pa + nsig, P, yb[(size_t)(N - n + j) * p + (a - m)]);
-          if (use_sr) put_sym(d, GA, GS, Pa + nsig + 1, P, ys_prev[(size_t)b * p + (a - m)]);
+          if (j >= n) put_sym(d, GA, GS, Pa1 + a, P, 1.0);
+          if (j < n) put_sym(d, GA, GS, Pa0 + nsig + 1, P, yb[(size_t)(N - n + j) * p + (a - m)]);
         }
       }
       if (tid == 0) {
-        put_sym(d, GA, GS, Pa + nsig, Pone, 1.0);
-        if (use_sr) put_sym(d, GA, GS, Pa + nsig + 1, Pone, 1.0);
+        put_sym(d, GA, GS, Pa0 + nsig, Pone, 1.0);
+        put_sym(d, GA, GS, Pa0 + nsig + 1, Pone, 1.0);
       }
     }
     __syncthreads();
@@ -1005,7 +1059,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     factor_columns<true>(sM, d.nb1, d.nbA, d.nb1, &s_flag);
     DDQC_PHASE(1);
     {
-      const int nblk = tri(d.nbt);
+      const int nblk = tri(d.nbt + 1);
       for (int bb = warp; bb < nblk; bb += 2 * kWarps) {
         const int b2 = bb + kWarps;
         const bool two = b2 < nblk;
@@ -1045,25 +1099,54 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     __syncthreads();
     DDQC_PHASE(2);
 
-    // ---- B. alpha_sr:  e = D_s (S1 + D_s)^-1 b_s restricted to R2 -----------------------------------
-    const int ncol_all = d.nb2 + d.nb3;
-    const int aug_t = nsig, aug_b = nsig + 1;                 // aug indices of tau and b_s
+    // ---- B. alpha_sr = alpha of the optimal reachable equilibrium for y_r -----------------------------
+    //   (u_sr, y_sr) = argmin lamb_alpha_s rho' (G + D_s)^-1 rho + |y_s - y_r|_S^2, u_s in U_s,
+    //   rho = A_u u_s + A_y y_s + e_one;   v_sr = H alpha_sr = rho - e,  e = D_s (G + D_s)^-1 rho on R2
+    const int ncol_all = d.nb2 + d.nb3, tb = ncol_all;        // tb: the aug block row held in shared memory
+    const int aug_t = nsig;                                   // phase C: aug index of the c-row (T_u, T_y before it)
     const int Paug = d.n2p + d.n3p;                           // trailing position of the first aug row
+    if (tid < 8) s_coef[tid] = 0.0;
+    for (int q = tid; q < d.n2p; q += kThreads) s_e[q] = 0.0;
+    __syncthreads();
     if (use_sr) {
       const double ds = lam_as / lam_ss;
       {
         const double2* src = reinterpret_cast<const double2*>(GS);
         double2* dst = reinterpret_cast<double2*>(sM);
 #pragma unroll 4
-        for (int e = tid; e < d.gs / 2; e += kThreads) dst[e] = src[e];
+        for (int e = tid; e < d.gs / 2; e += kThreads) dst[e] = src[e];  // block rows 0..tb: matrix + aug group 0
       }
       __syncthreads();
       for (int q = tid; q < d.n2; q += kThreads) *elem_tri(sM, q, q) += ds;
       __syncthreads();
       factor_columns<false>(sM, 0, d.nbt, ncol_all, &s_flag);
+      schur_trailing(sM, d.nbt, ncol_all);  // aug x aug block: -K_s' (G + D_s)^-1 K_s
+      __syncthreads();
       DDQC_PHASE(3);
-      // y = L^-1 b_s sits in the b_s row; z = L^-T y by blocked back-substitution
-      for (int q = tid; q < 8 * ncol_all; q += kThreads) s_yv[q] = *elem_tri(sM, Paug + aug_b, q);
+      if (tid == 0) {
+        // 6-variable box QP for the equilibrium (bounds on u_s only)
+        double Hs[36], fs[6], lo[6], hi[6], x[6];
+        for (int a = 0; a < nsig; ++a) {
+          for (int c = 0; c < nsig; ++c) Hs[a * 6 + c] = -2.0 * lam_as * *elem_tri(sM, Paug + (a > c ? a : c), Paug + (a > c ? c : a));
+          fs[a] = -2.0 * lam_as * *elem_tri(sM, Paug + nsig, Paug + a);
+          lo[a] = a < m ? cfg.Us_lo[a] : -INFINITY;
+          hi[a] = a < m ? cfg.Us_hi[a] : INFINITY;
+        }
+        for (int i = 0; i < p; ++i) {
+          Hs[(m + i) * 6 + m + i] += 2.0 * cfg.S[i];
+          fs[m + i] -= 2.0 * cfg.S[i] * y_r[(size_t)b * p + i];
+        }
+        if (!small_box_qp(Hs, fs, lo, hi, nsig, x)) s_flag = 1;
+        for (int a = 0; a < nsig; ++a) s_coef[a] = x[a];
+        s_coef[nsig] = 1.0;
+      }
+      __syncthreads();
+      // y = L^-1 rho = combination of the forward-substituted aug rows; z = L^-T y
+      for (int q = tid; q < 8 * ncol_all; q += kThreads) {
+        double acc = 0.0;
+        for (int a = 0; a <= nsig; ++a) acc += s_coef[a] * *elem_tri(sM, Paug + a, q);
+        s_yv[q] = acc;
+      }
       __syncthreads();
       backsub_blocked(sM, ncol_all, s_yv);
       for (int q = tid; q < d.n2p; q += kThreads) s_e[q] = q < d.n2 ? ds * s_yv[q] : 0.0;
@@ -1071,32 +1154,55 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       DDQC_PHASE(4);
     }
 
-    // ---- C. main system: S1 + D_0, c = tau - b_s + e, eliminate R2, Schur on [R3 | aug] --------------
+    // ---- C. main system: S1 + D_0, aug rows (T_u, T_y, c), c = tau - rho + e; eliminate R2 ------------
     {
       const double2* src = reinterpret_cast<const double2*>(GS);
       double2* dst = reinterpret_cast<double2*>(sM);
 #pragma unroll 4
-      for (int e = tid; e < d.gs / 2; e += kThreads) dst[e] = src[e];
+      for (int e = tid; e < tri(tb) * 32; e += kThreads) dst[e] = src[e];  // block rows 0..tb-1
+      // aug block row: T rows from workspace block row tb+1, the c-row combined from block row tb
+      const double* g0 = GS + (size_t)tri(tb) * 64;       // aug group 0 blocks (tb, J)
+      const double* g1 = GS + (size_t)tri(tb + 1) * 64;   // aug group 1 blocks (tb + 1, J)
+      double* sa = sM + (size_t)tri(tb) * 64;
+      for (int e = tid; e < tb * 64; e += kThreads) {
+        const int J = e >> 6, a = (e >> 3) & 7, c = e & 7, q = 8 * J + c;
+        double v = 0.0;
+        if (a < nsig) v = g1[J * 64 + eoff(a, c)];
+        else if (a == nsig) {
+          v = g0[J * 64 + eoff(nsig + 1, c)];
+          for (int k = 0; k <= nsig; ++k) v -= s_coef[k] * g0[J * 64 + eoff(k, c)];
+          if (q < d.n2) v += s_e[q];
+        }
+        sa[J * 64 + eoff(a, c)] = v;
+      }
+      if (tid < 64) {
+        const int a = tid >> 3, c = tid & 7;
+        const double* b00 = g0 + (size_t)tb * 64;        // (tb, tb)     : group 0 x group 0 (lower)
+        const double* b10 = g1 + (size_t)tb * 64;        // (tb+1, tb)   : group 1 rows x group 0 columns
+        const double* b11 = g1 + (size_t)(tb + 1) * 64;  // (tb+1, tb+1) : group 1 x group 1 (lower)
+        const int hi = a > c ? a : c, lo = a > c ? c : a;
+        double v = 0.0;
+        if (hi < nsig) v = b11[eoff(hi, lo)];
+        else if (hi == nsig && lo < nsig) {  // c-row against a T row
+          v = b10[eoff(lo, nsig + 1)];
+          for (int k = 0; k <= nsig; ++k) v -= s_coef[k] * b10[eoff(lo, k)];
+        } else if (hi == nsig && lo == nsig) {  // w' B w, w = (-coef[0..nsig], +1 on tau)
+          for (int i = 0; i <= nsig + 1; ++i) {
+            const double wi = i <= nsig ? -s_coef[i] : 1.0;
+            for (int k = 0; k <= nsig + 1; ++k) {
+              const double wk = k <= nsig ? -s_coef[k] : 1.0;
+              v += wi * wk * b00[eoff(i > k ? i : k, i > k ? k : i)];
+            }
+          }
+        }
+        sa[tb * 64 + eoff(a, c)] = v;
+      }
     }
     __syncthreads();
     for (int q = tid; q < d.n2; q += kThreads) {
       const int j = q / p, comp = q % p;
       const double w = (j < n || j >= L) ? lam_s : cfg.Q[comp] * lam_s / (cfg.Q[comp] + lam_s);
       *elem_tri(sM, q, q) += lam_a / w;
-    }
-    if (use_sr) {
-      for (int q = tid; q < 8 * ncol_all; q += kThreads) {
-        double* ct = elem_tri(sM, Paug + aug_t, q);
-        *ct = *ct - *elem_tri(sM, Paug + aug_b, q) + (q < d.n2 ? s_e[q] : 0.0);
-      }
-      if (tid < aug_t) {
-        double* ct = elem_tri(sM, Paug + aug_t, Paug + tid);
-        *ct -= *elem_tri(sM, Paug + aug_b, Paug + tid);
-      }
-      if (tid == 0) {
-        double* ctt = elem_tri(sM, Paug + aug_t, Paug + aug_t);
-        *ctt += -2.0 * *elem_tri(sM, Paug + aug_b, Paug + aug_t) + *elem_tri(sM, Paug + aug_b, Paug + aug_b);
-      }
     }
     __syncthreads();
     factor_columns<false>(sM, 0, d.nbt, d.nb2, &s_flag);
@@ -1107,20 +1213,14 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     // ---- sweep: S7 (dense, lower) <- Schur complement on [R3 (n3) | T_u, T_y, c] ---------------------
     const int nS = d.nS, ldS = d.ldS, nx = d.nx, ldq = d.ldq;
     double* S7 = sM;
-    {
-      // the source blocks start at (tri(nb2) + nb2) * 64 >= nS * ldS (checked on the host), so the
-      // copy cannot overwrite a block that is still to be read.  Full symmetric storage.
-      for (int e = tid; e < nS * nS; e += kThreads) {
-        const int i = e / nS, k = e % nS;
-        const int hi = i > k ? i : k, lo = i > k ? k : i;
-        const int Pi = hi < d.n3 ? d.n2p + hi : Paug + (hi - d.n3);
-        const int Pk = lo < d.n3 ? d.n2p + lo : Paug + (lo - d.n3);
-        S7[i * ldS + k] = *elem_tri(sM, Pi, Pk);
-      }
-    }
-    __syncthreads();
-    if (sweep_threads(nS, 10) <= kThreads) sweep_lower<10>(S7, ldS, nS, d.n3, s_vec);
-    else sweep_lower<20>(S7, ldS, nS, d.n3, s_vec);
+    // entry (i, k), i >= k, of the Schur complement on [R3 (n3) | T_u, T_y, c], read from the block layout
+    auto schur = [&](int i, int k) {
+      const int Pi = i < d.n3 ? d.n2p + i : Paug + (i - d.n3);
+      const int Pk = k < d.n3 ? d.n2p + k : Paug + (k - d.n3);
+      return *elem_tri(sM, Pi, Pk);
+    };
+    if (sweep_threads(nS, 10) <= kThreads) sweep_lower<10>(S7, ldS, nS, d.n3, s_vec, schur);
+    else sweep_lower<20>(S7, ldS, nS, d.n3, s_vec, schur);
     DDQC_PHASE(6);
 
     // ---- box QP assembly: Hq = 2 lamb_alpha Z + structure, f ----------------------------------------
@@ -1342,11 +1442,9 @@ int check_cfg(const DdqcMpcConfig* c) {
   if (!c) return DDQC_E_NULL;
   if (c->m < 1 || c->p < 1 || c->m > kMaxSig || c->p > kMaxSig || c->n < 1 || c->L <= c->n) return DDQC_E_SHAPE;
   const Dims d = make_dims(*c);
-  if (d.C < 1 || d.nx > kMaxNx || (d.m + d.p) * d.ell > kMaxPos) return DDQC_E_SHAPE;
+  if (d.C < 1 || d.nx > kMaxNx || (d.m + d.p) * d.ell > kMaxPos || d.m + d.p + 2 > 8) return DDQC_E_SHAPE;
   if (sweep_threads(d.nS, 20) > kThreads) return DDQC_E_SHAPE;
   if (smem_bytes(d) + 4608 > (size_t)kSmemLimit) return DDQC_E_SHAPE;
-  // the dense copy of the final Schur complement must not overlap the blocks it is read from
-  if (d.nS * d.ldS > (d.nb2 * (d.nb2 + 1) / 2 + d.nb2) * 64) return DDQC_E_SHAPE;
   if (c->alpha_reg_type != 0 && c->alpha_reg_type != 2) return DDQC_E_CONFIG;
   return 0;
 }
@@ -1373,7 +1471,7 @@ extern "C" int64_t ddqc_ddmpc_workspace_bytes(const DdqcMpcConfig* cfg, int64_t 
 }
 
 extern "C" int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg, void* ws, const double* u_win, const double* y_win,
-                                const double* y_r, const double* us_prev, const double* ys_prev,
+                                const double* y_r,
                                 const int32_t* have_prev, const double* lamb, int8_t* act_state, double* u_opt,
                                 double* us_opt,
                                 double* ys_opt, int32_t* status, int32_t* iters, int64_t batch, void* stream) {
@@ -1381,7 +1479,6 @@ extern "C" int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg, void* ws, const double
   if (rc) return rc;
   if (!ws || !u_win || !y_win || !y_r || !u_opt || !us_opt || !ys_opt || !status || !iters || !have_prev)
     return DDQC_E_NULL;
-  if (cfg->alpha_reg_type == 0 && (!us_prev || !ys_prev)) return DDQC_E_NULL;
   if (batch < 0) return DDQC_E_SHAPE;
   if (batch == 0) return 0;
   const Dims d = make_dims(*cfg);
@@ -1398,8 +1495,8 @@ extern "C" int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg, void* ws, const double
   e = cudaMemsetAsync(ws, 0, 256, st);
   if (e != cudaSuccess) return (int)e;
   double* slots = reinterpret_cast<double*>(static_cast<char*>(ws) + 256);
-  ddmpc_solve_kernel<<<grid, kThreads, smem, st>>>(*cfg, slots, static_cast<int*>(ws), u_win, y_win, y_r, us_prev,
-                                                   ys_prev, have_prev, lamb, act_state, u_opt, us_opt, ys_opt, status,
+  ddmpc_solve_kernel<<<grid, kThreads, smem, st>>>(*cfg, slots, static_cast<int*>(ws), u_win, y_win, y_r,
+                                                   have_prev, lamb, act_state, u_opt, us_opt, ys_opt, status,
                                                    iters, (int)batch, g_phase_clk);
   return (int)cudaGetLastError();
 }

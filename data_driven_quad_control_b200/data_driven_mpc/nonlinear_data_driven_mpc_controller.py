@@ -147,8 +147,6 @@ class BatchedNonlinearDataDrivenMPC:
         self.set_output_setpoint(y_r)
         self.us = torch.zeros((self.B, m), **f64)  # last optimal equilibrium input
         self.ys = torch.zeros((self.B, p), **f64)
-        self._us_prev = torch.zeros_like(self.us)
-        self._ys_prev = torch.zeros_like(self.ys)
         self._have_prev = torch.zeros((self.B,), dtype=torch.int32, device=dev)
         self.optimal_u = torch.zeros((self.B, self.L + 1, m), **f64)
         self.status = torch.zeros((self.B,), dtype=torch.int32, device=dev)
@@ -168,12 +166,9 @@ class BatchedNonlinearDataDrivenMPC:
 
     def update_and_solve_data_driven_mpc(self) -> None:
         """One solve of every controller of the batch on its current (u, y) window."""
-        # the equilibrium of the previous solve parameterises alpha_sr (type APPROXIMATED)
-        self._us_prev.copy_(self.us)
-        self._ys_prev.copy_(self.ys)
         rc = self._lib.ddqc_ddmpc_solve(
             C.byref(self._cfg), self._ws.data_ptr(), self.u.data_ptr(), self.y.data_ptr(), self.y_r.data_ptr(),
-            self._us_prev.data_ptr(), self._ys_prev.data_ptr(), self._have_prev.data_ptr(),
+            self._have_prev.data_ptr(),
             self._lamb.data_ptr() if self._lamb is not None else None, self._act_state.data_ptr() if self._act_state is not None else None, self.optimal_u.data_ptr(), self.us.data_ptr(), self.ys.data_ptr(), self.status.data_ptr(),
             self.iters.data_ptr(), self.B, _lib.stream_ptr(self.device),
         )  # fmt: skip

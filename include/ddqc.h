@@ -265,8 +265,8 @@ int64_t ddqc_ddmpc_workspace_bytes(const DdqcMpcConfig* cfg_host, int64_t batch)
 /* update_and_solve_data_driven_mpc for a batch of controllers.
  *  u_win [B][N][m], y_win [B][N][p] : rolling input/output windows (float64)
  *  y_r   [B][p]                      : output setpoints
- *  us_prev, ys_prev [B][m],[B][p]    : previous optimal equilibrium (alpha_reg_type 0);
- *  have_prev [B] int32               : 0 -> alpha_sr = 0 and cold active set (first solve)
+ *  have_prev [B] int32               : 0 -> cold active set (first solve); alpha_sr (alpha_reg_type 0) is the
+ *                                      alpha of the optimal reachable equilibrium for y_r and needs no history
  *  lamb [B][4] (or NULL)            : per-controller (lamb_alpha, lamb_sigma, lamb_alpha_s, lamb_sigma_s)
  *                                      overriding the config values (grid search over the regularisation
  *                                      weights, configs/data_driven_mpc/dd_mpc_grid_search_params.yaml:92-111)
@@ -279,8 +279,7 @@ int64_t ddqc_ddmpc_workspace_bytes(const DdqcMpcConfig* cfg_host, int64_t batch)
  *  iters [B] int32 = pivoting passes + (interior-point iterations << 16)
  *  ws: ddqc_ddmpc_workspace_bytes() bytes, 256-byte aligned; its first 256 bytes are the work counter */
 int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg_host, void* ws, const double* u_win,
-                     const double* y_win, const double* y_r, const double* us_prev,
-                     const double* ys_prev, const int32_t* have_prev, const double* lamb,
+                     const double* y_win, const double* y_r, const int32_t* have_prev, const double* lamb,
                      int8_t* act_state,
                      double* u_opt, double* us_opt, double* ys_opt, int32_t* status, int32_t* iters,
                      int64_t batch, void* stream);

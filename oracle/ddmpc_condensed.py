@@ -110,6 +110,38 @@ def box_qp_active_set(Hq, f, lo, hi, x0=None, max_iter=200):
     raise RuntimeError("block principal pivoting did not converge")
 
 
+def v_sr_optimal_reachable(prm: MPCParams, G, y_r):
+    """v_sr = H alpha_sr for alpha_sr = least-norm alpha of the optimal reachable equilibrium for y_r
+    (ddmpc_oracle.solve_alpha_sr), in row space: with M_s = G + D_s, rho = A_u u_s + A_y y_s + e_one,
+      (u_s, y_s) = argmin lamb_alpha_s rho' M_s^-1 rho + |y_s - y_r|_S^2,  u_s in U_s   (a 6-variable box QP)
+      v_sr = rho - D_s M_s^-1 rho.
+    Rows in the canonical order of `hankel_gram`: inputs, outputs, ones."""
+    m, p, ell = prm.m, prm.p, prm.ell
+    r = G.shape[0]
+    Ds = np.zeros(r)
+    Ds[m * ell : (m + p) * ell] = prm.lamb_alpha_s / prm.lamb_sigma_s
+    Ks = np.zeros((r, m + p))
+    for j in range(ell):
+        Ks[j * m : (j + 1) * m, :m] = np.eye(m)
+        Ks[m * ell + j * p : m * ell + (j + 1) * p, m:] = np.eye(p)
+    e1 = np.zeros(r)
+    e1[-1] = 1.0
+    Lc = np.linalg.cholesky(G + np.diag(Ds))
+    X = np.linalg.solve(Lc, np.concatenate([Ks, e1[:, None]], axis=1))
+    Z = X.T @ X
+    Hs = 2 * prm.lamb_alpha_s * Z[: m + p, : m + p]
+    fs = 2 * prm.lamb_alpha_s * Z[: m + p, m + p]
+    for i in range(p):
+        Hs[m + i, m + i] += 2 * prm.S[i]
+        fs[m + i] -= 2 * prm.S[i] * y_r[i]
+    lo = np.concatenate([prm.Us[:, 0], np.full(p, -np.inf)])
+    hi = np.concatenate([prm.Us[:, 1], np.full(p, np.inf)])
+    t, _ = box_qp_active_set(Hs, fs, lo, hi)
+    rho = Ks @ t + e1
+    z = np.linalg.solve(Lc.T, np.linalg.solve(Lc, rho))
+    return rho - Ds * z, t[:m], t[m:]
+
+
 def solve_condensed(prm: MPCParams, u_win, y_win, y_r, us_prev=None, ys_prev=None, x0=None):
     n, m, p, L, ell = prm.n, prm.m, prm.p, prm.L, prm.ell
     G, _ = hankel_gram(u_win, y_win, ell)
@@ -121,14 +153,10 @@ def solve_condensed(prm: MPCParams, u_win, y_win, y_r, us_prev=None, ys_prev=Non
     tau[m * ell : m * ell + n * p] = y_past.ravel()
     tau[-1] = 1.0
 
-    # alpha_sr only enters through v_sr = H alpha_sr
+    # alpha_sr only enters through v_sr = H alpha_sr (us_prev / ys_prev are unused: kept for call compatibility)
     v_sr = np.zeros(r)
-    if prm.alpha_reg_type == APPROXIMATED and us_prev is not None:
-        Ds = np.zeros(r)
-        Ds[m * ell : (m + p) * ell] = prm.lamb_alpha_s / prm.lamb_sigma_s
-        b_s = np.concatenate([np.tile(us_prev, ell), np.tile(ys_prev, ell), [1.0]])
-        c_s = np.linalg.solve(G + np.diag(Ds), b_s)
-        v_sr = b_s - Ds * c_s
+    if prm.alpha_reg_type == APPROXIMATED:
+        v_sr, _, _ = v_sr_optimal_reachable(prm, G, np.asarray(y_r, float).ravel())
 
     D0 = np.where(np.isfinite(w), prm.lamb_alpha / w, 0.0)
     Lc = np.linalg.cholesky(G + np.diag(D0))
@@ -272,40 +300,49 @@ def solve_condensed_v2(prm,u_win,y_win,y_r,us_prev=None,ys_prev=None,state0=None
     w,B,T=row_classes(prm)
     assert (B==R3).all()
     tau=np.zeros(r); tau[:n*m]=u_win[-n:].ravel(); tau[m*ell:m*ell+n*p]=y_win[-n:].ravel(); tau[-1]=1.0
-    use_sr=prm.alpha_reg_type==APPROXIMATED and us_prev is not None
-    bs=np.concatenate([np.tile(us_prev,ell),np.tile(ys_prev,ell),[1.0]]) if use_sr else np.zeros(r)
-    # augmented matrix in order [R1 | R2 | R3 | aug(T_u, T_y, tau, bs)]
+    use_sr=prm.alpha_reg_type==APPROXIMATED
+    y_r=np.asarray(y_r,float).ravel()
+    # augmented right-hand sides carried as extra rows, in the kernel's order:
+    #   group 0: A_u (all input rows, per component), A_y (all output rows), e_one, tau   (alpha_sr system + c-row)
+    #   group 1: T_u (terminal input rows), T_y (free + terminal output rows)             (main system)
+    Au=np.zeros((r,m)); Ay=np.zeros((r,p))
+    for j in range(ell):
+        Au[j*m:(j+1)*m,:]=np.eye(m); Ay[m*ell+j*p:m*ell+(j+1)*p,:]=np.eye(p)
+    e1=np.zeros(r); e1[-1]=1.0
     order=np.concatenate([R1,R2,R3])
-    K=np.concatenate([T,tau[:,None],bs[:,None]],axis=1)  # r x 8
-    na=K.shape[1]
+    K=np.concatenate([Au,Ay,e1[:,None],tau[:,None],T],axis=1)  # r x (2(m+p)+2)
+    na0,na=m+p+2,K.shape[1]
     A=np.zeros((r+na,r+na)); A[:r,:r]=G[np.ix_(order,order)]; A[r:,:r]=K[order].T; A[:r,r:]=K[order]
-    # phase A: eliminate R1
-    S40,_,_=chol_partial(A,n1)      # order [R2 | R3 | aug8]
-    nt=S40.shape[0]
-    e_row=np.zeros(n2)
+    # phase A: eliminate R1 (shared by both regularised systems)
+    S1,_,_=chol_partial(A,n1)      # order [R2 | R3 | aug group 0 | aug group 1]
+    nm=n2+n3
+    e_row=np.zeros(n2); coef=np.zeros(na0); coef[m+p+1]=0.0
     if use_sr:
         ds=prm.lamb_alpha_s/prm.lamb_sigma_s
-        # phase B: order [R3 | R2 | bs]
-        idx=np.concatenate([np.arange(n2,n2+n3),np.arange(n2),[nt-1]])
-        Sb=S40[np.ix_(idx,idx)].copy()
-        Sb[np.arange(n3,n3+n2),np.arange(n3,n3+n2)]+=ds
-        Lb=np.linalg.cholesky(Sb[:-1,:-1])
-        yv=np.linalg.solve(Lb,Sb[:-1,-1])
-        Lyy=Lb[n3:,n3:]
-        zy=np.linalg.solve(Lyy.T,yv[n3:])
-        e_row=ds*zy
-    # phase C: order [R2 | R3 | T_u,T_y,tau,bs,e]
-    Sc=np.zeros((nt+1,nt+1)); Sc[:nt,:nt]=S40
-    Sc[nt,:n2]=e_row; Sc[:n2,nt]=e_row
+        # phase B: S1 + D_s with aug group 0: factor everything; the aug x aug Schur block is -K_s' M_s^-1 K_s
+        Sb=S1[:nm+na0,:nm+na0].copy()
+        Sb[np.arange(n2),np.arange(n2)]+=ds
+        Sa,Lb,Lab=chol_partial(Sb,nm)           # Lab: forward-substituted aug rows (na0 x nm)
+        Hs=-2*prm.lamb_alpha_s*Sa[:m+p,:m+p]; fs=-2*prm.lamb_alpha_s*Sa[:m+p,m+p]
+        for i in range(p):
+            Hs[m+i,m+i]+=2*prm.S[i]; fs[m+i]-=2*prm.S[i]*y_r[i]
+        lo_s=np.concatenate([prm.Us[:,0],np.full(p,-np.inf)]); hi_s=np.concatenate([prm.Us[:,1],np.full(p,np.inf)])
+        t_sr,_=box_qp_active_set(Hs,fs,lo_s,hi_s)
+        coef=np.concatenate([t_sr,[1.0,0.0]])   # rho = A_u u_sr + A_y y_sr + e_one
+        yv=Lab.T@coef                           # L^-1 rho restricted to [R2 | R3]
+        z=np.linalg.solve(Lb.T,yv)              # back-substitution
+        e_row=ds*z[:n2]                         # v_sr = rho - [e on R2]
+    # phase C: S1 + D_0 with aug rows (T_u, T_y, c),  c = tau - rho + e
+    W=np.zeros((nm+na,nm+m+p+1)); W[:nm,:nm]=np.eye(nm)
+    for k in range(m+p): W[nm+na0+k,nm+k]=1.0  # T rows
+    W[nm+m+p+1,nm+m+p]=1.0                     # tau
+    W[nm:nm+na0,nm+m+p]-=coef                  # - rho (coef has 0 on the tau slot)
+    Sc=W.T@S1@W
+    Sc[nm+m+p,:n2]+=e_row; Sc[:n2,nm+m+p]+=e_row
     D0=prm.lamb_alpha/w[R2]
     Sc[np.arange(n2),np.arange(n2)]+=D0
-    S,_,_=chol_partial(Sc,n2)       # (n3 + 9)
-    # combine aug: c = tau - bs + e
+    S7,_,_=chol_partial(Sc,n2)       # (n3 + 7): Schur complement on [R3 | T_u, T_y, c]
     nB=n3
-    Cm=np.zeros((nB+9,nB+7)); Cm[:nB,:nB]=np.eye(nB)
-    for k in range(6): Cm[nB+k,nB+k]=1
-    Cm[nB+6,nB+6]=1; Cm[nB+7,nB+6]=-1; Cm[nB+8,nB+6]=1
-    S7=Cm.T@S@Cm
     Z=-sweep(S7,nB); Z[:nB,nB:]*=-1; Z[nB:,:nB]*=-1
     nx=nB+m+p
     Hq=2*prm.lamb_alpha*Z[:nx,:nx]; f=2*prm.lamb_alpha*Z[:nx,nx]
@@ -328,5 +365,5 @@ def solve_condensed_v2(prm,u_win,y_win,y_r,us_prev=None,ys_prev=None,state0=None
         x,state=(x2,state2) if ok2 else (xi,st)
     u_s, y_s = x[nB:nB+m], x[nB+m:]
     u_pred = np.vstack([x[:nB].reshape(L-n, m), np.tile(u_s, (n+1, 1))])  # ubar_0..ubar_L
-    return dict(x=x,state=state,Hq=Hq,f=f,info=info,u_opt=u_pred,us=u_s,ys=y_s)
+    return dict(x=x,state=state,Hq=Hq,f=f,lo=lo,hi=hi,info=info,u_opt=u_pred,us=u_s,ys=y_s)
 

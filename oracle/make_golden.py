@@ -125,13 +125,13 @@ def make_env(action_type: int, name: str, N=32, T=200):
 def make_ddmpc():
     import ddmpc_oracle as mo
 
-    # default sizes on PID-stabilised drone data (BASELINE configs[3] shape), 3 closed-loop solves
+    # default sizes on PID-stabilised drone data (BASELINE configs[3] shape), 4 closed-loop solves
     u, y, st = mo.collect_initial_data(seed=0)
     prm = mo.default_params()
     y_r = np.array([1.0, 1.0, 2.5])
     ctrl = mo.NonlinearDDMPCOracle(**mo.ctor_kwargs(prm, u, y, y_r), solve_on_init=False)
     rec = {k: [] for k in ("u_opt", "us", "ys", "y_next", "kkt")}
-    for t in range(3):
+    for t in range(4):
         ctrl.update_and_solve_data_driven_mpc()
         k = mo.kkt_residuals(*ctrl.last["qp"], ctrl.last["z"], *ctrl.last["mult"])
         u0 = ctrl.get_optimal_control_input_at_step(0)

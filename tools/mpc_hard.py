@@ -10,7 +10,6 @@ prm = mo.default_params()
 kw = mo.ctor_kwargs(prm, d["u"][0], d["y"][0], np.array([1, 1, 2.5]))
 kw["u"], kw["y"], kw["y_r"] = d["u"], d["y"], np.tile(np.array([[1, 1, 2.5]]), (n, 1))
 ctrl = BatchedNonlinearDataDrivenMPC(**kw, device="cuda", solve_on_init=False)
-ctrl.us.copy_(torch.from_numpy(d["us_prev"])); ctrl.ys.copy_(torch.from_numpy(d["ys_prev"])); ctrl._have_prev.fill_(1)
 ctrl._act_state = None
 ctrl.update_and_solve_data_driven_mpc(); torch.cuda.synchronize()
 print("status", ctrl.status.cpu().tolist(), "passes", ctrl.pivoting_passes.cpu().tolist(), "ipm", ctrl.ipm_iterations.cpu().tolist())
