@@ -782,52 +782,75 @@ __device__ void sweep_lower(double* __restrict__ S, int ld, int nS, int npiv, do
 }
 
 // ---- tiny box QP (<= 6 variables) by one thread: min 0.5 x'Hx + f'x, lo <= x <= hi, H SPD -------------
-// block principal pivoting with Gaussian elimination on the free block; used for the optimal reachable
-// equilibrium (u_sr, y_sr) of the alpha_sr system.
-__device__ bool small_box_qp(const double* H, const double* f, const double* lo, const double* hi, int nv, double* x) {
-  int st[6] = {0, 0, 0, 0, 0, 0};
+// Block principal pivoting; the system of a pass keeps the fixed size 6 (active variables and unused slots
+// become identity rows with the bound as right-hand side), so every array index is static and the whole
+// routine lives in registers.  Used for the optimal reachable equilibrium (u_sr, y_sr) of the alpha_sr system.
+// Not inlined: its ~100 live registers must not weigh on the register allocation of the solver kernel.  Inputs
+// (H 36, f 6, lo 6, hi 6 doubles) and the result x (6) are passed through shared memory at `io`.
+__device__ __noinline__ bool small_box_qp(double* io, int nv) {
+  double H[36], f[6], lo[6], hi[6], x[6];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) H[i] = io[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { f[i] = io[36 + i]; lo[i] = io[42 + i]; hi[i] = io[48 + i]; x[i] = 0.0; }
+  int st[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) st[i] = i < nv ? 0 : 2;  // 2: unused slot (x = 0)
   for (int pass = 0; pass < 64; ++pass) {
-    double A[6][7];
-    int idx[6], k = 0;
-    for (int i = 0; i < nv; ++i) {
-      x[i] = st[i] < 0 ? lo[i] : (st[i] > 0 ? hi[i] : 0.0);
-      if (st[i] == 0) idx[k++] = i;
+    double A[36], r[6], xb[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xb[i] = st[i] == 0 ? 0.0 : (st[i] == 2 ? 0.0 : (st[i] < 0 ? lo[i] : hi[i]));
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double ra = -f[a];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const bool fa = st[a] == 0, fj = st[j] == 0;
+        A[a * 6 + j] = (fa && fj) ? H[a * 6 + j] : (a == j ? 1.0 : 0.0);
+        if (fa && !fj) ra -= H[a * 6 + j] * xb[j];
+      }
+      r[a] = st[a] == 0 ? ra : xb[a];
     }
-    for (int a = 0; a < k; ++a) {
-      double r = -f[idx[a]];
-      for (int j = 0; j < nv; ++j)
-        if (st[j] != 0) r -= H[idx[a] * 6 + j] * x[j];
-      for (int c = 0; c < k; ++c) A[a][c] = H[idx[a] * 6 + idx[c]];
-      A[a][k] = r;
-    }
-    for (int c = 0; c < k; ++c) {  // Gaussian elimination with partial pivoting
-      int pr = c;
-      for (int a = c + 1; a < k; ++a)
-        if (fabs(A[a][c]) > fabs(A[pr][c])) pr = a;
-      if (!(fabs(A[pr][c]) > 0.0)) return false;
-      for (int j = c; j <= k; ++j) { const double t = A[c][j]; A[c][j] = A[pr][j]; A[pr][j] = t; }
-      for (int a = c + 1; a < k; ++a) {
-        const double fct = A[a][c] / A[c][c];
-        for (int j = c; j <= k; ++j) A[a][j] -= fct * A[c][j];
+    // LDL^T-free Gaussian elimination of the SPD system (no pivoting needed)
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      ok = ok && A[c * 6 + c] > 0.0;
+      const double inv = 1.0 / A[c * 6 + c];
+#pragma unroll
+      for (int a = c + 1; a < 6; ++a) {
+        const double fct = A[a * 6 + c] * inv;
+#pragma unroll
+        for (int j = c + 1; j < 6; ++j) A[a * 6 + j] -= fct * A[c * 6 + j];
+        r[a] -= fct * r[c];
       }
     }
-    for (int a = k - 1; a >= 0; --a) {
-      double v = A[a][k];
-      for (int c = a + 1; c < k; ++c) v -= A[a][c] * x[idx[c]];
-      x[idx[a]] = v / A[a][a];
+    if (!ok) return false;
+#pragma unroll
+    for (int a = 5; a >= 0; --a) {
+      double v = r[a];
+#pragma unroll
+      for (int c = a + 1; c < 6; ++c) v -= A[a * 6 + c] * x[c];
+      x[a] = v / A[a * 6 + a];
     }
     bool changed = false;
-    for (int i = 0; i < nv; ++i) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
       if (st[i] == 0) {
         if (x[i] < lo[i]) { st[i] = -1; changed = true; }
         else if (x[i] > hi[i]) { st[i] = 1; changed = true; }
-      } else {
+      } else if (st[i] != 2) {
         double gi = f[i];
-        for (int j = 0; j < nv; ++j) gi += H[i * 6 + j] * x[j];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) gi += H[i * 6 + j] * x[j];
         if ((st[i] < 0 && gi < 0.0) || (st[i] > 0 && gi > 0.0)) { st[i] = 0; changed = true; }
       }
     }
-    if (!changed) return true;
+    if (!changed) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) io[54 + i] = x[i];
+      return true;
+    }
   }
   return false;
 }
@@ -1125,19 +1148,20 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       DDQC_PHASE(3);
       if (tid == 0) {
         // 6-variable box QP for the equilibrium (bounds on u_s only)
-        double Hs[36], fs[6], lo[6], hi[6], x[6];
-        for (int a = 0; a < nsig; ++a) {
-          for (int c = 0; c < nsig; ++c) Hs[a * 6 + c] = -2.0 * lam_as * *elem_tri(sM, Paug + (a > c ? a : c), Paug + (a > c ? c : a));
-          fs[a] = -2.0 * lam_as * *elem_tri(sM, Paug + nsig, Paug + a);
-          lo[a] = a < m ? cfg.Us_lo[a] : -INFINITY;
-          hi[a] = a < m ? cfg.Us_hi[a] : INFINITY;
+        double* io = s_vec;  // free at this point: H 36 | f 6 | lo 6 | hi 6 | x 6
+        for (int a = 0; a < 6; ++a) {
+          for (int c = 0; c < 6; ++c)
+            io[a * 6 + c] = (a < nsig && c < nsig) ? -2.0 * lam_as * *elem_tri(sM, Paug + (a > c ? a : c), Paug + (a > c ? c : a)) : 0.0;
+          io[36 + a] = a < nsig ? -2.0 * lam_as * *elem_tri(sM, Paug + nsig, Paug + a) : 0.0;
+          io[42 + a] = a < m ? cfg.Us_lo[a] : -INFINITY;
+          io[48 + a] = a < m ? cfg.Us_hi[a] : INFINITY;
+          if (a >= m && a < nsig) {
+            io[a * 6 + a] += 2.0 * cfg.S[a - m];
+            io[36 + a] -= 2.0 * cfg.S[a - m] * y_r[(size_t)b * p + (a - m)];
+          }
         }
-        for (int i = 0; i < p; ++i) {
-          Hs[(m + i) * 6 + m + i] += 2.0 * cfg.S[i];
-          fs[m + i] -= 2.0 * cfg.S[i] * y_r[(size_t)b * p + i];
-        }
-        if (!small_box_qp(Hs, fs, lo, hi, nsig, x)) s_flag = 1;
-        for (int a = 0; a < nsig; ++a) s_coef[a] = x[a];
+        if (!small_box_qp(io, nsig)) s_flag = 1;
+        for (int a = 0; a < nsig; ++a) s_coef[a] = io[54 + a];
         s_coef[nsig] = 1.0;
       }
       __syncthreads();
