@@ -48,6 +48,7 @@ def collect_initial_input_output_data_batched(
     N: int,
     generator: torch.Generator | None = None,
     np_randoms=None,
+    excite_mask: torch.Tensor | None = None,
 ) -> tuple[torch.Tensor, torch.Tensor]:
     """Returns (u_N, y_N) with shapes (num_envs, N, m) and (num_envs, N, 3), float64.
 
@@ -70,6 +71,8 @@ def collect_initial_input_output_data_batched(
         pe = torch.from_numpy(pe_np).to(dev).permute(1, 0, 2).contiguous()
     else:
         pe = ur[:, 0] + (ur[:, 1] - ur[:, 0]) * torch.rand((N, B, m), device=dev, generator=generator, dtype=torch.float64)
+    if excite_mask is not None:  # drones outside the mask are only stabilised (controller comparison: the
+        pe = pe * excite_mask.to(dev, torch.float64).reshape(1, B, 1)  # other controllers' drones keep hovering)
     u_N = torch.empty((B, N, m), dtype=torch.float64, device=dev)
     y_N = torch.empty((B, N, 3), dtype=torch.float64, device=dev)
     with torch.no_grad():
