@@ -44,6 +44,9 @@ namespace {
 #define DDQC_MPC_THREADS 512
 #endif
 constexpr int kThreads = DDQC_MPC_THREADS;
+#ifndef DDQC_BULK_ALL
+#define DDQC_BULK_ALL 1  // 1: warps 4, 8, 12 (warp 0's SM sub-partition) also take part in the lookahead updates
+#endif
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxNx = 128;    // max box-QP variables
 constexpr int kMaxSig = 8;     // max m, p
@@ -339,9 +342,9 @@ __device__ void factor_columns(double* __restrict__ M, int nb1, int nrows, int n
       const int bw = warp - 1;
       // warps 4, 8, 12 share warp 0's SM sub-partition and its FP64 pipe: they sit out the tensor-core
       // bulk so that the diagonal-block chain is not queued behind 16-cycle DMMA issues
-      if (K > 0 && K + 1 < ncols && (warp & 3) != 0) {
-        const int bw12 = (warp >> 2) * 3 + (warp & 3) - 1;
-        for (int I = K + 1 + 2 * bw12; I < nrows; I += 2 * (kWarps - kWarps / 4)) {
+      if (K > 0 && K + 1 < ncols && (DDQC_BULK_ALL || (warp & 3) != 0)) {
+        const int bw12 = DDQC_BULK_ALL ? bw : (warp >> 2) * 3 + (warp & 3) - 1;
+        for (int I = K + 1 + 2 * bw12; I < nrows; I += 2 * (DDQC_BULK_ALL ? kBulk : kWarps - kWarps / 4)) {
           const bool two = I + 1 < nrows;
           double2 s0, s1;
           syrk_pair<RECT>(M, nb1, I, I + 1, two, K + 1, K, g, t, s0, s1);
@@ -1029,17 +1032,22 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
           const double* wb = sW + bs * N;
           const short* pa = s_ppos + a * ell;
           const short* pb = s_ppos + bs * ell;
+          // one loop of (almost) the same length for every task: walk the first diagonal, then switch to the
+          // second one - lanes with different diagonal lengths stay converged
+          const int len0 = ell - (d0 > 0 ? d0 : -d0), len1 = d1 <= -ell ? 0 : ell - (d1 > 0 ? d1 : -d1);
+          int j = d0 > 0 ? d0 : 0, k = d0 > 0 ? 0 : -d0;
+          double f = d0 >= 0 ? sT[(d0 * nsig + a) * ldT + bs] : sT[(-d0 * nsig + bs) * ldT + a];
 #pragma unroll 1
-          for (int rep = 0; rep < 2; ++rep) {
-            const int dl = rep ? d1 : d0;
-            if (dl <= -ell) continue;
-            int j = dl > 0 ? dl : 0, k = dl > 0 ? 0 : -dl;
-            double f = dl >= 0 ? sT[(dl * nsig + a) * ldT + bs] : sT[(-dl * nsig + bs) * ldT + a];
-            for (;; ++j, ++k) {
-              put_sym(d, GA, GS, pa[j], pb[k], f);
-              if (j + 1 >= ell || k + 1 >= ell) break;
-              f += wa[j + C] * wb[k + C] - wa[j] * wb[k];
+          for (int s2 = 0; s2 < len0 + len1; ++s2) {
+            if (s2 == len0) {  // second diagonal
+              j = d1 > 0 ? d1 : 0;
+              k = d1 > 0 ? 0 : -d1;
+              f = d1 >= 0 ? sT[(d1 * nsig + a) * ldT + bs] : sT[(-d1 * nsig + bs) * ldT + a];
             }
+            put_sym(d, GA, GS, pa[j], pb[k], f);
+            if (j + 1 < ell && k + 1 < ell) f += wa[j + C] * wb[k + C] - wa[j] * wb[k];
+            ++j;
+            ++k;
           }
         }
         // ones row: G[(j,a), one] = sum_c w_a[j+c] = T[(j,a)][nsig];  G[one][one] = C
