@@ -358,7 +358,7 @@ def run_policy_leg(env, dev, N: int, steps: int = 100, warm: int = 10) -> dict:
             "peak": peak, "unit": "TFLOP/s", "frac": flops_tc / (ms_pol * 1e-3) / 1e12 / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained",
             "algorithmic_tflops": flops_alg / (ms_pol * 1e-3) / 1e12,
-            "traffic": 69.6e6 if N == 1 << 20 else None, "traffic_source": "profiles/r1a_policy_mlp_ncu_full.csv (67.2 MB read = the obs tile, 2.4 MB written)",
+            "traffic": 69.2e6 if N == 1 << 20 else None, "traffic_source": "profiles/r1b_policy_mlp_ncu_full.csv (67.2 MB read = the obs tile, 2.0 MB written)",
         },
         "gpu_launches": 3 * steps,
     }
@@ -511,8 +511,8 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
             "peak": fp64_peak, "unit": "TFLOP/s", "frac": batch * flops / (avg * 1e-3) / 1e12 / fp64_peak,
             "peak_source": "FP64 tensor (DMMA m8n8k4) = FP64 FMA pipe, 64 FMA/clk/SM, measured 37.1 TFLOP/s with "
             "tools/ubench_fp64.cu (MEASURED_PEAKS.json carries no fp64 figure)",
-            "flops_per_solve": flops, "traffic": 123.9e6 if batch == 4096 else None,
-            "traffic_source": "profiles/r1b_ddmpc_solve_ncu_full.csv (DRAM bytes per launch of 4096 solves; the workspace slots stay in L2)",
+            "flops_per_solve": flops, "traffic": 148.2e6 if batch == 4096 else None,
+            "traffic_source": "profiles/r1d_ddmpc_solve_ncu_full.csv (DRAM bytes per launch of 4096 solves; the workspace slots stay in L2)",
         },
         "gpu_launches": T,
     }
