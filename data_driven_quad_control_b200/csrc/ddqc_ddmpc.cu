@@ -17,13 +17,15 @@
 //        R1 = past-input rows, ones row, terminal-input rows (hard, shared by both systems)
 //        R2 = output rows (soft: diagonal regularisation D differs between the two systems)
 //        R3 = predicted-input rows (the box-constrained decision variables y_B)
-//        aug = right-hand sides carried as extra rows: T_u (m), T_y (p), tau, b_s
+//        aug = right-hand sides carried as extra rows: A_u (m), A_y (p), e_one, tau | T_u (m), T_y (p)
 //   A. Eliminate R1 (left-looking blocked Cholesky of the panel in shared memory), then
 //      S1 = trailing - L L^T streamed through global memory once.  S1 is used twice:
-//   B. alpha_sr system: S1 + D_s, factor everything, forward substitution comes for free in the
-//      b_s row, blocked back-substitution gives z, e = D_s z on R2  (v_sr = b_s - e).
-//   C. main system: S1 + D_0, c-row = tau - b_s + e, eliminate R2 only; the Schur complement on
-//      [R3 | aug] is swept on R3 (Gauss-Jordan) which yields the box-QP Hessian and gradient.
+//   B. alpha_sr system (alpha of the optimal reachable equilibrium for y_r): S1 + D_s with the aug rows
+//      A_u, A_y, e_one is factored completely; the aug x aug Schur block gives a 6-variable box QP for
+//      (u_sr, y_sr); rho = A_u u_sr + A_y y_sr + e_one is forward-substituted for free (same combination
+//      of the aug rows), a blocked back-substitution gives e = D_s (G + D_s)^-1 rho on R2 (v_sr = rho - e).
+//   C. main system: S1 + D_0, aug rows T_u, T_y and c = tau - rho + e, eliminate R2 only; the Schur
+//      complement on [R3 | aug] is swept on R3 (Gauss-Jordan) which yields the box-QP Hessian and gradient.
 //   D. box QP: block principal pivoting in the space of the FREE variables, warm-started from
 //      the previous solve's active set (shifted one step); primal-dual interior point fallback
 //      followed by a pivoting polish when pivoting does not settle.
@@ -57,8 +59,8 @@ constexpr int kMaxPos = 1024;  // max (m + p) * ell
 struct Dims {
   int n, m, p, L, N, ell, C;
   int n1, n2, n3, na;        // class sizes (rows)
-  int n1p, n2p, n3p, nap;    // padded to multiples of 8
-  int nb1, nb2, nb3, nba;    // in 8x8 blocks
+  int n1p, n2p, n3p;         // padded to multiples of 8
+  int nb1, nb2, nb3;         // in 8x8 blocks
   int nbt, nbA;              // trailing block rows, all block rows
   int nx, nS, ldS, ldq;
   int ga, gs, gsg;           // doubles: R1 panel (rect), trailing in shared memory / in the workspace (block-packed lower)
@@ -75,8 +77,8 @@ __host__ __device__ inline Dims make_dims(const DdqcMpcConfig& c) {
   d.n2 = c.p * d.ell;
   d.n3 = (c.L - c.n) * c.m;
   d.na = c.m + c.p + 2;  // aug group 0: A_u, A_y, e_one, tau (group 1: T_u, T_y); each fits one block row
-  d.n1p = rup8(d.n1); d.n2p = rup8(d.n2); d.n3p = rup8(d.n3); d.nap = rup8(d.na);
-  d.nb1 = d.n1p / 8; d.nb2 = d.n2p / 8; d.nb3 = d.n3p / 8; d.nba = d.nap / 8;
+  d.n1p = rup8(d.n1); d.n2p = rup8(d.n2); d.n3p = rup8(d.n3);
+  d.nb1 = d.n1p / 8; d.nb2 = d.n2p / 8; d.nb3 = d.n3p / 8;
   d.nbt = d.nb2 + d.nb3 + 1;      // block rows held in shared memory (matrix + ONE aug block row)
   d.nbA = d.nb1 + d.nbt + 1;      // block rows of the R1 panel (both aug block rows)
   d.nx = d.n3 + c.m + c.p;
