@@ -224,7 +224,53 @@ def run_b200(args) -> dict:
             "h2d_bytes_per_step": N * A * 4,
             "d2h_bytes_per_step": N * (env.num_obs * 4 + 4 + 1),
             "steps": Ke,
+            "mode": "synchronous: the results of step k are on the host before the actions of step k+1 are sent",
         }
+        # streaming variant of the same loop (extra information, not the headline): outputs are staged on the device
+        # and drained by a copy stream while the next step's actions are uploaded and its kernel runs; the host waits
+        # for the results of step k-1 before it launches step k+1
+        copy_s, up_s = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        main_s = torch.cuda.current_stream()
+        stage = [(torch.empty((N, env.num_obs), device=dev), torch.empty((N,), device=dev), torch.empty((N,), dtype=torch.bool, device=dev)) for _ in range(2)]
+        h_out = [(torch.empty((N, env.num_obs)).pin_memory(), torch.empty((N,)).pin_memory(), torch.empty((N,), dtype=torch.bool).pin_memory()) for _ in range(2)]
+        ev_up = [torch.cuda.Event() for _ in range(2)]
+        ev_stage = [torch.cuda.Event() for _ in range(2)]
+        ev_down = [torch.cuda.Event() for _ in range(2)]
+        ev_used = [torch.cuda.Event() for _ in range(2)]
+        for e in ev_used + ev_down:
+            e.record(main_s)
+        barrier()
+        for it in range(-2, Ke):
+            if it == 0:
+                barrier()
+                t0.record()
+            b = it % 2
+            with torch.cuda.stream(up_s):
+                up_s.wait_event(ev_used[b])  # the kernel that last read d_act[b] is done
+                d_act[b].copy_(h_act[b], non_blocking=True)
+                ev_up[b].record(up_s)
+            main_s.wait_event(ev_up[b])
+            obs, rew, rst, _ = env.step(d_act[b])
+            ev_used[b].record(main_s)
+            main_s.wait_event(ev_down[b])  # the staging buffers of parity b have been drained
+            stage[b][0].copy_(obs)
+            stage[b][1].copy_(rew)
+            stage[b][2].copy_(rst)
+            ev_stage[b].record(main_s)
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(ev_stage[b])
+                for hbuf, dbuf in zip(h_out[b], stage[b]):
+                    hbuf.copy_(dbuf, non_blocking=True)
+                ev_down[b].record(copy_s)
+            ev_down[1 - b].synchronize()  # results of the previous step are on the host
+        ev_down[(Ke - 1) % 2].synchronize()
+        t1.record()
+        barrier()
+        p_ms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(p_ms, op=dist.ReduceOp.MAX)
+        e2e["streaming_value"] = N * world * Ke / (float(p_ms.item()) * 1e-3)
+        e2e["streaming_mode"] = "double-buffered: D2H of step k overlaps H2D + kernel of step k+1 (one step of result latency)"
 
     # ---- final all-reduce of rollout statistics (the only collective of the path)
     from data_driven_quad_control_b200.parallel import allreduce_rollout_stats

@@ -55,6 +55,8 @@ constexpr int kMaxSig = 8;     // max m, p
 constexpr int kMaxSlots = 160; // workspace slots (>= SM count)
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kMaxPos = 1024;  // max (m + p) * ell
+constexpr int kRepackQ = (((kMaxNx / 8 + 2) * (kMaxNx / 8 + 3) / 2) * 64 + kThreads - 1) / kThreads;  // Schur repack, values per thread
+constexpr int kAsmRows = (kMaxNx + 1 + kWarps - 1) / kWarps, kAsmCols = (kMaxNx + 31) / 32;               // Hq/f assembly: rows per warp, columns per lane
 
 struct Dims {
   int n, m, p, L, N, ell, C;
@@ -94,10 +96,10 @@ __host__ __device__ inline Dims make_dims(const DdqcMpcConfig& c) {
 // extra shared-memory doubles behind the matrix region
 __host__ __device__ inline int extra_doubles(const Dims& d) { return 8 * d.nbt + d.n2p + 2 * (d.nS + 22) + 64 + 8; }
 
-// S7 (dense, nS x ldS) and the block-packed factor of the free block (up to nx variables) share one area
+// block-packed factor of the free block of the box QP (up to nx variables)
 __host__ __device__ inline int qp_scratch_doubles(const Dims& d) {
-  const int nbq = (d.nx + 7) >> 3, fblk = nbq * (nbq + 1) / 2 * 64, s7 = d.nS * d.ldS;
-  return ((fblk > s7 ? fblk : s7) + 1) & ~1;
+  const int nbq = (d.nx + 7) >> 3;
+  return nbq * (nbq + 1) / 2 * 64;
 }
 
 __host__ __device__ inline int region_doubles(const Dims& d) {
@@ -108,6 +110,8 @@ __host__ __device__ inline int region_doubles(const Dims& d) {
   // box-QP stage: S7 | Hq | 20 vectors ; the block-packed factor scratch aliases S7
   const int qp = qp_scratch_doubles(d) + d.nx * d.ldq + 20 * kMaxNx;
   if (qp > r) r = qp;
+  const int nr2 = 2 * d.nb3 + 1, zmat = nr2 * (nr2 + 1) / 2 * 64;  // [R3 | aug | E] matrix of the Z computation
+  if (zmat > r) r = zmat;
   return (r + 1) & ~1;  // keep everything behind the region 16-byte aligned
 }
 
@@ -707,81 +711,75 @@ __device__ int ipm_solve(const QpWork& q, int max_it) {
   return done ? (it + 1) : -(it + 1);
 }
 
-// ---- Gauss-Jordan sweep of the leading `npiv` pivots of a symmetric matrix (lower triangle) -------------
-// Sweeping pivot j is the symmetric rank-1 update  A <- A - p p^T / d - 2 e_j e_j^T  with
-// p = A[:, j] - e_j, d = A[j][j]: the same update for every entry; the constant -2 on the swept
-// diagonal entries commutes with the later updates and is applied once at the end.
-// The source is read through `load(i, k)` (i >= k) once, before the first barrier, and the result is written
-// to the dense matrix S afterwards, so S may alias the source storage.
-// Thread t owns CH consecutive entries of one row of the lower triangle and keeps them in REGISTERS
-// for the whole sweep (the matrix is read once and written once: the phase is otherwise bound by
-// shared-memory bandwidth); per pivot it reads p[row] and its CH-chunk of p.  The owners of row /
-// column j+1 publish the next p into a double buffer, so one barrier per pivot suffices.
-__host__ __device__ inline int sweep_threads(int nS, int ch) {
-  int tot = 0;
-  for (int i = 0; i < nS; ++i) tot += (i + ch) / ch;
-  return tot;
-}
+// ---- two staging steps of the Z computation, kept out of line so that their register arrays do not weigh on
+// the register allocation of the rest of the solver --------------------------------------------------------
 
-template <int CH, class Load>
-__device__ void sweep_lower(double* __restrict__ S, int ld, int nS, int npiv, double* __restrict__ vbuf, Load load) {
+// S (lower blocks (nb2+i, nb2+j) of the factored matrix) -> [S | E] from offset 0, E = identity below S
+__device__ __noinline__ void repack_schur(double* __restrict__ sM, int nb2, int nb3) {
   const int tid = threadIdx.x;
-  // thread -> (row, k0): rows in order, ceil((row + 1) / CH) threads each
-  int row = -1, k0 = 0;
-  {
-    int t = tid;
-    // rows r with (r + CH) / CH == c threads: r in [CH (c-1), CH c - 1]; closed form by groups of CH rows
-    for (int c = 1; row < 0; ++c) {
-      const int r_lo = CH * (c - 1), r_hi = min(CH * c - 1, nS - 1);
-      if (r_lo >= nS) break;
-      const int cnt = (r_hi - r_lo + 1) * c;
-      if (t < cnt) { row = r_lo + t / c; k0 = (t % c) * CH; }
-      else t -= cnt;
-    }
-  }
-  const bool own = row >= 0;
-  const int vstride = ((nS + CH + 1) & ~1);
-  double* vb0 = vbuf;
-  double* vb1 = vbuf + vstride;
-  double val[CH];
+  const int nsb = nb3 + 1, nsrc = tri(nsb) * 64, nr2 = 2 * nb3 + 1;
+  double keep[kRepackQ];  // source and destination overlap: through registers
 #pragma unroll
-  for (int e = 0; e < CH; ++e) val[e] = (own && k0 + e <= row) ? load(row, k0 + e) : 0.0;
-  for (int i = tid; i < vstride; i += kThreads) {
-    vb0[i] = i < nS ? load(i, 0) - (i == 0 ? 1.0 : 0.0) : 0.0;
-    vb1[i] = 0.0;
+  for (int qq = 0; qq < kRepackQ; ++qq) {
+    const int e = tid + qq * kThreads;
+    keep[qq] = 0.0;
+    if (e < nsrc) {
+      const int bb = e >> 6;
+      int i = (int)((sqrtf(8.0f * bb + 1.0f) - 1.0f) * 0.5f);
+      while (tri(i + 1) <= bb) ++i;
+      while (tri(i) > bb) --i;
+      const int j = bb - tri(i);
+      keep[qq] = sM[(size_t)(tri(nb2 + i) + nb2 + j) * 64 + (e & 63)];
+    }
   }
   __syncthreads();
-  for (int j = 0; j < npiv; ++j) {
-    const double* vc = (j & 1) ? vb1 : vb0;
-    double* vn = (j & 1) ? vb0 : vb1;
-    if (own) {
-      const double pi = vc[row] * (-1.0 / (vc[j] + 1.0));
-      const double2* pk = reinterpret_cast<const double2*>(vc + k0);
+  double2* z2 = reinterpret_cast<double2*>(sM);
+  for (int e = tid; e < tri(nr2) * 32; e += kThreads) z2[e] = make_double2(0.0, 0.0);
+  __syncthreads();
 #pragma unroll
-      for (int e = 0; e < CH; e += 2) {
-        const double2 pv = pk[e >> 1];
-        val[e] = fma(pi, pv.x, val[e]);
-        val[e + 1] = fma(pi, pv.y, val[e + 1]);
-      }
-      if (row == j + 1) {
+  for (int qq = 0; qq < kRepackQ; ++qq) {
+    const int e = tid + qq * kThreads;
+    if (e < nsrc) sM[e] = keep[qq];  // same block order (tri(i) + j), now from offset 0
+  }
+  for (int e = tid; e < 8 * nb3; e += kThreads) *elem_tri(sM, 8 * nsb + e, e) = 1.0;
+  __syncthreads();
+}
+
+// Hq = scale * Z[:nx, :nx], f = scale * Z[nx, :nx] read from the trailing blocks of the [R3 | aug | E] matrix;
+// Hq overlaps the matrix it is read from: through registers.  A warp takes whole rows, lanes the columns.
+__device__ __noinline__ void assemble_hq(const double* __restrict__ sM, double* __restrict__ Hq, double* __restrict__ f,
+                                         double scale, int nb3, int n3, int nx, int ldq) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pa = 8 * nb3, pe = 8 * (nb3 + 1);
+  double keep[kAsmRows][kAsmCols];
 #pragma unroll
-        for (int e = 0; e < CH; ++e)
-          if (k0 + e <= row) vn[k0 + e] = (k0 + e == row) ? val[e] - 1.0 : val[e];
-      } else if (row > j + 1) {
-        const int en = j + 1 - k0;
-        if ((unsigned)en < (unsigned)CH) {
+  for (int rr = 0; rr < kAsmRows; ++rr) {
+    const int i = warp + rr * kWarps;  // i in [0, nx]: row nx is the c-row (gradient)
+    const int ii = i < nx ? i : nx;
+    const int Pi = ii < n3 ? pe + ii : pa + (ii - n3);
 #pragma unroll
-          for (int e = 0; e < CH; ++e)
-            if (e == en) vn[row] = val[e];
-        }
+    for (int kk = 0; kk < kAsmCols; ++kk) {
+      const int k = lane + 32 * kk;
+      keep[rr][kk] = 0.0;
+      if (i <= nx && k < nx) {
+        const int Pk = k < n3 ? pe + k : pa + (k - n3);
+        const int hi = Pi > Pk ? Pi : Pk, lo = Pi > Pk ? Pk : Pi;
+        keep[rr][kk] = scale * sM[(size_t)(tri(hi >> 3) + (lo >> 3)) * 64 + eoff(hi & 7, lo & 7)];
       }
     }
-    __syncthreads();
   }
-  if (own) {
+  __syncthreads();
 #pragma unroll
-    for (int e = 0; e < CH; ++e)
-      if (k0 + e <= row) S[row * ld + k0 + e] = val[e] - ((k0 + e == row && row < npiv) ? 2.0 : 0.0);
+  for (int rr = 0; rr < kAsmRows; ++rr) {
+    const int i = warp + rr * kWarps;
+#pragma unroll
+    for (int kk = 0; kk < kAsmCols; ++kk) {
+      const int k = lane + 32 * kk;
+      if (i <= nx && k < nx) {
+        if (i < nx) Hq[i * ldq + k] = keep[rr][kk];
+        else f[k] = keep[rr][kk];
+      }
+    }
   }
   __syncthreads();
 }
@@ -906,7 +904,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
   double* sx = smem + region_doubles(d);   // extras
   double* s_yv = sx;                       // 8*nbt : back-substitution vector
   double* s_e = s_yv + 8 * d.nbt;          // n2p   : e = D_s z on R2
-  double* s_vec = s_e + d.n2p;             // 2*(nS+2) : sweep pivot-column double buffer
+  double* s_vec = s_e + d.n2p;             // scratch: inputs / result of the equilibrium QP
   double* s_red = s_vec + 2 * (d.nS + 22);  // 64
   double* s_coef = s_red + 64;              // 8: rho = sum_a coef[a] * (aug group 0 row a)
   __shared__ int s_flag;
@@ -1245,45 +1243,31 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     DDQC_PHASE(5);
 
     // ---- sweep: S7 (dense, lower) <- Schur complement on [R3 (n3) | T_u, T_y, c] ---------------------
-    const int nS = d.nS, ldS = d.ldS, nx = d.nx, ldq = d.ldq;
-    double* S7 = sM;
-    // entry (i, k), i >= k, of the Schur complement on [R3 (n3) | T_u, T_y, c], read from the block layout
-    auto schur = [&](int i, int k) {
-      const int Pi = i < d.n3 ? d.n2p + i : Paug + (i - d.n3);
-      const int Pk = k < d.n3 ? d.n2p + k : Paug + (k - d.n3);
-      return *elem_tri(sM, Pi, Pk);
-    };
-    if (sweep_threads(nS, 10) <= kThreads) sweep_lower<10>(S7, ldS, nS, d.n3, s_vec, schur);
-    else sweep_lower<20>(S7, ldS, nS, d.n3, s_vec, schur);
+    // ---- Z = K'(G + D_0)^-1 K from the Schur complement S on [R3 | aug] WITHOUT a scalar Gauss-Jordan sweep:
+    // append an identity block E below S, [R3 (nb3) | aug (1) | E (nb3)], eliminate R3 once more on the tensor
+    // cores; the trailing blocks are then  (aug,aug) = S_aa - S_aB S_BB^-1 S_Ba = -Z_aa,  (E,aug) = -S_BB^-1 S_Ba
+    // = -Z_Ba,  (E,E) = -S_BB^-1 = -Z_BB:   Z = -trailing, one sign for all blocks.
+    const int nr2 = 2 * d.nb3 + 1;
+    repack_schur(sM, d.nb2, d.nb3);
+    __syncthreads();
+    factor_columns<false>(sM, 0, nr2, d.nb3, &s_flag);
+    schur_trailing(sM, nr2, d.nb3);
+    __syncthreads();
     DDQC_PHASE(6);
 
     // ---- box QP assembly: Hq = 2 lamb_alpha Z + structure, f ----------------------------------------
+    const int nx = d.nx, ldq = d.ldq;
     double* Hq = sM + qp_scratch_doubles(d);
     double* qv = Hq + nx * ldq;  // 20 vectors of kMaxNx
     QpWork q;
     q.Hq = Hq; q.ldq = ldq; q.nx = nx;
-    q.F = sM; q.ldf = ldS;
+    q.F = sM; q.ldf = 0;
     q.f = qv; q.lo = qv + kMaxNx; q.hi = qv + 2 * kMaxNx; q.x = qv + 3 * kMaxNx; q.g = qv + 4 * kMaxNx;
     q.rhs = qv + 5 * kMaxNx; q.rs = qv + 6 * kMaxNx; q.sl = qv + 7 * kMaxNx; q.su = qv + 8 * kMaxNx;
     q.zl = qv + 9 * kMaxNx; q.zu = qv + 10 * kMaxNx; q.dx = qv + 11 * kMaxNx; q.dzl = qv + 12 * kMaxNx;
     q.dzu = qv + 13 * kMaxNx; q.rd = qv + 14 * kMaxNx; q.dg = qv + 15 * kMaxNx;
     q.s_red = s_red; q.state = s_state; q.idx = s_idx; q.verdict = s_verdict; q.s_flag = &s_flag;
-    {
-      const double la2 = 2.0 * lam_a;
-      for (int e = tid; e < nS * nx; e += kThreads) {
-        const int i = e / nx, k = e % nx;  // i in [0, nS), k in [0, nx)
-        if (k > i) continue;
-        const double sw = S7[i * ldS + k];
-        const bool iB = i < d.n3, kB = k < d.n3;
-        const double z = (iB == kB) ? -sw : sw;
-        if (i < nx) {
-          Hq[i * ldq + k] = la2 * z;
-          Hq[k * ldq + i] = la2 * z;
-        } else {
-          q.f[k] = la2 * z;
-        }
-      }
-    }
+    assemble_hq(sM, Hq, q.f, -2.0 * lam_a, d.nb3, d.n3, nx, ldq);  // Z = -trailing
     __syncthreads();
     if (tid == 0) {
       const int nB = d.n3;
@@ -1477,7 +1461,6 @@ int check_cfg(const DdqcMpcConfig* c) {
   if (c->m < 1 || c->p < 1 || c->m > kMaxSig || c->p > kMaxSig || c->n < 1 || c->L <= c->n) return DDQC_E_SHAPE;
   const Dims d = make_dims(*c);
   if (d.C < 1 || d.nx > kMaxNx || (d.m + d.p) * d.ell > kMaxPos || d.m + d.p + 2 > 8) return DDQC_E_SHAPE;
-  if (sweep_threads(d.nS, 20) > kThreads) return DDQC_E_SHAPE;
   if (smem_bytes(d) + 4608 > (size_t)kSmemLimit) return DDQC_E_SHAPE;
   if (c->alpha_reg_type != 0 && c->alpha_reg_type != 2) return DDQC_E_CONFIG;
   return 0;
