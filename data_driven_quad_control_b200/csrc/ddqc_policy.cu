@@ -197,16 +197,25 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
   uint32_t phase = 0;
 
   const long long n_tiles = (n + kTileM - 1) / kTileM;
-  for (long long tile = (long long)blockIdx.x * 2 + wg; tile < n_tiles; tile += (long long)gridDim.x * 2) {
+  const long long tile_step = (long long)gridDim.x * 2;
+  // observation chunk of this thread (row, 8 of the 16 inputs), software-pipelined: the loads of the NEXT tile are
+  // issued while the layer-2 MMAs of the current one run, so no tile starts with an exposed global-memory round trip
+  float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+  {
+    const long long t0 = (long long)blockIdx.x * 2 + wg;
+    if (t0 < n_tiles && t0 * kTileM + row < n) {
+      const float4* src = reinterpret_cast<const float4*>(obs + (t0 * kTileM + row) * kIn + 8 * half);
+      o0 = __ldg(src);
+      o1 = __ldg(src + 1);
+    }
+  }
+  for (long long tile = (long long)blockIdx.x * 2 + wg; tile < n_tiles; tile += tile_step) {
     const long long grow = tile * kTileM + row;
     const bool valid = grow < n;
     // ---- 1. observation row -> layer-1 operand tile (each thread one 8-element K chunk) ----
     {
       float y[8];
-      const float4* src = reinterpret_cast<const float4*>(obs + (valid ? grow : 0) * kIn + 8 * half);
-      const float4 v0 = valid ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 v1 = valid ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-      y[0] = v0.x; y[1] = v0.y; y[2] = v0.z; y[3] = v0.w; y[4] = v1.x; y[5] = v1.y; y[6] = v1.z; y[7] = v1.w;
+      y[0] = o0.x; y[1] = o0.y; y[2] = o0.z; y[3] = o0.w; y[4] = o1.x; y[5] = o1.y; y[6] = o1.z; y[7] = o1.w;
       const uint32_t off = core_off(row, 8 * half, kIn / 8);
       store_chunk(wgs, kA1Hi + off, kA1Lo + off, y);
     }
@@ -264,6 +273,16 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
         }
       }
       umma_commit(mbar);
+    }
+    {  // prefetch the next tile's observation chunk
+      const long long nrow = (tile + tile_step) * kTileM + row;
+      o0 = make_float4(0.f, 0.f, 0.f, 0.f);
+      o1 = o0;
+      if (tile + tile_step < n_tiles && nrow < n) {
+        const float4* src = reinterpret_cast<const float4*>(obs + nrow * kIn + 8 * half);
+        o0 = __ldg(src);
+        o1 = __ldg(src + 1);
+      }
     }
     mbar_wait(mbar, phase);
     phase ^= 1;
