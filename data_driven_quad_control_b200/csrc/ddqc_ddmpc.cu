@@ -98,7 +98,7 @@ __host__ __device__ inline int extra_doubles(const Dims& d) { return 8 * d.nbt +
 
 // block-packed factor of the free block of the box QP (up to nx variables)
 __host__ __device__ inline int qp_scratch_doubles(const Dims& d) {
-  const int nbq = (d.nx + 7) >> 3;
+  const int nbq = ((d.nx + 7) >> 3) + 1;  // + the right-hand-side block row
   return nbq * (nbq + 1) / 2 * 64;
 }
 
@@ -169,45 +169,7 @@ __device__ __forceinline__ void syrk_pair(const double* __restrict__ M, int nb1,
   s1.x = b0.x + b1.x; s1.y = b0.y + b1.y;
 }
 
-// Cholesky of one 8x8 block by one warp.  Lane l holds M[l>>3][l&7] and M[(l>>3)+4][l&7]; the pivot
-// loop is ROLLED on purpose: this code sits on the critical path of every block column and an
-// unrolled version (hundreds of straight-line instructions executed by a single warp) spends most
-// of its time in instruction-cache misses.  On exit the block holds L strictly below the diagonal
-// and 1/L_ii ON the diagonal; the strict upper triangle is left as it was.
 #define LT(i, c) a[(i) * ((i) + 1) / 2 + (c)]
-__device__ __forceinline__ bool chol8_warp(double* blk, int lane) {
-  const int r0 = lane >> 3, c = lane & 7;
-  double A = blk[eoff(r0, c)], B = blk[eoff(r0 + 4, c)];
-  bool ok = true;
-  double dj = shfl_d(A, 0);
-  // One shuffle round per pivot: the column-j entries every lane needs, plus the two values that give
-  // the NEXT pivot (d_{j+1} = a_{j+1,j+1} - l_{j+1,j}^2), so the chain is rsqrt -> scale -> shuffle -> fma.
-  // Branch-free on purpose (selects, masked multipliers): a divergent `if` costs more than the arithmetic.
-#pragma unroll 1
-  for (int j = 0; j < 8; ++j) {
-    ok = ok && (dj > 0.0);
-    dj = dj > 0.0 ? dj : 1.0;
-    const double r = rsqrt(dj);
-    const bool cj = c == j;
-    A = cj ? ((r0 == j) ? r : A * r) : A;
-    B = cj ? ((r0 + 4 == j) ? r : B * r) : B;
-    const int jn = (j + 1) & 7, ln = (jn & 3) << 3;
-    const double x1 = shfl_d(A, (r0 << 3) | j), x2 = shfl_d(B, (r0 << 3) | j);
-    const double y1 = shfl_d(A, ((c & 3) << 3) | j), y2 = shfl_d(B, ((c & 3) << 3) | j);
-    const double sn = jn < 4 ? A : B;
-    const double ln_j = shfl_d(sn, ln | j);    // l_{j+1,j}
-    const double dn = shfl_d(sn, ln | jn);     // a_{j+1,j+1} before this pivot's update
-    const double lc = c < 4 ? y1 : y2;
-    const double ma = (c > j && r0 >= c) ? lc : 0.0, mb = (c > j && r0 + 4 >= c) ? lc : 0.0;
-    A = fma(-x1, ma, A);
-    B = fma(-x2, mb, B);
-    dj = fma(-ln_j, ln_j, dn);
-  }
-  if (r0 >= c) blk[eoff(r0, c)] = A;
-  if (r0 + 4 >= c) blk[eoff(r0 + 4, c)] = B;
-  return ok;
-}
-
 // load the factor of a diagonal block (36 values, broadcast reads) into registers
 __device__ __forceinline__ void load_diag(const double* dk, double (&a)[36]) {
   // 16-byte broadcast reads (the XOR-4 swizzle keeps even/odd column pairs adjacent)
@@ -221,11 +183,19 @@ __device__ __forceinline__ void load_diag(const double* dk, double (&a)[36]) {
     }
 }
 
-// Cholesky of one 8x8 block with every lane factoring the whole block redundantly in registers: no
-// shuffles and no shared-memory traffic on the 8-pivot dependency chain (rsqrt -> scale -> fma), no
-// divergent code.  The factor stays in `a` (the caller solves its own block against it straight from
-// registers) and is published to shared memory by identical 16-byte stores from all lanes.
-__device__ __forceinline__ bool chol8_regs(double* blk, double (&a)[36]) {
+// Cholesky of one 8x8 diagonal block AND the inverse of its factor, every lane working on the whole block
+// redundantly in registers: no shuffles and no shared-memory traffic on the 8-pivot dependency chain
+// (rsqrt -> scale -> fma), no divergent code.  The factor is then inverted in place, column by column (column j
+// of L is not needed once column j of L^-1 is done).  On exit the block holds W = L^-1 (zeros above the
+// diagonal): every triangular solve against this block is then a product with W - two DMMAs for an 8x8 block
+// (`trsm8_dmma`), an 8x8 mat-vec in the substitutions - instead of a dependent chain.  Published by identical
+// 16-byte stores from all lanes.  (Interleaving the inverse with the pivots - the row operations of a forward
+// substitution on the identity - was measured 40 % slower: the extra FP64 issues delay the pivot chain.)
+#ifndef DDQC_INV_SPLIT
+#define DDQC_INV_SPLIT 1  // 1: each lane inverts one column of the factor (0: every lane the whole factor)
+#endif
+__device__ __forceinline__ bool chol8_inv(double* blk, int lane) {
+  double a[36];
   load_diag(blk, a);
   bool ok = true;
 #pragma unroll
@@ -242,39 +212,53 @@ __device__ __forceinline__ bool chol8_regs(double* blk, double (&a)[36]) {
 #pragma unroll
       for (int i = c; i < 8; ++i) LT(i, c) = fma(-LT(i, j), LT(c, j), LT(i, c));
   }
+#if DDQC_INV_SPLIT
+  // lane l computes column l & 7 of W: forward substitution of the unit vector e_j (static indices; the entries
+  // above the diagonal come out as exact zeros)
+  const int jc = lane & 7;
+  double w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    double s = i == jc ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < i; ++k) s = fma(-LT(i, k), w[k], s);
+    w[i] = s * LT(i, i);
+  }
+  __syncwarp();
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) blk[eoff(i, jc)] = w[i];
+  }
+#else
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int i = j + 1; i < 8; ++i) {
+      double s = LT(i, j) * LT(j, j);
+#pragma unroll
+      for (int k = j + 1; k < i; ++k) s = fma(LT(i, k), LT(k, j), s);
+      LT(i, j) = -s * LT(i, i);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int c = 0; c <= i; c += 2)
-      *reinterpret_cast<double2*>(blk + eoff(i, c)) = make_double2(LT(i, c), c + 1 <= i ? LT(i, c + 1) : 0.0);
+    for (int c = 0; c < 8; c += 2)
+      *reinterpret_cast<double2*>(blk + eoff(i, c)) = make_double2(c <= i ? LT(i, c) : 0.0, c + 1 <= i ? LT(i, c + 1) : 0.0);
+#endif
   return ok;
 }
 
-// X <- X L^-T for one 8x8 block held as an accumulator fragment (thread (g,t): X[g][2t], X[g][2t+1]).
-// The four lanes of a quad all-gather their row (6 shuffles off the dependency chain), solve it
-// redundantly in registers and keep their own two entries.
-__device__ __forceinline__ void trsm8_frag(double2& v, const double (&a)[36], int t) {
-  const bool o1 = t & 1, o2 = t & 2;
-  const double p0 = __shfl_xor_sync(0xffffffffu, v.x, 1), p1 = __shfl_xor_sync(0xffffffffu, v.y, 1);
-  double q[4];
-  q[0] = o1 ? p0 : v.x; q[1] = o1 ? p1 : v.y; q[2] = o1 ? v.x : p0; q[3] = o1 ? v.y : p1;
-  double x[8];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const double pe = __shfl_xor_sync(0xffffffffu, q[e], 2);
-    x[e] = o2 ? pe : q[e];
-    x[4 + e] = o2 ? q[e] : pe;
-  }
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    double acc = x[c];
-#pragma unroll
-    for (int k = 0; k < c; ++k) acc -= x[k] * LT(c, k);
-    x[c] = acc * LT(c, c);
-  }
-  const double e0 = o1 ? x[2] : x[0], e1 = o1 ? x[3] : x[1], e2 = o1 ? x[6] : x[4], e3 = o1 ? x[7] : x[5];
-  v.x = o2 ? e2 : e0;
-  v.y = o2 ? e3 : e1;
+// X <- X L^-T for one 8x8 block on the tensor cores: two DMMAs against W = L^-1 (B operand fragments kb0, kb1 of
+// the diagonal block).  The block is read as an A operand and written back as an accumulator fragment; mma.sync
+// orders the reads of all lanes before the writes.
+__device__ __forceinline__ void trsm8_dmma(double* blk, double kb0, double kb1, int g, int t) {
+  const double x0 = ld_ab(blk, g, t, 0), x1 = ld_ab(blk, g, t, 1);
+  double2 acc = {0.0, 0.0};
+  dmma(acc, x0, kb0);
+  dmma(acc, x1, kb1);
+  __syncwarp();
+  st_c(blk, g, t, acc);
 }
 
 // Left-looking blocked Cholesky of block columns [0, ncols) of a matrix of `nrows` block rows held
@@ -285,13 +269,32 @@ __device__ __forceinline__ void trsm8_frag(double2& v, const double (&a)[36], in
 //   factor (K,K) -> solve block (K+1,K) -> rank-8 update of (K+1,K+1) -> factor (K+1,K+1) -> ...
 // Warp 0 owns exactly that chain and never waits for the bulk of the work; warps 1..15 own
 // everything else and run one barrier behind it.  Per block column K:
-//   warp 0 : factor (K,K) | barrier A | solve (K+1,K) | arrive B | update (K+1,K+1) with column K
+//   warp 0 : factor (K,K), leaving W = L_KK^-1 in its place | barrier A | solve (K+1,K) | arrive B
+//            | update (K+1,K+1) with column K
 //   bulk   : update column K+1 with columns < K (the tensor-core bulk, overlaps warp 0's factor)
 //            | barrier A | solve (I,K), I >= K+2 | wait B | update (I,K+1), I >= K+2 with column K
-// Barrier A is a full 512-thread barrier (publishes the diagonal factor); B is asymmetric: warp 0 only
-// arrives (it has nothing to wait for), the bulk warps synchronise on it.
+// Barrier A is a full 512-thread barrier (publishes W); B is asymmetric: warp 0 only arrives (it has nothing to
+// wait for), the bulk warps synchronise on it.  Every solve is X <- X W^T on the tensor cores (trsm8_dmma).
 __device__ __forceinline__ void bar_sync_named(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive_named(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
+
+// developer sub-phase probe (-DDDQC_PROF_SUB; slots 24..39 of the phase buffer): a barrier + the time since the
+// previous probe point.  It perturbs the schedule and is compiled out of the product.
+#ifdef DDQC_PROF_SUB
+__device__ long long* g_subclk = nullptr;
+__shared__ long long s_tsub;
+#define DDQC_SUB(k)                                                                                          \
+  do {                                                                                                       \
+    __syncthreads();                                                                                         \
+    if (g_subclk && threadIdx.x == 0) {                                                                      \
+      const long long t_now = clock64();                                                                     \
+      if ((k) >= 0) atomicAdd((unsigned long long*)&g_subclk[24 + (k)], (unsigned long long)(t_now - s_tsub)); \
+      s_tsub = t_now;                                                                                        \
+    }                                                                                                        \
+  } while (0)
+#else
+#define DDQC_SUB(k)
+#endif
 
 #ifdef DDQC_PROF_FACTOR
 __device__ long long* g_fprof = nullptr;
@@ -316,18 +319,15 @@ __device__ void factor_columns(double* __restrict__ M, int nb1, int nrows, int n
   long long tp = clock64();
 #endif
   for (int K = 0; K < ncols; ++K) {
+    double* dk = M + (size_t)bidx<RECT>(K, K, nb1) * 64;
     if (warp == 0) {
-      double* dk = M + (size_t)bidx<RECT>(K, K, nb1) * 64;
-      double a[36];
-      if (!chol8_regs(dk, a) && lane == 0) *s_flag = 1;
+      if (!chol8_inv(dk, lane) && lane == 0) *s_flag = 1;  // the diagonal block now holds W = L_KK^-1
+      __syncwarp();
       FPROF(0);
       bar_sync_named(1);
       FPROF(1);
       if (K + 1 < nrows) {
-        double* b0 = M + (size_t)bidx<RECT>(K + 1, K, nb1) * 64;
-        double2 v = ld_c(b0, g, t);
-        trsm8_frag(v, a, t);
-        st_c(b0, g, t, v);
+        trsm8_dmma(M + (size_t)bidx<RECT>(K + 1, K, nb1) * 64, ld_ab(dk, g, t, 0), ld_ab(dk, g, t, 1), g, t);
         __syncwarp();
       }
       FPROF(2);
@@ -346,8 +346,8 @@ __device__ void factor_columns(double* __restrict__ M, int nb1, int nrows, int n
       FPROF(3);
     } else {
       const int bw = warp - 1;
-      // warps 4, 8, 12 share warp 0's SM sub-partition and its FP64 pipe: they sit out the tensor-core
-      // bulk so that the diagonal-block chain is not queued behind 16-cycle DMMA issues
+      // DDQC_BULK_ALL == 0: warps 4, 8, 12 share warp 0's SM sub-partition and its FP64 pipe and sit out the
+      // tensor-core bulk so that the diagonal-block chain is not queued behind 16-cycle DMMA issues
       if (K > 0 && K + 1 < ncols && (DDQC_BULK_ALL || (warp & 3) != 0)) {
         const int bw12 = DDQC_BULK_ALL ? bw : (warp >> 2) * 3 + (warp & 3) - 1;
         for (int I = K + 1 + 2 * bw12; I < nrows; I += 2 * (DDQC_BULK_ALL ? kBulk : kWarps - kWarps / 4)) {
@@ -370,14 +370,8 @@ __device__ void factor_columns(double* __restrict__ M, int nb1, int nrows, int n
       bar_sync_named(1);
       FPROF(1);
       if (K + 2 + bw < nrows) {
-        double a[36];
-        load_diag(M + (size_t)bidx<RECT>(K, K, nb1) * 64, a);
-        for (int I = K + 2 + bw; I < nrows; I += kBulk) {
-          double* b0 = M + (size_t)bidx<RECT>(I, K, nb1) * 64;
-          double2 v = ld_c(b0, g, t);
-          trsm8_frag(v, a, t);
-          st_c(b0, g, t, v);
-        }
+        const double ib0 = ld_ab(dk, g, t, 0), ib1 = ld_ab(dk, g, t, 1);
+        for (int I = K + 2 + bw; I < nrows; I += kBulk) trsm8_dmma(M + (size_t)bidx<RECT>(I, K, nb1) * 64, ib0, ib1, g, t);
       }
       FPROF(2);
       bar_sync_named(2);
@@ -401,57 +395,76 @@ __device__ void factor_columns(double* __restrict__ M, int nb1, int nrows, int n
   __syncthreads();
 }
 
-// L y' = y (in place) for the leading ncols block columns of a factored block-packed matrix
+// y_K <- W y_K (TRANS: W^T y_K) for one diagonal block holding W = L_KK^-1, by lanes 0..7 of one warp
+template <bool TRANS>
+__device__ __forceinline__ void diag_apply(const double* __restrict__ dk, double* __restrict__ yk, int lane) {
+  double acc = 0.0;
+  if (lane < 8) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc = fma(TRANS ? dk[eoff(c, lane)] : dk[eoff(lane, c)], yk[c], acc);
+  }
+  __syncwarp();
+  if (lane < 8) yk[lane] = acc;
+  __syncwarp();
+}
+
+// L y' = y (in place) for the leading ncols block columns of a factored block-packed matrix (diagonal blocks hold
+// the inverses of their factors).  One barrier per block column: warp 0 takes block row K+1 of the update and
+// applies the next diagonal inverse right away, the other warps update the rows below.
 __device__ void fwdsub_blocked(const double* __restrict__ M, int ncols, double* __restrict__ y) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int K = 0; K < ncols; ++K) {
+  if (warp == 0 && ncols > 0) diag_apply<false>(M, y, lane);
+  __syncthreads();
+  for (int K = 0; K + 1 < ncols; ++K) {
     if (warp == 0) {
-      const double* dk = M + (size_t)(tri(K) + K) * 64;
-      double val = lane < 8 ? y[8 * K + lane] : 0.0;
+      const double* blk = M + (size_t)(tri(K + 1) + K) * 64;
+      if (lane < 8) {
+        double acc = y[8 * (K + 1) + lane];
 #pragma unroll
-      for (int gg = 0; gg < 8; ++gg) {  // branch-free: selects and masked multipliers
-        const double zg = shfl_d(val, gg) * dk[eoff(gg, gg)];
-        const double lg = (lane > gg && lane < 8) ? dk[eoff(lane & 7, gg)] : 0.0;
-        val = (lane == gg) ? zg : fma(-lg, zg, val);
+        for (int c = 0; c < 8; ++c) acc = fma(-blk[eoff(lane, c)], y[8 * K + c], acc);
+        y[8 * (K + 1) + lane] = acc;
       }
-      if (lane < 8) y[8 * K + lane] = val;
-    }
-    __syncthreads();
-    if (tid < 8 * (ncols - K - 1)) {
-      const int I = K + 1 + (tid >> 3), gr = tid & 7;
-      const double* blk = M + (size_t)(tri(I) + K) * 64;
-      double acc = y[8 * I + gr];
+      __syncwarp();
+      diag_apply<false>(M + (size_t)(tri(K + 1) + K + 1) * 64, y + 8 * (K + 1), lane);
+    } else {
+      for (int e = tid - 32; e < 8 * (ncols - K - 2); e += kThreads - 32) {
+        const int I = K + 2 + (e >> 3), gr = e & 7;
+        const double* blk = M + (size_t)(tri(I) + K) * 64;
+        double acc = y[8 * I + gr];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc -= blk[eoff(gr, c)] * y[8 * K + c];
-      y[8 * I + gr] = acc;
+        for (int c = 0; c < 8; ++c) acc = fma(-blk[eoff(gr, c)], y[8 * K + c], acc);
+        y[8 * I + gr] = acc;
+      }
     }
     __syncthreads();
   }
 }
 
-// L^T z = y (in place)
+// L^T z = y (in place), same organisation from the last block column upwards
 __device__ void backsub_blocked(const double* __restrict__ M, int ncols, double* __restrict__ y) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int K = ncols - 1; K >= 0; --K) {
+  if (warp == 0 && ncols > 0) diag_apply<true>(M + (size_t)(tri(ncols - 1) + ncols - 1) * 64, y + 8 * (ncols - 1), lane);
+  __syncthreads();
+  for (int K = ncols - 1; K > 0; --K) {
     if (warp == 0) {
-      const double* dk = M + (size_t)(tri(K) + K) * 64;
-      double val = lane < 8 ? y[8 * K + lane] : 0.0;
+      const double* blk = M + (size_t)(tri(K) + K - 1) * 64;
+      if (lane < 8) {
+        double acc = y[8 * (K - 1) + lane];
 #pragma unroll
-      for (int gg = 7; gg >= 0; --gg) {  // branch-free: selects and masked multipliers
-        const double zg = shfl_d(val, gg) * dk[eoff(gg, gg)];
-        const double lg = (lane < gg) ? dk[eoff(gg, lane & 7)] : 0.0;
-        val = (lane == gg) ? zg : fma(-lg, zg, val);
+        for (int gg = 0; gg < 8; ++gg) acc = fma(-blk[eoff(gg, lane)], y[8 * K + gg], acc);
+        y[8 * (K - 1) + lane] = acc;
       }
-      if (lane < 8) y[8 * K + lane] = val;
-    }
-    __syncthreads();
-    if (tid < 8 * K) {
-      const int J = tid >> 3, c = tid & 7;
-      const double* blk = M + (size_t)(tri(K) + J) * 64;
-      double acc = y[tid];
+      __syncwarp();
+      diag_apply<true>(M + (size_t)(tri(K - 1) + K - 1) * 64, y + 8 * (K - 1), lane);
+    } else {
+      for (int e = tid - 32; e < 8 * (K - 1); e += kThreads - 32) {
+        const int J = e >> 3, c = e & 7;
+        const double* blk = M + (size_t)(tri(K) + J) * 64;
+        double acc = y[e];
 #pragma unroll
-      for (int gg = 0; gg < 8; ++gg) acc -= blk[eoff(gg, c)] * y[8 * K + gg];
-      y[tid] = acc;
+        for (int gg = 0; gg < 8; ++gg) acc = fma(-blk[eoff(gg, c)], y[8 * K + gg], acc);
+        y[e] = acc;
+      }
     }
     __syncthreads();
   }
@@ -526,29 +539,34 @@ struct QpWork {
 
 // Gather the principal submatrix Hq[idx, idx] (idx = q.idx when `use_idx`, identity otherwise) plus an
 // optional diagonal into block-packed storage at q.F (padded with identity rows to a multiple of 8)
-// and factor it on the tensor cores.
-__device__ void qp_factor(const QpWork& q, int k, bool use_idx, const double* diag) {
+// and factor it on the tensor cores.  With `rhs` the right-hand side rides along as row 0 of an extra block
+// row: the triangular solves of the factorisation forward-substitute it for free (y = L^-1 rhs ends up in
+// that row), so only the back-substitution remains.
+__device__ void qp_factor(const QpWork& q, int k, bool use_idx, const double* diag, const double* rhs) {
   const int tid = threadIdx.x;
-  const int nbq = (k + 7) >> 3, kp = nbq * 8;
+  const int nbq = (k + 7) >> 3, kp = nbq * 8, nrows = nbq + (rhs ? 1 : 0);
   double2* z = reinterpret_cast<double2*>(q.F);
-  for (int e = tid; e < tri(nbq) * 32; e += kThreads) z[e] = make_double2(0.0, 0.0);
+  for (int e = tid; e < tri(nrows) * 32; e += kThreads) z[e] = make_double2(0.0, 0.0);
   __syncthreads();
-  for (int a = tid >> 5; a < kp; a += kWarps) {
+  for (int a = tid >> 5; a < kp + (rhs ? 1 : 0); a += kWarps) {
     const int ia = a < k ? (use_idx ? q.idx[a] : a) : 0;
-    for (int c = tid & 31; c <= a; c += 32) {
+    for (int c = tid & 31; c <= a && c < kp; c += 32) {
       double v;
       if (a < k) {
         const int ic = use_idx ? q.idx[c] : c;
         v = q.Hq[ia * q.ldq + ic];
         if (a == c && diag) v += diag[a];
-      } else {
+      } else if (a < kp) {
         v = a == c ? 1.0 : 0.0;
+      } else {
+        v = c < k ? rhs[c] : 0.0;
       }
       *elem_tri(q.F, a, c) = v;
     }
   }
   __syncthreads();
-  factor_columns<false>(q.F, 0, nbq, nbq, q.s_flag);
+  DDQC_SUB(13);
+  factor_columns<false>(q.F, 0, nrows, nbq, q.s_flag);
 }
 
 // One pass of block principal pivoting in the free space.  Returns the number of infeasible
@@ -573,16 +591,24 @@ __device__ int bpp_pass(const QpWork& q, double tol_g, int* last) {
   }
   __syncthreads();
   const int kf = q.idx[kMaxNx];
+  DDQC_SUB(-1);
   matvec_sym(q.Hq, q.ldq, nx, q.x, q.f, q.g);
-  qp_factor(q, kf, true, nullptr);
-  if (tid < 8 * ((kf + 7) >> 3)) q.rhs[tid] = tid < kf ? -q.g[q.idx[tid]] : 0.0;
   __syncthreads();
-  fwdsub_blocked(q.F, (kf + 7) >> 3, q.rhs);
-  backsub_blocked(q.F, (kf + 7) >> 3, q.rhs);
+  DDQC_SUB(8);
+  const int nbf = (kf + 7) >> 3;
+  if (tid < kf) q.rhs[tid] = -q.g[q.idx[tid]];
+  __syncthreads();
+  qp_factor(q, kf, true, nullptr, q.rhs);
+  DDQC_SUB(9);
+  if (tid < 8 * nbf) q.rhs[tid] = *elem_tri(q.F, 8 * nbf, tid);  // y = L^-1 rhs
+  __syncthreads();
+  backsub_blocked(q.F, nbf, q.rhs);
+  DDQC_SUB(10);
   if (tid < kf) q.x[q.idx[tid]] = q.rhs[tid];
   __syncthreads();
   matvec_sym(q.Hq, q.ldq, nx, q.x, q.f, q.g);
   __syncthreads();
+  DDQC_SUB(11);
   const double tol_x = 1e-10;
   int v = 0;
   if (tid < nx) {
@@ -599,6 +625,7 @@ __device__ int bpp_pass(const QpWork& q, double tol_g, int* last) {
   const int ninf = __syncthreads_count(v != 0);
   const double lastd = block_reduce(v != 0 ? (double)tid : -1.0, RED_MAX, q.s_red);
   *last = (int)lastd;
+  DDQC_SUB(12);
   return ninf;
 }
 
@@ -664,7 +691,7 @@ __device__ int ipm_solve(const QpWork& q, int max_it) {
     const double dg = (il ? zl / sl : 0.0) + (iu ? zu / su : 0.0);
     if (act) q.dg[tid] = dg;
     __syncthreads();
-    qp_factor(q, nx, false, q.dg);
+    qp_factor(q, nx, false, q.dg, nullptr);
     const int nbq = (nx + 7) >> 3;
     if (tid < 8 * nbq) q.rhs[tid] = act ? -gi : 0.0;  // affine right-hand side
     __syncthreads();
@@ -929,7 +956,6 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       t_prev = t_now;                                                                      \
     }                                                                                      \
   } while (0)
-
   for (;;) {
     __syncthreads();
     if (tid == 0) {
@@ -948,6 +974,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     const double* yb = y_win + (size_t)b * N * p;
 
     // ---- 0. stage the (u, y) window signal-major; Gram -> workspace slot -------------------------
+    DDQC_SUB(-1);
     double* sW = sM;
     double* sT = sM + nsig * N;  // first block column of G, (ell*nsig) x ldT
     for (int e = tid; e < N * m; e += kThreads) sW[(e % m) * N + e / m] = ub[e];
@@ -963,6 +990,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       for (int e = tid; e < cnt; e += kThreads) zs[e] = make_double2(0.0, 0.0);
     }
     __syncthreads();
+    DDQC_SUB(0);
     {
       // pad rows (identity) of the three classes
       const int npad = (d.n1p - d.n1) + (d.n2p - d.n2) + (d.n3p - d.n3);
@@ -976,35 +1004,46 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
         else P = d.n1p + d.n2p + d.n3 + (k - (d.n2p - d.n2));
         put_sym(d, GA, GS, P, q, P == q ? 1.0 : 0.0);
       }
+      DDQC_SUB(1);
       // First block column of G on the tensor cores:  T[(j,a)][b] = sum_c w_a[j+c] w_b[c]  (b = nsig
       // is the all-ones signal), i.e. [Hankel rows] x [first block row]^T, K = C.  Operands are read
       // straight from the window, H is never materialised.
       {
         const int nrho = ell * nsig, nrb = (nrho + 7) >> 3, ncb = (nsig + 1 + 7) >> 3, ldT = ncb * 8;
-        for (int task = warp; task < nrb * ncb; task += kWarps) {
-          const int rb = task / ncb, cb = task % ncb;
-          const int rho = rb * 8 + g;
-          const bool av = rho < nrho;
-          const double* wa = sW + (av ? (rho % nsig) * N + rho / nsig : 0);
+        // a warp takes two row blocks at a time against the same B fragments (four independent accumulator chains)
+        for (int cb = 0; cb < ncb; ++cb) {
           const int bsig = cb * 8 + g;
           const bool bv = bsig < nsig, bone = bsig == nsig;
           const double* wb = sW + (bv ? bsig * N : 0);
-          double2 acc0 = {0.0, 0.0}, acc1 = {0.0, 0.0};
-          for (int c0 = 0; c0 < C; c0 += 8) {
-            const int ca = c0 + t, cbb = c0 + 4 + t;
-            const double a0 = (av && ca < C) ? wa[ca] : 0.0;
-            const double b0 = ca < C ? (bv ? wb[ca] : (bone ? 1.0 : 0.0)) : 0.0;
-            const double a1 = (av && cbb < C) ? wa[cbb] : 0.0;
-            const double b1 = cbb < C ? (bv ? wb[cbb] : (bone ? 1.0 : 0.0)) : 0.0;
-            dmma(acc0, a0, b0);
-            dmma(acc1, a1, b1);
-          }
-          if (av) {
-            sT[rho * ldT + cb * 8 + 2 * t] = acc0.x + acc1.x;
-            sT[rho * ldT + cb * 8 + 2 * t + 1] = acc0.y + acc1.y;
+          for (int rb0 = warp; rb0 < nrb; rb0 += 2 * kWarps) {
+            const int rho0 = rb0 * 8 + g, rho1 = (rb0 + kWarps) * 8 + g;
+            const bool av0 = rho0 < nrho, av1 = rho1 < nrho;
+            const double* wa0 = sW + (av0 ? (rho0 % nsig) * N + rho0 / nsig : 0);
+            const double* wa1 = sW + (av1 ? (rho1 % nsig) * N + rho1 / nsig : 0);
+            double2 p0 = {0.0, 0.0}, p1 = {0.0, 0.0}, q0 = {0.0, 0.0}, q1 = {0.0, 0.0};
+#pragma unroll 2
+            for (int c0 = 0; c0 < C; c0 += 8) {
+              const int ca = c0 + t, cbb = c0 + 4 + t;
+              const bool va = ca < C, vb = cbb < C;
+              const double b0 = va ? (bv ? wb[ca] : (bone ? 1.0 : 0.0)) : 0.0;
+              const double b1 = vb ? (bv ? wb[cbb] : (bone ? 1.0 : 0.0)) : 0.0;
+              dmma(p0, (av0 && va) ? wa0[ca] : 0.0, b0);
+              dmma(p1, (av0 && vb) ? wa0[cbb] : 0.0, b1);
+              dmma(q0, (av1 && va) ? wa1[ca] : 0.0, b0);
+              dmma(q1, (av1 && vb) ? wa1[cbb] : 0.0, b1);
+            }
+            if (av0) {
+              sT[rho0 * ldT + cb * 8 + 2 * t] = p0.x + p1.x;
+              sT[rho0 * ldT + cb * 8 + 2 * t + 1] = p0.y + p1.y;
+            }
+            if (av1) {
+              sT[rho1 * ldT + cb * 8 + 2 * t] = q0.x + q1.x;
+              sT[rho1 * ldT + cb * 8 + 2 * t + 1] = q0.y + q1.y;
+            }
           }
         }
         __syncthreads();
+        DDQC_SUB(2);
         // every other entry follows from the Hankel structure by a two-term recurrence along the
         // block diagonals.  A task walks two diagonals whose lengths add up to ~ell, so all tasks
         // cost the same: (a < b, u): delta = u and delta = u - ell;  (a == a, u): delta = u and ell-1-u.
@@ -1050,6 +1089,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
             ++k;
           }
         }
+        DDQC_SUB(3);
         // ones row: G[(j,a), one] = sum_c w_a[j+c] = T[(j,a)][nsig];  G[one][one] = C
         const int Pone = n * m;
         for (int e = tid; e < nrho; e += kThreads) put_sym(d, GA, GS, s_ppos[(e % nsig) * ell + e / nsig], Pone, sT[e * ldT + nsig]);
@@ -1077,6 +1117,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       }
     }
     __syncthreads();
+    DDQC_SUB(4);
     DDQC_PHASE(0);
 
     // ---- A. eliminate R1: panel in shared memory, S1 = trailing - L L^T through global ------------
@@ -1154,6 +1195,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       schur_trailing(sM, d.nbt, ncol_all);  // aug x aug block: -K_s' (G + D_s)^-1 K_s
       __syncthreads();
       DDQC_PHASE(3);
+      DDQC_SUB(-1);
       if (tid == 0) {
         // 6-variable box QP for the equilibrium (bounds on u_s only)
         double* io = s_vec;  // free at this point: H 36 | f 6 | lo 6 | hi 6 | x 6
@@ -1173,6 +1215,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
         s_coef[nsig] = 1.0;
       }
       __syncthreads();
+      DDQC_SUB(7);
       // y = L^-1 rho = combination of the forward-substituted aug rows; z = L^-T y
       for (int q = tid; q < 8 * ncol_all; q += kThreads) {
         double acc = 0.0;
@@ -1267,30 +1310,41 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     q.zl = qv + 9 * kMaxNx; q.zu = qv + 10 * kMaxNx; q.dx = qv + 11 * kMaxNx; q.dzl = qv + 12 * kMaxNx;
     q.dzu = qv + 13 * kMaxNx; q.rd = qv + 14 * kMaxNx; q.dg = qv + 15 * kMaxNx;
     q.s_red = s_red; q.state = s_state; q.idx = s_idx; q.verdict = s_verdict; q.s_flag = &s_flag;
+    DDQC_SUB(-1);
     assemble_hq(sM, Hq, q.f, -2.0 * lam_a, d.nb3, d.n3, nx, ldq);  // Z = -trailing
     __syncthreads();
-    if (tid == 0) {
+    DDQC_SUB(5);
+    {
+      // structure of the tracking cost: R on (u_k - u_s) for the L-n predicted inputs and, with u_k = u_s, on the n
+      // terminal inputs against nothing / on (u_s - u_past) ... in short every |.|_R, |.|_Q, |.|_S term that is not a
+      // function of alpha alone.  One thread per predicted input, one warp per equilibrium component (its sum over
+      // the n past samples is a strided warp reduction instead of n dependent global loads by one thread).
       const int nB = d.n3;
-      for (int bi = 0; bi < nB; ++bi) {
-        const int comp = bi % m;
+      if (tid < nB) {
+        const int comp = tid % m;
         const double w2 = 2.0 * cfg.R[comp];
-        Hq[bi * ldq + bi] += w2;
-        Hq[bi * ldq + nB + comp] -= w2;
-        Hq[(nB + comp) * ldq + bi] -= w2;
-        Hq[(nB + comp) * ldq + nB + comp] += w2;
+        Hq[tid * ldq + tid] += w2;
+        Hq[tid * ldq + nB + comp] -= w2;
+        Hq[(nB + comp) * ldq + tid] -= w2;
       }
-      for (int i = 0; i < m; ++i) {
-        double su = 0.0;
-        for (int j = 0; j < n; ++j) su += ub[(size_t)(N - n + j) * m + i];
-        Hq[(nB + i) * ldq + nB + i] += 2.0 * n * cfg.R[i];
-        q.f[nB + i] += -2.0 * cfg.R[i] * su;
-      }
-      for (int i = 0; i < p; ++i) {
-        double sy = 0.0;
-        for (int j = 0; j < n; ++j) sy += yb[(size_t)(N - n + j) * p + i];
-        const int qq = nB + m + i;
-        Hq[qq * ldq + qq] += 2.0 * (n * cfg.Q[i] + cfg.S[i]);
-        q.f[qq] += -2.0 * (cfg.Q[i] * sy + cfg.S[i] * y_r[(size_t)b * p + i]);
+      if (warp < nsig) {
+        const int i = warp;
+        double sum = 0.0;
+        for (int j = lane; j < n; j += 32)
+          sum += i < m ? ub[(size_t)(N - n + j) * m + i] : yb[(size_t)(N - n + j) * p + (i - m)];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) {
+          const int qq = nB + i;
+          if (i < m) {
+            Hq[qq * ldq + qq] += 2.0 * (L - n) * cfg.R[i] + 2.0 * n * cfg.R[i];
+            q.f[qq] += -2.0 * cfg.R[i] * sum;
+          } else {
+            const int c = i - m;
+            Hq[qq * ldq + qq] += 2.0 * (n * cfg.Q[c] + cfg.S[c]);
+            q.f[qq] += -2.0 * (cfg.Q[c] * sum + cfg.S[c] * y_r[(size_t)b * p + c]);
+          }
+        }
       }
     }
     const bool warm = act_state != nullptr && have_prev[b] != 0;
@@ -1320,6 +1374,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       s_state[tid] = st;
     }
     __syncthreads();
+    DDQC_SUB(6);
     DDQC_PHASE(7);
 
     // ---- D. box QP ------------------------------------------------------------------------------------
@@ -1461,7 +1516,7 @@ int check_cfg(const DdqcMpcConfig* c) {
   if (c->m < 1 || c->p < 1 || c->m > kMaxSig || c->p > kMaxSig || c->n < 1 || c->L <= c->n) return DDQC_E_SHAPE;
   const Dims d = make_dims(*c);
   if (d.C < 1 || d.nx > kMaxNx || (d.m + d.p) * d.ell > kMaxPos || d.m + d.p + 2 > 8) return DDQC_E_SHAPE;
-  if (smem_bytes(d) + 4608 > (size_t)kSmemLimit) return DDQC_E_SHAPE;
+  if (smem_bytes(d) + 6144 > (size_t)kSmemLimit) return DDQC_E_SHAPE;  // 6144 >= static shared memory of the kernel
   if (c->alpha_reg_type != 0 && c->alpha_reg_type != 2) return DDQC_E_CONFIG;
   return 0;
 }
@@ -1475,6 +1530,9 @@ extern "C" int ddqc_ddmpc_debug_phase_buffer(void* dev_ptr) {
   g_phase_clk = static_cast<long long*>(dev_ptr);
 #ifdef DDQC_PROF_FACTOR
   cudaMemcpyToSymbol(g_fprof, &g_phase_clk, sizeof(void*));
+#endif
+#ifdef DDQC_PROF_SUB
+  cudaMemcpyToSymbol(g_subclk, &g_phase_clk, sizeof(void*));
 #endif
 
   return 0;
