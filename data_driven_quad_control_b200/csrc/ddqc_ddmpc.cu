@@ -275,6 +275,13 @@ __device__ __forceinline__ void trsm8_dmma(double* blk, double kb0, double kb1, 
 //            | barrier A | solve (I,K), I >= K+2 | wait B | update (I,K+1), I >= K+2 with column K
 // Barrier A is a full 512-thread barrier (publishes W); B is asymmetric: warp 0 only arrives (it has nothing to
 // wait for), the bulk warps synchronise on it.  Every solve is X <- X W^T on the tensor cores (trsm8_dmma).
+// Measured and dropped (tools/ubench_chol8.cu, the DDQC_PROF_FACTOR stage counters): the FP64 pipe is per SM
+// sub-partition and a dependent DFMA chain queued behind streaming DMMAs of the same sub-partition runs 5x slower,
+// so the chain of warp 0 (~2.3 k cycles per column, 1.1 k alone) and the bulk (~2.5 k) are within 10 % of each
+// other; taking warps 4, 8, 12 out of the lookahead (DDQC_BULK_ALL=0) moves the bound from the chain to the bulk
+// without changing the total, and factoring block columns in pairs (one barrier pair per 16 columns, six
+// independent DMMAs per block row against the inverse of the 16x16 diagonal factor, a helper warp for the second
+// chain row) cut the lookahead by a third but lengthened the chain by as much.
 __device__ __forceinline__ void bar_sync_named(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive_named(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
 
@@ -300,9 +307,9 @@ __shared__ long long s_tsub;
 __device__ long long* g_fprof = nullptr;
 #define FPROF(k)                                                                            \
   do {                                                                                      \
-    if (g_fprof && lane == 0 && warp < 2) {                                                 \
+    if (g_fprof && lane == 0 && (warp == 0 || warp == 2)) {                                                 \
       const long long tn = clock64();                                                       \
-      atomicAdd((unsigned long long*)&g_fprof[12 + warp * 6 + (k)], (unsigned long long)(tn - tp)); \
+      atomicAdd((unsigned long long*)&g_fprof[12 + (warp ? 6 : 0) + (k)], (unsigned long long)(tn - tp)); \
       tp = tn;                                                                              \
     }                                                                                       \
   } while (0)
@@ -487,6 +494,18 @@ __device__ void schur_trailing(double* __restrict__ M, int nrows, int c0) {
     cv.x -= s0.x; cv.y -= s0.y;
     st_c(blk, g, t, cv);
   }
+}
+
+// workspace slot (global, L2-resident) -> shared memory, n2 16-byte pieces, as asynchronous copies that do not
+// pass through registers: all of a thread's pieces are in flight at once (the plain load/store loop waits for an
+// L2 round trip every four pieces).  Ends with the data visible to the calling thread; the caller synchronises.
+__device__ __forceinline__ void copy_slot_to_smem(double* __restrict__ dst, const double* __restrict__ src, int n2) {
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(dst);
+  const double2* s2 = reinterpret_cast<const double2*>(src);
+  for (int e = threadIdx.x; e < n2; e += kThreads)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + 16u * (uint32_t)e), "l"(s2 + e) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // pointer to element (hi, lo), hi >= lo, of the block-packed lower-triangular matrix
@@ -898,18 +917,73 @@ __device__ __forceinline__ int pos_of(const Dims& d, int a, int j) {
 
 // write element (P, Q) of the permuted, padded Gram matrix into the workspace slot (GA panel or
 // GS trailing), mirroring inside diagonal blocks so that every block is fully defined
-__device__ __forceinline__ void put_sym(const Dims& d, double* __restrict__ GA, double* __restrict__ GS, int P, int Q,
+__device__ __forceinline__ void put_sym(int n1p, int nb1, double* __restrict__ GA, double* __restrict__ GS, int P, int Q,
                                         double v) {
   const int hi = P > Q ? P : Q, lo = P > Q ? Q : P;
-  if (lo < d.n1p) {
-    double* blk = GA + (size_t)((hi >> 3) * d.nb1 + (lo >> 3)) * 64;
+  if (lo < n1p) {
+    double* blk = GA + (size_t)((hi >> 3) * nb1 + (lo >> 3)) * 64;
     blk[eoff(hi & 7, lo & 7)] = v;
     if ((hi >> 3) == (lo >> 3)) blk[eoff(lo & 7, hi & 7)] = v;
   } else {
-    const int h = hi - d.n1p, l = lo - d.n1p;
+    const int h = hi - n1p, l = lo - n1p;
     double* blk = GS + (size_t)(tri(h >> 3) + (l >> 3)) * 64;
     blk[eoff(h & 7, l & 7)] = v;
     if ((h >> 3) == (l >> 3)) blk[eoff(l & 7, h & 7)] = v;
+  }
+}
+__device__ __forceinline__ void put_sym(const Dims& d, double* __restrict__ GA, double* __restrict__ GS, int P, int Q,
+                                        double v) {
+  put_sym(d.n1p, d.nb1, GA, GS, P, Q, v);
+}
+
+// Every entry of G outside its first block column follows from the Hankel structure by a two-term recurrence along
+// the block diagonals.  A task walks two diagonals whose lengths add up to ~ell, so all tasks cost the same:
+// (a < b, u): delta = u and delta = u - ell;  (a == a, u): delta = u and ell-1-u.  Kept out of line: the loop runs
+// ~32 k times per solve and must not inherit the register pressure (spills) of the solver kernel around it.
+__device__ __noinline__ void gram_walk(int n1p, int nb1, int N, int ell, int C, int nsig, const double* __restrict__ sW,
+                                       const double* __restrict__ sT, int ldT, const short* __restrict__ s_ppos,
+                                       double* __restrict__ GA, double* __restrict__ GS) {
+  const int nlt = nsig * (nsig - 1) / 2, half = (ell + 1) / 2;
+  const int ntask = nlt * ell + nsig * half;
+  for (int tk = threadIdx.x; tk < ntask; tk += kThreads) {
+    int a, bs, u, d0, d1;
+    if (tk < nlt * ell) {
+      int pi = tk / ell;
+      u = tk % ell;
+      a = 0;
+      while (pi >= nsig - 1 - a) { pi -= nsig - 1 - a; ++a; }
+      bs = a + 1 + pi;
+      d0 = u;
+      d1 = u - ell;  // invalid (-ell) for u == 0
+    } else {
+      const int r2 = tk - nlt * ell;
+      a = bs = r2 / half;
+      u = r2 % half;
+      d0 = u;
+      d1 = ell - 1 - u;
+      if (d1 == d0) d1 = -ell;
+    }
+    const double* wa = sW + a * N;
+    const double* wb = sW + bs * N;
+    const short* pa = s_ppos + a * ell;
+    const short* pb = s_ppos + bs * ell;
+    // one loop of (almost) the same length for every task: walk the first diagonal, then switch to the
+    // second one - lanes with different diagonal lengths stay converged
+    const int len0 = ell - (d0 > 0 ? d0 : -d0), len1 = d1 <= -ell ? 0 : ell - (d1 > 0 ? d1 : -d1);
+    int j = d0 > 0 ? d0 : 0, k = d0 > 0 ? 0 : -d0;
+    double f = d0 >= 0 ? sT[(d0 * nsig + a) * ldT + bs] : sT[(-d0 * nsig + bs) * ldT + a];
+#pragma unroll 1
+    for (int s2 = 0; s2 < len0 + len1; ++s2) {
+      if (s2 == len0) {  // second diagonal
+        j = d1 > 0 ? d1 : 0;
+        k = d1 > 0 ? 0 : -d1;
+        f = d1 >= 0 ? sT[(d1 * nsig + a) * ldT + bs] : sT[(-d1 * nsig + bs) * ldT + a];
+      }
+      put_sym(n1p, nb1, GA, GS, pa[j], pb[k], f);
+      if (j + 1 < ell && k + 1 < ell) f += wa[j + C] * wb[k + C] - wa[j] * wb[k];
+      ++j;
+      ++k;
+    }
   }
 }
 
@@ -1044,51 +1118,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
         }
         __syncthreads();
         DDQC_SUB(2);
-        // every other entry follows from the Hankel structure by a two-term recurrence along the
-        // block diagonals.  A task walks two diagonals whose lengths add up to ~ell, so all tasks
-        // cost the same: (a < b, u): delta = u and delta = u - ell;  (a == a, u): delta = u and ell-1-u.
-        const int nlt = nsig * (nsig - 1) / 2, half = (ell + 1) / 2;
-        const int ntask = nlt * ell + nsig * half;
-        for (int tk = tid; tk < ntask; tk += kThreads) {
-          int a, bs, u, d0, d1;
-          if (tk < nlt * ell) {
-            int pi = tk / ell;
-            u = tk % ell;
-            a = 0;
-            while (pi >= nsig - 1 - a) { pi -= nsig - 1 - a; ++a; }
-            bs = a + 1 + pi;
-            d0 = u;
-            d1 = u - ell;  // invalid (-ell) for u == 0
-          } else {
-            const int r2 = tk - nlt * ell;
-            a = bs = r2 / half;
-            u = r2 % half;
-            d0 = u;
-            d1 = ell - 1 - u;
-            if (d1 == d0) d1 = -ell;
-          }
-          const double* wa = sW + a * N;
-          const double* wb = sW + bs * N;
-          const short* pa = s_ppos + a * ell;
-          const short* pb = s_ppos + bs * ell;
-          // one loop of (almost) the same length for every task: walk the first diagonal, then switch to the
-          // second one - lanes with different diagonal lengths stay converged
-          const int len0 = ell - (d0 > 0 ? d0 : -d0), len1 = d1 <= -ell ? 0 : ell - (d1 > 0 ? d1 : -d1);
-          int j = d0 > 0 ? d0 : 0, k = d0 > 0 ? 0 : -d0;
-          double f = d0 >= 0 ? sT[(d0 * nsig + a) * ldT + bs] : sT[(-d0 * nsig + bs) * ldT + a];
-#pragma unroll 1
-          for (int s2 = 0; s2 < len0 + len1; ++s2) {
-            if (s2 == len0) {  // second diagonal
-              j = d1 > 0 ? d1 : 0;
-              k = d1 > 0 ? 0 : -d1;
-              f = d1 >= 0 ? sT[(d1 * nsig + a) * ldT + bs] : sT[(-d1 * nsig + bs) * ldT + a];
-            }
-            put_sym(d, GA, GS, pa[j], pb[k], f);
-            if (j + 1 < ell && k + 1 < ell) f += wa[j + C] * wb[k + C] - wa[j] * wb[k];
-            ++j;
-            ++k;
-          }
-        }
+        gram_walk(d.n1p, d.nb1, N, ell, C, nsig, sW, sT, ldT, s_ppos, GA, GS);
         DDQC_SUB(3);
         // ones row: G[(j,a), one] = sum_c w_a[j+c] = T[(j,a)][nsig];  G[one][one] = C
         const int Pone = n * m;
@@ -1121,12 +1151,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     DDQC_PHASE(0);
 
     // ---- A. eliminate R1: panel in shared memory, S1 = trailing - L L^T through global ------------
-    {
-      const double2* src = reinterpret_cast<const double2*>(GA);
-      double2* dst = reinterpret_cast<double2*>(sM);
-#pragma unroll 4
-      for (int e = tid; e < d.ga / 2; e += kThreads) dst[e] = src[e];
-    }
+    copy_slot_to_smem(sM, GA, d.ga / 2);
     __syncthreads();
     factor_columns<true>(sM, d.nb1, d.nbA, d.nb1, &s_flag);
     DDQC_PHASE(1);
@@ -1182,12 +1207,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     __syncthreads();
     if (use_sr) {
       const double ds = lam_as / lam_ss;
-      {
-        const double2* src = reinterpret_cast<const double2*>(GS);
-        double2* dst = reinterpret_cast<double2*>(sM);
-#pragma unroll 4
-        for (int e = tid; e < d.gs / 2; e += kThreads) dst[e] = src[e];  // block rows 0..tb: matrix + aug group 0
-      }
+      copy_slot_to_smem(sM, GS, d.gs / 2);  // block rows 0..tb: matrix + aug group 0
       __syncthreads();
       for (int q = tid; q < d.n2; q += kThreads) *elem_tri(sM, q, q) += ds;
       __syncthreads();
@@ -1231,10 +1251,14 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
 
     // ---- C. main system: S1 + D_0, aug rows (T_u, T_y, c), c = tau - rho + e; eliminate R2 ------------
     {
-      const double2* src = reinterpret_cast<const double2*>(GS);
-      double2* dst = reinterpret_cast<double2*>(sM);
-#pragma unroll 4
-      for (int e = tid; e < tri(tb) * 32; e += kThreads) dst[e] = src[e];  // block rows 0..tb-1
+      // block rows 0..tb-1 (asynchronous: the aug block row below is assembled while they arrive)
+      {
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(sM);
+        const double2* s2 = reinterpret_cast<const double2*>(GS);
+        for (int e = tid; e < tri(tb) * 32; e += kThreads)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + 16u * (uint32_t)e), "l"(s2 + e) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
       // aug block row: T rows from workspace block row tb+1, the c-row combined from block row tb
       const double* g0 = GS + (size_t)tri(tb) * 64;       // aug group 0 blocks (tb, J)
       const double* g1 = GS + (size_t)tri(tb + 1) * 64;   // aug group 1 blocks (tb + 1, J)
@@ -1272,6 +1296,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
         }
         sa[tb * 64 + eoff(a, c)] = v;
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     for (int q = tid; q < d.n2; q += kThreads) {
