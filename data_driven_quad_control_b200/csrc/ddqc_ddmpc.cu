@@ -830,68 +830,87 @@ __device__ __noinline__ void assemble_hq(const double* __restrict__ sM, double* 
   __syncthreads();
 }
 
-// ---- tiny box QP (<= 6 variables) by one thread: min 0.5 x'Hx + f'x, lo <= x <= hi, H SPD -------------
-// Block principal pivoting; the system of a pass keeps the fixed size 6 (active variables and unused slots
-// become identity rows with the bound as right-hand side), so every array index is static and the whole
-// routine lives in registers.  Used for the optimal reachable equilibrium (u_sr, y_sr) of the alpha_sr system.
-// Not inlined: its ~100 live registers must not weigh on the register allocation of the solver kernel.  Inputs
-// (H 36, f 6, lo 6, hi 6 doubles) and the result x (6) are passed through shared memory at `io`.
+// ---- tiny box QP (<= 6 variables): min 0.5 x'Hx + f'x, lo <= x <= hi, H SPD -----------------------------------
+// Used for the optimal reachable equilibrium (u_sr, y_sr) of the alpha_sr system.  The system of a given active set
+// keeps the fixed size 6 (active variables and unused slots become identity rows with the bound as right-hand
+// side), so every array index is static and everything lives in registers.  Inputs (H 36, f 6, lo 6, hi 6
+// doubles) are read from shared memory at `io`.  Not inlined: their ~100 live registers must not weigh on the
+// register allocation of the solver kernel.
+
+// x for the active set st (0 free, -1 at lo, +1 at hi, 2 unused slot); false when a pivot is not positive.
+// H, f, lo, hi stay in shared memory (io); only the lower triangle of the working matrix (LDL^T, 21 entries), the
+// right-hand side and x live in registers, so that the routine fits the 128 registers of the solver kernel
+// without spilling (the first version kept H and a full 6x6 copy: 1.7 kB of spill traffic per call).
+#define A6(a, j) A[(a) * ((a) + 1) / 2 + (j)]
+__device__ __forceinline__ bool qp6_solve_set(const double* __restrict__ io, const int (&st)[6], double (&x)[6]) {
+  double A[21], r[6], xb[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) xb[i] = st[i] == 0 ? 0.0 : (st[i] == 2 ? 0.0 : (st[i] < 0 ? io[42 + i] : io[48 + i]));
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    double ra = -io[36 + a];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const bool fa = st[a] == 0, fj = st[j] == 0;
+      const double h = io[a * 6 + j];
+      if (j <= a) A6(a, j) = (fa && fj) ? h : (a == j ? 1.0 : 0.0);
+      if (fa && !fj) ra -= h * xb[j];
+    }
+    r[a] = st[a] == 0 ? ra : xb[a];
+  }
+  // LDL^T of the SPD system (no pivoting needed); the diagonal keeps 1 / d
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    ok = ok && A6(c, c) > 0.0;
+    const double inv = 1.0 / A6(c, c);
+    A6(c, c) = inv;
+    double tc[6];
+#pragma unroll
+    for (int a = c + 1; a < 6; ++a) tc[a] = A6(a, c);
+#pragma unroll
+    for (int a = c + 1; a < 6; ++a) {
+      const double l = tc[a] * inv;
+#pragma unroll
+      for (int j = c + 1; j <= a; ++j) A6(a, j) -= l * tc[j];
+      r[a] -= l * r[c];
+      A6(a, c) = l;
+    }
+  }
+#pragma unroll
+  for (int a = 5; a >= 0; --a) {
+    double v = r[a] * A6(a, a);
+#pragma unroll
+    for (int c = a + 1; c < 6; ++c) v -= A6(c, a) * x[c];
+    x[a] = v;
+  }
+  return ok;
+}
+
+// gradient component i of the QP at x
+__device__ __forceinline__ double qp6_grad(const double* __restrict__ io, int i, const double (&x)[6]) {
+  double gi = io[36 + i];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) gi += io[i * 6 + j] * x[j];
+  return gi;
+}
+
+// Serial version: block principal pivoting by one thread.  Result at io[54..59].
 __device__ __noinline__ bool small_box_qp(double* io, int nv) {
-  double H[36], f[6], lo[6], hi[6], x[6];
-#pragma unroll
-  for (int i = 0; i < 36; ++i) H[i] = io[i];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) { f[i] = io[36 + i]; lo[i] = io[42 + i]; hi[i] = io[48 + i]; x[i] = 0.0; }
+  double x[6];
   int st[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) st[i] = i < nv ? 0 : 2;  // 2: unused slot (x = 0)
+  for (int i = 0; i < 6; ++i) { st[i] = i < nv ? 0 : 2; x[i] = 0.0; }
   for (int pass = 0; pass < 64; ++pass) {
-    double A[36], r[6], xb[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) xb[i] = st[i] == 0 ? 0.0 : (st[i] == 2 ? 0.0 : (st[i] < 0 ? lo[i] : hi[i]));
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      double ra = -f[a];
-#pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        const bool fa = st[a] == 0, fj = st[j] == 0;
-        A[a * 6 + j] = (fa && fj) ? H[a * 6 + j] : (a == j ? 1.0 : 0.0);
-        if (fa && !fj) ra -= H[a * 6 + j] * xb[j];
-      }
-      r[a] = st[a] == 0 ? ra : xb[a];
-    }
-    // LDL^T-free Gaussian elimination of the SPD system (no pivoting needed)
-    bool ok = true;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      ok = ok && A[c * 6 + c] > 0.0;
-      const double inv = 1.0 / A[c * 6 + c];
-#pragma unroll
-      for (int a = c + 1; a < 6; ++a) {
-        const double fct = A[a * 6 + c] * inv;
-#pragma unroll
-        for (int j = c + 1; j < 6; ++j) A[a * 6 + j] -= fct * A[c * 6 + j];
-        r[a] -= fct * r[c];
-      }
-    }
-    if (!ok) return false;
-#pragma unroll
-    for (int a = 5; a >= 0; --a) {
-      double v = r[a];
-#pragma unroll
-      for (int c = a + 1; c < 6; ++c) v -= A[a * 6 + c] * x[c];
-      x[a] = v / A[a * 6 + a];
-    }
+    if (!qp6_solve_set(io, st, x)) return false;
     bool changed = false;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       if (st[i] == 0) {
-        if (x[i] < lo[i]) { st[i] = -1; changed = true; }
-        else if (x[i] > hi[i]) { st[i] = 1; changed = true; }
+        if (x[i] < io[42 + i]) { st[i] = -1; changed = true; }
+        else if (x[i] > io[48 + i]) { st[i] = 1; changed = true; }
       } else if (st[i] != 2) {
-        double gi = f[i];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) gi += H[i * 6 + j] * x[j];
+        const double gi = qp6_grad(io, i, x);
         if ((st[i] < 0 && gi < 0.0) || (st[i] > 0 && gi > 0.0)) { st[i] = 0; changed = true; }
       }
     }
@@ -902,6 +921,43 @@ __device__ __noinline__ bool small_box_qp(double* io, int nv) {
     }
   }
   return false;
+}
+
+// Parallel version: the calling thread tests ONE active set - digit i (base 3) of `combo` says whether the bounded
+// variable i < nbnd is free, at its lower or at its upper bound; variables >= nbnd are free - and returns whether
+// its solution satisfies the optimality conditions.  With nbnd <= 5 all 3^nbnd sets are tested at once by
+// different threads (one solve instead of a pass per change of the active set); the QP is strictly convex, so
+// exactly one set passes (several only when a variable sits on a bound with a zero multiplier - any of them is
+// the optimum).
+__device__ __noinline__ bool small_box_qp_combo(const double* io, int nv, int nbnd, int combo, double (&x)[6]) {
+  int st[6];
+  int cc = combo;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    st[i] = i < nv ? 0 : 2;
+    if (i < nbnd) {
+      const int dgt = cc % 3;
+      cc /= 3;
+      st[i] = dgt == 0 ? 0 : (dgt == 1 ? -1 : 1);
+    }
+    x[i] = 0.0;
+  }
+  bool ok = qp6_solve_set(io, st, x);
+  double fs = 1.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) fs = fmax(fs, fabs(io[36 + i]));
+  const double tol_g = 1e-9 * fs;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    if (st[i] == 0) {
+      const double lo = io[42 + i], hi = io[48 + i];
+      ok = ok && (x[i] >= lo - 1e-12 * (1.0 + fabs(lo))) && (x[i] <= hi + 1e-12 * (1.0 + fabs(hi)));
+    } else if (st[i] != 2) {
+      const double gi = qp6_grad(io, i, x);
+      ok = ok && (st[i] < 0 ? gi >= -tol_g : gi <= tol_g);
+    }
+  }
+  return ok;
 }
 
 // ---- Gram generation -------------------------------------------------------------------------------
@@ -1216,23 +1272,44 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       __syncthreads();
       DDQC_PHASE(3);
       DDQC_SUB(-1);
-      if (tid == 0) {
-        // 6-variable box QP for the equilibrium (bounds on u_s only)
-        double* io = s_vec;  // free at this point: H 36 | f 6 | lo 6 | hi 6 | x 6
-        for (int a = 0; a < 6; ++a) {
-          for (int c = 0; c < 6; ++c)
-            io[a * 6 + c] = (a < nsig && c < nsig) ? -2.0 * lam_as * *elem_tri(sM, Paug + (a > c ? a : c), Paug + (a > c ? c : a)) : 0.0;
-          io[36 + a] = a < nsig ? -2.0 * lam_as * *elem_tri(sM, Paug + nsig, Paug + a) : 0.0;
+      {
+        // 6-variable box QP for the equilibrium (bounds on u_s only): H 36 | f 6 | lo 6 | hi 6 | x 6 at s_vec (free
+        // at this point), assembled by 42 threads, every active set tested by its own thread
+        double* io = s_vec;
+        if (tid < 36) {
+          const int a = tid / 6, c = tid % 6;
+          double v = (a < nsig && c < nsig) ? -2.0 * lam_as * *elem_tri(sM, Paug + (a > c ? a : c), Paug + (a > c ? c : a)) : 0.0;
+          if (a == c && a >= m && a < nsig) v += 2.0 * cfg.S[a - m];
+          io[tid] = v;
+        } else if (tid < 42) {
+          const int a = tid - 36;
+          double v = a < nsig ? -2.0 * lam_as * *elem_tri(sM, Paug + nsig, Paug + a) : 0.0;
+          if (a >= m && a < nsig) v -= 2.0 * cfg.S[a - m] * y_r[(size_t)b * p + (a - m)];
+          io[36 + a] = v;
           io[42 + a] = a < m ? cfg.Us_lo[a] : -INFINITY;
           io[48 + a] = a < m ? cfg.Us_hi[a] : INFINITY;
-          if (a >= m && a < nsig) {
-            io[a * 6 + a] += 2.0 * cfg.S[a - m];
-            io[36 + a] -= 2.0 * cfg.S[a - m] * y_r[(size_t)b * p + (a - m)];
-          }
         }
-        if (!small_box_qp(io, nsig)) s_flag = 1;
-        for (int a = 0; a < nsig; ++a) s_coef[a] = io[54 + a];
-        s_coef[nsig] = 1.0;
+        if (tid == 0) s_next = 0x7fffffff;  // the work index was copied to `b`; reused as the winner slot
+        __syncthreads();
+        int ncombo = 1;
+        for (int i = 0; i < m; ++i) ncombo *= 3;
+        double xq[6];
+        if (tid < ncombo && ncombo <= kThreads) {
+          if (small_box_qp_combo(io, nsig, m, tid, xq)) atomicMin(&s_next, tid);
+        }
+        __syncthreads();
+        const int win = s_next;
+        if (win == 0x7fffffff) {  // no set passed the tolerances (or m too large): serial pivoting
+          if (tid == 0) {
+            if (!small_box_qp(io, nsig)) s_flag = 1;
+            for (int a = 0; a < nsig; ++a) s_coef[a] = io[54 + a];
+            s_coef[nsig] = 1.0;
+          }
+        } else if (tid == win) {
+          for (int a = 0; a < 6; ++a)
+            if (a < nsig) s_coef[a] = xq[a];
+          s_coef[nsig] = 1.0;
+        }
       }
       __syncthreads();
       DDQC_SUB(7);
