@@ -215,3 +215,36 @@ def test_other_problem_shapes_match_oracle(build_lib, n, L, N):
             np.testing.assert_allclose(gpu.optimal_u[b].cpu().numpy(), orc.optimal_u, rtol=0, atol=TOL)
             orc.store_input_output_measurement(orc.optimal_u[0], y[b, -1])
         gpu.store_input_output_measurement(torch.from_numpy(np.stack([o.u[-1] for o in orcs])).cuda(), torch.from_numpy(y[:, -1].copy()).cuda())
+
+
+def test_full_batch_4096_default_size(build_lib):
+    """BASELINE configs[3] scale: 4096 default-size controllers in one launch.  Size-independent properties - every
+    controller converges, the result of a controller does not depend on its place in the batch (a permuted batch
+    returns the permuted result bit for bit: persistent CTAs pull controllers from a work counter, so the CTA,
+    workspace slot and order that serve a controller differ between the two launches) - plus the literal-QP
+    oracle on a sample."""
+    import os
+
+    import ddmpc_oracle as mo
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ddmpc_default.npz"))
+    prm = mo.default_params()
+    B = 4096
+    rng = np.random.default_rng(7)
+    u = np.repeat(g["u"][None], B, 0) + 1e-3 * rng.standard_normal((B,) + g["u"].shape)
+    y = np.repeat(g["y"][None], B, 0) + 1e-4 * rng.standard_normal((B,) + g["y"].shape)
+    y_r = np.tile(g["y_r"][None], (B, 1)) + 0.2 * rng.uniform(-1, 1, (B, 3))
+    gpu = _batched(prm, u, y, y_r, solve_on_init=False)
+    gpu.update_and_solve_data_driven_mpc()
+    assert (gpu.status.cpu().numpy() == 0).all(), int((gpu.status != 0).sum())
+    uo = gpu.optimal_u.cpu().numpy()
+    lo, hi = np.asarray(prm.U)[:, 0], np.asarray(prm.U)[:, 1]
+    assert np.isfinite(uo).all() and (uo >= lo - 1e-9).all() and (uo <= hi + 1e-9).all()
+    perm = rng.permutation(B)
+    gpu2 = _batched(prm, u[perm], y[perm], y_r[perm], solve_on_init=False)
+    gpu2.update_and_solve_data_driven_mpc()
+    assert np.array_equal(gpu2.optimal_u.cpu().numpy(), uo[perm])
+    assert np.array_equal(gpu2.us.cpu().numpy(), gpu.us.cpu().numpy()[perm])
+    for b in (0, 1733, 4095):
+        orc = mo.NonlinearDDMPCOracle(**mo.ctor_kwargs(prm, u[b], y[b], y_r[b]))
+        np.testing.assert_allclose(uo[b], orc.optimal_u, rtol=0, atol=TOL)
