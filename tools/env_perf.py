@@ -1,6 +1,6 @@
 """Developer probe: time env_step for the kernel variant selected with DDQC_LIB."""
 import os, sys, json
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import make_env
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
