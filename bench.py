@@ -307,6 +307,8 @@ def run_b200(args) -> dict:
         },
         "clocks": clocks,
         "e2e": e2e,
+        "cold_start": {"value": batch / (cold_ms * 1e-3), "unit": "solves/s", "ms_per_batch_solve": cold_ms,
+                       "pivoting_passes_mean": cold_passes, "failed_controllers": cold_failed},
         "gpu_launches": K,
         "roofline": {
             "bound": "hbm",
@@ -519,6 +521,54 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
         iters.append(ctrl.iters.clone())  # passes + (interior-point iterations << 16)
     torch.cuda.synchronize()
     t_loop = time.perf_counter() - t_loop0
+    # end to end through the reference-facing calls with HOST buffers, as the reference's loop makes them
+    # (controller_evaluation.py:366-414): float64 host measurement (u_k, y_k) in -> store -> solve -> optimal input of
+    # step 0 read back to the host; the env step that produces y_k runs between the timed regions
+    E = min(T, 10)
+    u_h = torch.empty((batch, 3), dtype=torch.float64).pin_memory()
+    y_h = torch.empty((batch, 3), dtype=torch.float64).pin_memory()
+    o_h = torch.empty((batch, 3), dtype=torch.float64).pin_memory()
+    u_h.copy_(ctrl.get_optimal_control_input_at_step(0))
+    y_h.copy_(env.get_pos().to(torch.float64))
+    torch.cuda.synchronize()
+    e2e_ms = 0.0
+    for _ in range(E):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        ctrl.store_input_output_measurement(u_h.to(dev, non_blocking=True), y_h.to(dev, non_blocking=True))
+        ctrl.update_and_solve_data_driven_mpc()
+        o_h.copy_(ctrl.get_optimal_control_input_at_step(0), non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_ms += max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+        u0 = o_h.to(dev)
+        env.step(linear_interpolate(x=u0.to(torch.float32), x_min=bounds[:, 0], x_max=bounds[:, 1], y_min=-1, y_max=1))
+        u_h.copy_(o_h)
+        y_h.copy_(env.get_pos().to(torch.float64))
+        torch.cuda.synchronize()
+    e2e = {"value": batch * E / (e2e_ms * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": 2 * batch * 3 * 8,
+           "d2h_bytes_per_step": batch * 3 * 8, "steps": E,
+           "mode": "pinned host (u_k, y_k) float64 -> store_input_output_measurement -> update_and_solve_data_driven_mpc -> "
+                   "optimal input on the host; max(device time, wall clock) per step"}  # fmt: skip
+    # cold start (SURVEY 8d, configs[3]: "warm and cold reported separately"): a fresh batch of controllers on the same
+    # initial data - no previous solve, no active-set warm start - after the kernel module has been loaded
+    cold = BatchedNonlinearDataDrivenMPC(
+        n=P["n"], m=3, p=3, u=u_N, y=y_N, L=P["L"], Q=np.kron(np.eye(ell), np.diag(P["Q"])),
+        R=np.kron(np.eye(ell), np.diag(P["R"])), S=np.diag(P["S"]), y_r=np.array(P["y_r"]), lamb_alpha=P["lamb_alpha"],
+        lamb_sigma=P["lamb_sigma"], U=P["U"], Us=P["Us"], alpha_reg_type=AlphaRegType.APPROXIMATED,
+        lamb_alpha_s=P["lamb_alpha_s"], lamb_sigma_s=P["lamb_sigma_s"], device=dev, solve_on_init=False,
+    )  # fmt: skip
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    c0.record()
+    cold.update_and_solve_data_driven_mpc()
+    c1.record()
+    torch.cuda.synchronize()
+    cold_ms = c0.elapsed_time(c1)
+    cold_passes = float(cold.pivoting_passes.float().mean())
+    cold_failed = int((cold.status != 0).sum())
+    del cold
     solve_ms = sorted(ev_a[t].elapsed_time(ev_b[t]) for t in range(warm, T + warm))
     med = solve_ms[len(solve_ms) // 2]
     avg = sum(solve_ms) / len(solve_ms)
@@ -538,6 +588,7 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
         "ms_per_batch_solve_avg": avg,
         "ms_per_batch_solve_median": med,
         "closed_loop_solves_per_s": batch * T / t_loop,
+        "e2e": e2e,
         "config": "n=6, L=35, N=350, m=p=3 (693-variable QP, 331 equalities, 111 box rows), alpha_reg_type=0, "
         "data: PID-stabilised hover at [0,0,1.5] + uniform excitation, obs noise 1e-4, y_r=[1,1,2.5]",
         "dtype": "f64",

@@ -126,40 +126,18 @@ __device__ __forceinline__ void store_chunk(uint8_t* smem, uint32_t off_hi, uint
   *reinterpret_cast<uint4*>(smem + off_lo) = l;
 }
 
-// tanh(x) = 1 - 2 / (1 + exp(2x)).  Callers pass xs = 2 log2(e) x (the scale is folded into the bias add: one FFMA).
-// The epilogue evaluates 256 tanh per env row and the 16-lane MUFU pipe is its busiest unit (ncu: XU 53 % against
-// FMA 21 %, ALU 16 %), so the exponential of DDQC_POLICY_POLY_MASK's elements (3 of every 4) is computed on the FMA
-// pipe instead: round-to-nearest split xs = j + f by the 1.5*2^23 trick, degree-4 minimax polynomial for 2^f on
-// [-1/2, 1/2] (relative error 2.6e-6, i.e. <= 1.3e-6 on tanh), j added into the exponent field.  The remaining
-// elements keep ex2.approx; both paths share the rcp.approx.  Saturation: the MUFU path by exp -> inf / 0, the
-// polynomial path by the clamp to +-64.
-#ifndef DDQC_POLICY_POLY_MASK
-#define DDQC_POLICY_POLY_MASK 0x7
-#endif
+// tanh(x) = 1 - 2 / (1 + exp(2x)): ex2.approx + rcp.approx, absolute error ~1e-7; saturates cleanly (exp -> inf gives 1,
+// exp -> 0 gives -1), so no clamp is needed.  Callers pass xs = 2 log2(e) x: the scale is folded into the bias add (the
+// biases are stored pre-scaled), one FFMA.  Measured and dropped: the exponential of 2-4 of every 4 elements on the FMA
+// pipe (round-to-nearest split + degree-4 minimax 2^f + exponent insert) to unload the MUFU pipe (ncu: XU 53 % busy,
+// the busiest unit) - 0.225 / 0.239 / 0.250 ms against 0.217 ms: the epilogue is bound by issued instructions per
+// tile, not by the MUFU rate, and each polynomial exponential costs ~9 more of them.
 constexpr float kTanhScale = 2.885390081777927f;
-__device__ __forceinline__ float tanh_mufu(float xs) {
+__device__ __forceinline__ float tanh_acc(float xs) {
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xs));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return fmaf(-2.0f, r, 1.0f);
-}
-__device__ __forceinline__ float tanh_poly(float xs) {
-  xs = fminf(fmaxf(xs, -64.0f), 64.0f);
-  const float t = xs + 12582912.0f;  // low mantissa bits = round(xs)
-  const float f = xs - (t - 12582912.0f);
-  float p = 0.0095701077952981f;
-  p = fmaf(p, f, 0.05591755360364914f);
-  p = fmaf(p, f, 0.24024741351604462f);
-  p = fmaf(p, f, 0.6931218504905701f);
-  p = fmaf(p, f, 0.9999992847442627f);
-  const float e = __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return fmaf(-2.0f, r, 1.0f);
-}
-template <int I>
-__device__ __forceinline__ float tanh_acc(float xs) {
-  return ((DDQC_POLICY_POLY_MASK >> (I & 3)) & 1) ? tanh_poly(xs) : tanh_mufu(xs);
 }
 
 template <bool SPLIT>
@@ -274,10 +252,10 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
       for (int c = 0; c < 4; ++c) {
         const float4 ba = *reinterpret_cast<const float4*>(sB1 + c0 + 8 * c), bb = *reinterpret_cast<const float4*>(sB1 + c0 + 8 * c + 4);
         float y[8];
-        y[0] = tanh_acc<0>(fmaf(v[8 * c], kTanhScale, ba.x)); y[1] = tanh_acc<1>(fmaf(v[8 * c + 1], kTanhScale, ba.y));
-        y[2] = tanh_acc<2>(fmaf(v[8 * c + 2], kTanhScale, ba.z)); y[3] = tanh_acc<3>(fmaf(v[8 * c + 3], kTanhScale, ba.w));
-        y[4] = tanh_acc<0>(fmaf(v[8 * c + 4], kTanhScale, bb.x)); y[5] = tanh_acc<1>(fmaf(v[8 * c + 5], kTanhScale, bb.y));
-        y[6] = tanh_acc<2>(fmaf(v[8 * c + 6], kTanhScale, bb.z)); y[7] = tanh_acc<3>(fmaf(v[8 * c + 7], kTanhScale, bb.w));
+        y[0] = tanh_acc(fmaf(v[8 * c], kTanhScale, ba.x)); y[1] = tanh_acc(fmaf(v[8 * c + 1], kTanhScale, ba.y));
+        y[2] = tanh_acc(fmaf(v[8 * c + 2], kTanhScale, ba.z)); y[3] = tanh_acc(fmaf(v[8 * c + 3], kTanhScale, ba.w));
+        y[4] = tanh_acc(fmaf(v[8 * c + 4], kTanhScale, bb.x)); y[5] = tanh_acc(fmaf(v[8 * c + 5], kTanhScale, bb.y));
+        y[6] = tanh_acc(fmaf(v[8 * c + 6], kTanhScale, bb.z)); y[7] = tanh_acc(fmaf(v[8 * c + 7], kTanhScale, bb.w));
         const uint32_t off = core_off(row, c0 + 8 * c, kHid / 8);
         store_chunk(wgs, kA2Hi + off, kA2Lo + off, y);
       }
@@ -326,10 +304,10 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 bq = *reinterpret_cast<const float4*>(sB2 + c0 + 4 * q);
-        v[4 * q] = tanh_acc<0>(fmaf(v[4 * q], kTanhScale, bq.x));
-        v[4 * q + 1] = tanh_acc<1>(fmaf(v[4 * q + 1], kTanhScale, bq.y));
-        v[4 * q + 2] = tanh_acc<2>(fmaf(v[4 * q + 2], kTanhScale, bq.z));
-        v[4 * q + 3] = tanh_acc<3>(fmaf(v[4 * q + 3], kTanhScale, bq.w));
+        v[4 * q] = tanh_acc(fmaf(v[4 * q], kTanhScale, bq.x));
+        v[4 * q + 1] = tanh_acc(fmaf(v[4 * q + 1], kTanhScale, bq.y));
+        v[4 * q + 2] = tanh_acc(fmaf(v[4 * q + 2], kTanhScale, bq.z));
+        v[4 * q + 3] = tanh_acc(fmaf(v[4 * q + 3], kTanhScale, bq.w));
       }
 #pragma unroll
       for (int j = 0; j < kMaxOut; ++j) {
