@@ -133,11 +133,45 @@ __device__ __forceinline__ void store_chunk(uint8_t* smem, uint32_t off_hi, uint
 // the busiest unit) - 0.225 / 0.239 / 0.250 ms against 0.217 ms: the epilogue is bound by issued instructions per
 // tile, not by the MUFU rate, and each polynomial exponential costs ~9 more of them.
 constexpr float kTanhScale = 2.885390081777927f;
-__device__ __forceinline__ float tanh_acc(float xs) {
+[[maybe_unused]] __device__ __forceinline__ float tanh_acc(float xs) {
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xs));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return fmaf(-2.0f, r, 1.0f);
+}
+
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2: two fp32 results per issued instruction) ----------------
+// The epilogue is bound by issued instructions (4 warps per scheduler), so everything in it that is not a MUFU or a
+// conversion runs two elements per instruction: the tanh argument, 1 + e, 1 - 2r, the bf16 split residual and the
+// output-layer accumulation.
+#ifndef DDQC_POLICY_F32X2
+#define DDQC_POLICY_F32X2 1
+#endif
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk2(float a, float b) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) { f2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// tanh of two pre-scaled arguments
+__device__ __forceinline__ f2_t tanh2(f2_t xs) {
+  float x0, x1, e0, e1, d0, d1, r0, r1;
+  upk2(xs, x0, x1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+  upk2(add2(pk2(e0, e1), pk2(1.0f, 1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+  return fma2(pk2(-2.0f, -2.0f), pk2(r0, r1), pk2(1.0f, 1.0f));
+}
+// bf16 hi/lo split of a packed pair; the residual y - hi is one FFMA2
+__device__ __forceinline__ void split_pair2(f2_t y, uint32_t& hi, uint32_t& lo) {
+  float a, b, ra, rb;
+  upk2(y, a, b);
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  upk2(fma2(pk2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u)), pk2(-1.0f, -1.0f), y), ra, rb);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 template <bool SPLIT>
@@ -251,6 +285,17 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float4 ba = *reinterpret_cast<const float4*>(sB1 + c0 + 8 * c), bb = *reinterpret_cast<const float4*>(sB1 + c0 + 8 * c + 4);
+#if DDQC_POLICY_F32X2
+        const f2_t sc = pk2(kTanhScale, kTanhScale);
+        uint4 h, l;
+        split_pair2(tanh2(fma2(pk2(v[8 * c], v[8 * c + 1]), sc, pk2(ba.x, ba.y))), h.x, l.x);
+        split_pair2(tanh2(fma2(pk2(v[8 * c + 2], v[8 * c + 3]), sc, pk2(ba.z, ba.w))), h.y, l.y);
+        split_pair2(tanh2(fma2(pk2(v[8 * c + 4], v[8 * c + 5]), sc, pk2(bb.x, bb.y))), h.z, l.z);
+        split_pair2(tanh2(fma2(pk2(v[8 * c + 6], v[8 * c + 7]), sc, pk2(bb.z, bb.w))), h.w, l.w);
+        const uint32_t off = core_off(row, c0 + 8 * c, kHid / 8);
+        *reinterpret_cast<uint4*>(wgs + kA2Hi + off) = h;
+        *reinterpret_cast<uint4*>(wgs + kA2Lo + off) = l;
+#else
         float y[8];
         y[0] = tanh_acc(fmaf(v[8 * c], kTanhScale, ba.x)); y[1] = tanh_acc(fmaf(v[8 * c + 1], kTanhScale, ba.y));
         y[2] = tanh_acc(fmaf(v[8 * c + 2], kTanhScale, ba.z)); y[3] = tanh_acc(fmaf(v[8 * c + 3], kTanhScale, ba.w));
@@ -258,6 +303,7 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
         y[6] = tanh_acc(fmaf(v[8 * c + 6], kTanhScale, bb.z)); y[7] = tanh_acc(fmaf(v[8 * c + 7], kTanhScale, bb.w));
         const uint32_t off = core_off(row, c0 + 8 * c, kHid / 8);
         store_chunk(wgs, kA2Hi + off, kA2Lo + off, y);
+#endif
       }
     }
     fence_async_smem();
@@ -294,6 +340,45 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
     tc_fence_after();
     // ---- 5. h2 = tanh(D2 + b2); action = h2 W3^T + b3 on the CUDA cores (partial over this column half) ----
     float out[kMaxOut];
+#if DDQC_POLICY_F32X2
+    f2_t out2[kMaxOut];  // (even, odd) column partial sums
+#pragma unroll
+    for (int j = 0; j < kMaxOut; ++j) out2[j] = pk2(0.0f, 0.0f);
+#pragma unroll 1
+    for (int cb = 0; cb < 2; ++cb) {
+      const int c0 = half * 64 + cb * 32;
+      float v[32];
+      tmem_ld32(d2 + lane_addr + c0, v);
+      const f2_t sc = pk2(kTanhScale, kTanhScale);
+      f2_t h[16];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 bq = *reinterpret_cast<const float4*>(sB2 + c0 + 4 * q);
+        h[2 * q] = tanh2(fma2(pk2(v[4 * q], v[4 * q + 1]), sc, pk2(bq.x, bq.y)));
+        h[2 * q + 1] = tanh2(fma2(pk2(v[4 * q + 2], v[4 * q + 3]), sc, pk2(bq.z, bq.w)));
+      }
+#pragma unroll
+      for (int j = 0; j < kMaxOut; ++j) {
+        if (j < n_out) {  // uniform
+          const float4* w = reinterpret_cast<const float4*>(sW3 + j * kHid + c0);
+          f2_t acc = out2[j];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 ww = w[q];
+            acc = fma2(h[2 * q], pk2(ww.x, ww.y), acc);
+            acc = fma2(h[2 * q + 1], pk2(ww.z, ww.w), acc);
+          }
+          out2[j] = acc;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxOut; ++j) {
+      float e, o;
+      upk2(out2[j], e, o);
+      out[j] = e + o;
+    }
+#else
 #pragma unroll
     for (int j = 0; j < kMaxOut; ++j) out[j] = 0.0f;
 #pragma unroll 1
@@ -326,6 +411,7 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
         }
       }
     }
+#endif
     tc_fence_before();  // the TMEM reads above are ordered before the next tile's MMAs (via the next wg_sync)
     if (half == 1) *reinterpret_cast<float4*>(part + row * kMaxOut) = make_float4(out[0], out[1], out[2], out[3]);
     wg_sync(wg);
