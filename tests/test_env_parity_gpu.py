@@ -134,6 +134,30 @@ def test_lazy_buffers_match_materialized(build_lib):
         _ = env_a.base_euler
 
 
+@pytest.mark.parametrize("N,T", [(4096, 300), (1 << 20, 3), ((1 << 20) - 77, 2)])
+def test_baseline_sizes_bit_exact(build_lib, N, T):
+    """BASELINE configs[1] (4096 envs) and configs[2] (2^20 envs per GPU, plus a ragged size whose last CTA is partly
+    idle) on the kernel variant the bench times (CTBR_FIXED_YAW, lean buffers, auto target updates): every output of
+    every env identical to the oracle, and the all-reduced rollout statistics equal to the oracle's sums."""
+    env, orc = _make_pair(N, "CTBR_FIXED_YAW", True, materialize=False)
+    acts = np.random.RandomState(11).uniform(-1.0, 1.0, (T, N, 3)).astype(np.float32)
+    env.reset()
+    orc.reset()
+    n_reset, rew_sum = 0, 0.0
+    for t in range(T):
+        env.step(torch.from_numpy(acts[t]).cuda())
+        orc.step(acts[t])
+        _compare_step(env, orc, t)
+        n_reset += int(orc.reset_buf.sum())
+        rew_sum += float(orc.rew_buf.astype(np.float64).sum())
+    stats = env.rollout_stats()
+    assert int(stats["resets"]) == n_reset
+    assert int(stats["env_steps"]) == N * T
+    assert abs(float(stats["reward_sum"]) - rew_sum) <= 2e-6 * max(1.0, abs(rew_sum))
+    if N == 4096:
+        assert n_reset > 1000  # the rollout exercises the reset / PID-flush / resample paths
+
+
 def test_timeouts_and_episode_length_assignment(build_lib):
     """Zero actions hover forever: every env times out on step max_episode_length+1 (strict >)."""
     env, orc = _make_pair(8, "CTBR_FIXED_YAW", False, env_over={"episode_length_s": 0.4})
