@@ -158,7 +158,7 @@ class MpcConfig(C.Structure):
         ("N", i32),
         ("alpha_reg_type", i32),
         ("max_iter", i32),
-        ("pad0", i32),
+        ("gram_refresh", i32),
         ("Q", f64 * 8),
         ("R", f64 * 8),
         ("S", f64 * 8),
@@ -197,10 +197,11 @@ SIGNATURES = {
         [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, vp, P(f32), f32, f32, f32, vp, i64, vp],
     ),
     "ddqc_ddmpc_workspace_bytes": (i64, [P(MpcConfig), i64]),
-    "ddqc_ddmpc_solve": (C.c_int, [P(MpcConfig), vp] + [vp] * 11 + [i64, vp]),
-    "ddqc_ddmpc_store": (C.c_int, [P(MpcConfig), vp, vp, vp, vp, i64, vp]),
+    "ddqc_ddmpc_gram_cache_bytes": (i64, [P(MpcConfig), i64]),
+    "ddqc_ddmpc_solve": (C.c_int, [P(MpcConfig), vp] + [vp] * 11 + [i64, vp, vp]),
+    "ddqc_ddmpc_store": (C.c_int, [P(MpcConfig), vp, vp, vp, vp, i64, vp, vp]),
     "ddqc_ddmpc_action": (C.c_int, [P(MpcConfig), vp, C.c_int32, vp, vp, vp, i64, vp]),
-    "ddqc_ddmpc_post_step": (C.c_int, [P(MpcConfig), vp, vp, vp, vp, i64, i64, vp, vp, C.c_double, vp, vp, vp, vp, C.c_int32, i64, vp]),
+    "ddqc_ddmpc_post_step": (C.c_int, [P(MpcConfig), vp, vp, vp, vp, i64, i64, vp, vp, C.c_double, vp, vp, vp, vp, C.c_int32, i64, vp, vp]),
     "ddqc_ddmpc_debug_phase_buffer": (C.c_int, [vp]),
     "ddqc_policy_mlp_forward": (C.c_int, [vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp]),
 }

@@ -117,6 +117,34 @@ __host__ __device__ inline int region_doubles(const Dims& d) {
 
 __host__ __device__ inline size_t slot_doubles(const Dims& d) { return (size_t)d.ga + d.gsg; }
 
+// ---- per-controller Gram cache (optional) ---------------------------------------------------------
+// Between two solves of a closed loop the window moves by one sample, so the Hankel matrix drops its first column and
+// gains a last one: G' = G - a a' + b b' with a = old first column, b = new last column.  With a cache the permuted,
+// block-packed G of every controller persists in HBM (1.2 GB for 4096 default-size controllers) and a solve whose
+// window moved by exactly one sample since the cached G applies the rank-2 correction block by block (coalesced 16-byte
+// traffic, two DFMAs per entry) instead of regenerating G (DMMA first block column + 32 k scattered stores).  G is
+// regenerated from the window when the cache is empty, the window moved by more than one sample, or `gram_refresh`
+// incremental updates have accumulated (bounds the rounding drift: each update rounds at ulp(G_ij), the same size as the
+// error of a fresh accumulation).  Per controller: kCacheHdr doubles of header
+//   [0] int64 state: 0 empty, 1 valid, 2 valid + window moved one sample, 3 valid + moved more than one
+//   [1] int64 age:   incremental updates since the last regeneration
+//   [2 ..] the sample (u, y) that the last shift dropped
+// followed by slot_doubles(d) doubles in the layout of a workspace slot.
+constexpr int kCacheHdr = 24;
+constexpr int kGramRefreshDefault = 128;
+__host__ __device__ inline size_t cache_stride(const Dims& d) { return (size_t)kCacheHdr + slot_doubles(d); }
+// called by the window-shifting kernels before they overwrite the first sample (threads 0 .. max(m, p) - 1 take part)
+__device__ __forceinline__ void cache_note_shift(double* __restrict__ cache, const Dims& d, int b, const double* ub,
+                                                 const double* yb) {
+  if (!cache) return;
+  double* h = cache + (size_t)b * cache_stride(d);
+  const long long st = *reinterpret_cast<long long*>(h);
+  if (st == 0) return;
+  if (threadIdx.x < d.m) h[2 + threadIdx.x] = ub[threadIdx.x];
+  if (threadIdx.x < d.p) h[2 + d.m + threadIdx.x] = yb[threadIdx.x];
+  if (threadIdx.x == 0) *reinterpret_cast<long long*>(h) = st == 1 ? 2 : 3;
+}
+
 // ---- 8x8 block layout ---------------------------------------------------------------------------
 // element (g, c) of a block sits at g*8 + (c ^ 4*((g>>1)&1)): every DMMA operand fragment (8 rows
 // x 4 consecutive columns) covers all 32 banks exactly twice and every accumulator fragment is a
@@ -1050,7 +1078,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
                    const double* __restrict__ y_r, const int32_t* __restrict__ have_prev,
                    const double* __restrict__ lamb, int8_t* __restrict__ act_state, double* __restrict__ u_opt, double* __restrict__ us_opt,
                    double* __restrict__ ys_opt, int32_t* __restrict__ status, int32_t* __restrict__ iters,
-                   const int batch, long long* __restrict__ phase_clk) {
+                   const int batch, long long* __restrict__ phase_clk, double* __restrict__ gram_cache) {
   extern __shared__ __align__(16) double smem[];
   const Dims d = make_dims(cfg);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
@@ -1066,6 +1094,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
   double* s_coef = s_red + 64;              // 8: rho = sum_a coef[a] * (aug group 0 row a)
   __shared__ int s_flag;
   __shared__ int s_next;
+  __shared__ int s_gmode;  // Gram of this solve: 0 regenerate, 1 cached + rank-2 correction, 2 cached as is
   __shared__ int s_state[kMaxNx];
   __shared__ int s_idx[kMaxNx + 1];
   __shared__ int s_verdict[kMaxNx];
@@ -1089,12 +1118,23 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
   for (;;) {
     __syncthreads();
     if (tid == 0) {
-      s_next = atomicAdd(work_counter, 1);
+      const int nb = atomicAdd(work_counter, 1);
+      s_next = nb;
       s_flag = 0;
+      int gm = 0;
+      if (gram_cache && nb < batch) {
+        const long long* h = reinterpret_cast<const long long*>(gram_cache + (size_t)nb * cache_stride(d));
+        const int refresh = cfg.gram_refresh > 0 ? cfg.gram_refresh : kGramRefreshDefault;
+        if (h[0] == 1) gm = 2;
+        else if (h[0] == 2 && h[1] < refresh) gm = 1;
+      }
+      s_gmode = gm;
     }
     __syncthreads();
     const int b = s_next;
     if (b >= batch) break;
+    const int gmode = s_gmode;
+    double* gc = gram_cache ? gram_cache + (size_t)b * cache_stride(d) : nullptr;
     t_prev = clock64();
     const bool use_sr = cfg.alpha_reg_type == 0;
     // regularisation weights: per controller when `lamb` is given (grid search over lambda), else from the config
@@ -1107,8 +1147,28 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     DDQC_SUB(-1);
     double* sW = sM;
     double* sT = sM + nsig * N;  // first block column of G, (ell*nsig) x ldT
-    for (int e = tid; e < N * m; e += kThreads) sW[(e % m) * N + e / m] = ub[e];
-    for (int e = tid; e < N * p; e += kThreads) sW[(m + e % p) * N + e / p] = yb[e];
+    if (gmode == 0) {
+      for (int e = tid; e < N * m; e += kThreads) sW[(e % m) * N + e / m] = ub[e];
+      for (int e = tid; e < N * p; e += kThreads) sW[(m + e % p) * N + e / p] = yb[e];
+    } else {
+      // a (old first Hankel column) and b (new last column) by position in the elimination order; pad and aug
+      // positions stay 0, the ones row has a = b = 1 (its entries move by b_P - a_P)
+      const int ntot = d.n1p + d.n2p + d.n3p + 16;
+      double* s_a = sM;
+      double* s_b = sM + ntot;
+      for (int e = tid; e < 2 * ntot; e += kThreads) sM[e] = 0.0;
+      __syncthreads();
+      if (gmode == 1) {
+        for (int e = tid; e < nsig * ell; e += kThreads) {
+          const int a = e / ell, j = e % ell, P = s_ppos[e];
+          const double* w = a < m ? ub + a : yb + (a - m);
+          const int st = a < m ? m : p;
+          s_a[P] = j == 0 ? gc[2 + a] : w[(size_t)(j - 1) * st];
+          s_b[P] = w[(size_t)(j + C - 1) * st];
+        }
+        if (tid == 0) { s_a[n * m] = 1.0; s_b[n * m] = 1.0; }
+      }
+    }
     // aug block rows and pad rows: explicit zeros first
     {
       const int r0 = d.nb1 + d.nb2 + d.nb3;  // first aug block row (all-rows numbering)
@@ -1121,7 +1181,63 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     }
     __syncthreads();
     DDQC_SUB(0);
-    {
+    if (gmode != 0) {
+      // cached G (+ rank-2 correction) -> workspace slot and back to the cache: one warp per 8x8 block, one double2 per
+      // lane; the aug block rows are regenerated below
+      const int ntot = d.n1p + d.n2p + d.n3p + 16;
+      const double* s_a = sM;
+      const double* s_b = sM + ntot;
+      double* cG = gc + kCacheHdr;
+      const int r0 = d.nb1 + d.nb2 + d.nb3, tb0 = d.nb2 + d.nb3;
+      const int nga = r0 * d.nb1, ngs = tri(tb0);
+      const int gq = lane >> 2, c2 = (lane & 3) * 2, cl = c2 ^ ((gq & 2) << 1), off = gq * 8 + c2;
+      // The cached blocks come from HBM: staged through shared memory in chunks with every 16-byte piece of a chunk
+      // in flight at once (a load-use loop pays one DRAM round trip per block: 38 x 1.7 k cycles).  Each thread
+      // consumes exactly the pieces it copied (chunk sizes are multiples of the warp count), so no barrier is needed.
+      // The cache is streamed (read once, written once per solve): evict-first in L2, so that it does not push the
+      // workspace slots, the spill area and the kernel's own instructions out of L2 (measured: without the hints
+      // every later phase of the solve slows down by 5-10 %).
+      uint64_t pol_stream;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+      double* stage = sM + 2 * ntot;
+      const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+      const int CH = ((region_doubles(d) - 2 * ntot) / 64) & ~(kWarps - 1);
+      for (int c0 = 0; c0 < nga + ngs; c0 += CH) {
+        const int c1 = c0 + CH < nga + ngs ? c0 + CH : nga + ngs;
+        for (int bi = c0 + warp; bi < c1; bi += kWarps) {
+          const size_t base = (bi < nga ? (size_t)bi * 64 : (size_t)d.ga + (size_t)(bi - nga) * 64) + off;
+          asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(stage_s + 8u * (uint32_t)((bi - c0) * 64 + off)), "l"(cG + base), "l"(pol_stream) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        for (int bi = c0 + warp; bi < c1; bi += kWarps) {
+          int hi, lo;
+          size_t base;
+          if (bi < nga) {
+            hi = (bi / d.nb1) * 8 + gq;
+            lo = (bi % d.nb1) * 8 + cl;
+            base = (size_t)bi * 64 + off;
+          } else {
+            const int bb = bi - nga;
+            int I = (int)((sqrtf(8.0f * bb + 1.0f) - 1.0f) * 0.5f);
+            while (tri(I + 1) <= bb) ++I;
+            while (tri(I) > bb) --I;
+            hi = d.n1p + I * 8 + gq;
+            lo = d.n1p + (bb - tri(I)) * 8 + cl;
+            base = (size_t)d.ga + (size_t)bb * 64 + off;
+          }
+          double2 v = *reinterpret_cast<const double2*>(stage + (bi - c0) * 64 + off);
+          if (gmode == 1) {
+            const double ah = s_a[hi], bh = s_b[hi];
+            const double2 al = *reinterpret_cast<const double2*>(s_a + lo), bl = *reinterpret_cast<const double2*>(s_b + lo);
+            v.x = fma(bh, bl.x, fma(-ah, al.x, v.x));
+            v.y = fma(bh, bl.y, fma(-ah, al.y, v.y));
+            asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(cG + base), "d"(v.x), "d"(v.y), "l"(pol_stream) : "memory");
+          }
+          *reinterpret_cast<double2*>(slot + base) = v;
+        }
+      }
+    } else {
       // pad rows (identity) of the three classes
       const int npad = (d.n1p - d.n1) + (d.n2p - d.n2) + (d.n3p - d.n3);
       const int ntot = d.n1p + d.n2p + d.n3p + 16;
@@ -1181,6 +1297,8 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
         for (int e = tid; e < nrho; e += kThreads) put_sym(d, GA, GS, s_ppos[(e % nsig) * ell + e / nsig], Pone, sT[e * ldT + nsig]);
         if (tid == 0) put_sym(d, GA, GS, Pone, Pone, (double)C);
       }
+    }
+    {
       const int Pone = n * m;
       // aug rows.  group 0 (block row tb): A_u (m: ones on ALL input rows of a component), A_y (p), e_one, tau;
       //            group 1 (block row tb + 1): T_u (m: ones on the terminal input rows), T_y (p: free + terminal outputs)
@@ -1203,6 +1321,20 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       }
     }
     __syncthreads();
+    if (gc) {
+      if (gmode == 0) {  // regenerated: G (slot layout) -> cache
+        const double2* src = reinterpret_cast<const double2*>(slot);
+        double2* dst = reinterpret_cast<double2*>(gc + kCacheHdr);
+        const int n2 = (int)(slot_doubles(d) / 2);
+#pragma unroll 4
+        for (int e = tid; e < n2; e += kThreads) __stcs(dst + e, __ldcg(src + e));
+      }
+      if (tid == 0) {
+        long long* h = reinterpret_cast<long long*>(gc);
+        h[1] = gmode == 0 ? 0 : h[1] + (gmode == 1 ? 1 : 0);
+        h[0] = 1;
+      }
+    }
     DDQC_SUB(4);
     DDQC_PHASE(0);
 
@@ -1519,14 +1651,16 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
   }
 }
 
-__global__ void ddmpc_store_kernel(const int N, const int m, const int p, double* __restrict__ u_win,
+__global__ void ddmpc_store_kernel(const DdqcMpcConfig cfg, double* __restrict__ u_win,
                                    double* __restrict__ y_win, const double* __restrict__ u_new,
-                                   const double* __restrict__ y_new, const int batch) {
+                                   const double* __restrict__ y_new, const int batch, double* __restrict__ gram_cache) {
   // one CTA per controller: shift the window one sample (in place, ordered) and append
+  const int N = cfg.N, m = cfg.m, p = cfg.p;
   const int b = blockIdx.x;
   if (b >= batch) return;
   double* ub = u_win + (size_t)b * N * m;
   double* yb = y_win + (size_t)b * N * p;
+  if (gram_cache) cache_note_shift(gram_cache, make_dims(cfg), b, ub, yb);
   // in-place shift needs read-before-write ordering: go through registers in chunks of the CTA
   for (int base = 0; base < (N - 1) * m; base += blockDim.x) {
     const int e = base + threadIdx.x;
@@ -1567,18 +1701,20 @@ __global__ void ddmpc_action_kernel(const double* __restrict__ u_opt, const int 
 // shifts the windows, appends (u_applied, y), accumulates |y - y_r|^2 and raises the early-stop flag
 // when |y - y_r| - d0 > max_inc (controller_evaluation.py:424-447).  Controllers that already stopped
 // (fail_step >= 0) keep their windows and sums frozen, like an aborted evaluation.
-__global__ void ddmpc_post_step_kernel(const int N, const int m, const int p, double* __restrict__ u_win,
+__global__ void ddmpc_post_step_kernel(const DdqcMpcConfig cfg, double* __restrict__ gram_cache, double* __restrict__ u_win,
                                        double* __restrict__ y_win, const double* __restrict__ u_new,
                                        const float* __restrict__ y_meas, const long long y_rs, const long long y_cs,
                                        const double* __restrict__ y_r, const double* __restrict__ d0,
                                        const double max_inc, double* __restrict__ sq_sum, int32_t* __restrict__ n_acc,
                                        int32_t* __restrict__ fail_step, double* __restrict__ y_log, const int step,
                                        const int batch) {
+  const int N = cfg.N, m = cfg.m, p = cfg.p;
   const int b = blockIdx.x;
   if (b >= batch) return;
   if (fail_step[b] >= 0) return;  // uniform per CTA
   double* ub = u_win + (size_t)b * N * m;
   double* yb = y_win + (size_t)b * N * p;
+  if (gram_cache) cache_note_shift(gram_cache, make_dims(cfg), b, ub, yb);
   for (int base = 0; base < (N - 1) * m; base += blockDim.x) {
     const int e = base + threadIdx.x;
     double v = (e < (N - 1) * m) ? ub[e + m] : 0.0;
@@ -1647,11 +1783,17 @@ extern "C" int64_t ddqc_ddmpc_workspace_bytes(const DdqcMpcConfig* cfg, int64_t 
   return 256 + (int64_t)(slot_doubles(d) * sizeof(double)) * (slots > 0 ? slots : 1);
 }
 
+extern "C" int64_t ddqc_ddmpc_gram_cache_bytes(const DdqcMpcConfig* cfg, int64_t batch) {
+  if (check_cfg(cfg) != 0 || batch < 0) return -1;
+  return (int64_t)(cache_stride(make_dims(*cfg)) * sizeof(double)) * batch;
+}
+
 extern "C" int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg, void* ws, const double* u_win, const double* y_win,
                                 const double* y_r,
                                 const int32_t* have_prev, const double* lamb, int8_t* act_state, double* u_opt,
                                 double* us_opt,
-                                double* ys_opt, int32_t* status, int32_t* iters, int64_t batch, void* stream) {
+                                double* ys_opt, int32_t* status, int32_t* iters, int64_t batch, void* gram_cache,
+                                void* stream) {
   int rc = check_cfg(cfg);
   if (rc) return rc;
   if (!ws || !u_win || !y_win || !y_r || !u_opt || !us_opt || !ys_opt || !status || !iters || !have_prev)
@@ -1674,18 +1816,18 @@ extern "C" int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg, void* ws, const double
   double* slots = reinterpret_cast<double*>(static_cast<char*>(ws) + 256);
   ddmpc_solve_kernel<<<grid, kThreads, smem, st>>>(*cfg, slots, static_cast<int*>(ws), u_win, y_win, y_r,
                                                    have_prev, lamb, act_state, u_opt, us_opt, ys_opt, status,
-                                                   iters, (int)batch, g_phase_clk);
+                                                   iters, (int)batch, g_phase_clk, static_cast<double*>(gram_cache));
   return (int)cudaGetLastError();
 }
 
 extern "C" int ddqc_ddmpc_store(const DdqcMpcConfig* cfg, double* u_win, double* y_win, const double* u_new,
-                                const double* y_new, int64_t batch, void* stream) {
+                                const double* y_new, int64_t batch, void* gram_cache, void* stream) {
   int rc = check_cfg(cfg);
   if (rc) return rc;
   if (!u_win || !y_win || !u_new || !y_new) return DDQC_E_NULL;
   if (batch <= 0) return batch == 0 ? 0 : DDQC_E_SHAPE;
-  ddmpc_store_kernel<<<(unsigned)batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(cfg->N, cfg->m, cfg->p, u_win, y_win,
-                                                                                    u_new, y_new, (int)batch);
+  ddmpc_store_kernel<<<(unsigned)batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(*cfg, u_win, y_win, u_new, y_new, (int)batch,
+                                                                                    static_cast<double*>(gram_cache));
   return (int)cudaGetLastError();
 }
 
@@ -1705,14 +1847,15 @@ extern "C" int ddqc_ddmpc_action(const DdqcMpcConfig* cfg, const double* u_opt, 
 extern "C" int ddqc_ddmpc_post_step(const DdqcMpcConfig* cfg, double* u_win, double* y_win, const double* u_applied,
                                     const float* y_meas, int64_t y_rs, int64_t y_cs, const double* y_r,
                                     const double* d0, double max_inc, double* sq_sum, int32_t* n_acc,
-                                    int32_t* fail_step, double* y_log, int32_t step, int64_t batch, void* stream) {
+                                    int32_t* fail_step, double* y_log, int32_t step, int64_t batch, void* gram_cache,
+                                    void* stream) {
   int rc = check_cfg(cfg);
   if (rc) return rc;
   if (!u_win || !y_win || !u_applied || !y_meas || !y_r || !d0 || !sq_sum || !n_acc || !fail_step) return DDQC_E_NULL;
   if (batch < 0 || step < 0) return DDQC_E_SHAPE;
   if (batch == 0) return 0;
   ddmpc_post_step_kernel<<<(unsigned)batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      cfg->N, cfg->m, cfg->p, u_win, y_win, u_applied, y_meas, (long long)y_rs, (long long)y_cs, y_r, d0, max_inc,
+      *cfg, static_cast<double*>(gram_cache), u_win, y_win, u_applied, y_meas, (long long)y_rs, (long long)y_cs, y_r, d0, max_inc,
       sq_sum, n_acc, fail_step, y_log, step, (int)batch);
   return (int)cudaGetLastError();
 }

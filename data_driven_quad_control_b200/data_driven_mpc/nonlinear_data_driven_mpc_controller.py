@@ -75,6 +75,8 @@ class BatchedNonlinearDataDrivenMPC:
         solve_on_init: bool = True,
         max_iter: int = 12,
         warm_start: bool = True,
+        gram_cache: bool | None = None,
+        gram_refresh: int = 128,
     ):
         if ext_out_incr_in:
             raise NotImplementedError("ext_out_incr_in=True (extended output / input increments) is not supported")
@@ -111,6 +113,7 @@ class BatchedNonlinearDataDrivenMPC:
         cfg.n, cfg.m, cfg.p, cfg.L, cfg.N = self.n, self.m, self.p, self.L, self.N
         cfg.alpha_reg_type = art.value
         cfg.max_iter = int(max_iter)
+        cfg.gram_refresh = int(gram_refresh)
         qw = _block_diag_weights(Q, ell, p, "Q")
         rw = _block_diag_weights(R, ell, m, "R")
         sw = _block_diag_weights(S, 1, p, "S")
@@ -142,6 +145,12 @@ class BatchedNonlinearDataDrivenMPC:
         if ws_bytes < 0:
             raise ValueError("unsupported problem size for the GPU solver (see ddqc_ddmpc.cu limits)")
         self._ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        # Per-controller Gram cache (ddqc.h): G persists in HBM between solves and follows the one-sample window shift
+        # by a rank-2 correction.  `gram_cache=None` enables it when it fits in a quarter of the free device memory.
+        gc_bytes = self._lib.ddqc_ddmpc_gram_cache_bytes(C.byref(cfg), self.B)
+        if gram_cache is None:
+            gram_cache = gc_bytes <= torch.cuda.mem_get_info(dev)[0] // 4
+        self._gram_cache = torch.zeros((gc_bytes,), dtype=torch.uint8, device=dev) if gram_cache else None
 
         self.y_r = torch.zeros((self.B, p), **f64)
         self.set_output_setpoint(y_r)
@@ -170,10 +179,20 @@ class BatchedNonlinearDataDrivenMPC:
             C.byref(self._cfg), self._ws.data_ptr(), self.u.data_ptr(), self.y.data_ptr(), self.y_r.data_ptr(),
             self._have_prev.data_ptr(),
             self._lamb.data_ptr() if self._lamb is not None else None, self._act_state.data_ptr() if self._act_state is not None else None, self.optimal_u.data_ptr(), self.us.data_ptr(), self.ys.data_ptr(), self.status.data_ptr(),
-            self.iters.data_ptr(), self.B, _lib.stream_ptr(self.device),
+            self.iters.data_ptr(), self.B, self.gram_cache_ptr, _lib.stream_ptr(self.device),
         )  # fmt: skip
         _lib.check(rc, "ddqc_ddmpc_solve")
         self._have_prev.fill_(1)
+
+    @property
+    def gram_cache_ptr(self):
+        """Device pointer of the Gram cache (None when it is off), for the C-ABI calls that shift the windows."""
+        return self._gram_cache.data_ptr() if self._gram_cache is not None else None
+
+    def invalidate_gram_cache(self) -> None:
+        """Call after writing `self.u` / `self.y` directly: the next solve regenerates G from the windows."""
+        if self._gram_cache is not None:
+            self._gram_cache.zero_()
 
     @property
     def pivoting_passes(self) -> torch.Tensor:
@@ -200,7 +219,7 @@ class BatchedNonlinearDataDrivenMPC:
         y_c = y_c.to(device=self.device, dtype=torch.float64).reshape(self.B, self.p).contiguous()
         rc = self._lib.ddqc_ddmpc_store(
             C.byref(self._cfg), self.u.data_ptr(), self.y.data_ptr(), u_c.data_ptr(), y_c.data_ptr(), self.B,
-            _lib.stream_ptr(self.device),
+            self.gram_cache_ptr, _lib.stream_ptr(self.device),
         )
         _lib.check(rc, "ddqc_ddmpc_store")
 

@@ -92,7 +92,7 @@ def sim_nonlinear_dd_mpc_control_loop_batched(
             rc = lib.ddqc_ddmpc_post_step(
                 cfg, ctrl.u.data_ptr(), ctrl.y.data_ptr(), u_applied.data_ptr(), y.data_ptr(), y.stride(0), y.stride(1),
                 y_r.data_ptr(), d0.data_ptr(), max_inc, sq_sum.data_ptr(), n_acc.data_ptr(), fail_step.data_ptr(),
-                y_log.data_ptr() if record else None, k, B, _lib.stream_ptr(dev),
+                y_log.data_ptr() if record else None, k, B, ctrl.gram_cache_ptr, _lib.stream_ptr(dev),
             )  # fmt: skip
             _lib.check(rc, "ddqc_ddmpc_post_step")
             if record:

@@ -253,7 +253,7 @@ typedef struct DdqcMpcConfig {
   int32_t n, m, p, L, N;        /* estimated order, inputs, outputs, horizon, window length */
   int32_t alpha_reg_type;       /* 0 approximated, 1 previous, 2 zero */
   int32_t max_iter;             /* pivoting passes before the interior-point fallback (<=0: 12) */
-  int32_t pad0;
+  int32_t gram_refresh;         /* Gram cache: incremental updates between regenerations (<=0: 128) */
   double Q[8], R[8], S[8];      /* diagonal weights (first p / m / p entries) */
   double lamb_alpha, lamb_sigma, lamb_alpha_s, lamb_sigma_s;
   double U_lo[8], U_hi[8], Us_lo[8], Us_hi[8];
@@ -282,11 +282,19 @@ int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg_host, void* ws, const double* u_wi
                      const double* y_win, const double* y_r, const int32_t* have_prev, const double* lamb,
                      int8_t* act_state,
                      double* u_opt, double* us_opt, double* ys_opt, int32_t* status, int32_t* iters,
-                     int64_t batch, void* stream);
+                     int64_t batch, void* gram_cache, void* stream);
+
+/* Optional per-controller Gram cache (`gram_cache`, or NULL, of ddqc_ddmpc_solve / _store / _post_step): the block-packed
+ * Gram matrix of every controller's Hankel matrix persists between solves; a solve whose window moved by exactly one
+ * sample (one store_input_output_measurement) since the cached matrix applies the rank-2 correction
+ * G' = G - (old first column)(..)' + (new last column)(..)' instead of regenerating G from the window.  The buffer
+ * (ddqc_ddmpc_gram_cache_bytes() bytes, 16-byte aligned, ZEROED by the caller before the first solve and whenever the
+ * windows are rewritten other than through _store / _post_step) belongs to the caller like every other buffer. */
+int64_t ddqc_ddmpc_gram_cache_bytes(const DdqcMpcConfig* cfg_host, int64_t batch);
 
 /* store_input_output_measurement for a batch: shift each window one sample and append. */
 int ddqc_ddmpc_store(const DdqcMpcConfig* cfg_host, double* u_win, double* y_win,
-                     const double* u_new, const double* y_new, int64_t batch, void* stream);
+                     const double* u_new, const double* y_new, int64_t batch, void* gram_cache, void* stream);
 
 /* Closed-loop evaluation of a batch of controllers without host round trips
  * (sim_nonlinear_dd_mpc_control_loop_parallel, data_driven_mpc/utilities/param_grid_search/
@@ -306,7 +314,7 @@ int ddqc_ddmpc_post_step(const DdqcMpcConfig* cfg_host, double* u_win, double* y
                          const double* u_applied, const float* y_meas, int64_t y_rs, int64_t y_cs,
                          const double* y_r, const double* d0, double max_inc, double* sq_sum,
                          int32_t* n_acc, int32_t* fail_step, double* y_log, int32_t step,
-                         int64_t batch, void* stream);
+                         int64_t batch, void* gram_cache, void* stream);
 
 /* Developer aid: device buffer of 12 int64 cycle counters accumulated per solver phase (NULL: off). */
 int ddqc_ddmpc_debug_phase_buffer(void* dev_ptr);

@@ -248,3 +248,65 @@ def test_full_batch_4096_default_size(build_lib):
     for b in (0, 1733, 4095):
         orc = mo.NonlinearDDMPCOracle(**mo.ctor_kwargs(prm, u[b], y[b], y_r[b]))
         np.testing.assert_allclose(uo[b], orc.optimal_u, rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("shape", ["small", "default"])
+def test_gram_cache_follows_the_window_like_a_regeneration(build_lib, shape):
+    """The per-controller Gram cache (rank-2 correction per one-sample shift) against the regeneration of G from the
+    window in a closed loop: same optimal inputs to 1e-6 (the two differ by rounding of order ulp(G_ij) only), through
+    every cache transition - first solve (fill), one shift (update), refresh after `gram_refresh` updates, a second
+    solve without a shift (reuse), two shifts between solves (regenerate), direct window write + invalidate."""
+    import os
+
+    import ddmpc_oracle as mo
+
+    if shape == "small":
+        prm, B = _small_params(), 6
+        u, y, plants = _synthetic_windows(prm, 3, B, return_plants=True)
+        y_r = np.tile(np.array([[0.2, -0.1, 0.1]]), (B, 1))
+    else:
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ddmpc_default.npz"))
+        prm, B = mo.default_params(), 5
+        rng = np.random.default_rng(2)
+        u = np.repeat(g["u"][None], B, 0) + 1e-3 * rng.standard_normal((B,) + g["u"].shape)
+        y = np.repeat(g["y"][None], B, 0) + 1e-4 * rng.standard_normal((B,) + g["y"].shape)
+        y_r = np.tile(g["y_r"][None], (B, 1))
+        plants = None
+    a = _batched(prm, u, y, y_r, solve_on_init=False, gram_cache=True, gram_refresh=4)
+    b = _batched(prm, u, y, y_r, solve_on_init=False, gram_cache=False)
+    assert a.gram_cache_ptr is not None and b.gram_cache_ptr is None
+    rng = np.random.default_rng(9)
+    worst = 0.0
+
+    def solve_both():
+        nonlocal worst
+        a.update_and_solve_data_driven_mpc()
+        b.update_and_solve_data_driven_mpc()
+        assert (a.status.cpu().numpy() == 0).all() and (b.status.cpu().numpy() == 0).all()
+        ua, ub = a.optimal_u.cpu().numpy(), b.optimal_u.cpu().numpy()
+        worst = max(worst, float(np.abs(ua - ub).max()))
+        np.testing.assert_allclose(ua, ub, rtol=0, atol=1e-6)
+
+    def store_both():
+        u0 = b.get_optimal_control_input_at_step(0).cpu().numpy()
+        if plants is not None:
+            yk = np.stack([plants[i].step(u0[i]) for i in range(B)])
+        else:
+            yk = b.y[:, -1].cpu().numpy() + 1e-3 * rng.standard_normal((B, prm.p))
+        for c in (a, b):
+            c.store_input_output_measurement(torch.from_numpy(u0).cuda(), torch.from_numpy(yk).cuda())
+
+    solve_both()  # fill
+    for _ in range(11):  # update x4, regenerate, update ...
+        store_both()
+        solve_both()
+    solve_both()  # reuse (no shift since the last solve)
+    store_both()
+    store_both()
+    solve_both()  # two shifts: regenerate
+    assert torch.equal(a.u, b.u) and torch.equal(a.y, b.y)
+    for c in (a, b):
+        c.y[:, -1] += 1e-3
+    a.invalidate_gram_cache()
+    solve_both()
+    print(f"gram cache vs regeneration ({shape}): max |du| = {worst:.3e}")

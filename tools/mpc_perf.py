@@ -11,10 +11,14 @@ rng = np.random.default_rng(0)
 u = np.repeat(g["u"][None], B, 0) + 1e-3 * rng.standard_normal((B, 350, 3))
 y = np.repeat(g["y"][None], B, 0) + 1e-4 * rng.standard_normal((B, 350, 3))
 P = bench.MPC_DEFAULT; ell = 42
-ctrl = BatchedNonlinearDataDrivenMPC(n=6, m=3, p=3, u=u, y=y, L=35, Q=np.kron(np.eye(ell), np.diag(P["Q"])), R=np.kron(np.eye(ell), np.diag(P["R"])), S=np.diag(P["S"]), y_r=np.array(P["y_r"]), lamb_alpha=50.0, lamb_sigma=1e9, U=P["U"], Us=P["Us"], alpha_reg_type=0, lamb_alpha_s=1.0, lamb_sigma_s=1e7, solve_on_init=False)
+ctrl = BatchedNonlinearDataDrivenMPC(n=6, m=3, p=3, u=u, y=y, L=35, Q=np.kron(np.eye(ell), np.diag(P["Q"])), R=np.kron(np.eye(ell), np.diag(P["R"])), S=np.diag(P["S"]), y_r=np.array(P["y_r"]), lamb_alpha=50.0, lamb_sigma=1e9, U=P["U"], Us=P["Us"], alpha_reg_type=0, lamb_alpha_s=1.0, lamb_sigma_s=1e7, solve_on_init=False,
+                                     gram_cache=os.environ.get("GRAM_CACHE", "1") == "1")
 lib = _lib.load()
 clk = torch.zeros(48, dtype=torch.int64, device="cuda")
 ctrl.update_and_solve_data_driven_mpc(); torch.cuda.synchronize()
+# one closed-loop step: the timed solve sees a window that moved by one sample (Gram cache: rank-2 update path)
+ctrl.store_input_output_measurement(ctrl.get_optimal_control_input_at_step(0).clone(), ctrl.y[:, -1].clone() + 1e-3)
+torch.cuda.synchronize()
 lib.ddqc_ddmpc_debug_phase_buffer(clk.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); ctrl.update_and_solve_data_driven_mpc(); e1.record(); torch.cuda.synchronize()
