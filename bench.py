@@ -421,7 +421,7 @@ MPC_DEFAULT = dict(n=6, N=350, L=35, Q=[10.0, 10, 10], R=[10.0, 1, 1], S=[1000.0
                    init_hover_pos=[0.0, 0.0, 1.5], y_r=[1.0, 1.0, 2.5])  # fmt: skip
 
 
-def ddmpc_flops_per_solve(n=6, m=3, p=3, L=35, N=350, passes=1.0) -> float:
+def ddmpc_flops_per_solve(n=6, m=3, p=3, L=35, N=350, passes=1.0, gram_cached=False) -> float:
     """Algorithmic floating-point operations of one solve of the condensed algorithm (ddqc_ddmpc.cu,
     DESIGN.md section 4), counted from its loops with symmetric halves counted once:
     Gram first block column (dense) + diagonal recurrences; elimination of R1 on the augmented matrix;
@@ -437,6 +437,8 @@ def ddmpc_flops_per_solve(n=6, m=3, p=3, L=35, N=350, passes=1.0) -> float:
         return sum((rows - k) ** 2 for k in range(cols))
 
     gram = 2.0 * (nsig * ell) * (nsig + 1) * C + 4.0 * (nsig * ell + 1) ** 2 / 2
+    if gram_cached:  # rank-2 correction of the cached Gram matrix: two FMAs per entry of the symmetric half
+        gram = 4.0 * (nsig * ell + 1) ** 2 / 2
     phase_a = elim(n1 + n2 + n3 + na, n1)
     phase_b = elim(n2 + n3 + 1, n2 + n3) + 2.0 * (n2 + n3) ** 2
     phase_c = elim(n2 + n3 + na - 1, n2)
@@ -575,7 +577,7 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
     it_all = (it_raw & 0xFFFF).float()
     ipm_all = (it_raw >> 16).float()
     dist_end = torch.linalg.norm(env.base_pos - y_r, dim=1)
-    flops = ddmpc_flops_per_solve(passes=float(it_all.mean()))
+    flops = ddmpc_flops_per_solve(passes=float(it_all.mean()), gram_cached=ctrl.gram_cache_ptr is not None)
     fp64_peak = 37.1  # TFLOP/s: DMMA m8n8k4 / DFMA, measured on this pool's B200 by tools/ubench_fp64.cu
     return {
         "metric": "DD-MPC QP solves/s",
@@ -592,6 +594,8 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
         "config": "n=6, L=35, N=350, m=p=3 (693-variable QP, 331 equalities, 111 box rows), alpha_reg_type=0, "
         "data: PID-stabilised hover at [0,0,1.5] + uniform excitation, obs noise 1e-4, y_r=[1,1,2.5]",
         "dtype": "f64",
+        "gram_cache": "per-controller Gram matrix cached in HBM, rank-2 correction per one-sample window shift, regenerated every "
+        "128 updates (flops_per_solve counts the correction, not a regeneration)" if ctrl.gram_cache_ptr is not None else "off",
         "pivoting_passes_mean": float(it_all.mean()),
         "pivoting_passes_max": float(it_all.max()),
         "ipm_fallback_fraction": float((ipm_all > 0).float().mean()),

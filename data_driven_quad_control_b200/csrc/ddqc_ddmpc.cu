@@ -1147,6 +1147,34 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     DDQC_SUB(-1);
     double* sW = sM;
     double* sT = sM + nsig * N;  // first block column of G, (ell*nsig) x ldT
+    // Cached G (gmode != 0): the non-aug blocks of the cache - nga panel blocks, then ngs trailing blocks - stream
+    // from HBM through two shared-memory stages of gCH blocks each: warp w owns blocks w, w + 16, ... of every chunk
+    // and lane l the l-th 16-byte piece of a block, in the copy and in the arithmetic alike, so a thread only ever
+    // reads pieces it copied itself and the pipeline needs no barrier.  The cache is read once and written once per
+    // solve: evict-first in L2, so that it does not push the workspace slots, the spill area and the kernel's own
+    // instructions out of L2 (without the hints every later phase of the solve slows down by 5-10 %).
+    // What bounds this path is the HBM bandwidth of ONE SM (~25 GB/s: its outstanding-request budget over the DRAM
+    // latency), i.e. ~30 k cycles for the 300 KB of a cached G.  Measured and dropped: a bulk L2 prefetch of the next
+    // controller's cache a third of a solve ahead - the phases it overlaps (sweep, QP assembly, pivoting) lose more
+    // to the extra L2 traffic than the fetch gains (648 k against 670 k solves/s).
+    const int g_ntot = d.n1p + d.n2p + d.n3p + 16;
+    const int gr0 = d.nb1 + d.nb2 + d.nb3, gtb0 = d.nb2 + d.nb3;
+    const int nga = gr0 * d.nb1, ngs = tri(gtb0);
+    const int gCH = (((region_doubles(d) - 2 * g_ntot) / 128)) & ~(kWarps - 1);
+    const int g_nch = (nga + ngs + gCH - 1) / gCH;
+    const int g_off = (lane >> 2) * 8 + (lane & 3) * 2;  // this lane's double2 inside an 8x8 block
+    uint64_t pol_stream;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    auto gram_fetch = [&](int c) {
+      const int c0 = c * gCH, c1 = c0 + gCH < nga + ngs ? c0 + gCH : nga + ngs;
+      const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(sM + 2 * g_ntot + (c & 1) * gCH * 64);
+      const double* cG = gc + kCacheHdr;
+      for (int bi = c0 + warp; bi < c1; bi += kWarps) {
+        const size_t base = (bi < nga ? (size_t)bi * 64 : (size_t)d.ga + (size_t)(bi - nga) * 64) + g_off;
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(st_s + 8u * (uint32_t)((bi - c0) * 64 + g_off)), "l"(cG + base), "l"(pol_stream) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     if (gmode == 0) {
       for (int e = tid; e < N * m; e += kThreads) sW[(e % m) * N + e / m] = ub[e];
       for (int e = tid; e < N * p; e += kThreads) sW[(m + e % p) * N + e / p] = yb[e];
@@ -1156,6 +1184,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       const int ntot = d.n1p + d.n2p + d.n3p + 16;
       double* s_a = sM;
       double* s_b = sM + ntot;
+      gram_fetch(0);  // the first chunk of the cached G is on its way while a and b are built
       for (int e = tid; e < 2 * ntot; e += kThreads) sM[e] = 0.0;
       __syncthreads();
       if (gmode == 1) {
@@ -1182,51 +1211,48 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     __syncthreads();
     DDQC_SUB(0);
     if (gmode != 0) {
-      // cached G (+ rank-2 correction) -> workspace slot and back to the cache: one warp per 8x8 block, one double2 per
-      // lane; the aug block rows are regenerated below
-      const int ntot = d.n1p + d.n2p + d.n3p + 16;
+      // cached G (+ rank-2 correction) -> workspace slot and back to the cache; the aug block rows are regenerated below
       const double* s_a = sM;
-      const double* s_b = sM + ntot;
+      const double* s_b = sM + g_ntot;
       double* cG = gc + kCacheHdr;
-      const int r0 = d.nb1 + d.nb2 + d.nb3, tb0 = d.nb2 + d.nb3;
-      const int nga = r0 * d.nb1, ngs = tri(tb0);
-      const int gq = lane >> 2, c2 = (lane & 3) * 2, cl = c2 ^ ((gq & 2) << 1), off = gq * 8 + c2;
-      // The cached blocks come from HBM: staged through shared memory in chunks with every 16-byte piece of a chunk
-      // in flight at once (a load-use loop pays one DRAM round trip per block: 38 x 1.7 k cycles).  Each thread
-      // consumes exactly the pieces it copied (chunk sizes are multiples of the warp count), so no barrier is needed.
-      // The cache is streamed (read once, written once per solve): evict-first in L2, so that it does not push the
-      // workspace slots, the spill area and the kernel's own instructions out of L2 (measured: without the hints
-      // every later phase of the solve slows down by 5-10 %).
-      uint64_t pol_stream;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-      double* stage = sM + 2 * ntot;
-      const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
-      const int CH = ((region_doubles(d) - 2 * ntot) / 64) & ~(kWarps - 1);
-      for (int c0 = 0; c0 < nga + ngs; c0 += CH) {
-        const int c1 = c0 + CH < nga + ngs ? c0 + CH : nga + ngs;
-        for (int bi = c0 + warp; bi < c1; bi += kWarps) {
-          const size_t base = (bi < nga ? (size_t)bi * 64 : (size_t)d.ga + (size_t)(bi - nga) * 64) + off;
-          asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(stage_s + 8u * (uint32_t)((bi - c0) * 64 + off)), "l"(cG + base), "l"(pol_stream) : "memory");
+      const int gq = lane >> 2, cl = ((lane & 3) * 2) ^ ((gq & 2) << 1);
+      // block walk of this warp (bi = warp, warp + 16, ...): panel blocks by (row, col), trailing blocks by (I, J)
+      int bi = warp, row = warp / d.nb1, col = warp % d.nb1, I = 0, J = 0;
+      bool in_gs = false;
+      for (int c = 0; c < g_nch; ++c) {
+        if (c + 1 < g_nch) {
+          gram_fetch(c + 1);
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        for (int bi = c0 + warp; bi < c1; bi += kWarps) {
+        const int c0 = c * gCH, c1 = c0 + gCH < nga + ngs ? c0 + gCH : nga + ngs;
+        const double* stage = sM + 2 * g_ntot + (c & 1) * gCH * 64;
+        for (; bi < c1; bi += kWarps) {
           int hi, lo;
           size_t base;
           if (bi < nga) {
-            hi = (bi / d.nb1) * 8 + gq;
-            lo = (bi % d.nb1) * 8 + cl;
-            base = (size_t)bi * 64 + off;
+            hi = row * 8 + gq;
+            lo = col * 8 + cl;
+            base = (size_t)bi * 64 + g_off;
+            col += kWarps;
+            while (col >= d.nb1) { col -= d.nb1; ++row; }
           } else {
             const int bb = bi - nga;
-            int I = (int)((sqrtf(8.0f * bb + 1.0f) - 1.0f) * 0.5f);
-            while (tri(I + 1) <= bb) ++I;
-            while (tri(I) > bb) --I;
+            if (!in_gs) {
+              in_gs = true;
+              I = (int)((sqrtf(8.0f * bb + 1.0f) - 1.0f) * 0.5f);
+              while (tri(I + 1) <= bb) ++I;
+              while (tri(I) > bb) --I;
+              J = bb - tri(I);
+            }
             hi = d.n1p + I * 8 + gq;
-            lo = d.n1p + (bb - tri(I)) * 8 + cl;
-            base = (size_t)d.ga + (size_t)bb * 64 + off;
+            lo = d.n1p + J * 8 + cl;
+            base = (size_t)d.ga + (size_t)bb * 64 + g_off;
+            J += kWarps;
+            while (J > I) { J -= I + 1; ++I; }
           }
-          double2 v = *reinterpret_cast<const double2*>(stage + (bi - c0) * 64 + off);
+          double2 v = *reinterpret_cast<const double2*>(stage + (bi - c0) * 64 + g_off);
           if (gmode == 1) {
             const double ah = s_a[hi], bh = s_b[hi];
             const double2 al = *reinterpret_cast<const double2*>(s_a + lo), bl = *reinterpret_cast<const double2*>(s_b + lo);
