@@ -1115,6 +1115,17 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       t_prev = t_now;                                                                      \
     }                                                                                      \
   } while (0)
+  // Gram-cache geometry (see the cached path below): panel blocks nga, non-aug trailing blocks ngs, two shared-memory
+  // stages of gCH blocks behind the panel, the correction vectors a, b at the tail of the matrix region
+  const int g_ntot = d.n1p + d.n2p + d.n3p + 16;
+  const int gr0 = d.nb1 + d.nb2 + d.nb3, gtb0 = d.nb2 + d.nb3;
+  const int nga = gr0 * d.nb1, ngs = tri(gtb0);
+  const int g_cap = region_doubles(d) - 2 * g_ntot - d.ga;
+  const int gCH = g_cap > 0 ? ((g_cap / 128) & ~(kWarps - 1)) : 0;
+  const int g_nch = gCH > 0 ? (ngs + gCH - 1) / gCH : 0;
+  const int g_off = g * 8 + ((2 * t) ^ ((g & 2) << 1));  // this lane's double2 of an 8x8 block = its DMMA accumulator fragment
+  double* s_a = sM + region_doubles(d) - 2 * g_ntot;
+  double* s_b = s_a + g_ntot;
   for (;;) {
     __syncthreads();
     if (tid == 0) {
@@ -1122,7 +1133,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       s_next = nb;
       s_flag = 0;
       int gm = 0;
-      if (gram_cache && nb < batch) {
+      if (gram_cache && gCH >= kWarps && nb < batch) {
         const long long* h = reinterpret_cast<const long long*>(gram_cache + (size_t)nb * cache_stride(d));
         const int refresh = cfg.gram_refresh > 0 ? cfg.gram_refresh : kGramRefreshDefault;
         if (h[0] == 1) gm = 2;
@@ -1147,32 +1158,33 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     DDQC_SUB(-1);
     double* sW = sM;
     double* sT = sM + nsig * N;  // first block column of G, (ell*nsig) x ldT
-    // Cached G (gmode != 0): the non-aug blocks of the cache - nga panel blocks, then ngs trailing blocks - stream
-    // from HBM through two shared-memory stages of gCH blocks each: warp w owns blocks w, w + 16, ... of every chunk
-    // and lane l the l-th 16-byte piece of a block, in the copy and in the arithmetic alike, so a thread only ever
-    // reads pieces it copied itself and the pipeline needs no barrier.  The cache is read once and written once per
-    // solve: evict-first in L2, so that it does not push the workspace slots, the spill area and the kernel's own
-    // instructions out of L2 (without the hints every later phase of the solve slows down by 5-10 %).
-    // What bounds this path is the HBM bandwidth of ONE SM (~25 GB/s: its outstanding-request budget over the DRAM
-    // latency), i.e. ~30 k cycles for the 300 KB of a cached G.  Measured and dropped: a bulk L2 prefetch of the next
-    // controller's cache a third of a solve ahead - the phases it overlaps (sweep, QP assembly, pivoting) lose more
-    // to the extra L2 traffic than the fetch gains (648 k against 670 k solves/s).
-    const int g_ntot = d.n1p + d.n2p + d.n3p + 16;
-    const int gr0 = d.nb1 + d.nb2 + d.nb3, gtb0 = d.nb2 + d.nb3;
-    const int nga = gr0 * d.nb1, ngs = tri(gtb0);
-    const int gCH = (((region_doubles(d) - 2 * g_ntot) / 128)) & ~(kWarps - 1);
-    const int g_nch = (nga + ngs + gCH - 1) / gCH;
-    const int g_off = (lane >> 2) * 8 + (lane & 3) * 2;  // this lane's double2 inside an 8x8 block
+    // Cached G (gmode != 0).  The panel blocks of the cache are copied straight to where phase A factors the panel and
+    // corrected in place; the trailing blocks stream through two stages behind the panel INSIDE phase A's trailing
+    // update, which consumes them as DMMA accumulator fragments: cache -> (rank-2 correction -> cache) -> S1 -> slot,
+    // so G itself never travels through the workspace slot.  Warp w owns blocks w, w + 16, ... and lane l the l-th
+    // 16-byte piece of a block, in the copies and in the arithmetic alike: a thread only ever reads pieces it copied
+    // itself and the pipeline needs no barrier.  The cache is read once and written once per solve: evict-first in
+    // L2, so that it does not push the workspace slots, the spill area and the kernel's own instructions out of L2
+    // (without the hints every later phase of the solve slows down by 5-10 %).  One SM pulls only ~25 GB/s from HBM
+    // (its outstanding-request budget over the DRAM latency), ~30 k cycles for a cached G: the first two chunks are
+    // requested before the correction vectors are built and arrive under the panel factorisation.  Measured and
+    // dropped: a bulk L2 prefetch of the next controller's cache a third of a solve ahead - the phases it overlaps
+    // (sweep, QP assembly, pivoting) lose more to the extra L2 traffic than the fetch gains.
     uint64_t pol_stream;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-    auto gram_fetch = [&](int c) {
-      const int c0 = c * gCH, c1 = c0 + gCH < nga + ngs ? c0 + gCH : nga + ngs;
-      const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(sM + 2 * g_ntot + (c & 1) * gCH * 64);
+    auto gram_fetch_panel = [&]() {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sM);
       const double* cG = gc + kCacheHdr;
-      for (int bi = c0 + warp; bi < c1; bi += kWarps) {
-        const size_t base = (bi < nga ? (size_t)bi * 64 : (size_t)d.ga + (size_t)(bi - nga) * 64) + g_off;
-        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(st_s + 8u * (uint32_t)((bi - c0) * 64 + g_off)), "l"(cG + base), "l"(pol_stream) : "memory");
-      }
+      for (int bi = warp; bi < nga; bi += kWarps)
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + 8u * (uint32_t)(bi * 64 + g_off)), "l"(cG + (size_t)bi * 64 + g_off), "l"(pol_stream) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto gram_fetch = [&](int c) {  // trailing chunk c -> stage c & 1 (an empty group when c is past the end)
+      const int c0 = c * gCH, c1 = c0 + gCH < ngs ? c0 + gCH : ngs;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sM + d.ga + (c & 1) * gCH * 64);
+      const double* cG = gc + kCacheHdr + d.ga;
+      for (int bb = c0 + warp; bb < c1; bb += kWarps)
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + 8u * (uint32_t)((bb - c0) * 64 + g_off)), "l"(cG + (size_t)bb * 64 + g_off), "l"(pol_stream) : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if (gmode == 0) {
@@ -1181,11 +1193,10 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     } else {
       // a (old first Hankel column) and b (new last column) by position in the elimination order; pad and aug
       // positions stay 0, the ones row has a = b = 1 (its entries move by b_P - a_P)
-      const int ntot = d.n1p + d.n2p + d.n3p + 16;
-      double* s_a = sM;
-      double* s_b = sM + ntot;
-      gram_fetch(0);  // the first chunk of the cached G is on its way while a and b are built
-      for (int e = tid; e < 2 * ntot; e += kThreads) sM[e] = 0.0;
+      gram_fetch_panel();
+      gram_fetch(0);
+      gram_fetch(1);
+      for (int e = tid; e < 2 * g_ntot; e += kThreads) s_a[e] = 0.0;
       __syncthreads();
       if (gmode == 1) {
         for (int e = tid; e < nsig * ell; e += kThreads) {
@@ -1201,7 +1212,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     // aug block rows and pad rows: explicit zeros first
     {
       const int r0 = d.nb1 + d.nb2 + d.nb3;  // first aug block row (all-rows numbering)
-      double2* za = reinterpret_cast<double2*>(GA + (size_t)r0 * d.nb1 * 64);
+      double2* za = reinterpret_cast<double2*>((gmode ? sM : GA) + (size_t)r0 * d.nb1 * 64);
       for (int e = tid; e < 2 * d.nb1 * 32; e += kThreads) za[e] = make_double2(0.0, 0.0);
       const int tb = d.nb2 + d.nb3;
       double2* zs = reinterpret_cast<double2*>(GS + (size_t)tri(tb) * 64);
@@ -1211,56 +1222,23 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     __syncthreads();
     DDQC_SUB(0);
     if (gmode != 0) {
-      // cached G (+ rank-2 correction) -> workspace slot and back to the cache; the aug block rows are regenerated below
-      const double* s_a = sM;
-      const double* s_b = sM + g_ntot;
-      double* cG = gc + kCacheHdr;
-      const int gq = lane >> 2, cl = ((lane & 3) * 2) ^ ((gq & 2) << 1);
-      // block walk of this warp (bi = warp, warp + 16, ...): panel blocks by (row, col), trailing blocks by (I, J)
-      int bi = warp, row = warp / d.nb1, col = warp % d.nb1, I = 0, J = 0;
-      bool in_gs = false;
-      for (int c = 0; c < g_nch; ++c) {
-        if (c + 1 < g_nch) {
-          gram_fetch(c + 1);
-          asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        const int c0 = c * gCH, c1 = c0 + gCH < nga + ngs ? c0 + gCH : nga + ngs;
-        const double* stage = sM + 2 * g_ntot + (c & 1) * gCH * 64;
-        for (; bi < c1; bi += kWarps) {
-          int hi, lo;
-          size_t base;
-          if (bi < nga) {
-            hi = row * 8 + gq;
-            lo = col * 8 + cl;
-            base = (size_t)bi * 64 + g_off;
-            col += kWarps;
-            while (col >= d.nb1) { col -= d.nb1; ++row; }
-          } else {
-            const int bb = bi - nga;
-            if (!in_gs) {
-              in_gs = true;
-              I = (int)((sqrtf(8.0f * bb + 1.0f) - 1.0f) * 0.5f);
-              while (tri(I + 1) <= bb) ++I;
-              while (tri(I) > bb) --I;
-              J = bb - tri(I);
-            }
-            hi = d.n1p + I * 8 + gq;
-            lo = d.n1p + J * 8 + cl;
-            base = (size_t)d.ga + (size_t)bb * 64 + g_off;
-            J += kWarps;
-            while (J > I) { J -= I + 1; ++I; }
-          }
-          double2 v = *reinterpret_cast<const double2*>(stage + (bi - c0) * 64 + g_off);
-          if (gmode == 1) {
-            const double ah = s_a[hi], bh = s_b[hi];
-            const double2 al = *reinterpret_cast<const double2*>(s_a + lo), bl = *reinterpret_cast<const double2*>(s_b + lo);
-            v.x = fma(bh, bl.x, fma(-ah, al.x, v.x));
-            v.y = fma(bh, bl.y, fma(-ah, al.y, v.y));
-            asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(cG + base), "d"(v.x), "d"(v.y), "l"(pol_stream) : "memory");
-          }
-          *reinterpret_cast<double2*>(slot + base) = v;
+      // panel blocks of the cached G: rank-2 correction in place (shared memory) and back to the cache
+      asm volatile("cp.async.wait_group 2;" ::: "memory");
+      if (gmode == 1) {
+        double* cG = gc + kCacheHdr;
+        int row = warp / d.nb1, col = warp % d.nb1;
+        for (int bi = warp; bi < nga; bi += kWarps) {
+          const int hi = row * 8 + g, lo = col * 8 + 2 * t;
+          double2* pv = reinterpret_cast<double2*>(sM + (size_t)bi * 64 + g_off);
+          double2 v = *pv;
+          const double ah = s_a[hi], bh = s_b[hi];
+          const double2 al = *reinterpret_cast<const double2*>(s_a + lo), bl = *reinterpret_cast<const double2*>(s_b + lo);
+          v.x = fma(bh, bl.x, fma(-ah, al.x, v.x));
+          v.y = fma(bh, bl.y, fma(-ah, al.y, v.y));
+          asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(cG + (size_t)bi * 64 + g_off), "d"(v.x), "d"(v.y), "l"(pol_stream) : "memory");
+          *pv = v;
+          col += kWarps;
+          while (col >= d.nb1) { col -= d.nb1; ++row; }
         }
       }
     } else {
@@ -1326,6 +1304,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     }
     {
       const int Pone = n * m;
+      double* GA = gmode ? sM : slot;  // cached path: the panel already lives in shared memory
       // aug rows.  group 0 (block row tb): A_u (m: ones on ALL input rows of a component), A_y (p), e_one, tau;
       //            group 1 (block row tb + 1): T_u (m: ones on the terminal input rows), T_y (p: free + terminal outputs)
       const int Pa0 = d.n1p + d.n2p + d.n3p, Pa1 = Pa0 + 8;
@@ -1365,13 +1344,54 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     DDQC_PHASE(0);
 
     // ---- A. eliminate R1: panel in shared memory, S1 = trailing - L L^T through global ------------
-    copy_slot_to_smem(sM, GA, d.ga / 2);
+    if (gmode == 0) copy_slot_to_smem(sM, GA, d.ga / 2);
     __syncthreads();
     factor_columns<true>(sM, d.nb1, d.nbA, d.nb1, &s_flag);
     DDQC_PHASE(1);
+    if (gmode != 0) {
+      // cached path: trailing blocks cache -> stage -> (correction -> cache) -> S1 = G - L L' -> slot
+      double* cG = gc + kCacheHdr + d.ga;
+      int bb = warp, I = 0, J = 0;
+      {
+        I = (int)((sqrtf(8.0f * bb + 1.0f) - 1.0f) * 0.5f);
+        while (tri(I + 1) <= bb) ++I;
+        while (tri(I) > bb) --I;
+        J = bb - tri(I);
+      }
+      for (int c = 0; c < g_nch; ++c) {
+        if (c + 1 < g_nch) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const int c0 = c * gCH, c1 = c0 + gCH < ngs ? c0 + gCH : ngs;
+        const double* stage = sM + d.ga + (c & 1) * gCH * 64;
+        for (; bb < c1; bb += kWarps) {
+          double2 v = *reinterpret_cast<const double2*>(stage + (bb - c0) * 64 + g_off);
+          if (gmode == 1) {
+            const int hi = d.n1p + I * 8 + g, lo = d.n1p + J * 8 + 2 * t;
+            const double ah = s_a[hi], bh = s_b[hi];
+            const double2 al = *reinterpret_cast<const double2*>(s_a + lo), bl = *reinterpret_cast<const double2*>(s_b + lo);
+            v.x = fma(bh, bl.x, fma(-ah, al.x, v.x));
+            v.y = fma(bh, bl.y, fma(-ah, al.y, v.y));
+            asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(cG + (size_t)bb * 64 + g_off), "d"(v.x), "d"(v.y), "l"(pol_stream) : "memory");
+          }
+          const double* pi = sM + (size_t)(d.nb1 + I) * d.nb1 * 64;
+          const double* pj = sM + (size_t)(d.nb1 + J) * d.nb1 * 64;
+          double2 a0 = {0.0, 0.0}, a1 = {0.0, 0.0};
+          for (int Jc = 0; Jc < d.nb1; ++Jc) {
+            dmma(a0, ld_ab(pi + Jc * 64, g, t, 0), ld_ab(pj + Jc * 64, g, t, 0));
+            dmma(a1, ld_ab(pi + Jc * 64, g, t, 1), ld_ab(pj + Jc * 64, g, t, 1));
+          }
+          v.x -= a0.x + a1.x;
+          v.y -= a0.y + a1.y;
+          *reinterpret_cast<double2*>(GS + (size_t)bb * 64 + g_off) = v;
+          J += kWarps;
+          while (J > I) { J -= I + 1; ++I; }
+        }
+        gram_fetch(c + 2);  // into the stage just consumed
+      }
+    }
     {
       const int nblk = tri(d.nbt + 1);
-      for (int bb = warp; bb < nblk; bb += 2 * kWarps) {
+      for (int bb = (gmode ? ngs : 0) + warp; bb < nblk; bb += 2 * kWarps) {
         const int b2 = bb + kWarps;
         const bool two = b2 < nblk;
         int i0 = (int)((sqrtf(8.0f * bb + 1.0f) - 1.0f) * 0.5f);

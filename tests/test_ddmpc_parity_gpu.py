@@ -250,7 +250,7 @@ def test_full_batch_4096_default_size(build_lib):
         np.testing.assert_allclose(uo[b], orc.optimal_u, rtol=0, atol=TOL)
 
 
-@pytest.mark.parametrize("shape", ["small", "default"])
+@pytest.mark.parametrize("shape", ["small", "default", "L30"])
 def test_gram_cache_follows_the_window_like_a_regeneration(build_lib, shape):
     """The per-controller Gram cache (rank-2 correction per one-sample shift) against the regeneration of G from the
     window in a closed loop: same optimal inputs to 1e-6 (the two differ by rounding of order ulp(G_ij) only), through
@@ -267,6 +267,8 @@ def test_gram_cache_follows_the_window_like_a_regeneration(build_lib, shape):
     else:
         g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ddmpc_default.npz"))
         prm, B = mo.default_params(), 5
+        if shape == "L30":  # second shape bucket of the reference's grid (dd_mpc_grid_search_params.yaml:93-100)
+            prm.L = 30
         rng = np.random.default_rng(2)
         u = np.repeat(g["u"][None], B, 0) + 1e-3 * rng.standard_normal((B,) + g["u"].shape)
         y = np.repeat(g["y"][None], B, 0) + 1e-4 * rng.standard_normal((B,) + g["y"].shape)
@@ -310,3 +312,5 @@ def test_gram_cache_follows_the_window_like_a_regeneration(build_lib, shape):
     a.invalidate_gram_cache()
     solve_both()
     print(f"gram cache vs regeneration ({shape}): max |du| = {worst:.3e}")
+    if shape != "small":  # (small shapes have no room for the stages: the kernel regenerates G and the runs are identical)
+        assert worst > 0.0, "the cached path was not exercised"
