@@ -341,10 +341,12 @@ def run_b200(args) -> dict:
         torch.cuda.empty_cache()
         leg = run_ddmpc_leg(dev, args.ddmpc_batch, args.ddmpc_steps)
         # controllers are sharded by index like the envs: aggregate solves/s is the sum over ranks
-        v = torch.tensor([leg["value"], leg["closed_loop_solves_per_s"]], device=dev, dtype=torch.float64)
+        v = torch.tensor([leg["value"], leg["closed_loop_solves_per_s"], leg["e2e"]["value"], leg["cold_start"]["value"]],
+                         device=dev, dtype=torch.float64)  # fmt: skip
         if world > 1:
             dist.all_reduce(v)
         leg["value"], leg["closed_loop_solves_per_s"] = float(v[0]), float(v[1])
+        leg["e2e"]["value"], leg["cold_start"]["value"] = float(v[2]), float(v[3])
         leg["n_gpus"] = world
         line["ddmpc"] = leg
         line["gpu_launches"] += leg["gpu_launches"]
