@@ -314,3 +314,30 @@ def test_gram_cache_follows_the_window_like_a_regeneration(build_lib, shape):
     print(f"gram cache vs regeneration ({shape}): max |du| = {worst:.3e}")
     if shape != "small":  # (small shapes have no room for the stages: the kernel regenerates G and the runs are identical)
         assert worst > 0.0, "the cached path was not exercised"
+
+
+@pytest.mark.parametrize("n,L", [(4, 30), (4, 35), (6, 30)])
+def test_reference_grid_shapes_match_oracle(build_lib, n, L):
+    """The other three QP shapes of the reference's parameter grid (configs/data_driven_mpc/dd_mpc_grid_search_params.yaml:
+    93-100: n in {4, 6}, L in {30, 35}; N = 350) on the PID-stabilised drone data, three closed-loop steps (the second and
+    third on the Gram-cache path) against the literal-QP oracle."""
+    import os
+
+    import ddmpc_oracle as mo
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ddmpc_default.npz"))
+    prm = mo.default_params()
+    prm.n, prm.L = n, L
+    u, y, y_r = g["u"], g["y"], g["y_r"]
+    gpu = _batched(prm, u[None], y[None], y_r[None], solve_on_init=False)
+    orc = mo.NonlinearDDMPCOracle(**mo.ctor_kwargs(prm, u, y, y_r), solve_on_init=False)
+    rng = np.random.default_rng(4)
+    for t in range(3):
+        gpu.update_and_solve_data_driven_mpc()
+        orc.update_and_solve_data_driven_mpc()
+        assert int(gpu.status[0]) == 0
+        np.testing.assert_allclose(gpu.optimal_u[0].cpu().numpy(), orc.optimal_u, rtol=0, atol=TOL)
+        y_new = orc.y[-1] + 1e-3 * rng.standard_normal(3)
+        u0 = orc.optimal_u[0].copy()
+        orc.store_input_output_measurement(u0, y_new)
+        gpu.store_input_output_measurement(u0[None], y_new[None])
