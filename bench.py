@@ -113,6 +113,28 @@ def make_env(num_envs: int, device, seed: int, materialize=False):
     )  # fmt: skip
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> str:
+    """One process per GPU: run the rank (and first-touch its pinned host buffers) on the CPUs next to its GPU, so that
+    the e2e leg's host<->device copies do not cross the socket interconnect.  Best effort; reports what it did."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+        handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "not bound (empty intersection with the allowed CPUs)"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to {len(cpus)} CPUs next to GPU {idx}"
+    except Exception as exc:  # noqa: BLE001 - affinity is an optimisation, never a failure
+        return f"not bound ({type(exc).__name__})"
+
+
 def load_peaks() -> tuple[float, str]:
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -132,6 +154,7 @@ def run_b200(args) -> dict:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else "not bound (single rank)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -304,6 +327,7 @@ def run_b200(args) -> dict:
             "l2_policy": "working set 374 MB per step > 126 MB L2 (no flush needed)",
             "launch": "CUDA graph of 16 HoverEnv.step calls replayed" if G else "eager, one launch per step",
             "parallelism": f"envs sharded by index over {world} rank(s); one all-reduce of rollout statistics at the end",
+            "cpu_affinity": affinity,
         },
         "clocks": clocks,
         "e2e": e2e,

@@ -69,6 +69,9 @@ def make_env_factory(device):
 def run_grid_search(config: str = DEFAULT_CONFIG, seed: int = 0, device="cuda", output_dir: str | None = None) -> dict:
     init, fixed, evalp, grid = load_dd_mpc_grid_search_params(config)
     make_env = make_env_factory(device)
+    # the measurement noise of `HoverEnv.get_pos(add_noise=True)` comes from torch's global generator (as in the reference):
+    # seeded here, two runs with the same seed evaluate the same noise realisation and write the same report
+    torch.manual_seed(seed)
     t0 = time.perf_counter()
     env = make_env(evalp.num_collections_per_N)
     env.reset()

@@ -20,6 +20,8 @@ else raises NotImplementedError / ValueError instead of silently solving a diffe
 
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from enum import Enum
 
@@ -149,7 +151,7 @@ class BatchedNonlinearDataDrivenMPC:
         # by a rank-2 correction.  `gram_cache=None` enables it when it fits in a quarter of the free device memory.
         gc_bytes = self._lib.ddqc_ddmpc_gram_cache_bytes(C.byref(cfg), self.B)
         if gram_cache is None:
-            gram_cache = gc_bytes <= torch.cuda.mem_get_info(dev)[0] // 4
+            gram_cache = gc_bytes <= torch.cuda.mem_get_info(dev)[0] // 4 and os.environ.get("DDQC_GRAM_CACHE", "1") != "0"
         self._gram_cache = torch.zeros((gc_bytes,), dtype=torch.uint8, device=dev) if gram_cache else None
 
         self.y_r = torch.zeros((self.B, p), **f64)
