@@ -761,6 +761,8 @@ def run_reference(args) -> dict:
         "config": {"workload": "HoverEnv.step random-action rollout, CTBR_FIXED_YAW (bounded CPU sample)", "sample": best["sample"]},
         "cpu_baseline": best,
         "e2e": {"value": best["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        # second half of BASELINE's metric on the same arm: the literal-QP oracle, one controller per process
+        "ddmpc": {"metric": "DD-MPC QP solves/s", **cpu_ddmpc_baseline(3)},
         "wall_s": time.perf_counter() - t_all,
     }
 
