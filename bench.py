@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--no-ddmpc", action="store_true", help="skip the DD-MPC leg")
     ap.add_argument("--no-policy", action="store_true", help="skip the policy-rollout leg (BASELINE configs[2])")
     ap.add_argument("--ddmpc-batch", type=int, default=4096)
-    ap.add_argument("--ddmpc-steps", type=int, default=20)
+    ap.add_argument("--ddmpc-steps", type=int, default=50, help="closed-loop solves timed (SURVEY 8d configs[3]: T = 50)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every timed env step eagerly instead of replaying a CUDA graph")
@@ -624,6 +624,7 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
         "128 updates (flops_per_solve counts the correction, not a regeneration)" if ctrl.gram_cache_ptr is not None else "off",
         "pivoting_passes_mean": float(it_all.mean()),
         "pivoting_passes_max": float(it_all.max()),
+        "pivoting_passes_hist": torch.bincount(it_all.flatten().long().cpu(), minlength=4).tolist(),
         "ipm_fallback_fraction": float((ipm_all > 0).float().mean()),
         "ipm_iterations_mean_when_used": float(ipm_all[ipm_all > 0].mean()) if bool((ipm_all > 0).any()) else 0.0,
         "failed_controllers": int((status != 0).sum()),
