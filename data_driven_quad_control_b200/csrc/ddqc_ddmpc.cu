@@ -18,6 +18,10 @@
 //        R2 = output rows (soft: diagonal regularisation D differs between the two systems)
 //        R3 = predicted-input rows (the box-constrained decision variables y_B)
 //        aug = right-hand sides carried as extra rows: A_u (m), A_y (p), e_one, tau | T_u (m), T_y (p)
+//      Closed loop (optional per-controller Gram cache in HBM): when the window moved by one sample since the cached
+//      G, step 0 is the rank-2 correction G' = G - a a' + b b' (a = old first, b = new last Hankel column) instead,
+//      fused with step A: cached panel blocks are corrected where the panel is factored, trailing blocks stream
+//      through two shared-memory stages straight into the S1 update (see "Gram cache" below).
 //   A. Eliminate R1 (left-looking blocked Cholesky of the panel in shared memory), then
 //      S1 = trailing - L L^T streamed through global memory once.  S1 is used twice:
 //   B. alpha_sr system (alpha of the optimal reachable equilibrium for y_r): S1 + D_s with the aug rows
@@ -25,7 +29,8 @@
 //      (u_sr, y_sr); rho = A_u u_sr + A_y y_sr + e_one is forward-substituted for free (same combination
 //      of the aug rows), a blocked back-substitution gives e = D_s (G + D_s)^-1 rho on R2 (v_sr = rho - e).
 //   C. main system: S1 + D_0, aug rows T_u, T_y and c = tau - rho + e, eliminate R2 only; the Schur
-//      complement on [R3 | aug] is swept on R3 (Gauss-Jordan) which yields the box-QP Hessian and gradient.
+//      complement on [R3 | aug] is eliminated once more with an identity block appended (tensor cores), which yields
+//      Z = K'(G + D_0)^-1 K, i.e. the box-QP Hessian and gradient.
 //   D. box QP: block principal pivoting in the space of the FREE variables, warm-started from
 //      the previous solve's active set (shifted one step); primal-dual interior point fallback
 //      followed by a pivoting polish when pivoting does not settle.
