@@ -341,3 +341,35 @@ def test_reference_grid_shapes_match_oracle(build_lib, n, L):
         u0 = orc.optimal_u[0].copy()
         orc.store_input_output_measurement(u0, y_new)
         gpu.store_input_output_measurement(u0[None], y_new[None])
+
+
+def test_gram_cache_drift_over_a_refresh_period(build_lib):
+    """140 consecutive one-sample shifts with the default refresh period (128 rank-2 corrections between
+    regenerations): the optimal inputs of the cached path stay within 1e-6 of the regenerating path at every step,
+    i.e. the rounding of the corrections does not accumulate into the solution."""
+    import os
+
+    import ddmpc_oracle as mo
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ddmpc_default.npz"))
+    prm, B = mo.default_params(), 4
+    rng = np.random.default_rng(12)
+    u = np.repeat(g["u"][None], B, 0) + 1e-3 * rng.standard_normal((B,) + g["u"].shape)
+    y = np.repeat(g["y"][None], B, 0) + 1e-4 * rng.standard_normal((B,) + g["y"].shape)
+    y_r = np.tile(g["y_r"][None], (B, 1))
+    a = _batched(prm, u, y, y_r, solve_on_init=False, gram_cache=True)
+    b = _batched(prm, u, y, y_r, solve_on_init=False, gram_cache=False)
+    worst = []
+    for t in range(140):
+        a.update_and_solve_data_driven_mpc()
+        b.update_and_solve_data_driven_mpc()
+        worst.append(float((a.optimal_u - b.optimal_u).abs().max()))
+        # a smooth excursion of the outputs and the applied optimal input: the window keeps changing
+        u0 = b.get_optimal_control_input_at_step(0).clone()
+        yk = b.y[:, -1] + torch.from_numpy(2e-3 * np.sin(0.1 * t) + 1e-4 * rng.standard_normal((B, 3))).cuda()
+        for c in (a, b):
+            c.store_input_output_measurement(u0, yk)
+    assert int((a.status != 0).sum()) == 0 and int((b.status != 0).sum()) == 0
+    print(f"gram cache drift: max |du| first 10 steps {max(worst[:10]):.2e}, steps 118-127 {max(worst[118:128]):.2e}, "
+          f"after the regeneration {max(worst[129:]):.2e}")
+    assert max(worst) <= 1e-6
