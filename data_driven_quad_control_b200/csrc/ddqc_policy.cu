@@ -18,7 +18,8 @@
 //      (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM) and commits to an mbarrier;
 //   3. every thread reads its TMEM lane (tcgen05.ld 32x32b.x32), adds the bias, applies tanh, splits
 //      to bf16 hi/lo and writes the layer-2 operand tile;
-//   4. D2 = A2 W2^T (8 K-steps x 3 products), same commit / wait;
+//   4. D2 = A2 W2^T (8 K-steps x 3 products) issued in two K halves - the first as soon as both thread halves
+//      have written their first 32 columns, so it runs under the rest of step 3 - one commit / wait;
 //   5. bias + tanh, then the A-wide output layer (A <= 4, 384 FMAs per env) on the CUDA cores
 //      straight from the registers; 12-byte action rows are stored coalesced.
 // The hi/lo split (two bf16 = 16 mantissa bits per operand, cross term lo*lo dropped, ~1e-5 relative
@@ -146,6 +147,9 @@ constexpr float kTanhScale = 2.885390081777927f;
 // output-layer accumulation.
 #ifndef DDQC_POLICY_F32X2
 #define DDQC_POLICY_F32X2 1
+#endif
+#ifndef DDQC_POLICY_KSPLIT
+#define DDQC_POLICY_KSPLIT 1  // layer-2 MMAs issued in two K halves, the first under the layer-1 epilogue (0.2002 vs 0.2035 ms)
 #endif
 typedef unsigned long long f2_t;
 __device__ __forceinline__ f2_t pk2(float a, float b) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
@@ -305,25 +309,30 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
         store_chunk(wgs, kA2Hi + off, kA2Lo + off, y);
 #endif
       }
-    }
-    fence_async_smem();
-    tc_fence_before();
-    wg_sync(wg);
-    // ---- 4. D2 = A2 W2^T ----
-    if (wtid == 0) {
-      tc_fence_after();
+      // ---- 4. D2 = A2 W2^T, K split in two: the 64 columns both thread halves have just written (cb*32 .. +32 and
+      // 64 + cb*32 .. +32) are contracted while the warpgroup computes its other 64 columns, so half of the layer-2
+      // tensor work is hidden under the layer-1 epilogue instead of being waited for
+      if (DDQC_POLICY_KSPLIT || cb == 1) {
+        fence_async_smem();
+        tc_fence_before();
+        wg_sync(wg);
+        if (wtid == 0) {
+          tc_fence_after();
 #pragma unroll 1
-      for (int ks = 0; ks < kHid / 16; ++ks) {
-        const uint32_t ko = ks * 256;  // two 16-byte K chunks per MMA
-        const uint64_t ah = make_desc(wga + kA2Hi + ko, 128, (kHid / 8) * 128), al = make_desc(wga + kA2Lo + ko, 128, (kHid / 8) * 128);
-        const uint64_t bh = make_desc(sbase + kW2Hi + ko, 128, (kHid / 8) * 128), bl = make_desc(sbase + kW2Lo + ko, 128, (kHid / 8) * 128);
-        umma_bf16(d2, ah, bh, ks > 0);
-        if (SPLIT) {
-          umma_bf16(d2, al, bh, 1);
-          umma_bf16(d2, ah, bl, 1);
+          for (int kq = 0; kq < (DDQC_POLICY_KSPLIT ? 4 : 8); ++kq) {
+            const int ks = DDQC_POLICY_KSPLIT ? (kq >> 1) * 4 + cb * 2 + (kq & 1) : kq;
+            const uint32_t ko = ks * 256;  // two 16-byte K chunks per MMA
+            const uint64_t ah = make_desc(wga + kA2Hi + ko, 128, (kHid / 8) * 128), al = make_desc(wga + kA2Lo + ko, 128, (kHid / 8) * 128);
+            const uint64_t bh = make_desc(sbase + kW2Hi + ko, 128, (kHid / 8) * 128), bl = make_desc(sbase + kW2Lo + ko, 128, (kHid / 8) * 128);
+            umma_bf16(d2, ah, bh, DDQC_POLICY_KSPLIT ? (cb | kq) != 0 : kq > 0);
+            if (SPLIT) {
+              umma_bf16(d2, al, bh, 1);
+              umma_bf16(d2, ah, bl, 1);
+            }
+          }
+          if (cb == 1) umma_commit(mbar);
         }
       }
-      umma_commit(mbar);
     }
     {  // prefetch the next tile's observation chunk
       const long long nrow = (tile + tile_step) * kTileM + row;
