@@ -41,6 +41,12 @@ def test_argument_validation_without_gpu(build_lib):
     cfg = _lib.MpcConfig()
     cfg.n, cfg.m, cfg.p, cfg.L, cfg.N = 6, 3, 3, 35, 350
     assert lib.ddqc_ddmpc_workspace_bytes(ctypes.byref(cfg), 4096) > 0
+    # Gram cache: 24 header doubles + one workspace-slot image (R1 panel 34x5 blocks + trailing tri(29) blocks of 64) per controller
+    assert lib.ddqc_ddmpc_gram_cache_bytes(ctypes.byref(cfg), 1) == 8 * (24 + 64 * (34 * 5 + 29 * 30 // 2))
+    assert lib.ddqc_ddmpc_gram_cache_bytes(ctypes.byref(cfg), 4096) == 4096 * lib.ddqc_ddmpc_gram_cache_bytes(ctypes.byref(cfg), 1)
+    assert lib.ddqc_ddmpc_gram_cache_bytes(ctypes.byref(cfg), -1) == -1
+    assert lib.ddqc_ddmpc_solve(ctypes.byref(cfg), *([None] * 12), 16, None, None) == -1  # null buffers, with or without a cache
+    assert lib.ddqc_ddmpc_store(ctypes.byref(cfg), None, None, None, None, 16, None, None) == -1
     cfg.alpha_reg_type = 1
     assert lib.ddqc_ddmpc_workspace_bytes(ctypes.byref(cfg), 4096) == -1
     cfg.alpha_reg_type, cfg.N = 0, 4000  # H would have > 512 rows? no: rows fixed by l; C large is fine
