@@ -500,7 +500,7 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
                    termination_if_y_greater_than=100.0, termination_if_z_greater_than=10.0)  # fmt: skip
     at = EnvActionType.CTBR_FIXED_YAW
     env = HoverEnv(batch, env_cfg, obs_cfg, get_reward_cfg_by_action_type(at), cmd_cfg, device=dev, action_type=at,
-                   auto_target_updates=False, seed=77, materialize_buffers=True)  # fmt: skip
+                   auto_target_updates=False, seed=77, materialize_buffers=True, independent_envs=True)  # fmt: skip
     env.reset()
     hover = torch.tensor(P["init_hover_pos"], device=dev).repeat(batch, 1)
     yaw = torch.zeros(batch, device=dev)

@@ -18,7 +18,7 @@ STAT_COPIES = 32
 EP_RING = 1024
 
 ACT_ROTOR_RPMS, ACT_CTBR, ACT_CTBR_FIXED_YAW = 0, 1, 2
-F_ACTION_LATENCY, F_AUTO_TARGET, F_NEED_EULER = 1, 2, 4
+F_ACTION_LATENCY, F_AUTO_TARGET, F_NEED_EULER, F_INDEPENDENT_ENVS = 1, 2, 4, 8
 
 f32, i32, u32, u64, f64 = C.c_float, C.c_int32, C.c_uint32, C.c_uint64, C.c_double
 vp = C.c_void_p

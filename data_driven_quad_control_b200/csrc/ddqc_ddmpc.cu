@@ -1149,6 +1149,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     __syncthreads();
     const int b = s_next;
     if (b >= batch) break;
+    if (have_prev[b] < 0) continue;  // skipped controller (an aborted evaluation run): nothing of it is touched
     const int gmode = s_gmode;
     double* gc = gram_cache ? gram_cache + (size_t)b * cache_stride(d) : nullptr;
     t_prev = clock64();

@@ -65,7 +65,8 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
   const int lane = threadIdx.x & 31;
   const int copy = (blockIdx.x + (threadIdx.x >> 5)) % DDQC_STAT_COPIES;
   const uint64_t ev = ctl->rng_event;
-  const bool pid_pending = ctl->pid_reset_pending != 0u;
+  const bool indep = (P.flags & DDQC_F_INDEPENDENT_ENVS) != 0u;  // per-env instead of batch-global reset side effects
+  const bool pid_pending = !indep && ctl->pid_reset_pending != 0u;
 
   float rew_total = 0.0f;
   bool did_reset = false, did_timeout = false;
@@ -235,6 +236,13 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
   }
 
     if (did_reset) {  // reset_idx (hover_env.py:556-595)
+      if (USES_CTBR && indep && live) {  // ctbr_controller.reset() of this env's own instance
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          S.pid_integral[j * n + i] = 0.0f;
+          S.pid_prev_error[j * n + i] = 0.0f;
+        }
+      }
       V3 ip{P.init_pos[0], P.init_pos[1], P.init_pos[2]};
       p = ip;
       rel = V3{cmd_new.x - ip.x, cmd_new.y - ip.y, cmd_new.z - ip.z};  // A16, old (pre-reset-resample) command
@@ -474,7 +482,7 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
   const unsigned int n_fix = __ldcg(&ctl->fixup_count);
 
   // A16: some env reset this step -> envs that only resampled their target see fresh rel_pos
-  if (n_reset > 0) {
+  if (n_reset > 0 && !indep) {
     for (unsigned int s = lane; s < n_fix; s += 32) {
       int e = __ldcg(&O.fixup_idx[s]);
       const float* fv = O.fixup_val + (size_t)s * 8;
@@ -516,7 +524,7 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
     ctl->ep_ring[row][7] = (float)n_reset;
     ctl->ep_row = row;
     ctl->n_reset_last = n_reset;
-    ctl->pid_reset_pending = USES_CTBR ? (n_reset > 0 ? 1u : 0u) : 0u;
+    ctl->pid_reset_pending = (USES_CTBR && !indep) ? (n_reset > 0 ? 1u : 0u) : 0u;
     ctl->total_resets += n_reset;
     ctl->total_timeouts += f_cnt[1];
     ctl->total_env_steps += (uint64_t)n;

@@ -58,6 +58,12 @@ reset_idx_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O
       for (int j = 0; j < A; ++j) S.last_actions[j * n + e] = 0.0f;
       S.episode_length[e] = 0;
       S.hover_counter[e] = 0;
+      if ((P.flags & DDQC_F_INDEPENDENT_ENVS) && P.action_type != DDQC_ACT_ROTOR_RPMS && S.pid_integral && S.pid_prev_error) {
+        for (int c = 0; c < 3; ++c) {  // independent instances: the rate PID of the reset envs only
+          S.pid_integral[c * n + e] = 0.0f;
+          S.pid_prev_error[c * n + e] = 0.0f;
+        }
+      }
       if (O.reset) O.reset[e] = 1;
       for (int k = 0; k < DDQC_NUM_REWARDS; ++k) {
         atomicAdd(&s_sums[k], S.episode_sums[k * n + e]);
@@ -85,7 +91,7 @@ reset_idx_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O
     __threadfence();
     finalize_episode_stats(ctl, P.episode_length_s, true);
     // ctbr_controller.reset(): whole-batch PID zero (hover_env.py:592-593), applied lazily
-    if (P.action_type != DDQC_ACT_ROTOR_RPMS) ctl->pid_reset_pending = 1u;
+    if (P.action_type != DDQC_ACT_ROTOR_RPMS && !(P.flags & DDQC_F_INDEPENDENT_ENVS)) ctl->pid_reset_pending = 1u;
   }
 }
 

@@ -61,7 +61,9 @@ def make_env_factory(device):
                        termination_if_y_greater_than=100.0, termination_if_z_greater_than=10.0)  # fmt: skip
         at = EnvActionType.CTBR_FIXED_YAW
         return HoverEnv(num_envs, env_cfg, obs_cfg, get_reward_cfg_by_action_type(at), cmd_cfg, device=device, action_type=at,
-                        auto_target_updates=False, materialize_buffers=True)  # fmt: skip
+                        auto_target_updates=False, materialize_buffers=True, independent_envs=True)  # fmt: skip
+        # independent_envs: every evaluation run of the reference has its own single-env HoverEnv (one worker process per
+        # run, parallel_grid_search.py:133-155); a crashed drone of one run must not reset the rate PID of the others
 
     return make_env
 

@@ -175,16 +175,22 @@ class BatchedNonlinearDataDrivenMPC:
             t = t.reshape(1, self.p).expand(self.B, self.p)
         self.y_r.copy_(t.reshape(self.B, self.p))
 
-    def update_and_solve_data_driven_mpc(self) -> None:
-        """One solve of every controller of the batch on its current (u, y) window."""
+    def update_and_solve_data_driven_mpc(self, skip: torch.Tensor | None = None) -> None:
+        """One solve of every controller of the batch on its current (u, y) window.  `skip` ((B,) bool, optional):
+        controllers left out of this solve - their outputs and status keep their last values (used by the batched
+        evaluator for runs the reference would have aborted)."""
+        have_prev = self._have_prev if skip is None else torch.where(skip, -1, self._have_prev).to(torch.int32)
         rc = self._lib.ddqc_ddmpc_solve(
             C.byref(self._cfg), self._ws.data_ptr(), self.u.data_ptr(), self.y.data_ptr(), self.y_r.data_ptr(),
-            self._have_prev.data_ptr(),
+            have_prev.data_ptr(),
             self._lamb.data_ptr() if self._lamb is not None else None, self._act_state.data_ptr() if self._act_state is not None else None, self.optimal_u.data_ptr(), self.us.data_ptr(), self.ys.data_ptr(), self.status.data_ptr(),
             self.iters.data_ptr(), self.B, self.gram_cache_ptr, _lib.stream_ptr(self.device),
         )  # fmt: skip
         _lib.check(rc, "ddqc_ddmpc_solve")
-        self._have_prev.fill_(1)
+        if skip is None:
+            self._have_prev.fill_(1)
+        else:  # a skipped controller keeps the history it had (it may be solved again later)
+            self._have_prev.masked_fill_(~skip, 1)
 
     @property
     def gram_cache_ptr(self):

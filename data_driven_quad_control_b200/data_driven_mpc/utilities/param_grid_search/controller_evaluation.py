@@ -81,7 +81,9 @@ def sim_nonlinear_dd_mpc_control_loop_batched(
     u_log = torch.zeros((num_steps, B, m), **f64) if record else None
     cfg = C.byref(ctrl._cfg)
     for t in range(0, num_steps, n_mpc_step):
-        ctrl.update_and_solve_data_driven_mpc()
+        # runs that already stopped (drift criterion or a failed solve) are aborted evaluations in the reference
+        # (controller_evaluation.py:424-447): their controllers are left out of the solve
+        ctrl.update_and_solve_data_driven_mpc(skip=(fail_step >= 0) | solver_failed)
         solver_failed |= ctrl.status != 0
         for k in range(t, min(t + n_mpc_step, num_steps)):
             rc = lib.ddqc_ddmpc_action(cfg, ctrl.optimal_u.data_ptr(), k - t, bounds.data_ptr(), action.data_ptr(),

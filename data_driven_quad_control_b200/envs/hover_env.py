@@ -73,6 +73,7 @@ def make_env_params(
     mixer: torch.Tensor | None = None,
     inv_sqrt_kf: float = 0.0,
     rate_pid_gains: list[list[float]] | None = None,
+    independent_envs: bool = False,
 ) -> _lib.EnvParams:
     """Fill the C parameter block.  Pure host code (no CUDA needed); every float is the fp32
     rounding of the double the reference computes in Python."""
@@ -91,6 +92,8 @@ def make_env_params(
         flags |= _lib.F_AUTO_TARGET
     if need_euler:
         flags |= _lib.F_NEED_EULER
+    if independent_envs:
+        flags |= _lib.F_INDEPENDENT_ENVS
     P.flags = flags
     P.clip_actions = env_cfg["clip_actions"]
 
@@ -216,6 +219,7 @@ class HoverEnv:
         *,
         seed: int = 0,
         materialize_buffers: bool | None = None,
+        independent_envs: bool = False,
     ):
         if show_viewer or env_cfg.get("visualize_camera", False):
             raise NotImplementedError("rendering (viewer / camera) is outside the B200 hot path")
@@ -290,7 +294,11 @@ class HoverEnv:
             mixer=mats["mixer"] if mats else None,
             inv_sqrt_kf=float(mats["inv_sqrt_KF"]) if mats else 0.0,
             rate_pid_gains=gains,
+            independent_envs=independent_envs,
         )  # fmt: skip
+        # independent_envs: env b behaves like its own `HoverEnv(num_envs=1)` (a reset zeroes the rate PID and refreshes
+        # rel_pos of that env only) - the semantics of the reference's one-env-per-process evaluation workers
+        self.independent_envs = bool(independent_envs)
 
         # ---- persistent SoA state -------------------------------------------------------------
         self._pos = torch.zeros((3, N), **f32)

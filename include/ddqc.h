@@ -45,6 +45,11 @@ extern "C" {
 #define DDQC_F_ACTION_LATENCY 1u    /* env_cfg["simulate_action_latency"]  (hover_env.py:386-388) */
 #define DDQC_F_AUTO_TARGET 2u       /* auto_target_updates                 (hover_env.py:473-478) */
 #define DDQC_F_NEED_EULER 4u        /* Euler angles feed a live threshold or a non-zero yaw reward */
+#define DDQC_F_INDEPENDENT_ENVS 8u  /* every env behaves like its own num_envs = 1 HoverEnv instance: a reset zeroes the rate
+                                     * PID of that env only and refreshes rel_pos of that env only.  The reference's two
+                                     * batch-global quirks (hover_env.py:563-564, 592-593) are per INSTANCE; its grid search and
+                                     * controller comparison run one single-env instance per worker process
+                                     * (parallel_grid_search.py:133-155), which is what a batched evaluation must reproduce */
 
 #define DDQC_NUM_REWARDS 7          /* target, closeness, hover_time, smooth, yaw, angular, crash */
 #define DDQC_STAT_COPIES 32         /* spread of the per-block statistics atomics */
@@ -266,7 +271,10 @@ int64_t ddqc_ddmpc_workspace_bytes(const DdqcMpcConfig* cfg_host, int64_t batch)
  *  u_win [B][N][m], y_win [B][N][p] : rolling input/output windows (float64)
  *  y_r   [B][p]                      : output setpoints
  *  have_prev [B] int32               : 0 -> cold active set (first solve); alpha_sr (alpha_reg_type 0) is the
- *                                      alpha of the optimal reachable equilibrium for y_r and needs no history
+ *                                      alpha of the optimal reachable equilibrium for y_r and needs no history;
+ *                                      < 0 -> the controller is skipped, its outputs, status, active set and Gram
+ *                                      cache stay untouched (an evaluation run the reference would have aborted,
+ *                                      controller_evaluation.py:424-447)
  *  lamb [B][4] (or NULL)            : per-controller (lamb_alpha, lamb_sigma, lamb_alpha_s, lamb_sigma_s)
  *                                      overriding the config values (grid search over the regularisation
  *                                      weights, configs/data_driven_mpc/dd_mpc_grid_search_params.yaml:92-111)

@@ -183,7 +183,12 @@ class EnvOracle:
         rate_pid_gains=((10.0, 0.0, 0.1),) * 3,
         rng=None,
         scale_rewards_by_dt=True,
+        independent_envs=False,
     ):
+        # independent_envs: every env is its own num_envs = 1 instance of the reference env, i.e. the two batch-global
+        # side effects of reset_idx (hover_env.py:563-564 rel_pos of ALL envs, :592-593 PID of ALL envs) reach the
+        # reset envs only - what the reference's one-env-per-process evaluation workers see
+        self.independent_envs = bool(independent_envs)
         N = self.num_envs = int(num_envs)
         self.action_type = action_type
         self.num_actions = A = NUM_ACTIONS[action_type]
@@ -295,8 +300,12 @@ class EnvOracle:
             return
         self.base_pos[idx] = self.base_init_pos
         self.last_base_pos[idx] = self.base_init_pos
-        self.rel_pos = self.commands - self.base_pos  # ALL envs (A16)
-        self.last_rel_pos = self.commands - self.last_base_pos
+        if self.independent_envs:
+            self.rel_pos[idx] = self.commands[idx] - self.base_pos[idx]
+            self.last_rel_pos[idx] = self.commands[idx] - self.last_base_pos[idx]
+        else:
+            self.rel_pos = self.commands - self.base_pos  # ALL envs (A16)
+            self.last_rel_pos = self.commands - self.last_base_pos
         self.base_quat[idx] = self.base_init_quat
         self.sim_pos[idx] = self.base_pos[idx]
         self.sim_quat[idx] = self.base_quat[idx]
@@ -312,7 +321,10 @@ class EnvOracle:
         for k in self.episode_sums:
             self.extras_episode["rew_" + k] = float(np.mean(self.episode_sums[k][idx])) / self.env_cfg["episode_length_s"]
             self.episode_sums[k][idx] = 0
-        if self.uses_ctbr:  # whole-batch PID reset (A17)
+        if self.uses_ctbr and self.independent_envs:
+            self.pid_integral[idx] = 0
+            self.pid_prev_error[idx] = 0
+        elif self.uses_ctbr:  # whole-batch PID reset (A17)
             self.pid_integral[:] = 0
             self.pid_prev_error[:] = 0
         self._resample_commands(idx, stream)

@@ -373,3 +373,32 @@ def test_gram_cache_drift_over_a_refresh_period(build_lib):
     print(f"gram cache drift: max |du| first 10 steps {max(worst[:10]):.2e}, steps 118-127 {max(worst[118:128]):.2e}, "
           f"after the regeneration {max(worst[129:]):.2e}")
     assert max(worst) <= 1e-6
+
+
+def test_skipped_controllers_are_left_untouched(build_lib):
+    """`update_and_solve_data_driven_mpc(skip=mask)` (have_prev < 0 in the C ABI): the masked controllers keep outputs,
+    status, active set and Gram cache; the others get exactly the result of an unmasked solve; a controller that was
+    skipped can be solved again later and then agrees with one that never was."""
+    prm, B = _small_params(), 6
+    prm.n, prm.L, prm.N = 4, 10, 160  # large enough for the Gram-cache path
+    u, y, plants = _synthetic_windows(prm, 5, B, return_plants=True)
+    y_r = np.tile(np.array([[0.2, -0.1, 0.1]]), (B, 1))
+    a = _batched(prm, u, y, y_r, solve_on_init=False)
+    b = _batched(prm, u, y, y_r, solve_on_init=False)
+    skip = torch.tensor([False, True, False, True, True, False], device="cuda")
+    for c in (a, b):
+        c.update_and_solve_data_driven_mpc()
+    for step in range(3):
+        u0 = b.get_optimal_control_input_at_step(0).clone()
+        yk = torch.from_numpy(np.stack([plants[i].step(u0[i].cpu().numpy()) for i in range(B)])).cuda()
+        for c in (a, b):
+            c.store_input_output_measurement(u0, yk)
+        before = a.optimal_u.clone()
+        a.update_and_solve_data_driven_mpc(skip=skip if step < 2 else None)
+        b.update_and_solve_data_driven_mpc()
+        if step < 2:
+            assert torch.equal(a.optimal_u[skip], before[skip])
+            assert torch.equal(a.optimal_u[~skip], b.optimal_u[~skip])
+        else:  # solved again after two skipped steps (Gram regenerated: the window moved by more than one sample)
+            np.testing.assert_allclose(a.optimal_u.cpu().numpy(), b.optimal_u.cpu().numpy(), rtol=0, atol=1e-6)
+        assert int((a.status != 0).sum()) == 0

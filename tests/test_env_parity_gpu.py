@@ -11,7 +11,8 @@ from conftest import default_cfgs
 pytestmark = pytest.mark.gpu
 
 
-def _make_pair(N, at_name, auto=True, seed=5, env_over=None, obs_over=None, reward_cfg=None, materialize=True):
+def _make_pair(N, at_name, auto=True, seed=5, env_over=None, obs_over=None, reward_cfg=None, materialize=True,
+               independent=False):
     import env_oracle as eo
     from data_driven_quad_control_b200.controllers.ctbr.ctbr_controller import build_ctbr_matrices
     from data_driven_quad_control_b200.envs.hover_env import HoverEnv
@@ -24,12 +25,12 @@ def _make_pair(N, at_name, auto=True, seed=5, env_over=None, obs_over=None, rewa
     obs_cfg.update(obs_over or {})
     cfgs_o = copy.deepcopy((env_cfg, obs_cfg, rew_cfg, cmd_cfg))
     env = HoverEnv(N, env_cfg, obs_cfg, rew_cfg, cmd_cfg, device="cuda", action_type=at, auto_target_updates=auto,
-                   seed=seed, materialize_buffers=materialize)
+                   seed=seed, materialize_buffers=materialize, independent_envs=independent)
     mats = build_ctbr_matrices(EnvDroneParams.get())
     orc = eo.EnvOracle(N, *cfgs_o, action_type=at.value, auto_target_updates=auto, mixer=mats["mixer"].numpy(),
                        inv_sqrt_kf=float(mats["inv_sqrt_KF"]),
                        rate_pid_gains=EnvCTBRControllerConfig.get()["ctbr_controller_params"]["rate_pid_gains"],
-                       rng=eo.PhiloxRng(seed))
+                       rng=eo.PhiloxRng(seed), independent_envs=independent)
     return env, orc
 
 
@@ -156,6 +157,30 @@ def test_baseline_sizes_bit_exact(build_lib, N, T):
     assert abs(float(stats["reward_sum"]) - rew_sum) <= 2e-6 * max(1.0, abs(rew_sum))
     if N == 4096:
         assert n_reset > 1000  # the rollout exercises the reset / PID-flush / resample paths
+
+
+@pytest.mark.parametrize("at_name,auto", [("CTBR_FIXED_YAW", False), ("CTBR", True), ("ROTOR_RPMS", True)])
+def test_independent_envs_bit_exact(build_lib, at_name, auto):
+    """independent_envs=True (every env its own num_envs = 1 instance: per-env PID reset and rel_pos refresh, the
+    semantics of the reference's one-env-per-process evaluation workers) against the oracle in the same mode, incl. an
+    external reset_idx in the middle of the rollout."""
+    N, T = 64, 300
+    env, orc = _make_pair(N, at_name, auto, independent=True)
+    acts = _actions(T, N, env.num_actions, 7)
+    env.reset()
+    orc.reset()
+    yaw_tol = 0.0 if at_name == "CTBR_FIXED_YAW" else 2e-6
+    nres = 0
+    for t in range(T):
+        if t == 150:
+            idx = [3, 17, 40]
+            env.reset_idx(torch.tensor(idx, device="cuda"))
+            orc.reset_idx(idx)
+        env.step(torch.from_numpy(acts[t]).cuda())
+        orc.step(acts[t])
+        _compare_step(env, orc, t, yaw_tol=yaw_tol)
+        nres += int(orc.reset_buf.sum())
+    assert nres > 200
 
 
 def test_timeouts_and_episode_length_assignment(build_lib):
