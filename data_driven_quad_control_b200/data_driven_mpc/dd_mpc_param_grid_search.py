@@ -62,8 +62,10 @@ def make_env_factory(device):
         at = EnvActionType.CTBR_FIXED_YAW
         return HoverEnv(num_envs, env_cfg, obs_cfg, get_reward_cfg_by_action_type(at), cmd_cfg, device=device, action_type=at,
                         auto_target_updates=False, materialize_buffers=True, independent_envs=True)  # fmt: skip
-        # independent_envs: every evaluation run of the reference has its own single-env HoverEnv (one worker process per
-        # run, parallel_grid_search.py:133-155); a crashed drone of one run must not reset the rate PID of the others
+        # independent_envs: the reference steps ONE env with num_envs = num_processes drones (dd_mpc_param_grid_search.py:
+        # 282-291), so a crashed drone zeroes the rate PID of the few runs that happen to be evaluated beside it.  With
+        # thousands of runs in one batch every crash would hit every run: the runs are decoupled instead (each behaves as
+        # with num_processes = 1), which also makes a run's score independent of its neighbours
 
     return make_env
 

@@ -297,7 +297,7 @@ class HoverEnv:
             independent_envs=independent_envs,
         )  # fmt: skip
         # independent_envs: env b behaves like its own `HoverEnv(num_envs=1)` (a reset zeroes the rate PID and refreshes
-        # rel_pos of that env only) - the semantics of the reference's one-env-per-process evaluation workers
+        # rel_pos of that env only) - an evaluation run of the reference's grid search as it is with num_processes = 1
         self.independent_envs = bool(independent_envs)
 
         # ---- persistent SoA state -------------------------------------------------------------

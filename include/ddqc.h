@@ -47,9 +47,11 @@ extern "C" {
 #define DDQC_F_NEED_EULER 4u        /* Euler angles feed a live threshold or a non-zero yaw reward */
 #define DDQC_F_INDEPENDENT_ENVS 8u  /* every env behaves like its own num_envs = 1 HoverEnv instance: a reset zeroes the rate
                                      * PID of that env only and refreshes rel_pos of that env only.  The reference's two
-                                     * batch-global quirks (hover_env.py:563-564, 592-593) are per INSTANCE; its grid search and
-                                     * controller comparison run one single-env instance per worker process
-                                     * (parallel_grid_search.py:133-155), which is what a batched evaluation must reproduce */
+                                     * batch-global reset side effects (hover_env.py:563-564, 592-593) couple the drones of one
+                                     * instance; its grid search steps one instance with num_envs = num_processes drones
+                                     * (dd_mpc_param_grid_search.py:282-291), so concurrent evaluation runs perturb each other
+                                     * in a scheduling-dependent way.  A batch of thousands of runs in one instance would
+                                     * couple them all; with this flag a run is what it is with num_processes = 1 */
 
 #define DDQC_NUM_REWARDS 7          /* target, closeness, hover_time, smooth, yaw, angular, crash */
 #define DDQC_STAT_COPIES 32         /* spread of the per-block statistics atomics */

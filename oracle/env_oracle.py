@@ -187,7 +187,7 @@ class EnvOracle:
     ):
         # independent_envs: every env is its own num_envs = 1 instance of the reference env, i.e. the two batch-global
         # side effects of reset_idx (hover_env.py:563-564 rel_pos of ALL envs, :592-593 PID of ALL envs) reach the
-        # reset envs only - what the reference's one-env-per-process evaluation workers see
+        # reset envs only - an evaluation run of the reference's grid search as it is with num_processes = 1
         self.independent_envs = bool(independent_envs)
         N = self.num_envs = int(num_envs)
         self.action_type = action_type

@@ -162,7 +162,7 @@ def test_baseline_sizes_bit_exact(build_lib, N, T):
 @pytest.mark.parametrize("at_name,auto", [("CTBR_FIXED_YAW", False), ("CTBR", True), ("ROTOR_RPMS", True)])
 def test_independent_envs_bit_exact(build_lib, at_name, auto):
     """independent_envs=True (every env its own num_envs = 1 instance: per-env PID reset and rel_pos refresh, the
-    semantics of the reference's one-env-per-process evaluation workers) against the oracle in the same mode, incl. an
+    decoupled evaluation runs of the batched grid search) against the oracle in the same mode, incl. an
     external reset_idx in the middle of the rollout."""
     N, T = 64, 300
     env, orc = _make_pair(N, at_name, auto, independent=True)
