@@ -343,10 +343,10 @@ def run_b200(args) -> dict:
             "bytes_per_env_step": ENV_BYTES_PER_STEP[A],
             "avg_launch_ms": avg_ms,
             "median_launch_ms": med_ms,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2**20 envs (130.1 + 162.3 MB), from
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2**20 envs (130.1 + 163.5 MB), from
             # profiles/r1h_env_step_ncu_full.csv; below the algorithmic 374 MB because part of the written state is
             # still in L2 at kernel end and is re-read from there by the next launch
-            "traffic": 292.4e6 * (N / float(1 << 20)) if N == 1 << 20 else None,
+            "traffic": 293.6e6 * (N / float(1 << 20)) if N == 1 << 20 else None,
             "traffic_source": "profiles/r1h_env_step_ncu_full.csv",
         },
         "rollout_stats": stats,
@@ -430,7 +430,7 @@ def run_policy_leg(env, dev, N: int, steps: int = 100, warm: int = 10) -> dict:
             "peak": peak, "unit": "TFLOP/s", "frac": flops_tc / (ms_pol * 1e-3) / 1e12 / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained",
             "algorithmic_tflops": flops_alg / (ms_pol * 1e-3) / 1e12,
-            "traffic": 70.2e6 if N == 1 << 20 else None, "traffic_source": "profiles/r1h_policy_mlp_ncu_full.csv (67.2 MB read = the obs tile, 3.0 MB written)",
+            "traffic": 69.1e6 if N == 1 << 20 else None, "traffic_source": "profiles/r1h_policy_mlp_ncu_full.csv (67.2 MB read = the obs tile, 1.9 MB written)",
         },
         "gpu_launches": 3 * steps,
     }
@@ -639,7 +639,7 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
             "peak": fp64_peak, "unit": "TFLOP/s", "frac": batch * flops / (avg * 1e-3) / 1e12 / fp64_peak,
             "peak_source": "FP64 tensor (DMMA m8n8k4) = FP64 FMA pipe, 64 FMA/clk/SM, measured 37.1 TFLOP/s with "
             "tools/ubench_fp64.cu (MEASURED_PEAKS.json carries no fp64 figure)",
-            "flops_per_solve": flops, "traffic": (2290.5e6 if ctrl.gram_cache_ptr is not None else 133.0e6) if batch == 4096 else None,
+            "flops_per_solve": flops, "traffic": (2292.3e6 if ctrl.gram_cache_ptr is not None else 133.0e6) if batch == 4096 else None,
             "traffic_source": "profiles/r1h_ddmpc_solve_ncu_full.csv (DRAM bytes per launch of 4096 solves: the 1.2 GB Gram cache read once and written once, evict-first; the workspace slots stay in L2; without the cache 133 MB)",
         },
         "gpu_launches": T,
