@@ -17,6 +17,8 @@ NUM_REWARDS = 7
 STAT_COPIES = 32
 EP_RING = 1024
 
+ABI_VERSION = 2  # include/ddqc.h: DDQC_ABI_VERSION
+
 ACT_ROTOR_RPMS, ACT_CTBR, ACT_CTBR_FIXED_YAW = 0, 1, 2
 F_ACTION_LATENCY, F_AUTO_TARGET, F_NEED_EULER, F_INDEPENDENT_ENVS = 1, 2, 4, 8
 
@@ -146,7 +148,7 @@ class EnvOut(C.Structure):
             "fixup_idx",
             "fixup_val",
         )
-    ]
+    ] + [("ep_row", u32), ("pad0", u32)]
 
 
 class MpcConfig(C.Structure):
@@ -230,6 +232,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    if lib.ddqc_abi_version() != ABI_VERSION:
+        raise DdqcError(f"{LIB_PATH} has ABI version {lib.ddqc_abi_version()}, this binding expects {ABI_VERSION}: rebuild")
     for which, cls in _STRUCTS.items():
         got = lib.ddqc_struct_size(which)
         if got != C.sizeof(cls):
@@ -263,6 +267,31 @@ def require_cuda(device) -> "torch.device":  # noqa: F821
     if dev.index is None:
         dev = torch.device("cuda", torch.cuda.current_device())
     return dev
+
+
+class _NullGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_GUARD = _NullGuard()
+
+
+def device_guard(device):
+    """Context manager that makes `device` the current CUDA device for a library call.
+
+    The entry points launch on the *current* device (the stream passed in belongs to `device`), so an object built
+    on `cuda:1` while `cuda:0` is current must switch for the duration of the call.  When `device` already is
+    current - every single-GPU process, every torchrun rank after `torch.cuda.set_device` - this is a no-op that
+    costs one `torch.cuda.current_device()` query."""
+    import torch
+
+    if torch.cuda.current_device() == device.index:
+        return _NULL_GUARD
+    return torch.cuda.device(device)
 
 
 def stream_ptr(device) -> int:

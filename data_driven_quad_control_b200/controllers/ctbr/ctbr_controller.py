@@ -90,11 +90,12 @@ class DroneCTBRController:
             raise ValueError("expected rate_measurements (N,3), rate_setpoints (N,3), thrust_setpoints (N,)")
         rpm = torch.empty((N, 4), dtype=torch.float32, device=dev)
         integ, prev = self.rate_pid_controller._state_ptrs()
-        rc = self._lib.ddqc_ctbr_compute(
-            ms.data_ptr(), ms.stride(0), ms.stride(1), sp.data_ptr(), sp.stride(0), sp.stride(1),
-            th.data_ptr(), th.stride(0), integ, prev, self._mixer_host, self._gains_host,
-            self.dt, self._inv_sqrt_kf_host, rpm.data_ptr(), N, _lib.stream_ptr(dev),
-        )  # fmt: skip
+        with _lib.device_guard(dev):
+            rc = self._lib.ddqc_ctbr_compute(
+                ms.data_ptr(), ms.stride(0), ms.stride(1), sp.data_ptr(), sp.stride(0), sp.stride(1),
+                th.data_ptr(), th.stride(0), integ, prev, self._mixer_host, self._gains_host,
+                self.dt, self._inv_sqrt_kf_host, rpm.data_ptr(), N, _lib.stream_ptr(dev),
+            )  # fmt: skip
         _lib.check(rc, "ddqc_ctbr_compute")
         return rpm
 

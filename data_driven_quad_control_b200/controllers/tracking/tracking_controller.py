@@ -50,12 +50,13 @@ class DroneTrackingController:
             raise ValueError("expected positions (N,3) and quaternions (N,4)")
         out = torch.empty((N, 4), dtype=torch.float32, device=dev)
         integ, prev = self.controller._state_ptrs()
-        rc = self._lib.ddqc_tracking_compute(
-            X.data_ptr(), X.stride(0), X.stride(1), Q.data_ptr(), Q.stride(0), Q.stride(1),
-            Xs.data_ptr(), Xs.stride(0), Xs.stride(1), Qs.data_ptr(), Qs.stride(0), Qs.stride(1),
-            integ, prev, self._gains_host, self.dt, float(self.drone_mass), float(self.kR),
-            out.data_ptr(), N, _lib.stream_ptr(dev),
-        )  # fmt: skip
+        with _lib.device_guard(dev):
+            rc = self._lib.ddqc_tracking_compute(
+                X.data_ptr(), X.stride(0), X.stride(1), Q.data_ptr(), Q.stride(0), Q.stride(1),
+                Xs.data_ptr(), Xs.stride(0), Xs.stride(1), Qs.data_ptr(), Qs.stride(0), Qs.stride(1),
+                integ, prev, self._gains_host, self.dt, float(self.drone_mass), float(self.kR),
+                out.data_ptr(), N, _lib.stream_ptr(dev),
+            )  # fmt: skip
         _lib.check(rc, "ddqc_tracking_compute")
         return out
 

@@ -39,8 +39,120 @@ namespace {
 // Measured and dropped: prefetch.global.L2 of the state of the env one wave (or half / two waves) of resident CTAs
 // ahead - 0.0734 / 0.0745 / 0.0803 ms per 2^20 envs against 0.0735 ms without (eager launches): the loads already
 // cover the DRAM latency with 32 warps per SM, the ~40 extra instructions per thread only cost issue slots.
+// DDQC_ENV_FINALIZE: where a step's statistics are folded.
+//   0  last CTA of the step kernel (bar.sync + device fence + ticket per CTA): round 1.  ncu showed warp 0 of every CTA
+//      waiting on the fence for half as long again as the CTA's work takes, with the registers of the three exited
+//      warps still held (CTA residency 1.5x the work), plus 9 % of the warp samples at the barrier;
+//   1  a second one-warp launch after the step kernel (stream order);
+//   2  the same with programmatic dependent launch: the finalisation is scheduled while the step kernel drains and
+//      the next step kernel while the finalisation runs; each waits (griddepcontrol.wait) before touching memory.
+#ifndef DDQC_ENV_FINALIZE
+#define DDQC_ENV_FINALIZE 2
+#endif
 constexpr int kThreads = DDQC_ENV_THREADS;
 constexpr int kMinBlocks = DDQC_ENV_MIN_BLOCKS;
+
+// Programmatic dependent launch (sm_90+): no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() {
+#if DDQC_ENV_FINALIZE == 2
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if DDQC_ENV_FINALIZE == 2
+  asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
+
+// ---- step finalisation ------------------------------------------------------------------
+// One warp, after every env of the step has been processed: fold the per-copy accumulators
+// (lane k < 8: sums, 8: resets, 9: time-outs), apply the A15/A16 fix-up list iff the step saw a
+// reset, write the extras["episode"] ring row named by the host (O.ep_row), raise the A17 flag,
+// bump the Philox event counter.
+template <int NOBS, bool LEAN, bool USES_CTBR>
+__device__ __forceinline__ void finalize_step(const DdqcEnvParams& P, const DdqcEnvState& S, const DdqcEnvOut& O,
+                                              DdqcEnvCtl* __restrict__ ctl, const int n, const int lane) {
+  const float obs_noise_std = LEAN ? 0.0f : P.obs_noise_std;
+  const bool indep = (P.flags & DDQC_F_INDEPENDENT_ENVS) != 0u;
+  const uint64_t ev = ctl->rng_event;
+  // warp 0 of the last CTA: fold the per-copy accumulators (lane k < 8: sums, 8: resets, 9: time-outs)
+  float f_acc = 0.0f;
+  unsigned int f_cnt_acc = 0u;
+  if (lane < 8) {
+    for (int c = 0; c < DDQC_STAT_COPIES; ++c) {
+      f_acc += __ldcg(&ctl->acc_sums[c][lane]);
+      ctl->acc_sums[c][lane] = 0.0f;
+    }
+  } else if (lane < 10) {
+    unsigned int* src = (lane == 8) ? ctl->acc_reset : ctl->acc_timeout;
+    for (int c = 0; c < DDQC_STAT_COPIES; ++c) {
+      f_cnt_acc += __ldcg(&src[c]);
+      src[c] = 0u;
+    }
+  }
+  float f_sums[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f_sums[k] = __shfl_sync(0xffffffffu, f_acc, k);
+  unsigned int f_cnt[2];
+  f_cnt[0] = __shfl_sync(0xffffffffu, f_cnt_acc, 8);
+  f_cnt[1] = __shfl_sync(0xffffffffu, f_cnt_acc, 9);
+  const unsigned int n_reset = f_cnt[0];
+  const unsigned int n_fix = __ldcg(&ctl->fixup_count);
+
+  // A16: some env reset this step -> envs that only resampled their target see fresh rel_pos
+  if (n_reset > 0 && !indep) {
+    for (unsigned int s = lane; s < n_fix; s += 32) {
+      int e = __ldcg(&O.fixup_idx[s]);
+      const float* fv = O.fixup_val + (size_t)s * 8;
+      O.rew[e] = __ldcg(&fv[0]);
+      S.episode_sums[0 * n + e] = __ldcg(&fv[1]);
+      S.episode_sums[1 * n + e] = __ldcg(&fv[2]);
+      float o0 = __ldcg(&fv[3]), o1 = __ldcg(&fv[4]), o2 = __ldcg(&fv[5]);
+      if (obs_noise_std > 0.0f) {  // same noise words as the main pass
+        float z[13];
+        philox_normals<13>((uint32_t)e, ev, DDQC_STREAM_OBS_NOISE, P.seed, z);
+        o0 = o0 + z[0] * obs_noise_std;
+        o1 = o1 + z[1] * obs_noise_std;
+        o2 = o2 + z[2] * obs_noise_std;
+      }
+      O.obs[(size_t)e * NOBS + 0] = o0;
+      O.obs[(size_t)e * NOBS + 1] = o1;
+      O.obs[(size_t)e * NOBS + 2] = o2;
+      if (!LEAN && O.rel_pos && O.last_rel_pos && O.last_base_pos) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float cm = __ldcg(&S.commands[c * n + e]);
+          O.rel_pos[c * n + e] = cm - __ldcg(&S.pos[c * n + e]);
+          O.last_rel_pos[c * n + e] = cm - __ldcg(&O.last_base_pos[c * n + e]);
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  if (lane == 0) {
+    const uint32_t row = O.ep_row % DDQC_EP_RING;  // named by the host, so its extras["episode"] views cannot drift
+    const uint32_t prev_row = ctl->ep_row;
+    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) {
+      float val = ctl->ep_ring[prev_row][k];
+      if (n_reset > 0) val = (f_sums[k] / (float)n_reset) / P.episode_length_s;
+      ctl->ep_ring[row][k] = val;
+      if (n_reset > 0) ctl->total_episode_sums[k] += (double)f_sums[k];
+    }
+    ctl->ep_ring[row][7] = (float)n_reset;
+    ctl->ep_row = row;
+    ctl->n_reset_last = n_reset;
+    ctl->pid_reset_pending = (USES_CTBR && !indep) ? (n_reset > 0 ? 1u : 0u) : 0u;
+    ctl->total_resets += n_reset;
+    ctl->total_timeouts += f_cnt[1];
+    ctl->total_env_steps += (uint64_t)n;
+    ctl->total_reward += (double)f_sums[7];
+    ctl->step_count += 1;
+    ctl->rng_event = ev + 1;
+    ctl->fixup_count = 0u;
+    ctl->blocks_done = 0u;
+  }
+}
 
 // ---- the fused step kernel -------------------------------------------------------------
 // LEAN = the throughput configuration: no Euler angles needed (thresholds >= 180 deg, yaw reward
@@ -64,6 +176,8 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
   const int i = live ? gid : n - 1;
   const int lane = threadIdx.x & 31;
   const int copy = (blockIdx.x + (threadIdx.x >> 5)) % DDQC_STAT_COPIES;
+  pdl_launch_dependents();  // the finalisation may be scheduled; it waits for this grid to complete
+  pdl_wait();               // the previous step's finalisation (and with it the previous step) has completed
   const uint64_t ev = ctl->rng_event;
   const bool indep = (P.flags & DDQC_F_INDEPENDENT_ENVS) != 0u;  // per-env instead of batch-global reset side effects
   const bool pid_pending = !indep && ctl->pid_reset_pending != 0u;
@@ -443,7 +557,8 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
     if (lane == 9 && tmask) atomicAdd(&ctl->acc_timeout[copy], (unsigned int)__popc(tmask));
   }
 
-  // -------------------------------------------------------------------- last-CTA finalisation
+#if DDQC_ENV_FINALIZE == 0
+  // -------------------------------------------------------------------- last-CTA finalisation (variant 0)
   // bar.sync orders every warp's stores / REDs before thread 0's device-scope fence (cumulative),
   // which releases them to whichever CTA draws the last ticket.  Only warp 0 stays for the ticket.
   __syncthreads();
@@ -456,85 +571,24 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
   is_last = __shfl_sync(0xffffffffu, is_last, 0);
   if (!is_last) return;
   __threadfence();
-
-  // warp 0 of the last CTA: fold the per-copy accumulators (lane k < 8: sums, 8: resets, 9: time-outs)
-  float f_acc = 0.0f;
-  unsigned int f_cnt_acc = 0u;
-  if (lane < 8) {
-    for (int c = 0; c < DDQC_STAT_COPIES; ++c) {
-      f_acc += __ldcg(&ctl->acc_sums[c][lane]);
-      ctl->acc_sums[c][lane] = 0.0f;
-    }
-  } else if (lane < 10) {
-    unsigned int* src = (lane == 8) ? ctl->acc_reset : ctl->acc_timeout;
-    for (int c = 0; c < DDQC_STAT_COPIES; ++c) {
-      f_cnt_acc += __ldcg(&src[c]);
-      src[c] = 0u;
-    }
-  }
-  float f_sums[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) f_sums[k] = __shfl_sync(0xffffffffu, f_acc, k);
-  unsigned int f_cnt[2];
-  f_cnt[0] = __shfl_sync(0xffffffffu, f_cnt_acc, 8);
-  f_cnt[1] = __shfl_sync(0xffffffffu, f_cnt_acc, 9);
-  const unsigned int n_reset = f_cnt[0];
-  const unsigned int n_fix = __ldcg(&ctl->fixup_count);
-
-  // A16: some env reset this step -> envs that only resampled their target see fresh rel_pos
-  if (n_reset > 0 && !indep) {
-    for (unsigned int s = lane; s < n_fix; s += 32) {
-      int e = __ldcg(&O.fixup_idx[s]);
-      const float* fv = O.fixup_val + (size_t)s * 8;
-      O.rew[e] = __ldcg(&fv[0]);
-      S.episode_sums[0 * n + e] = __ldcg(&fv[1]);
-      S.episode_sums[1 * n + e] = __ldcg(&fv[2]);
-      float o0 = __ldcg(&fv[3]), o1 = __ldcg(&fv[4]), o2 = __ldcg(&fv[5]);
-      if (obs_noise_std > 0.0f) {  // same noise words as the main pass
-        float z[13];
-        philox_normals<13>((uint32_t)e, ev, DDQC_STREAM_OBS_NOISE, P.seed, z);
-        o0 = o0 + z[0] * obs_noise_std;
-        o1 = o1 + z[1] * obs_noise_std;
-        o2 = o2 + z[2] * obs_noise_std;
-      }
-      O.obs[(size_t)e * NOBS + 0] = o0;
-      O.obs[(size_t)e * NOBS + 1] = o1;
-      O.obs[(size_t)e * NOBS + 2] = o2;
-      if (!LEAN && O.rel_pos && O.last_rel_pos && O.last_base_pos) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float cm = __ldcg(&S.commands[c * n + e]);
-          O.rel_pos[c * n + e] = cm - __ldcg(&S.pos[c * n + e]);
-          O.last_rel_pos[c * n + e] = cm - __ldcg(&O.last_base_pos[c * n + e]);
-        }
-      }
-    }
-  }
-
-  __syncwarp();
-  if (lane == 0) {
-    const uint32_t row = (ctl->ep_row + 1) % DDQC_EP_RING;
-    const uint32_t prev_row = ctl->ep_row;
-    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) {
-      float val = ctl->ep_ring[prev_row][k];
-      if (n_reset > 0) val = (f_sums[k] / (float)n_reset) / P.episode_length_s;
-      ctl->ep_ring[row][k] = val;
-      if (n_reset > 0) ctl->total_episode_sums[k] += (double)f_sums[k];
-    }
-    ctl->ep_ring[row][7] = (float)n_reset;
-    ctl->ep_row = row;
-    ctl->n_reset_last = n_reset;
-    ctl->pid_reset_pending = (USES_CTBR && !indep) ? (n_reset > 0 ? 1u : 0u) : 0u;
-    ctl->total_resets += n_reset;
-    ctl->total_timeouts += f_cnt[1];
-    ctl->total_env_steps += (uint64_t)n;
-    ctl->total_reward += (double)f_sums[7];
-    ctl->step_count += 1;
-    ctl->rng_event = ev + 1;
-    ctl->fixup_count = 0u;
-    ctl->blocks_done = 0u;
-  }
+  finalize_step<NOBS, LEAN, USES_CTBR>(P, S, O, ctl, n, lane);
+#endif
 }
+
+#if DDQC_ENV_FINALIZE != 0
+// Second launch of a step: one warp folds the statistics of the step kernel that has just completed
+// (the kernel boundary is the only ordering the stores, the REDs and the fix-up list need: the step
+// kernel itself has no barrier, no fence and no ticket, so a CTA's registers are released the moment
+// its last store is issued).
+template <int NOBS, bool LEAN, bool USES_CTBR>
+__global__ void __launch_bounds__(32, 1)
+env_finalize_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O, DdqcEnvCtl* __restrict__ ctl,
+                    const int n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  finalize_step<NOBS, LEAN, USES_CTBR>(P, S, O, ctl, n, (int)threadIdx.x);
+}
+#endif
 
 }  // namespace
 
@@ -563,12 +617,44 @@ extern "C" int ddqc_env_step(const DdqcEnvParams* P, const DdqcEnvState* S, cons
   const bool lean = !(P->flags & DDQC_F_NEED_EULER) && !(P->actuator_noise_std > 0.0f) && !(P->obs_noise_std > 0.0f) &&
                     !meas_override && !O->base_lin_vel && !O->base_ang_vel && !O->rel_pos && !O->last_rel_pos &&
                     !O->base_euler && !O->crash && !O->rpm && !O->last_base_pos;
+#if DDQC_ENV_FINALIZE == 2
+  cudaLaunchAttribute pdl_attr[1];
+  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+#endif
+  cudaError_t err = cudaSuccess;
+  auto launch = [&](auto kernel, dim3 g, dim3 b, auto... args) {
+    if (err != cudaSuccess) return;
+#if DDQC_ENV_FINALIZE == 2
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = g;
+    cfg.blockDim = b;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cfg.attrs = pdl_attr;
+    cfg.numAttrs = 1;
+    err = cudaLaunchKernelEx(&cfg, kernel, args...);
+#else
+    kernel<<<g, b, 0, st>>>(args...);
+    err = cudaGetLastError();
+#endif
+  };
+#if DDQC_ENV_FINALIZE == 0
+#define DDQC_FINALIZE(ACT, LEANV)
+#else
+#define DDQC_FINALIZE(ACT, LEANV)                                                                             \
+  launch(env_finalize_kernel<(ACT == DDQC_ACT_CTBR_FIXED_YAW ? 16 : 17), LEANV, (ACT != DDQC_ACT_ROTOR_RPMS)>, \
+         dim3(1), dim3(32), *P, *S, *O, ctl, n)
+#endif
 #define DDQC_LAUNCH(ACT)                                                                                      \
   do {                                                                                                        \
-    if (lean)                                                                                                 \
-      env_step_kernel<ACT, true><<<grid, block, 0, st>>>(*P, *S, *O, ctl, actions, meas_override, n);         \
-    else                                                                                                      \
-      env_step_kernel<ACT, false><<<grid, block, 0, st>>>(*P, *S, *O, ctl, actions, meas_override, n);        \
+    if (lean) {                                                                                               \
+      launch(env_step_kernel<ACT, true>, grid, block, *P, *S, *O, ctl, actions, meas_override, n);            \
+      DDQC_FINALIZE(ACT, true);                                                                               \
+    } else {                                                                                                  \
+      launch(env_step_kernel<ACT, false>, grid, block, *P, *S, *O, ctl, actions, meas_override, n);           \
+      DDQC_FINALIZE(ACT, false);                                                                              \
+    }                                                                                                         \
   } while (0)
   switch (P->action_type) {
     case DDQC_ACT_ROTOR_RPMS:
@@ -582,5 +668,6 @@ extern "C" int ddqc_env_step(const DdqcEnvParams* P, const DdqcEnvState* S, cons
       break;
   }
 #undef DDQC_LAUNCH
-  return (int)cudaGetLastError();
+#undef DDQC_FINALIZE
+  return (int)err;
 }

@@ -12,7 +12,7 @@ constexpr int kThreads = 256;
 
 // Shared tail of reset / restore launches: fold the per-copy accumulators into the
 // extras["episode"] ring (mean over the touched envs / episode_length_s, hover_env.py:583-589).
-__device__ void finalize_episode_stats(DdqcEnvCtl* ctl, float episode_length_s, bool bump_rng) {
+__device__ void finalize_episode_stats(DdqcEnvCtl* ctl, float episode_length_s, bool bump_rng, uint32_t ep_row) {
   float sums[DDQC_NUM_REWARDS];
   unsigned int cnt = 0;
   for (int k = 0; k < DDQC_NUM_REWARDS; ++k) sums[k] = 0.0f;
@@ -25,7 +25,7 @@ __device__ void finalize_episode_stats(DdqcEnvCtl* ctl, float episode_length_s, 
     cnt += __ldcg(&ctl->acc_reset[c]);
     ctl->acc_reset[c] = 0u;
   }
-  const uint32_t row = (ctl->ep_row + 1) % DDQC_EP_RING;
+  const uint32_t row = ep_row % DDQC_EP_RING;  // named by the host (DdqcEnvOut.ep_row)
   const uint32_t prev = ctl->ep_row;
   for (int k = 0; k < DDQC_NUM_REWARDS; ++k)
     ctl->ep_ring[row][k] = cnt ? (sums[k] / (float)cnt) / episode_length_s : ctl->ep_ring[prev][k];
@@ -89,7 +89,7 @@ reset_idx_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
     __threadfence();
-    finalize_episode_stats(ctl, P.episode_length_s, true);
+    finalize_episode_stats(ctl, P.episode_length_s, true, O.ep_row);
     // ctbr_controller.reset(): whole-batch PID zero (hover_env.py:592-593), applied lazily
     if (P.action_type != DDQC_ACT_ROTOR_RPMS && !(P.flags & DDQC_F_INDEPENDENT_ENVS)) ctl->pid_reset_pending = 1u;
   }
@@ -185,7 +185,7 @@ restore_state_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvO
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
     __threadfence();
-    finalize_episode_stats(ctl, P.episode_length_s, false);
+    finalize_episode_stats(ctl, P.episode_length_s, false, O.ep_row);
     ctl->pid_reset_pending = 0u;  // load_state() of the whole-batch PID follows on the host side
   }
 }

@@ -378,6 +378,13 @@ class HoverEnv:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def _next_episode_row(self) -> int:
+        """Row of the extras["episode"] ring the next launch writes (passed down as DdqcEnvOut.ep_row: the host, not
+        a device counter, names the row, so the views handed out here stay right under CUDA-graph replay)."""
+        row = (self._ep_row + 1) % _lib.EP_RING
+        self._out.ep_row = row
+        return row
+
     def _advance_episode_row(self) -> None:
         self._ep_row = (self._ep_row + 1) % _lib.EP_RING
         d = self._ep_dicts.get(self._ep_row)
@@ -389,7 +396,8 @@ class HoverEnv:
 
     def _flush_pid_reset(self) -> None:
         if self.uses_ctbr_actions:
-            rc = self._lib.ddqc_env_flush_pid_reset(C.byref(self._state), self._ctl.data_ptr(), self.num_envs, self._stream())
+            with _lib.device_guard(self.device):
+                rc = self._lib.ddqc_env_flush_pid_reset(C.byref(self._state), self._ctl.data_ptr(), self.num_envs, self._stream())
             _lib.check(rc, "ddqc_env_flush_pid_reset")
 
     def _ensure_body_vel(self) -> None:
@@ -398,9 +406,10 @@ class HoverEnv:
         if self._blv is None:
             self._blv = torch.empty((3, self.num_envs), dtype=torch.float32, device=self.device)
             self._bav = torch.empty((3, self.num_envs), dtype=torch.float32, device=self.device)
-        rc = self._lib.ddqc_env_body_vel(
-            C.byref(self._state), self.num_envs, self._blv.data_ptr(), self._bav.data_ptr(), self._stream()
-        )
+        with _lib.device_guard(self.device):
+            rc = self._lib.ddqc_env_body_vel(
+                C.byref(self._state), self.num_envs, self._blv.data_ptr(), self._bav.data_ptr(), self._stream()
+            )
         _lib.check(rc, "ddqc_env_body_vel")
         self._body_valid = True
 
@@ -499,10 +508,12 @@ class HoverEnv:
             self._ensure_body_vel()
             override = self._bav.data_ptr()
             self._meas_override_next = False
-        rc = self._lib.ddqc_env_step(
-            C.byref(self._params), C.byref(self._state), C.byref(self._out), self._ctl.data_ptr(),
-            a.data_ptr(), override, self.num_envs, self._stream(),
-        )  # fmt: skip
+        self._next_episode_row()
+        with _lib.device_guard(self.device):
+            rc = self._lib.ddqc_env_step(
+                C.byref(self._params), C.byref(self._state), C.byref(self._out), self._ctl.data_ptr(),
+                a.data_ptr(), override, self.num_envs, self._stream(),
+            )  # fmt: skip
         _lib.check(rc, "ddqc_env_step")
         self._body_valid = self._aux
         self.extras["time_outs"] = self._time_outs
@@ -514,10 +525,12 @@ class HoverEnv:
         if idx.numel() == 0:
             return
         cmd_old = self._commands.clone() if self._aux else None
-        rc = self._lib.ddqc_env_reset_idx(
-            C.byref(self._params), C.byref(self._state), C.byref(self._out), self._ctl.data_ptr(),
-            idx.data_ptr(), idx.numel(), self.num_envs, self._stream(),
-        )  # fmt: skip
+        self._next_episode_row()
+        with _lib.device_guard(self.device):
+            rc = self._lib.ddqc_env_reset_idx(
+                C.byref(self._params), C.byref(self._state), C.byref(self._out), self._ctl.data_ptr(),
+                idx.data_ptr(), idx.numel(), self.num_envs, self._stream(),
+            )  # fmt: skip
         _lib.check(rc, "ddqc_env_reset_idx")
         self._advance_episode_row()
         if self._aux:
@@ -560,9 +573,10 @@ class HoverEnv:
         broadcast = 1 if tgt.numel() == 3 else 0
         if not broadcast and tgt.shape != (idx.numel(), 3):
             raise ValueError("target_pos must have shape (len(envs_idx), 3) or (3,)")
-        rc = self._lib.ddqc_env_update_target(
-            C.byref(self._state), idx.data_ptr(), idx.numel(), self.num_envs, tgt.data_ptr(), broadcast, self._stream()
-        )
+        with _lib.device_guard(self.device):
+            rc = self._lib.ddqc_env_update_target(
+                C.byref(self._state), idx.data_ptr(), idx.numel(), self.num_envs, tgt.data_ptr(), broadcast, self._stream()
+            )
         _lib.check(rc, "ddqc_env_update_target")
 
     def get_current_state(self, envs_idx: torch.Tensor) -> EnvState:
@@ -577,13 +591,14 @@ class HoverEnv:
             ctbr_controller_state=self.ctbr_controller.get_state() if self.uses_ctbr_actions else None,
         )  # fmt: skip
         use_buf = self._body_valid and self._bav is not None
-        rc = self._lib.ddqc_env_get_state(
-            C.byref(self._params), C.byref(self._state), idx.data_ptr(), k, self.num_envs,
-            out.base_pos.data_ptr(), out.base_quat.data_ptr(), out.base_lin_vel.data_ptr(),
-            out.base_ang_vel.data_ptr(), out.commands.data_ptr(), out.episode_length.data_ptr(),
-            out.last_actions.data_ptr(), self._bav.data_ptr() if use_buf else None,
-            self._blv.data_ptr() if use_buf else None, self._stream(),
-        )  # fmt: skip
+        with _lib.device_guard(self.device):
+            rc = self._lib.ddqc_env_get_state(
+                C.byref(self._params), C.byref(self._state), idx.data_ptr(), k, self.num_envs,
+                out.base_pos.data_ptr(), out.base_quat.data_ptr(), out.base_lin_vel.data_ptr(),
+                out.base_ang_vel.data_ptr(), out.commands.data_ptr(), out.episode_length.data_ptr(),
+                out.last_actions.data_ptr(), self._bav.data_ptr() if use_buf else None,
+                self._blv.data_ptr() if use_buf else None, self._stream(),
+            )  # fmt: skip
         _lib.check(rc, "ddqc_env_get_state")
         return out
 
@@ -598,14 +613,18 @@ class HoverEnv:
         for t in (pos, quat, lin, ang, cmd, act):
             if t.shape[0] != k:
                 raise ValueError("saved_state does not match the number of env indices")
+        if k == 0:  # nothing is launched (and no ring row is consumed) for an empty index list
+            return
         # body-frame buffers must be valid for every env before the restored rows are patched in
         self._ensure_body_vel()
         out = self._make_out(force_body=True)
-        rc = self._lib.ddqc_env_restore_state(
-            C.byref(self._params), C.byref(self._state), C.byref(out), self._ctl.data_ptr(), idx.data_ptr(), k,
-            self.num_envs, pos.data_ptr(), quat.data_ptr(), lin.data_ptr(), ang.data_ptr(), cmd.data_ptr(),
-            ep.data_ptr(), act.data_ptr(), self._stream(),
-        )  # fmt: skip
+        out.ep_row = self._next_episode_row()
+        with _lib.device_guard(self.device):
+            rc = self._lib.ddqc_env_restore_state(
+                C.byref(self._params), C.byref(self._state), C.byref(out), self._ctl.data_ptr(), idx.data_ptr(), k,
+                self.num_envs, pos.data_ptr(), quat.data_ptr(), lin.data_ptr(), ang.data_ptr(), cmd.data_ptr(),
+                ep.data_ptr(), act.data_ptr(), self._stream(),
+            )  # fmt: skip
         _lib.check(rc, "ddqc_env_restore_state")
         self._advance_episode_row()
         self._meas_override_next = True  # next step measures the restored body rates (hover_env.py:729-735)

@@ -34,12 +34,11 @@ class FusedActorMLP:
             raise ValueError("inconsistent actor weight shapes")
         if (self.num_obs, self.hidden) != (16, 128) or not 1 <= self.num_actions <= 4:
             raise NotImplementedError("the fused kernel supports the shipped actor shape 16 -> 128 -> 128 -> A (A <= 4) only")
-        self._out: torch.Tensor | None = None
 
     @classmethod
     def from_checkpoint(cls, path: str, device="cuda", precision: str = "bf16x2") -> "FusedActorMLP":
         """rsl_rl checkpoint (`model_state_dict` with actor.{0,2,4}.{weight,bias}), e.g. models/demo_ctbr_fixed_yaw/model_1500.pt."""
-        sd = torch.load(path, map_location="cpu", weights_only=False)
+        sd = torch.load(path, map_location="cpu", weights_only=True)  # tensors only: no pickle code from a checkpoint
         return cls(sd.get("model_state_dict", sd), device, precision)
 
     @classmethod
@@ -50,21 +49,26 @@ class FusedActorMLP:
                                   torch.nn.Linear(128, num_actions))  # fmt: skip
         return cls({f"actor.{k}": v for k, v in net.state_dict().items()}, device, precision)
 
-    def act_inference(self, observations: torch.Tensor) -> torch.Tensor:
+    def act_inference(self, observations: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Actions for `observations` (N, 16).  Like the reference's `policy.act_inference`, every call returns a fresh
+        tensor; pass `out=` (float32, (N, A), contiguous, on this device) to reuse a buffer, e.g. inside a CUDA graph."""
         obs = observations
         if obs.dtype != torch.float32 or obs.device != self.device or not obs.is_contiguous():
             obs = obs.to(device=self.device, dtype=torch.float32).contiguous()
         if obs.ndim != 2 or obs.shape[1] != self.num_obs:
             raise ValueError(f"observations must have shape (N, {self.num_obs})")
         n = obs.shape[0]
-        if self._out is None or self._out.shape[0] != n:
-            self._out = torch.empty((n, self.num_actions), dtype=torch.float32, device=self.device)
-        rc = self._lib.ddqc_policy_mlp_forward(
-            obs.data_ptr(), n, self.num_obs, self.hidden, self.num_actions, self.W1.data_ptr(), self.b1.data_ptr(),
-            self.W2.data_ptr(), self.b2.data_ptr(), self.W3.data_ptr(), self.b3.data_ptr(), PRECISIONS[self.precision],
-            self._out.data_ptr(), _lib.stream_ptr(self.device),
-        )  # fmt: skip
+        if out is None:
+            out = torch.empty((n, self.num_actions), dtype=torch.float32, device=self.device)
+        elif out.shape != (n, self.num_actions) or out.dtype != torch.float32 or out.device != self.device or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous float32 tensor of shape {(n, self.num_actions)} on {self.device}")
+        with _lib.device_guard(self.device):
+            rc = self._lib.ddqc_policy_mlp_forward(
+                obs.data_ptr(), n, self.num_obs, self.hidden, self.num_actions, self.W1.data_ptr(), self.b1.data_ptr(),
+                self.W2.data_ptr(), self.b2.data_ptr(), self.W3.data_ptr(), self.b3.data_ptr(), PRECISIONS[self.precision],
+                out.data_ptr(), _lib.stream_ptr(self.device),
+            )  # fmt: skip
         _lib.check(rc, "ddqc_policy_mlp_forward")
-        return self._out
+        return out
 
     __call__ = act_inference

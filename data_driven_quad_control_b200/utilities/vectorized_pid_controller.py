@@ -75,11 +75,12 @@ class VectorizedPIDController:
             raise ValueError(f"setpoints / measurements must have shape {shape}")
         out = torch.empty(shape, dtype=torch.float32, device=self.device)
         integ, prev = self._state_ptrs()
-        rc = self._lib.ddqc_pid_compute(
-            sp.data_ptr(), sp.stride(0), sp.stride(1), ms.data_ptr(), ms.stride(0), ms.stride(1),
-            integ, prev, self._gains_host, self.dt, out.data_ptr(), self.num_envs, self.num_ctrls,
-            _lib.stream_ptr(self.device),
-        )  # fmt: skip
+        with _lib.device_guard(self.device):
+            rc = self._lib.ddqc_pid_compute(
+                sp.data_ptr(), sp.stride(0), sp.stride(1), ms.data_ptr(), ms.stride(0), ms.stride(1),
+                integ, prev, self._gains_host, self.dt, out.data_ptr(), self.num_envs, self.num_ctrls,
+                _lib.stream_ptr(self.device),
+            )  # fmt: skip
         _lib.check(rc, "ddqc_pid_compute")
         return out
 

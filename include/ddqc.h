@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DDQC_ABI_VERSION 1
+#define DDQC_ABI_VERSION 2
 
 #define DDQC_E_NULL (-1)    /* required pointer is NULL */
 #define DDQC_E_SHAPE (-2)   /* bad size / unsupported shape */
@@ -116,7 +116,7 @@ typedef struct DdqcEnvCtl {
   uint32_t pid_reset_pending;   /* A17: >=1 env reset in the previous launch -> whole-batch PID zero */
   uint32_t n_reset_last;
   uint32_t fixup_count;
-  uint32_t ep_row;              /* row of ep_ring holding the current extras["episode"] values */
+  uint32_t ep_row;              /* row of ep_ring written by the last launch (= its DdqcEnvOut.ep_row) */
   uint32_t pad0;
   uint32_t acc_reset[DDQC_STAT_COPIES];
   uint32_t acc_timeout[DDQC_STAT_COPIES];
@@ -157,6 +157,13 @@ typedef struct DdqcEnvOut {
   /* strict-reference fix-up list (A15/A16), capacity n */
   int32_t* fixup_idx;     /* [n] */
   float* fixup_val;       /* [n][8]: rew, sum_target, sum_closeness, obs0..2, rel(aux) unused */
+  /* Row of ctl->ep_ring that receives this launch's extras["episode"] values (hover_env.py:583-589), taken modulo
+   * DDQC_EP_RING.  The HOST names the row (step / reset_idx / restore_state each use the next one), so the host's
+   * views of the ring can never drift from the device: a replayed CUDA graph rewrites exactly the rows whose views
+   * were handed out during capture.  "No reset in this launch" copies the values of ctl->ep_row, the row the
+   * previous launch wrote (the reference leaves the previous dict in place). */
+  uint32_t ep_row;
+  uint32_t pad0;
 } DdqcEnvOut;
 
 /* ---------------------------------------------------------------------------------

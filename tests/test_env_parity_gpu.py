@@ -310,3 +310,94 @@ def test_configs0_hover_to_target_500_steps(build_lib, at_name):
         assert not orc.reset_buf.any() and not env.reset_buf.any()
     assert worst < 1e-4, worst
     assert np.abs(env.base_pos.cpu().numpy() - np.array([[0.0, 0.0, 1.5]])).max() < 5e-3  # it got there
+
+
+def test_extras_episode_under_graph_replay(build_lib):
+    """the extras["episode"] views must stay right when step() is replayed from a CUDA graph (the host
+    names the ring row of every launch, DdqcEnvOut.ep_row, so nothing can drift).  A captured 8-step graph replayed
+    3 times must leave every captured step's dict equal to what eager stepping produces for that step."""
+    N, K, R = 256, 8, 3
+    acts_np = _actions(K * (R + 1), N, 3, 11)
+    acts = torch.from_numpy(acts_np).cuda()
+
+    def fresh():
+        env, _ = _make_pair(N, "CTBR_FIXED_YAW", True, materialize=False)
+        env.reset()
+        return env
+
+    # eager reference: dict values of every step
+    env_e = fresh()
+    eager = []
+    for t in range(K * (R + 1)):
+        env_e.step(acts[t])
+        eager.append({k: float(v) for k, v in env_e.extras["episode"].items()})
+    pos_eager = env_e.base_pos.clone()
+
+    env_g = fresh()
+    static_a = torch.zeros((K, N, 3), device="cuda")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    dicts = []
+    with torch.cuda.stream(s):
+        static_a.copy_(acts[:K])
+        for t in range(K):  # warm-up = the first K steps, eagerly
+            env_g.step(static_a[t])
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for t in range(K):
+                env_g.step(static_a[t])
+                dicts.append(env_g.extras["episode"])  # views handed out during capture
+        for r in range(R):
+            static_a.copy_(acts[K * (r + 1) : K * (r + 2)])
+            g.replay()
+            s.synchronize()
+            for t in range(K):
+                want = eager[K * (r + 1) + t]
+                got = {k: float(v) for k, v in dicts[t].items()}
+                assert got == want, (r, t, got, want)
+    torch.cuda.synchronize()
+    assert torch.equal(env_g.base_pos, pos_eager)
+    # eager stepping after the replays continues on fresh rows and persists the last values when nobody resets
+    env_g.step(torch.zeros((N, 3), device="cuda"))
+    assert set(env_g.extras["episode"]) == set(eager[-1])
+
+
+def test_restore_with_empty_index_consumes_no_ring_row(build_lib):
+    env, _ = _make_pair(32, "CTBR_FIXED_YAW", True)
+    env.reset()
+    for _ in range(3):
+        env.step(torch.zeros((32, 3), device="cuda"))
+    st = env.get_current_state(torch.arange(0, device="cuda"))
+    row = env._ep_row
+    env.restore_from_state(torch.arange(0, device="cuda"), st)
+    assert env._ep_row == row
+    env.step(torch.zeros((32, 3), device="cuda"))
+    raw = env._ctl.cpu().numpy().tobytes()
+    from data_driven_quad_control_b200 import _lib
+
+    assert _lib.EnvCtl.from_buffer_copy(raw).ep_row == env._ep_row  # host and device agree on the current row
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_env_on_a_non_current_device(build_lib):
+    """objects built on cuda:1 while cuda:0 is current launch on their own device."""
+    from data_driven_quad_control_b200.learning.policy import FusedActorMLP
+
+    assert torch.cuda.current_device() == 0
+    env1, orc = _make_pair(64, "CTBR_FIXED_YAW", True)
+    env_cfg, obs_cfg, rew_cfg, cmd_cfg, at = default_cfgs("CTBR_FIXED_YAW")
+    from data_driven_quad_control_b200.envs.hover_env import HoverEnv
+
+    env = HoverEnv(64, env_cfg, obs_cfg, rew_cfg, cmd_cfg, device="cuda:1", action_type=at, seed=5, materialize_buffers=True)
+    acts = _actions(20, 64, 3, 4)
+    env.reset()
+    orc.reset()
+    for t in range(20):
+        env.step(torch.from_numpy(acts[t]).to("cuda:1"))
+        orc.step(acts[t])
+        assert np.array_equal(env.obs_buf.cpu().numpy(), orc.obs_buf)
+    pol = FusedActorMLP.random_init(device="cuda:1")
+    a1 = pol.act_inference(env.obs_buf)
+    a0 = FusedActorMLP.random_init(device="cuda:0").act_inference(env.obs_buf.to("cuda:0"))
+    assert torch.equal(a1.cpu(), a0.cpu())
+    assert torch.cuda.current_device() == 0

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(build_lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported by libddqc.so"
     loaded = _lib.load()  # also checks the ctypes struct sizes against ddqc_struct_size()
-    assert loaded.ddqc_abi_version() == 1
+    assert loaded.ddqc_abi_version() == _lib.ABI_VERSION == int(re.search(r"#define DDQC_ABI_VERSION (\d+)", header).group(1))
     assert loaded.ddqc_struct_size(99) == -1
 
 
