@@ -35,8 +35,8 @@ ENV_BYTES_PER_STEP = {3: 357, 4: 373}  # algorithmic HBM bytes p
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--no-ddmpc", action="store_true", help="skip the DD-MPC leg")
@@ -46,7 +46,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every timed env step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--small", action="store_true", help="also time configs[1] (4096 envs, CUDA-graph replay)")
+    ap.add_argument("--no-small", action="store_true", help="skip configs[1] (4096 envs) and configs[0] (single drone)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (2**20 envs in total)")
+    ap.add_argument("--no-grid", action="store_true", help="skip configs[4] (900-combination grid search + 3-way comparison)")
     return ap.parse_args()
 
 
@@ -143,6 +145,96 @@ def load_peaks() -> tuple[float, str]:
     return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel_tag: str) -> tuple[float | None, str | None]:
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the newest committed ncu summary of a kernel:
+    profiles/r<round><tag>_<kernel_tag>_ncu_full.csv, written by tools/ncu_summary.py from one `ncu --set full` capture."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{kernel_tag}_ncu_full.csv")))
+    if not files:
+        return None, None
+    total, scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    with open(files[-1]) as fh:
+        for line in fh:
+            parts = line.strip().split(",")
+            if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(parts[2]) * scale.get(parts[1], 1.0)
+    return (total or None), os.path.relpath(files[-1], ROOT)
+
+
+class Timer:
+    """Times regions of EXACTLY K steps, each bracketed by barrier + torch.cuda.synchronize() on both sides and by CUDA
+    events on the launching stream; a region's time is the MAX over ranks.  A region is repeated until at least
+    `min_total_s` seconds have been timed (>= 5 regions) and the MEDIAN region is reported, so that one rank's hiccup
+    inside a 1.5 ms region cannot decide the figure (round 1's 4-GPU line).  Inside a region the steps are replays of a
+    CUDA graph of G = min(K, 32) consecutive steps plus K % G eager launches (`--no-graph`: all eager)."""
+
+    def __init__(self, dev, world, use_graph: bool, min_total_s: float = 0.25, max_regions: int = 300):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.dev, self.world = torch, dist, dev, world
+        self.use_graph, self.min_total_s, self.max_regions = use_graph, min_total_s, max_regions
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, step_fn, K: int) -> dict:
+        torch = self.torch
+        G = min(K, 32) if self.use_graph else 0
+        graph = None
+        if G:
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    for t in range(G):
+                        step_fn(t)
+            torch.cuda.current_stream().wait_stream(side)
+        n_rep, rem = (K // G, K % G) if G else (0, K)
+
+        def region():
+            self.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n_rep):
+                graph.replay()
+            for t in range(rem):
+                step_fn(n_rep * G + t)
+            e1.record()
+            self.barrier()
+            return e0.elapsed_time(e1)
+
+        region()  # one untimed region (graph upload, caches)
+        first = region()
+        n_regions = int(min(self.max_regions, max(5, self.min_total_s * 1e3 / max(first, 1e-3) + 1)))
+        if self.world > 1:  # every rank must run the same number of regions
+            nr = torch.tensor([n_regions], device=self.dev)
+            self.dist.all_reduce(nr, op=self.dist.ReduceOp.MAX)
+            n_regions = int(nr.item())
+        local = torch.tensor([first] + [region() for _ in range(n_regions - 1)], device=self.dev, dtype=torch.float64)
+        worst = local.clone()
+        rank_medians = [float(local.median())]
+        if self.world > 1:
+            self.dist.all_reduce(worst, op=self.dist.ReduceOp.MAX)
+            gathered = [torch.zeros(1, device=self.dev, dtype=torch.float64) for _ in range(self.world)]
+            self.dist.all_gather(gathered, local.median().reshape(1))
+            rank_medians = [float(g) for g in gathered]
+        w = worst.sort().values
+        return {
+            "region_ms": float(w[len(w) // 2]), "region_ms_min": float(w[0]), "region_ms_max": float(w[-1]),
+            "regions": n_regions, "steps_per_region": K, "graph_steps": G, "eager_steps_per_region": rem,
+            "local_region_ms": float(local.median()), "rank_median_region_ms": rank_medians,
+        }  # fmt: skip
+
+
+TIMING_NOTE = ("regions of exactly --steps steps, barrier + synchronize on both sides, CUDA events on the launching stream, MAX over "
+               "ranks per region; the median of >= 5 regions (>= 0.25 s timed in total) is reported, min / max beside it")  # fmt: skip
+
+
 def run_b200(args) -> dict:
     import torch
     import torch.distributed as dist
@@ -157,6 +249,7 @@ def run_b200(args) -> dict:
     affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else "not bound (single rank)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    timer = Timer(dev, world, use_graph=not args.no_graph)
 
     N, K, W = args.envs_per_gpu, args.steps, args.warmup
     env = make_env(N, dev, seed=1234 + rank)
@@ -166,134 +259,20 @@ def run_b200(args) -> dict:
     gen = torch.Generator(device=dev).manual_seed(rank)
     actions = torch.rand((n_act, N, A), generator=gen, device=dev) * 2.0 - 1.0
     env.reset()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for t in range(W):
+    for t in range(max(W, 3)):
         env.step(actions[t % n_act])
     sampler = ClockSampler(local_rank)
-    barrier()
+    timer.barrier()
     if rank == 0:
         sampler.start()
-    # The timed region replays a CUDA graph of G = 16 consecutive `HoverEnv.step` calls (the step has no host
-    # synchronisation, so it captures as is); K % G trailing steps are launched eagerly.  Events bracket every
-    # replay, i.e. every G steps: per-step events cost 2.7 us each, a third of the launch gap they would measure.
-    G = 16 if (K >= 16 and not args.no_graph) else 0
-    graph = None
-    if G:
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                for t in range(G):
-                    env.step(actions[t % n_act])
-        torch.cuda.current_stream().wait_stream(side)
-        graph.replay()  # one untimed replay (counts as warm-up steps)
-        barrier()
-    n_rep = K // G if G else 0
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_rep + 2)]
-    ev[0].record()
-    for r in range(n_rep):
-        graph.replay()
-        ev[r + 1].record()
-    for t in range(n_rep * G if G else 0, K):
-        env.step(actions[t % n_act])
-    ev[n_rep + 1].record()
-    barrier()
+    head = timer.run(lambda t: env.step(actions[t % n_act]), K)
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = ev[0].elapsed_time(ev[n_rep + 1])
-    per_launch_ms = sorted(ev[r].elapsed_time(ev[r + 1]) / G for r in range(n_rep)) or [total_ms / K]
-    t_max = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t_max.item())
+    region_ms = head["region_ms"]
 
-    # ---- end-to-end: host buffers, H2D actions + D2H (obs, rew, reset) inside the timed region
+    # ---- end-to-end: host buffers, H2D actions + D2H (obs, rew, time_outs, reset) inside the timed region
     e2e = None
     if not args.no_e2e:
-        Ke = max(4, min(K, 20))
-        h_act = [torch.empty((N, A), dtype=torch.float32).pin_memory() for _ in range(2)]
-        for h in h_act:
-            h.uniform_(-1, 1)
-        d_act = [torch.empty((N, A), dtype=torch.float32, device=dev) for _ in range(2)]
-        h_obs = torch.empty((N, env.num_obs), dtype=torch.float32).pin_memory()
-        h_rew = torch.empty((N,), dtype=torch.float32).pin_memory()
-        h_rst = torch.empty((N,), dtype=torch.bool).pin_memory()
-        barrier()
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        for it in range(-2, Ke):
-            if it == 0:
-                barrier()
-                t0.record()
-            d_act[it % 2].copy_(h_act[it % 2], non_blocking=True)
-            obs, rew, rst, _ = env.step(d_act[it % 2])
-            h_obs.copy_(obs, non_blocking=True)
-            h_rew.copy_(rew, non_blocking=True)
-            h_rst.copy_(rst, non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the caller reads the results of every step
-        t1.record()
-        barrier()
-        e_ms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-        e2e = {
-            "value": N * world * Ke / (float(e_ms.item()) * 1e-3),
-            "unit": "env-steps/s",
-            "h2d_bytes_per_step": N * A * 4,
-            "d2h_bytes_per_step": N * (env.num_obs * 4 + 4 + 1),
-            "steps": Ke,
-            "mode": "synchronous: the results of step k are on the host before the actions of step k+1 are sent",
-        }
-        # streaming variant of the same loop (extra information, not the headline): outputs are staged on the device
-        # and drained by a copy stream while the next step's actions are uploaded and its kernel runs; the host waits
-        # for the results of step k-1 before it launches step k+1
-        copy_s, up_s = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        main_s = torch.cuda.current_stream()
-        stage = [(torch.empty((N, env.num_obs), device=dev), torch.empty((N,), device=dev), torch.empty((N,), dtype=torch.bool, device=dev)) for _ in range(2)]
-        h_out = [(torch.empty((N, env.num_obs)).pin_memory(), torch.empty((N,)).pin_memory(), torch.empty((N,), dtype=torch.bool).pin_memory()) for _ in range(2)]
-        ev_up = [torch.cuda.Event() for _ in range(2)]
-        ev_stage = [torch.cuda.Event() for _ in range(2)]
-        ev_down = [torch.cuda.Event() for _ in range(2)]
-        ev_used = [torch.cuda.Event() for _ in range(2)]
-        for e in ev_used + ev_down:
-            e.record(main_s)
-        barrier()
-        for it in range(-2, Ke):
-            if it == 0:
-                barrier()
-                t0.record()
-            b = it % 2
-            with torch.cuda.stream(up_s):
-                up_s.wait_event(ev_used[b])  # the kernel that last read d_act[b] is done
-                d_act[b].copy_(h_act[b], non_blocking=True)
-                ev_up[b].record(up_s)
-            main_s.wait_event(ev_up[b])
-            obs, rew, rst, _ = env.step(d_act[b])
-            ev_used[b].record(main_s)
-            main_s.wait_event(ev_down[b])  # the staging buffers of parity b have been drained
-            stage[b][0].copy_(obs)
-            stage[b][1].copy_(rew)
-            stage[b][2].copy_(rst)
-            ev_stage[b].record(main_s)
-            with torch.cuda.stream(copy_s):
-                copy_s.wait_event(ev_stage[b])
-                for hbuf, dbuf in zip(h_out[b], stage[b]):
-                    hbuf.copy_(dbuf, non_blocking=True)
-                ev_down[b].record(copy_s)
-            ev_down[1 - b].synchronize()  # results of the previous step are on the host
-        ev_down[(Ke - 1) % 2].synchronize()
-        t1.record()
-        barrier()
-        p_ms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(p_ms, op=dist.ReduceOp.MAX)
-        e2e["streaming_value"] = N * world * Ke / (float(p_ms.item()) * 1e-3)
-        e2e["streaming_mode"] = "double-buffered: D2H of step k overlaps H2D + kernel of step k+1 (one step of result latency)"
+        e2e = run_e2e_leg(env, dev, N, A, K, world, timer)
 
     # ---- final all-reduce of rollout statistics (the only collective of the path)
     from data_driven_quad_control_b200.parallel import allreduce_rollout_stats
@@ -301,17 +280,17 @@ def run_b200(args) -> dict:
     stats = allreduce_rollout_stats(env.rollout_stats())
 
     peak, peak_src = load_peaks()
-    med_ms = per_launch_ms[len(per_launch_ms) // 2]
-    avg_ms = total_ms / K
+    avg_ms = head["local_region_ms"] / K  # this rank's kernel time per step (rank 0 prints)
     achieved = ENV_BYTES_PER_STEP[A] * N / (avg_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic("env_step")
     line = {
         "metric": "env-steps/s",
-        "value": N * world * K / (total_ms_max * 1e-3),
+        "value": N * world * K / (region_ms * 1e-3),
         "unit": "env-steps/s",
         "n_gpus": world,
         "steps": K,
-        "warmup": W,
-        "ms_per_step": total_ms_max / K,
+        "warmup": max(W, 3),
+        "ms_per_step": region_ms / K,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
@@ -325,16 +304,20 @@ def run_b200(args) -> dict:
             "num_obs": env.num_obs,
             "decimation": env.decimation,
             "l2_policy": "working set 374 MB per step > 126 MB L2 (no flush needed)",
-            "launch": "CUDA graph of 16 HoverEnv.step calls replayed" if G else "eager, one launch per step",
+            "launch": f"CUDA graph of {head['graph_steps']} HoverEnv.step calls replayed (+ {head['eager_steps_per_region']} eager)"
+            if head["graph_steps"] else "eager, two launches per step",
+            "timing": TIMING_NOTE,
             "parallelism": f"envs sharded by index over {world} rank(s); one all-reduce of rollout statistics at the end",
             "cpu_affinity": affinity,
         },
+        "timing": head,
         "clocks": clocks,
         "e2e": e2e,
-        "gpu_launches": K,
+        # kernels launched inside ONE timed region of the headline: step kernel + finalisation kernel per step
+        "gpu_launches": 2 * K,
         "roofline": {
             "bound": "hbm",
-            "kernel": "env_step_kernel<CTBR_FIXED_YAW>",
+            "kernel": "env_step_kernel<CTBR_FIXED_YAW, lean, split finalisation>",
             "achieved": achieved,
             "peak": peak,
             "peak_source": peak_src,
@@ -342,27 +325,28 @@ def run_b200(args) -> dict:
             "frac": achieved / peak,
             "bytes_per_env_step": ENV_BYTES_PER_STEP[A],
             "avg_launch_ms": avg_ms,
-            "median_launch_ms": med_ms,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2**20 envs (130.1 + 163.5 MB), from
-            # profiles/r1h_env_step_ncu_full.csv; below the algorithmic 374 MB because part of the written state is
-            # still in L2 at kernel end and is re-read from there by the next launch
-            "traffic": 293.6e6 * (N / float(1 << 20)) if N == 1 << 20 else None,
-            "traffic_source": "profiles/r1h_env_step_ncu_full.csv",
+            "avg_launch_ms_note": "per step of the timed region = step kernel + its one-warp finalisation kernel + the gaps between them",
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2**20 envs, read from the committed ncu summary;
+            # below the algorithmic 374 MB because the rate-PID state is not re-read on steps after a reset (always, at
+            # this size) and part of the written state is still in L2 at kernel end
+            "traffic": traffic * (N / float(1 << 20)) if traffic and N == 1 << 20 else None,
+            "traffic_source": traffic_src,
         },
         "rollout_stats": stats,
     }
     if not args.no_policy:
-        leg = run_policy_leg(env, dev, N, steps=100, warm=10)
-        v = torch.tensor([leg["value"], leg["policy_forward_env_per_s"]], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(v)
-        leg["value"], leg["policy_forward_env_per_s"] = float(v[0]), float(v[1])
-        leg["n_gpus"] = world
+        leg = run_policy_leg(env, dev, N, K, timer, world)
         line["policy_rollout"] = leg
-        line["gpu_launches"] += leg["gpu_launches"]
+        line["gpu_launches_policy_rollout"] = leg["gpu_launches"]
+    del actions
+    if not args.no_strong:
+        line["strong_scaling"] = run_strong_leg(dev, rank, world, K, timer, line, with_policy=not args.no_policy)
+    if not args.no_small:
+        line["small_batch"] = run_small_leg(dev, rank, world, timer)
+        line["single_drone"] = run_single_drone_leg(dev)
+    del env
+    torch.cuda.empty_cache()
     if not args.no_ddmpc:
-        del env, actions
-        torch.cuda.empty_cache()
         leg = run_ddmpc_leg(dev, args.ddmpc_batch, args.ddmpc_steps)
         # controllers are sharded by index like the envs: aggregate solves/s is the sum over ranks
         v = torch.tensor([leg["value"], leg["closed_loop_solves_per_s"], leg["e2e"]["value"], leg["cold_start"]["value"]],
@@ -373,39 +357,127 @@ def run_b200(args) -> dict:
         leg["e2e"]["value"], leg["cold_start"]["value"] = float(v[2]), float(v[3])
         leg["n_gpus"] = world
         line["ddmpc"] = leg
-        line["gpu_launches"] += leg["gpu_launches"]
+        line["gpu_launches_ddmpc"] = leg["gpu_launches"]
+    if not args.no_grid:
+        line["grid_search"] = run_grid_leg(dev, rank, world, timer)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return line if rank == 0 else {}
 
 
+def run_e2e_leg(env, dev, N, A, K, world, timer) -> dict:
+    """The same metric through the public API with HOST buffers: every step uploads its actions from pinned memory and
+    downloads the step's results (`env.output_block`: obs | rew | time_outs | reset in one allocation, one copy)."""
+    import torch
+    import torch.distributed as dist
+
+    Ke = max(4, min(K, 20))
+    h_act = [torch.empty((N, A), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for h in h_act:
+        h.uniform_(-1, 1)
+    d_act = [torch.empty((N, A), dtype=torch.float32, device=dev) for _ in range(2)]
+    nbytes = env.output_block.numel()
+    h_out = [torch.empty((nbytes,), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def vmax(ms):
+        v = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
+
+    sync_ms = []
+    for _ in range(3):
+        timer.barrier()
+        for it in range(-2, Ke):
+            if it == 0:
+                timer.barrier()
+                t0.record()
+            d_act[it % 2].copy_(h_act[it % 2], non_blocking=True)
+            env.step(d_act[it % 2])
+            h_out[0].copy_(env.output_block, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller reads the results of every step
+        t1.record()
+        timer.barrier()
+        sync_ms.append(vmax(t0.elapsed_time(t1)))
+    e_ms = sorted(sync_ms)[1]
+    e2e = {
+        "value": N * world * Ke / (e_ms * 1e-3),
+        "unit": "env-steps/s",
+        "h2d_bytes_per_step": N * A * 4,
+        "d2h_bytes_per_step": nbytes,
+        "steps": Ke,
+        "repeats": 3,
+        "mode": "synchronous: the results of step k (one D2H copy of env.output_block) are on the host before the actions of "
+        "step k+1 are sent; median of 3 timed regions, max over ranks",
+    }
+    # streaming variant of the same loop (extra information, not the headline): outputs are staged on the device and
+    # drained by a copy stream while the next step's actions are uploaded and its kernel runs; the host waits for the
+    # results of step k-1 before it launches step k+1
+    copy_s, up_s = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    main_s = torch.cuda.current_stream()
+    stage = [torch.empty((nbytes,), dtype=torch.uint8, device=dev) for _ in range(2)]
+    ev_up = [torch.cuda.Event() for _ in range(2)]
+    ev_stage = [torch.cuda.Event() for _ in range(2)]
+    ev_down = [torch.cuda.Event() for _ in range(2)]
+    ev_used = [torch.cuda.Event() for _ in range(2)]
+    for e in ev_used + ev_down:
+        e.record(main_s)
+    timer.barrier()
+    for it in range(-2, Ke):
+        if it == 0:
+            timer.barrier()
+            t0.record()
+        b = it % 2
+        with torch.cuda.stream(up_s):
+            up_s.wait_event(ev_used[b])  # the kernel that last read d_act[b] is done
+            d_act[b].copy_(h_act[b], non_blocking=True)
+            ev_up[b].record(up_s)
+        main_s.wait_event(ev_up[b])
+        env.step(d_act[b])
+        ev_used[b].record(main_s)
+        main_s.wait_event(ev_down[b])  # the staging buffer of parity b has been drained
+        stage[b].copy_(env.output_block)
+        ev_stage[b].record(main_s)
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(ev_stage[b])
+            h_out[b].copy_(stage[b], non_blocking=True)
+            ev_down[b].record(copy_s)
+        ev_down[1 - b].synchronize()  # results of the previous step are on the host
+    ev_down[(Ke - 1) % 2].synchronize()
+    t1.record()
+    timer.barrier()
+    e2e["streaming_value"] = N * world * Ke / (vmax(t0.elapsed_time(t1)) * 1e-3)
+    e2e["streaming_mode"] = "double-buffered: D2H of step k overlaps H2D + kernel of step k+1 (one step of result latency)"
+    e2e["note"] = ("the reference's API exchanges DEVICE tensors (HoverEnv.step takes and returns torch tensors on the simulator's "
+                   "device); this host-buffer figure is PCIe-bound by construction and saturates the box's host memory system "
+                   "from 2 GPUs on")  # fmt: skip
+    return e2e
+
+
 # ------------------------------------------------------------------------------------------
 # policy-rollout leg (BASELINE configs[2]): random-init demo_ctbr_fixed_yaw-sized actor drives the env
 # ------------------------------------------------------------------------------------------
-def run_policy_leg(env, dev, N: int, steps: int = 100, warm: int = 10) -> dict:
+def policy_rollout_times(env, dev, K: int, timer, pol=None) -> tuple[dict, dict, object]:
+    """(rollout timing, policy-forward-only timing, policy): obs -> actor MLP -> env.step with static buffers."""
     import torch
 
     from data_driven_quad_control_b200.learning.policy import FusedActorMLP
 
-    pol = FusedActorMLP.random_init(num_actions=env.num_actions, seed=0, device=dev, precision="bf16x2")
-    obs, _ = env.get_observations()
-    for _ in range(warm):
-        obs, *_ = env.step(pol.act_inference(obs))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(steps):
-        obs, *_ = env.step(pol.act_inference(obs))
-    e1.record()
-    torch.cuda.synchronize()
-    ms_roll = e0.elapsed_time(e1) / steps
-    e0.record()
-    for _ in range(steps):
-        pol.act_inference(obs)
-    e1.record()
-    torch.cuda.synchronize()
-    ms_pol = e0.elapsed_time(e1) / steps
+    if pol is None:
+        pol = FusedActorMLP.random_init(num_actions=env.num_actions, seed=0, device=dev, precision="bf16x2")
+    act = torch.empty((env.num_envs, env.num_actions), dtype=torch.float32, device=dev)
+    for _ in range(5):
+        env.step(pol.act_inference(env.obs_buf, out=act))
+    roll = timer.run(lambda t: env.step(pol.act_inference(env.obs_buf, out=act)), K)
+    fwd = timer.run(lambda t: pol.act_inference(env.obs_buf, out=act), K)
+    return roll, fwd, pol
+
+
+def run_policy_leg(env, dev, N: int, K: int, timer, world: int) -> dict:
+    roll, fwd, _ = policy_rollout_times(env, dev, K, timer)
+    ms_roll, ms_pol = roll["region_ms"] / K, fwd["local_region_ms"] / K
     # tensor-core work of the kernel as executed: three bf16 products per layer-1/2 contraction
     flops_tc = N * 3 * 2.0 * (16 * 128 + 128 * 128)
     flops_alg = N * 2.0 * (16 * 128 + 128 * 128 + 128 * env.num_actions)
@@ -414,26 +486,211 @@ def run_policy_leg(env, dev, N: int, steps: int = 100, warm: int = 10) -> dict:
     if os.path.exists(path):
         with open(path) as fh:
             peak = float(json.load(fh).get("bf16_tflops_sustained", peak))
+    traffic, traffic_src = ncu_traffic("policy_mlp")
     return {
         "metric": "env-steps/s including the policy forward (obs -> actor MLP -> env.step, all on the device)",
-        "value": N / (ms_roll * 1e-3),
+        "value": N * world / (ms_roll * 1e-3),
         "unit": "env-steps/s",
+        "n_gpus": world,
         "envs_per_gpu": N,
-        "steps": steps,
+        "steps": K,
         "ms_per_step": ms_roll,
+        "timing": roll,
         "policy": "random-init actor 16-128-128-%d, tanh (shape of models/demo_ctbr_fixed_yaw/model_1500.pt), torch.manual_seed(0)" % env.num_actions,
         "policy_precision": "bf16 hi/lo split products on tcgen05, fp32 accumulation in TMEM (actions within 1e-4 of fp32)",
         "policy_forward_ms": ms_pol,
-        "policy_forward_env_per_s": N / (ms_pol * 1e-3),
+        "policy_forward_env_per_s": N * world / (fwd["region_ms"] / K * 1e-3),
         "roofline": {
             "bound": "tensor", "kernel": "policy_mlp_kernel<split>", "achieved": flops_tc / (ms_pol * 1e-3) / 1e12,
             "peak": peak, "unit": "TFLOP/s", "frac": flops_tc / (ms_pol * 1e-3) / 1e12 / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained",
+            "executed_vs_algorithmic": "achieved / frac count the three bf16 products per contraction the split executes",
             "algorithmic_tflops": flops_alg / (ms_pol * 1e-3) / 1e12,
-            "traffic": 69.1e6 if N == 1 << 20 else None, "traffic_source": "profiles/r1h_policy_mlp_ncu_full.csv (67.2 MB read = the obs tile, 1.9 MB written)",
+            "algorithmic_frac": flops_alg / (ms_pol * 1e-3) / 1e12 / peak,
+            "traffic": traffic if N == 1 << 20 else None, "traffic_source": traffic_src,
         },
-        "gpu_launches": 3 * steps,
+        # one timed region: policy kernel + env step kernel + env finalisation kernel per step
+        "gpu_launches": 3 * K,
     }
+
+
+def run_strong_leg(dev, rank: int, world: int, K: int, timer, line: dict, with_policy: bool) -> dict:
+    """BASELINE configs[2] as stated: 2**20 envs IN TOTAL, sharded by index over the ranks (strong scaling)."""
+    import torch
+
+    total = 1 << 20
+    n = total // world
+    out = {"metric": "env-steps/s, 2**20 envs in total over all ranks", "scaling": "strong", "total_envs": total,
+           "envs_per_gpu": n, "n_gpus": world, "steps": K, "timing_note": TIMING_NOTE}  # fmt: skip
+    ws_mb = n * 357 / 1e6
+    out["l2_policy"] = (f"working set {ws_mb:.0f} MB per step and GPU: " + ("larger than the 126 MB L2, streams from HBM" if ws_mb > 126 else
+                        "stays in the 126 MB L2 from step to step, which is the steady state of a rollout at this size (no flush: "
+                        "flushing would measure something a rollout never sees); the step is launch- and latency-bound here"))  # fmt: skip
+    if world == 1:
+        out["value"] = line["value"]
+        out["ms_per_step"] = line["ms_per_step"]
+        out["note"] = "at 1 GPU this is the headline workload (2**20 envs on one GPU)"
+        if with_policy:
+            out["with_policy"] = {"value": line["policy_rollout"]["value"], "ms_per_step": line["policy_rollout"]["ms_per_step"]}
+        return out
+    env = make_env(n, dev, seed=4321 + rank)
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    actions = torch.rand((16, n, env.num_actions), generator=gen, device=dev) * 2.0 - 1.0
+    env.reset()
+    for t in range(5):
+        env.step(actions[t])
+    t_env = timer.run(lambda t: env.step(actions[t % 16]), K)
+    out["value"] = total * K / (t_env["region_ms"] * 1e-3)
+    out["ms_per_step"] = t_env["region_ms"] / K
+    out["timing"] = t_env
+    if with_policy:
+        roll, fwd, _ = policy_rollout_times(env, dev, K, timer)
+        out["with_policy"] = {"value": total * K / (roll["region_ms"] * 1e-3), "ms_per_step": roll["region_ms"] / K,
+                              "policy_forward_ms": fwd["region_ms"] / K, "timing": roll}  # fmt: skip
+    return out
+
+
+def run_small_leg(dev, rank: int, world: int, timer) -> dict:
+    """BASELINE configs[1]: 4096 envs, random-action rollout of T = 1000 steps on one GPU (every rank runs its own
+    replica; the figure is per GPU).  Reported both as a user calls it (eager: two launches per step from Python) and
+    as CUDA-graph replays."""
+    import torch
+
+    n, T = 4096, 1000
+    env = make_env(n, dev, seed=99 + rank)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    actions = torch.rand((T, n, env.num_actions), generator=gen, device=dev) * 2.0 - 1.0  # SURVEY 8d: (T=1000, 4096, 3), seed 0
+    env.reset()
+    for t in range(10):
+        env.step(actions[t])
+    eager = Timer(dev, world, use_graph=False, min_total_s=0.1)
+    t_e = eager.run(lambda t: env.step(actions[t]), T)
+    t_g = timer.run(lambda t: env.step(actions[t % T]), T)
+    return {
+        "metric": "env-steps/s per GPU, BASELINE configs[1] (4096 envs, T = 1000 random-action steps)", "envs": n, "steps": T,
+        "eager": {"value": n * T / (t_e["local_region_ms"] * 1e-3), "us_per_step": t_e["local_region_ms"] / T * 1e3,
+                  "bound": "host launch overhead (Python + 1 fused kernel launch per step at this size)"},
+        "graph": {"value": n * T / (t_g["local_region_ms"] * 1e-3), "us_per_step": t_g["local_region_ms"] / T * 1e3,
+                  "bound": "launch latency of the device (one wave of 32 CTAs)"},
+        "l2_policy": "working set 1.5 MB: L2-resident by nature (no flush), latency-bound",
+    }  # fmt: skip
+
+
+def run_single_drone_leg(dev) -> dict:
+    """BASELINE configs[0]: the reference's examples/drone_tracking_controller_example.py, num_envs = 1: tracking
+    controller -> env.step toward [0, 0, 1.5] from the reset pose, 500 steps, for the `rpms` action type (external CTBR
+    controller, the example's default) and `ctbr`.  A latency figure (control steps per second of wall clock)."""
+    import torch
+
+    from data_driven_quad_control_b200.controllers.ctbr.ctbr_controller import DroneCTBRController
+    from data_driven_quad_control_b200.controllers.tracking.tracking_controller_config import TrackingCtrlDroneState
+    from data_driven_quad_control_b200.envs.hover_env import HoverEnv
+    from data_driven_quad_control_b200.envs.hover_env_config import (EnvActionType, EnvCTBRControllerConfig, EnvDroneParams,
+                                                                      get_cfgs)  # fmt: skip
+    from data_driven_quad_control_b200.utilities.drone_tracking_controller import (create_drone_tracking_controller,
+                                                                                   tracking_env_action)  # fmt: skip
+    from data_driven_quad_control_b200.utilities.math_utils import yaw_to_quaternion
+
+    out = {"metric": "control steps/s, single drone, 500-step hover-to-target (BASELINE configs[0])", "steps": 500}
+    for name, at in (("rpms", EnvActionType.ROTOR_RPMS), ("ctbr", EnvActionType.CTBR)):
+        env_cfg, obs_cfg, reward_cfg, cmd_cfg = get_cfgs()
+        env_cfg.update(episode_length_s=100, termination_if_close_to_ground=0.0, termination_if_x_greater_than=10.0,
+                       termination_if_y_greater_than=10.0, termination_if_z_greater_than=10.0)  # fmt: skip
+        env = HoverEnv(1, env_cfg, obs_cfg, reward_cfg, cmd_cfg, device=dev, auto_target_updates=False, action_type=at)
+        env.reset()
+        trk = create_drone_tracking_controller(env)
+        ctbr = None
+        if at is EnvActionType.ROTOR_RPMS:
+            ctbr = DroneCTBRController(EnvDroneParams.get(), EnvCTBRControllerConfig.get(), env.step_dt, 1, dev)
+        tgt = torch.tensor([[0.0, 0.0, 1.5]], device=dev)
+        env.update_target_pos(torch.arange(1, device=dev), tgt)
+        target = TrackingCtrlDroneState(X=tgt, Q=yaw_to_quaternion(torch.zeros(1, device=dev)))
+        cur = TrackingCtrlDroneState(X=env.get_pos(), Q=env.get_quat())
+
+        def loop(n_steps):
+            with torch.no_grad():
+                for _ in range(n_steps):
+                    cur.X, cur.Q = env.get_pos(), env.get_quat()
+                    env.step(tracking_env_action(env, trk, target, cur, ctbr))
+
+        loop(20)  # warm-up (module load, allocator)
+        env.reset()
+        trk.reset()
+        if ctbr is not None:
+            ctbr.reset()
+        env.update_target_pos(torch.arange(1, device=dev), tgt)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        loop(500)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        err = float((env.base_pos - tgt).abs().max())
+        out[name] = {"value": 500 / dt, "unit": "control steps/s", "ms_per_step": dt / 500 * 1e3, "final_max_abs_pos_error_m": err,
+                     "bound": "host: ~6 Python-level library calls per control step, no host synchronisation inside the loop"}  # fmt: skip
+    return out
+
+
+def run_grid_leg(dev, rank: int, world: int, timer) -> dict:
+    """BASELINE configs[4]: the reference's 900-combination DD-MPC parameter grid (dd_mpc_grid_search_params.yaml:92-111)
+    x 3 setpoints x 3 data sets x 200 closed-loop steps, combinations dealt round-robin to the ranks, ONE all-reduce of
+    the (900 x 3) result table; plus the 3-way tracking-controller / random-init policy / DD-MPC comparison
+    (controller_comparison_config.yaml:25-38: 2 setpoints x 175 steps) replicated over R env triples per GPU."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from data_driven_quad_control_b200.comparison.utilities.batched_controller_sim import batched_controller_comparison
+    from data_driven_quad_control_b200.data_driven_mpc import dd_mpc_param_grid_search as gsm
+    from data_driven_quad_control_b200.data_driven_mpc.nonlinear_data_driven_mpc_controller import AlphaRegType
+    from data_driven_quad_control_b200.learning.policy import FusedActorMLP
+
+    timer.barrier()
+    t0 = time.perf_counter()
+    summary = gsm.run_grid_search(seed=0, device=dev)
+    timer.barrier()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([summary["grid_search_s"], summary["data_collection_s"], wall], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gs_s, col_s, wall_s = (float(x) for x in t)
+    out = {
+        "metric": "DD-MPC parameter grid search (BASELINE configs[4])", "n_gpus": world, "combinations": summary["combinations"],
+        "successful": summary["successful"], "evaluation_runs": summary["evaluation_runs"],
+        "closed_loop_steps": summary["closed_loop_steps"], "grid_search_s": gs_s, "data_collection_s": col_s, "wall_s": wall_s,
+        "combinations_per_s": summary["combinations"] / gs_s, "closed_loop_steps_per_s": summary["closed_loop_steps"] / gs_s,
+        "best": summary["best"], "sharding": "combinations round-robin over the ranks, one all-reduce (sum) of the 900 x 3 result table; "
+        "every rank collects the same initial data (same seed)",
+        "note": "every evaluation run is its own independent env (independent_envs): a reference search with num_processes = 1 "
+        "(the reference's default num_processes = 10 couples the drones of concurrent runs through the env's batch-global resets)",
+    }  # fmt: skip
+    # 3-way comparison: R triples per GPU
+    R = 256
+    P = MPC_DEFAULT
+    ell = P["L"] + P["n"] + 1
+    env = gsm.make_env_factory(dev)(3 * R)
+    pol = FusedActorMLP.random_init(num_actions=3, seed=0, device=dev)
+    kw = dict(n=P["n"], m=3, p=3, N=P["N"], L=P["L"], Q=np.kron(np.eye(ell), np.diag(P["Q"])), R=np.kron(np.eye(ell), np.diag(P["R"])),
+              S=np.diag(P["S"]), lamb_alpha=P["lamb_alpha"], lamb_sigma=P["lamb_sigma"], U=np.array(P["U"]), Us=np.array(P["Us"]),
+              alpha_reg_type=AlphaRegType.APPROXIMATED, lamb_alpha_s=P["lamb_alpha_s"], lamb_sigma_s=P["lamb_sigma_s"])  # fmt: skip
+    setpoints, steps = [[1.0, 1.0, 1.5], [0.0, 0.0, 1.0]], 175
+    timer.barrier()
+    t0 = time.perf_counter()
+    traj = batched_controller_comparison(env, pol, kw, P["u_range"], P["init_hover_pos"], setpoints, steps, np.random.default_rng(rank))
+    timer.barrier()
+    cmp_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(cmp_s, op=dist.ReduceOp.MAX)
+    pos_end = np.stack([o[-1] for o in traj.system_outputs])  # (3R, 3)
+    err = np.abs(pos_end - np.asarray(setpoints[-1])).max(axis=1)
+    out["comparison"] = {
+        "triples_per_gpu": R, "n_gpus": world, "setpoints": setpoints, "steps_per_setpoint": steps, "wall_s": float(cmp_s),
+        "includes": "stabilisation at the hover position, N = 350 steps of DD-MPC data collection, 2 x 175 evaluation steps",
+        "closed_loop_env_steps_per_s": 3 * R * world * len(setpoints) * steps / float(cmp_s),
+        "final_error_tracking_median_m": float(np.median(err[:R])), "final_error_ddmpc_median_m": float(np.median(err[2 * R:])),
+        "final_error_policy_median_m": float(np.median(err[R:2 * R])),
+        "policy": "random-init actor (BASELINE configs[4]); it is not expected to reach the setpoints",
+    }  # fmt: skip
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -604,7 +861,10 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
     ipm_all = (it_raw >> 16).float()
     dist_end = torch.linalg.norm(env.base_pos - y_r, dim=1)
     flops = ddmpc_flops_per_solve(passes=float(it_all.mean()), gram_cached=ctrl.gram_cache_ptr is not None)
-    fp64_peak = 37.1  # TFLOP/s: DMMA m8n8k4 / DFMA, measured on this pool's B200 by tools/ubench_fp64.cu
+    # TFLOP/s: DMMA m8n8k4 = DFMA rate, 64 FMA/clk/SM (148 x 64 x 2 x 1.965 GHz = 37.2).  MEASURED_PEAKS.json carries no
+    # fp64 figure: this one is the BUILDER's own micro-benchmark (tools/ubench_fp64.cu, output in profiles/), not a driver number
+    fp64_peak = 37.1
+    mpc_traffic, mpc_traffic_src = ncu_traffic("ddmpc_solve")
     return {
         "metric": "DD-MPC QP solves/s",
         "value": batch / (avg * 1e-3),
@@ -637,10 +897,11 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
         "roofline": {
             "bound": "tensor", "kernel": "ddmpc_solve_kernel", "achieved": batch * flops / (avg * 1e-3) / 1e12,
             "peak": fp64_peak, "unit": "TFLOP/s", "frac": batch * flops / (avg * 1e-3) / 1e12 / fp64_peak,
-            "peak_source": "FP64 tensor (DMMA m8n8k4) = FP64 FMA pipe, 64 FMA/clk/SM, measured 37.1 TFLOP/s with "
-            "tools/ubench_fp64.cu (MEASURED_PEAKS.json carries no fp64 figure)",
-            "flops_per_solve": flops, "traffic": (2292.3e6 if ctrl.gram_cache_ptr is not None else 133.0e6) if batch == 4096 else None,
-            "traffic_source": "profiles/r1h_ddmpc_solve_ncu_full.csv (DRAM bytes per launch of 4096 solves: the 1.2 GB Gram cache read once and written once, evict-first; the workspace slots stay in L2; without the cache 133 MB)",
+            "peak_source": "builder-measured, not a driver number: FP64 tensor (DMMA m8n8k4) = FP64 FMA pipe, 64 FMA/clk/SM, "
+            "37.1 TFLOP/s with tools/ubench_fp64.cu (MEASURED_PEAKS.json carries no fp64 figure; nominal 148 x 64 x 2 x 1.965 GHz = 37.2)",
+            "flops_per_solve": flops, "traffic": mpc_traffic if batch == 4096 and ctrl.gram_cache_ptr is not None else None,
+            "traffic_source": (mpc_traffic_src or "") + " (DRAM bytes per launch of 4096 solves on the Gram-cache path: the 1.2 GB cache read once "
+            "and written once, evict-first; the workspace slots stay in L2)",
         },
         "gpu_launches": T,
     }
@@ -713,37 +974,67 @@ def _cpu_env_worker(arg):
     return time.perf_counter() - t0
 
 
-def cpu_env_baseline(steps: int, n_envs: int = 4096, procs: int | None = None) -> dict:
+def cpu_env_baseline(env_steps_per_proc: int = 8_000_000, batch_sizes=(4096, 16384, 65536), procs: int | None = None) -> dict:
+    """The numpy port of HoverEnv.step on all host cores, one process per core, timed at several batch sizes with the
+    same number of env-steps each; the FASTEST batch size is reported (round 1 timed 4096 envs only, where numpy's
+    per-call overhead still costs ~25 %)."""
     import multiprocessing as mp
 
     procs = procs or os.cpu_count() or 1
     ctx = mp.get_context("spawn")
+    tried = {}
+    t0 = time.perf_counter()
     with ctx.Pool(procs) as pool:
-        t0 = time.perf_counter()
-        times = pool.map(_cpu_env_worker, [(n_envs, steps, s) for s in range(procs)])
-        wall = time.perf_counter() - t0  # includes worker start-up; `value` uses the in-worker timers
-    value = procs * n_envs * steps / max(times)
+        for n_envs in batch_sizes:
+            steps = max(10, env_steps_per_proc // n_envs)
+            times = pool.map(_cpu_env_worker, [(n_envs, steps, s) for s in range(procs)])
+            tried[n_envs] = (procs * n_envs * steps / max(times), steps)
+    wall = time.perf_counter() - t0
+    n_best = max(tried, key=lambda k: tried[k][0])
+    value, steps = tried[n_best]
     return {
         "value": value,
         "unit": "env-steps/s",
         "cores": procs,
         "kind": "port",
-        "sample": f"oracle/env_oracle.py (numpy fp32 restatement of HoverEnv.step; the reference's Genesis/torch "
-        f"stack is not installable offline): {procs} processes x {n_envs} envs x {steps} steps, CTBR_FIXED_YAW",
+        "sample": f"oracle/env_oracle.py (numpy fp32 restatement of HoverEnv.step; the reference's Genesis/torch stack is not "
+        f"installable offline - profiles/r2_reference_stack_probe.log): {procs} processes x {n_best} envs x {steps} steps, "
+        f"CTBR_FIXED_YAW; fastest of the batch sizes {list(batch_sizes)}",
+        "by_batch_size": {str(k): v[0] for k, v in tried.items()},
+        "known_bias": "a vectorised numpy port without the reference's ~200 torch launches, host synchronisations and "
+        "torch<->Taichi hops per step: it is FASTER than the reference's own CPU path would be, so speed-ups quoted against it "
+        "are conservative; it is not the reference itself",
         "wall_s": wall,
     }
+
+
+def cpu_single_drone_baseline() -> dict:
+    """BASELINE configs[0] on the host: oracle env with one drone + the tracking-controller oracle, 500 steps."""
+    os.environ["DDQC_ORACLE_FAST_FMA"] = "1"
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+
+    import ddmpc_oracle as mo
+
+    _, _, st = mo.collect_initial_data(seed=0, N=1, settle_steps=0, obs_noise_std=0.0)  # builds env (1 drone) + tracking oracle
+    env, ctrl, act = st["env"], st["ctrl"], st["act"]
+    target = np.array([[0.0, 0.0, 1.5]], np.float32)
+    q_sp = np.array([[1.0, 0.0, 0.0, 0.0]], np.float32)
+    t0 = time.perf_counter()
+    for _ in range(500):
+        act(ctrl.compute(env.base_pos, env.base_quat, target, q_sp)[:, :3].astype(np.float64))
+    dt = time.perf_counter() - t0
+    return {"value": 500 / dt, "unit": "control steps/s", "ms_per_step": dt / 500 * 1e3, "cores": 1, "kind": "port",
+            "final_max_abs_pos_error_m": float(np.abs(env.base_pos - target).max()),
+            "sample": "oracle env (1 drone, CTBR_FIXED_YAW) + tracking-controller oracle, 500 steps toward [0, 0, 1.5]"}  # fmt: skip
 
 
 def run_reference(args) -> dict:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return {}
-    steps_per = 1000
-    vals = []
     t_all = time.perf_counter()
-    for _ in range(max(1, min(args.steps, 3))):
-        vals.append(cpu_env_baseline(steps_per))
-    best = max(vals, key=lambda d: d["value"])
+    best = cpu_env_baseline()
     n = best["cores"] * 4096
     return {
         "impl": "reference",
@@ -762,8 +1053,9 @@ def run_reference(args) -> dict:
         "config": {"workload": "HoverEnv.step random-action rollout, CTBR_FIXED_YAW (bounded CPU sample)", "sample": best["sample"]},
         "cpu_baseline": best,
         "e2e": {"value": best["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        # second half of BASELINE's metric on the same arm: the literal-QP oracle, one controller per process
+        # second half of BASELINE's metric on the same arm, one controller per process
         "ddmpc": {"metric": "DD-MPC QP solves/s", **cpu_ddmpc_baseline(3)},
+        "single_drone": cpu_single_drone_baseline(),
         "wall_s": time.perf_counter() - t_all,
     }
 
@@ -775,7 +1067,9 @@ def main():
     else:
         line = run_b200(args)
         if line and not args.no_cpu_baseline and int(os.environ.get("WORLD_SIZE", "1")) == 1:
-            line["cpu_baseline"] = cpu_env_baseline(2000)
+            line["cpu_baseline"] = cpu_env_baseline()
+            if "single_drone" in line:
+                line["single_drone"]["cpu_baseline"] = cpu_single_drone_baseline()
             if "ddmpc" in line:
                 line["ddmpc"]["cpu_baseline"] = cpu_ddmpc_baseline(3)
                 line["ddmpc"]["speedup_vs_cpu_baseline"] = line["ddmpc"]["value"] / line["ddmpc"]["cpu_baseline"]["value"]

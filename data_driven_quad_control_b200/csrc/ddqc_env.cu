@@ -23,6 +23,7 @@
 //           n_reset > 0.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ddqc_device.cuh"
 
@@ -30,27 +31,50 @@ using namespace ddqc;
 
 namespace {
 
-#ifndef DDQC_ENV_THREADS
-#define DDQC_ENV_THREADS 128
+// threads per CTA of the two launch shapes (1024 threads = 32 warps of 64 registers per SM either way)
+#ifndef DDQC_ENV_THREADS_FUSED
+#define DDQC_ENV_THREADS_FUSED 128
 #endif
-#ifndef DDQC_ENV_MIN_BLOCKS
-#define DDQC_ENV_MIN_BLOCKS 8
+#ifndef DDQC_ENV_THREADS_SPLIT
+#define DDQC_ENV_THREADS_SPLIT 256
 #endif
 // Measured and dropped: prefetch.global.L2 of the state of the env one wave (or half / two waves) of resident CTAs
 // ahead - 0.0734 / 0.0745 / 0.0803 ms per 2^20 envs against 0.0735 ms without (eager launches): the loads already
 // cover the DRAM latency with 32 warps per SM, the ~40 extra instructions per thread only cost issue slots.
-// DDQC_ENV_FINALIZE: where a step's statistics are folded.
-//   0  last CTA of the step kernel (bar.sync + device fence + ticket per CTA): round 1.  ncu showed warp 0 of every CTA
-//      waiting on the fence for half as long again as the CTA's work takes, with the registers of the three exited
-//      warps still held (CTA residency 1.5x the work), plus 9 % of the warp samples at the barrier;
-//   1  a second one-warp launch after the step kernel (stream order);
-//   2  the same with programmatic dependent launch: the finalisation is scheduled while the step kernel drains and
-//      the next step kernel while the finalisation runs; each waits (griddepcontrol.wait) before touching memory.
+// Where a step's statistics are folded (template parameter FUSED of the step kernel):
+//   FUSED   the last CTA of the step kernel does it (bar.sync + device fence + ticket per CTA): one launch per step,
+//           the lowest latency for small batches.  For large batches ncu showed warp 0 of every CTA waiting on the
+//           fence for half as long again as the CTA's work takes, with the registers of the three exited warps still
+//           held (CTA residency 1.5x the work), plus 9 % of the warp samples at the barrier: 70.8 us per 2^20 envs;
+//   !FUSED  a second one-warp launch (env_finalize_kernel) folds them; the step kernel has no barrier, no fence and no
+//           ticket.  DDQC_ENV_FINALIZE selects how the two are chained: 1 = stream order (66.0 us), 2 = programmatic
+//           dependent launch (64.7 us; 64.0 us with 256-thread CTAs): the finalisation is scheduled while the step
+//           kernel drains and the next step kernel while the finalisation runs; each waits (griddepcontrol.wait)
+//           before touching memory.
+// ddqc_env_step picks FUSED for n_env <= kFusedMaxEnvs (override: environment variable DDQC_ENV_FUSED_MAX_N).
 #ifndef DDQC_ENV_FINALIZE
 #define DDQC_ENV_FINALIZE 2
 #endif
-constexpr int kThreads = DDQC_ENV_THREADS;
-constexpr int kMinBlocks = DDQC_ENV_MIN_BLOCKS;
+#ifndef DDQC_ENV_FUSED_MAX_N
+#define DDQC_ENV_FUSED_MAX_N 32768
+#endif
+// State loads bypass L1 (ld.global.cg): every datum is read once, and the loads issued before griddepcontrol.wait must
+// not be served from lines an earlier grid left in this SM's L1.  Measured and dropped: streaming (evict-first) hints on
+// the outputs, on the state stores and on the state loads - 64.2 / 64.3 / 64.6 us per 2^20 envs against 63.9 us without.
+template <typename T>
+__device__ __forceinline__ T ld_state(const T* p) {
+  return __ldcg(p);
+}
+template <typename T>
+__device__ __forceinline__ void st_state(T* p, T v) {
+  *p = v;
+}
+template <typename T>
+__device__ __forceinline__ void st_out(T* p, T v) {
+  *p = v;
+}
+constexpr int kThreadsFused = DDQC_ENV_THREADS_FUSED;
+constexpr int kThreadsSplit = DDQC_ENV_THREADS_SPLIT;
 
 // Programmatic dependent launch (sm_90+): no-ops for a kernel launched without the attribute.
 __device__ __forceinline__ void pdl_wait() {
@@ -75,27 +99,30 @@ __device__ __forceinline__ void finalize_step(const DdqcEnvParams& P, const Ddqc
   const float obs_noise_std = LEAN ? 0.0f : P.obs_noise_std;
   const bool indep = (P.flags & DDQC_F_INDEPENDENT_ENVS) != 0u;
   const uint64_t ev = ctl->rng_event;
-  // warp 0 of the last CTA: fold the per-copy accumulators (lane k < 8: sums, 8: resets, 9: time-outs)
-  float f_acc = 0.0f;
-  unsigned int f_cnt_acc = 0u;
-  if (lane < 8) {
-    for (int c = 0; c < DDQC_STAT_COPIES; ++c) {
-      f_acc += __ldcg(&ctl->acc_sums[c][lane]);
-      ctl->acc_sums[c][lane] = 0.0f;
-    }
-  } else if (lane < 10) {
-    unsigned int* src = (lane == 8) ? ctl->acc_reset : ctl->acc_timeout;
-    for (int c = 0; c < DDQC_STAT_COPIES; ++c) {
-      f_cnt_acc += __ldcg(&src[c]);
-      src[c] = 0u;
+  // lane c folds copy c of the accumulators (two 16-byte loads + two counters, all 32 copies in flight at once) and
+  // clears it; a butterfly leaves every total in every lane
+  static_assert(DDQC_STAT_COPIES == 32, "one accumulator copy per lane");
+  float f_sums[8];
+  unsigned int f_cnt[2];
+  {
+    float4* acc = reinterpret_cast<float4*>(&ctl->acc_sums[lane][0]);
+    const float4 lo = __ldcg(acc), hi = __ldcg(acc + 1);
+    f_cnt[0] = __ldcg(&ctl->acc_reset[lane]);
+    f_cnt[1] = __ldcg(&ctl->acc_timeout[lane]);
+    acc[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    acc[1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    ctl->acc_reset[lane] = 0u;
+    ctl->acc_timeout[lane] = 0u;
+    f_sums[0] = lo.x, f_sums[1] = lo.y, f_sums[2] = lo.z, f_sums[3] = lo.w;
+    f_sums[4] = hi.x, f_sums[5] = hi.y, f_sums[6] = hi.z, f_sums[7] = hi.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f_sums[k] += __shfl_xor_sync(0xffffffffu, f_sums[k], o);
+      f_cnt[0] += __shfl_xor_sync(0xffffffffu, f_cnt[0], o);
+      f_cnt[1] += __shfl_xor_sync(0xffffffffu, f_cnt[1], o);
     }
   }
-  float f_sums[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) f_sums[k] = __shfl_sync(0xffffffffu, f_acc, k);
-  unsigned int f_cnt[2];
-  f_cnt[0] = __shfl_sync(0xffffffffu, f_cnt_acc, 8);
-  f_cnt[1] = __shfl_sync(0xffffffffu, f_cnt_acc, 9);
   const unsigned int n_reset = f_cnt[0];
   const unsigned int n_fix = __ldcg(&ctl->fixup_count);
 
@@ -130,36 +157,44 @@ __device__ __forceinline__ void finalize_step(const DdqcEnvParams& P, const Ddqc
   }
 
   __syncwarp();
-  if (lane == 0) {
-    const uint32_t row = O.ep_row % DDQC_EP_RING;  // named by the host, so its extras["episode"] views cannot drift
-    const uint32_t prev_row = ctl->ep_row;
-    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) {
-      float val = ctl->ep_ring[prev_row][k];
-      if (n_reset > 0) val = (f_sums[k] / (float)n_reset) / P.episode_length_s;
-      ctl->ep_ring[row][k] = val;
-      if (n_reset > 0) ctl->total_episode_sums[k] += (double)f_sums[k];
+  const uint32_t row = O.ep_row % DDQC_EP_RING;  // named by the host, so its extras["episode"] views cannot drift
+  const uint32_t prev_row = ctl->ep_row;
+  if (lane < DDQC_NUM_REWARDS) {  // lane k: reward term k of the ring row and of the running totals
+    float val = ctl->ep_ring[prev_row][lane];
+    float mine = 0.0f;
+#pragma unroll
+    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) mine = (lane == k) ? f_sums[k] : mine;
+    if (n_reset > 0) {
+      val = (mine / (float)n_reset) / P.episode_length_s;
+      ctl->total_episode_sums[lane] += (double)mine;
     }
+    ctl->ep_ring[row][lane] = val;
+  } else if (lane == 7) {
     ctl->ep_ring[row][7] = (float)n_reset;
-    ctl->ep_row = row;
-    ctl->n_reset_last = n_reset;
-    ctl->pid_reset_pending = (USES_CTBR && !indep) ? (n_reset > 0 ? 1u : 0u) : 0u;
+    ctl->total_reward += (double)f_sums[7];
+  } else if (lane == 8) {
     ctl->total_resets += n_reset;
     ctl->total_timeouts += f_cnt[1];
     ctl->total_env_steps += (uint64_t)n;
-    ctl->total_reward += (double)f_sums[7];
+  } else if (lane == 9) {
+    ctl->n_reset_last = n_reset;
+    ctl->pid_reset_pending = (USES_CTBR && !indep) ? (n_reset > 0 ? 1u : 0u) : 0u;
     ctl->step_count += 1;
     ctl->rng_event = ev + 1;
     ctl->fixup_count = 0u;
     ctl->blocks_done = 0u;
   }
+  __syncwarp();  // every lane has read ctl->ep_row
+  if (lane == 10) ctl->ep_row = row;
 }
 
 // ---- the fused step kernel -------------------------------------------------------------
 // LEAN = the throughput configuration: no Euler angles needed (thresholds >= 180 deg, yaw reward
 // scale 0), no actuator / observation noise, no materialised reference buffers, no measurement
 // override.  It is the same code with those branches compiled out (fewer registers, no spills).
-template <int ACT, bool LEAN>
-__global__ void __launch_bounds__(kThreads, kMinBlocks)
+template <int ACT, bool LEAN, bool FUSED, int THREADS>
+// (the full-featured instantiation gets 80 registers instead of 64: it spilled ~250 bytes per thread at 64)
+__global__ void __launch_bounds__(THREADS, (LEAN ? 1024 : 768) / THREADS)
 env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O, DdqcEnvCtl* __restrict__ ctl,
                 const float* __restrict__ actions, const float* __restrict__ meas_override, const int n) {
   constexpr int A = (ACT == DDQC_ACT_CTBR_FIXED_YAW) ? 3 : 4;
@@ -171,38 +206,45 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
 
   // Threads past the end (last CTA only) recompute env n-1 and skip every side effect, so the
   // body is straight-line code and the warp-level reductions below need no special casing.
-  const int gid = blockIdx.x * kThreads + threadIdx.x;
+  const int gid = blockIdx.x * THREADS + threadIdx.x;
   const bool live = gid < n;
   const int i = live ? gid : n - 1;
   const int lane = threadIdx.x & 31;
   const int copy = (blockIdx.x + (threadIdx.x >> 5)) % DDQC_STAT_COPIES;
-  pdl_launch_dependents();  // the finalisation may be scheduled; it waits for this grid to complete
-  pdl_wait();               // the previous step's finalisation (and with it the previous step) has completed
-  const uint64_t ev = ctl->rng_event;
   const bool indep = (P.flags & DDQC_F_INDEPENDENT_ENVS) != 0u;  // per-env instead of batch-global reset side effects
-  const bool pid_pending = !indep && ctl->pid_reset_pending != 0u;
+  if (!FUSED) pdl_launch_dependents();  // the finalisation may be scheduled; it waits for this grid to complete
 
   float rew_total = 0.0f;
   bool did_reset = false, did_timeout = false;
 
   {
     // ------------------------------------------------------------------ load state
-    V3 p{S.pos[i], S.pos[n + i], S.pos[2 * n + i]};
-    Q4 q{S.quat[i], S.quat[n + i], S.quat[2 * n + i], S.quat[3 * n + i]};
-    V3 v{S.vel[i], S.vel[n + i], S.vel[2 * n + i]};
-    V3 w{S.ang[i], S.ang[n + i], S.ang[2 * n + i]};
-    V3 cmd{S.commands[i], S.commands[n + i], S.commands[2 * n + i]};
+    V3 p{ld_state(&S.pos[i]), ld_state(&S.pos[n + i]), ld_state(&S.pos[2 * n + i])};
+    Q4 q{ld_state(&S.quat[i]), ld_state(&S.quat[n + i]), ld_state(&S.quat[2 * n + i]), ld_state(&S.quat[3 * n + i])};
+    V3 v{ld_state(&S.vel[i]), ld_state(&S.vel[n + i]), ld_state(&S.vel[2 * n + i])};
+    V3 w{ld_state(&S.ang[i]), ld_state(&S.ang[n + i]), ld_state(&S.ang[2 * n + i])};
+    V3 cmd{ld_state(&S.commands[i]), ld_state(&S.commands[n + i]), ld_state(&S.commands[2 * n + i])};
     float last_act[A], act[A];
 #pragma unroll
     for (int j = 0; j < A; ++j) {
-      last_act[j] = S.last_actions[j * n + i];
+      last_act[j] = ld_state(&S.last_actions[j * n + i]);
       act[j] = clipf(actions[(size_t)i * A + j], -P.clip_actions, P.clip_actions);  // A1
     }
-    int ep_len = S.episode_length[i];
-    int hover = S.hover_counter[i];
+    int ep_len = ld_state(&S.episode_length[i]);
+    int hover = ld_state(&S.hover_counter[i]);
     float sums[DDQC_NUM_REWARDS];
 #pragma unroll
-    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) sums[k] = S.episode_sums[k * n + i];
+    for (int k = 2; k < DDQC_NUM_REWARDS; ++k) sums[k] = ld_state(&S.episode_sums[k * n + i]);
+
+    // Everything above was written by the previous STEP kernel (or earlier), which had completed before the previous
+    // finalisation released this grid (it triggers its dependents after its own wait), so those loads are in flight
+    // while the finalisation still runs.  What the finalisation itself writes is read below the wait: the control
+    // block and the two episode sums its A15/A16 fix-ups may touch.
+    if (!FUSED) pdl_wait();
+    const uint64_t ev = ctl->rng_event;
+    const bool pid_pending = !indep && ctl->pid_reset_pending != 0u;
+    sums[0] = ld_state(&S.episode_sums[i]);
+    sums[1] = ld_state(&S.episode_sums[n + i]);
 
     // ------------------------------------------------------------------ action -> rpm
     float rpm[4];
@@ -218,8 +260,8 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
         if (!pid_pending) {  // A17: a reset anywhere in the previous launch zeroed every PID
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
-            integ[j] = S.pid_integral[j * n + i];
-            prev[j] = S.pid_prev_error[j * n + i];
+            integ[j] = ld_state(&S.pid_integral[j * n + i]);
+            prev[j] = ld_state(&S.pid_prev_error[j * n + i]);
           }
         }
         V3 meas;
@@ -243,8 +285,8 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
           prev[j] = err;
           c[j] = (P.pid_kp[j] * err + P.pid_ki[j] * integ[j]) + P.pid_kd[j] * deriv;
           if (live) {
-            S.pid_integral[j * n + i] = integ[j];
-            S.pid_prev_error[j * n + i] = prev[j];
+            st_state(&S.pid_integral[j * n + i], integ[j]);
+            st_state(&S.pid_prev_error[j * n + i], prev[j]);
           }
         }
         c[3] = y[0];
@@ -475,42 +517,42 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
 
     // ------------------------------------------------------------------ store
     if (live) {
-    S.pos[i] = p.x;
-    S.pos[n + i] = p.y;
-    S.pos[2 * n + i] = p.z;
-    S.quat[i] = q.w;
-    S.quat[n + i] = q.x;
-    S.quat[2 * n + i] = q.y;
-    S.quat[3 * n + i] = q.z;
-    S.vel[i] = v.x;
-    S.vel[n + i] = v.y;
-    S.vel[2 * n + i] = v.z;
-    S.ang[i] = w.x;
-    S.ang[n + i] = w.y;
-    S.ang[2 * n + i] = w.z;
-    S.commands[i] = cmd_new.x;
-    S.commands[n + i] = cmd_new.y;
-    S.commands[2 * n + i] = cmd_new.z;
+    st_state(&S.pos[i], p.x);
+    st_state(&S.pos[n + i], p.y);
+    st_state(&S.pos[2 * n + i], p.z);
+    st_state(&S.quat[i], q.w);
+    st_state(&S.quat[n + i], q.x);
+    st_state(&S.quat[2 * n + i], q.y);
+    st_state(&S.quat[3 * n + i], q.z);
+    st_state(&S.vel[i], v.x);
+    st_state(&S.vel[n + i], v.y);
+    st_state(&S.vel[2 * n + i], v.z);
+    st_state(&S.ang[i], w.x);
+    st_state(&S.ang[n + i], w.y);
+    st_state(&S.ang[2 * n + i], w.z);
+    st_state(&S.commands[i], cmd_new.x);
+    st_state(&S.commands[n + i], cmd_new.y);
+    st_state(&S.commands[2 * n + i], cmd_new.z);
 #pragma unroll
-    for (int j = 0; j < A; ++j) S.last_actions[j * n + i] = act[j];  // hover_env.py:544, all envs
-    S.episode_length[i] = ep_len;
-    S.hover_counter[i] = hover;
+    for (int j = 0; j < A; ++j) st_state(&S.last_actions[j * n + i], act[j]);  // hover_env.py:544, all envs
+    st_state(&S.episode_length[i], ep_len);
+    st_state(&S.hover_counter[i], hover);
 #pragma unroll
-    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) S.episode_sums[k * n + i] = sums[k];
+    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) st_state(&S.episode_sums[k * n + i], sums[k]);
 
     if (NOBS == 16) {
       float4* o4 = reinterpret_cast<float4*>(O.obs + (size_t)i * 16);
-      o4[0] = make_float4(obs[0], obs[1], obs[2], obs[3]);
-      o4[1] = make_float4(obs[4], obs[5], obs[6], obs[7]);
-      o4[2] = make_float4(obs[8], obs[9], obs[10], obs[11]);
-      o4[3] = make_float4(obs[12], obs[13], obs[14], obs[15]);
+      st_out(&o4[0], make_float4(obs[0], obs[1], obs[2], obs[3]));
+      st_out(&o4[1], make_float4(obs[4], obs[5], obs[6], obs[7]));
+      st_out(&o4[2], make_float4(obs[8], obs[9], obs[10], obs[11]));
+      st_out(&o4[3], make_float4(obs[12], obs[13], obs[14], obs[15]));
     } else {
 #pragma unroll
       for (int j = 0; j < NOBS; ++j) O.obs[(size_t)i * NOBS + j] = obs[j];
     }
-    O.rew[i] = rew;
-    O.reset[i] = did_reset ? 1 : 0;
-    O.time_outs[i] = did_timeout ? 1.0f : 0.0f;
+    st_out(&O.rew[i], rew);
+    st_out(&O.reset[i], (uint8_t)(did_reset ? 1 : 0));
+    st_out(&O.time_outs[i], did_timeout ? 1.0f : 0.0f);
 
     if (!LEAN && O.base_lin_vel) {
       O.base_lin_vel[i] = lin_b.x;
@@ -557,25 +599,24 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
     if (lane == 9 && tmask) atomicAdd(&ctl->acc_timeout[copy], (unsigned int)__popc(tmask));
   }
 
-#if DDQC_ENV_FINALIZE == 0
-  // -------------------------------------------------------------------- last-CTA finalisation (variant 0)
-  // bar.sync orders every warp's stores / REDs before thread 0's device-scope fence (cumulative),
-  // which releases them to whichever CTA draws the last ticket.  Only warp 0 stays for the ticket.
-  __syncthreads();
-  if (threadIdx.x >= 32) return;
-  int is_last = 0;
-  if (threadIdx.x == 0) {
+  if (FUSED) {
+    // ------------------------------------------------------------------ last-CTA finalisation
+    // bar.sync orders every warp's stores / REDs before thread 0's device-scope fence (cumulative),
+    // which releases them to whichever CTA draws the last ticket.  Only warp 0 stays for the ticket.
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    int is_last = 0;
+    if (threadIdx.x == 0) {
+      __threadfence();
+      is_last = (atomicAdd(&ctl->blocks_done, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    is_last = __shfl_sync(0xffffffffu, is_last, 0);
+    if (!is_last) return;
     __threadfence();
-    is_last = (atomicAdd(&ctl->blocks_done, 1u) == gridDim.x - 1) ? 1 : 0;
+    finalize_step<NOBS, LEAN, USES_CTBR>(P, S, O, ctl, n, lane);
   }
-  is_last = __shfl_sync(0xffffffffu, is_last, 0);
-  if (!is_last) return;
-  __threadfence();
-  finalize_step<NOBS, LEAN, USES_CTBR>(P, S, O, ctl, n, lane);
-#endif
 }
 
-#if DDQC_ENV_FINALIZE != 0
 // Second launch of a step: one warp folds the statistics of the step kernel that has just completed
 // (the kernel boundary is the only ordering the stores, the REDs and the fix-up list need: the step
 // kernel itself has no barrier, no fence and no ticket, so a CTA's registers are released the moment
@@ -584,11 +625,10 @@ template <int NOBS, bool LEAN, bool USES_CTBR>
 __global__ void __launch_bounds__(32, 1)
 env_finalize_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O, DdqcEnvCtl* __restrict__ ctl,
                     const int n) {
-  pdl_launch_dependents();
-  pdl_wait();
+  pdl_wait();               // the step kernel has completed and its stores / REDs are visible
+  pdl_launch_dependents();  // only now: the next step kernel loads state the completed step kernel wrote before ITS wait
   finalize_step<NOBS, LEAN, USES_CTBR>(P, S, O, ctl, n, (int)threadIdx.x);
 }
-#endif
 
 }  // namespace
 
@@ -612,49 +652,48 @@ extern "C" int ddqc_env_step(const DdqcEnvParams* P, const DdqcEnvState* S, cons
     return DDQC_E_NULL;
   if (P->action_type == DDQC_ACT_CTBR_FIXED_YAW && (reinterpret_cast<uintptr_t>(O->obs) & 15u)) return DDQC_E_ALIGN;
   const int n = (int)n_env;
-  dim3 grid((n + kThreads - 1) / kThreads), block(kThreads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool lean = !(P->flags & DDQC_F_NEED_EULER) && !(P->actuator_noise_std > 0.0f) && !(P->obs_noise_std > 0.0f) &&
                     !meas_override && !O->base_lin_vel && !O->base_ang_vel && !O->rel_pos && !O->last_rel_pos &&
                     !O->base_euler && !O->crash && !O->rpm && !O->last_base_pos;
-#if DDQC_ENV_FINALIZE == 2
+  static const int64_t fused_max_n = [] {
+    const char* e = getenv("DDQC_ENV_FUSED_MAX_N");
+    return e ? (int64_t)atoll(e) : (int64_t)DDQC_ENV_FUSED_MAX_N;
+  }();
+  const bool fused = n_env <= fused_max_n;
   cudaLaunchAttribute pdl_attr[1];
   pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
-#endif
   cudaError_t err = cudaSuccess;
   auto launch = [&](auto kernel, dim3 g, dim3 b, auto... args) {
     if (err != cudaSuccess) return;
-#if DDQC_ENV_FINALIZE == 2
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = g;
     cfg.blockDim = b;
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     cfg.attrs = pdl_attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (DDQC_ENV_FINALIZE == 2 && !fused) ? 1 : 0;
     err = cudaLaunchKernelEx(&cfg, kernel, args...);
-#else
-    kernel<<<g, b, 0, st>>>(args...);
-    err = cudaGetLastError();
-#endif
   };
-#if DDQC_ENV_FINALIZE == 0
-#define DDQC_FINALIZE(ACT, LEANV)
-#else
-#define DDQC_FINALIZE(ACT, LEANV)                                                                             \
-  launch(env_finalize_kernel<(ACT == DDQC_ACT_CTBR_FIXED_YAW ? 16 : 17), LEANV, (ACT != DDQC_ACT_ROTOR_RPMS)>, \
-         dim3(1), dim3(32), *P, *S, *O, ctl, n)
-#endif
+#define DDQC_LAUNCH2(ACT, LEANV)                                                                              \
+  do {                                                                                                        \
+    if (fused) {                                                                                              \
+      launch(env_step_kernel<ACT, LEANV, true, kThreadsFused>, dim3((n + kThreadsFused - 1) / kThreadsFused),  \
+             dim3(kThreadsFused), *P, *S, *O, ctl, actions, meas_override, n);                                \
+    } else {                                                                                                  \
+      launch(env_step_kernel<ACT, LEANV, false, kThreadsSplit>, dim3((n + kThreadsSplit - 1) / kThreadsSplit), \
+             dim3(kThreadsSplit), *P, *S, *O, ctl, actions, meas_override, n);                                \
+      launch(env_finalize_kernel<(ACT == DDQC_ACT_CTBR_FIXED_YAW ? 16 : 17), LEANV, (ACT != DDQC_ACT_ROTOR_RPMS)>, \
+             dim3(1), dim3(32), *P, *S, *O, ctl, n);                                                          \
+    }                                                                                                         \
+  } while (0)
 #define DDQC_LAUNCH(ACT)                                                                                      \
   do {                                                                                                        \
-    if (lean) {                                                                                               \
-      launch(env_step_kernel<ACT, true>, grid, block, *P, *S, *O, ctl, actions, meas_override, n);            \
-      DDQC_FINALIZE(ACT, true);                                                                               \
-    } else {                                                                                                  \
-      launch(env_step_kernel<ACT, false>, grid, block, *P, *S, *O, ctl, actions, meas_override, n);           \
-      DDQC_FINALIZE(ACT, false);                                                                              \
-    }                                                                                                         \
+    if (lean)                                                                                                 \
+      DDQC_LAUNCH2(ACT, true);                                                                                \
+    else                                                                                                      \
+      DDQC_LAUNCH2(ACT, false);                                                                               \
   } while (0)
   switch (P->action_type) {
     case DDQC_ACT_ROTOR_RPMS:
@@ -668,6 +707,6 @@ extern "C" int ddqc_env_step(const DdqcEnvParams* P, const DdqcEnvState* S, cons
       break;
   }
 #undef DDQC_LAUNCH
-#undef DDQC_FINALIZE
+#undef DDQC_LAUNCH2
   return (int)err;
 }

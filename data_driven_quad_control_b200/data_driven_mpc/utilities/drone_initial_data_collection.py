@@ -71,8 +71,10 @@ def collect_initial_input_output_data_batched(
         pe = torch.from_numpy(pe_np).to(dev).permute(1, 0, 2).contiguous()
     else:
         pe = ur[:, 0] + (ur[:, 1] - ur[:, 0]) * torch.rand((N, B, m), device=dev, generator=generator, dtype=torch.float64)
+    mask = None
     if excite_mask is not None:  # drones outside the mask are only stabilised (controller comparison: the
         pe = pe * excite_mask.to(dev, torch.float64).reshape(1, B, 1)  # other controllers' drones keep hovering)
+        mask = excite_mask.to(dev, torch.bool).reshape(B, 1)
     u_N = torch.empty((B, N, m), dtype=torch.float64, device=dev)
     y_N = torch.empty((B, N, 3), dtype=torch.float64, device=dev)
     with torch.no_grad():
@@ -81,6 +83,8 @@ def collect_initial_input_output_data_batched(
             cmd = stabilizing_controller.compute(state_setpoint=target, state_measurement=current)[:, :m]
             # the reference accumulates in float64 (numpy) and casts to the env's float32 only for the action
             u_k = torch.minimum(torch.maximum(cmd.to(torch.float64) + pe[k], lo), hi)
+            if mask is not None:  # the reference clips only the DD-MPC base env to U (:150-160); the other drones fly
+                u_k = torch.where(mask, u_k, cmd.to(torch.float64))  # the raw tracking command (env bounds only)
             action = linear_interpolate(x=u_k.to(torch.float32), x_min=bounds[:, 0], x_max=bounds[:, 1], y_min=-1, y_max=1)
             env.step(torch.clamp(action, -1, 1))
             u_N[:, k] = u_k

@@ -99,8 +99,11 @@ def evaluate_bucket(make_env: Callable[[int], HoverEnv], cache: DataDrivenCache,
     env = make_env(B)
     env.reset()
     idx = torch.arange(B, device=env.device)
-    pid = VectorizedControllerState(integral=torch.zeros((B, 3), device=env.device), prev_error=torch.zeros((B, 3), device=env.device))
-    state = stack_states([s.to(env.device) for s in states], pid)
+    states = [s.to(env.device) for s in states]
+    pid = None  # per-run rows of the rate-PID state saved right after the data collection (zero for caches without it)
+    if not any(s.ctbr_controller_state is not None for s in states):
+        pid = VectorizedControllerState(integral=torch.zeros((B, 3), device=env.device), prev_error=torch.zeros((B, 3), device=env.device))
+    state = stack_states(states, pid)
     env.restore_from_state(idx, state)
     env.update_target_pos(idx, torch.from_numpy(y_r).to(env.device, torch.float32))
     Q, R, S = _weights(fixed, n, L)
@@ -174,6 +177,7 @@ def collect_data_driven_cache(env: HoverEnv, stabilizing_controller, target_pos:
     entry = 0
     for N in N_values:
         env.restore_from_state(idx_all, copy.deepcopy(start))  # every length starts from the same stabilised hover
+        stabilizing_controller.reset()  # initial_data_collection_cache.py:141: no position-PID state leaks between collections
         u_N, y_N = collect_initial_input_output_data_batched(
             env, stabilizing_controller, target_pos, target_yaw, torch.as_tensor(np.asarray(input_bounds)),
             torch.as_tensor(np.asarray(u_range)), N, np_randoms=np_random.spawn(env.num_envs),

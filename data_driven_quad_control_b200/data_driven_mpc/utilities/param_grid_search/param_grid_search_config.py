@@ -86,16 +86,34 @@ def combinations_from_grid(param_grid: DDMPCParameterGrid) -> list[DDMPCCombinat
 
 
 def row_of_state(state: EnvState, row: int) -> EnvState:
-    """One-row view of a multi-env `EnvState` (the CTBR PID state is whole-batch and dropped)."""
+    """One-row copy of a multi-env `EnvState`, INCLUDING that env's row of the rate-PID state: the reference saves the
+    controller state right after a data collection and restores it before every evaluation run
+    (hover_env.py:680-695, 737-741), so a run starts with the `prev_error` / `integral` the collection left behind and
+    not with a derivative kick from zero."""
+    from data_driven_quad_control_b200.utilities.vectorized_pid_controller import VectorizedControllerState
+
     pick = lambda t: t[row : row + 1].clone()  # noqa: E731
+    pid = state.ctbr_controller_state
+    if pid is not None:
+        pid = VectorizedControllerState(integral=pick(pid.integral), prev_error=pick(pid.prev_error))
     return EnvState(base_pos=pick(state.base_pos), base_quat=pick(state.base_quat), base_lin_vel=pick(state.base_lin_vel),
                     base_ang_vel=pick(state.base_ang_vel), commands=pick(state.commands),
                     episode_length=pick(state.episode_length), last_actions=pick(state.last_actions),
-                    ctbr_controller_state=None)  # fmt: skip
+                    ctbr_controller_state=pid)  # fmt: skip
 
 
-def stack_states(states: list[EnvState], ctbr_state) -> EnvState:
+def stack_states(states: list[EnvState], ctbr_state=None) -> EnvState:
+    """Concatenates one-row states into the state of a batch.  The rate-PID rows are concatenated too (rows of states
+    that carry none are zero); an explicit `ctbr_state` overrides them."""
+    from data_driven_quad_control_b200.utilities.vectorized_pid_controller import VectorizedControllerState
+
     cat = lambda name: torch.cat([getattr(s, name) for s in states], dim=0)  # noqa: E731
+    if ctbr_state is None and any(s.ctbr_controller_state is not None for s in states):
+        ref = states[0].base_pos
+        zero = lambda s: torch.zeros((s.base_pos.shape[0], 3), dtype=torch.float32, device=ref.device)  # noqa: E731
+        part = lambda s, f: getattr(s.ctbr_controller_state, f).to(ref.device, torch.float32) if s.ctbr_controller_state is not None else zero(s)  # noqa: E731
+        ctbr_state = VectorizedControllerState(integral=torch.cat([part(s, "integral") for s in states], dim=0),
+                                               prev_error=torch.cat([part(s, "prev_error") for s in states], dim=0))  # fmt: skip
     return EnvState(base_pos=cat("base_pos"), base_quat=cat("base_quat"), base_lin_vel=cat("base_lin_vel"),
                     base_ang_vel=cat("base_ang_vel"), commands=cat("commands"), episode_length=cat("episode_length"),
                     last_actions=cat("last_actions"), ctbr_controller_state=ctbr_state)  # fmt: skip

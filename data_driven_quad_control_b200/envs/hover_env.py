@@ -316,10 +316,19 @@ class HoverEnv:
         self.episode_sums = {name: self._episode_sums[REWARD_NAMES.index(name)] for name in self.reward_scales}
 
         # ---- outputs ----------------------------------------------------------------------------
-        self.obs_buf = torch.zeros((N, self.num_obs), **f32)
-        self.rew_buf = torch.zeros((N,), **f32)
-        self.reset_buf = torch.ones((N,), dtype=torch.bool, device=dev)
-        self._time_outs = torch.zeros((N,), **f32)
+        # obs | rew | time_outs | reset live in ONE allocation (`output_block`, uint8), so that a caller who wants a
+        # step's results on the host fetches them with a single device-to-host copy instead of three
+        o_rew = N * self.num_obs * 4
+        o_tmo = o_rew + N * 4
+        o_rst = o_tmo + N * 4
+        self.output_block = torch.zeros((o_rst + N,), dtype=torch.uint8, device=dev)
+        self.obs_buf = self.output_block[:o_rew].view(torch.float32).view(N, self.num_obs)
+        self.rew_buf = self.output_block[o_rew:o_tmo].view(torch.float32)
+        self._time_outs = self.output_block[o_tmo:o_rst].view(torch.float32)
+        self.reset_buf = self.output_block[o_rst:].view(torch.bool)
+        self.reset_buf.fill_(True)
+        self.output_layout = {"obs": (0, (N, self.num_obs), "float32"), "rew": (o_rew, (N,), "float32"),
+                              "time_outs": (o_tmo, (N,), "float32"), "reset": (o_rst, (N,), "bool")}  # fmt: skip
         self._fixup_idx = torch.zeros((N,), dtype=torch.int32, device=dev)
         self._fixup_val = torch.zeros((N, 8), **f32)
         self._blv = self._bav = None  # body-frame velocity buffers (aux or on-demand cache)
@@ -583,6 +592,14 @@ class HoverEnv:
         idx = self._as_idx(envs_idx)
         k, A, dev = idx.numel(), self.num_actions, self.device
         f32 = dict(dtype=torch.float32, device=dev)
+        if k == 0:  # an empty selection is an empty state (nothing to launch)
+            return EnvState(
+                base_pos=torch.empty((0, 3), **f32), base_quat=torch.empty((0, 4), **f32),
+                base_lin_vel=torch.empty((0, 3), **f32), base_ang_vel=torch.empty((0, 3), **f32),
+                commands=torch.empty((0, 3), **f32), episode_length=torch.empty((0,), dtype=torch.int32, device=dev),
+                last_actions=torch.empty((0, A), **f32),
+                ctbr_controller_state=self.ctbr_controller.get_state() if self.uses_ctbr_actions else None,
+            )  # fmt: skip
         out = EnvState(
             base_pos=torch.empty((k, 3), **f32), base_quat=torch.empty((k, 4), **f32),
             base_lin_vel=torch.empty((k, 3), **f32), base_ang_vel=torch.empty((k, 3), **f32),

@@ -2,7 +2,7 @@
 import os, sys, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch, bench
-N = 1 << 20; dev = torch.device("cuda")
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20; dev = torch.device("cuda")
 env = bench.make_env(N, dev, 1); env.reset()
 acts = torch.rand((16, N, 3), device=dev) * 2 - 1
 for t in range(50): env.step(acts[t % 16])
@@ -35,4 +35,5 @@ try:
     out["graph_us_per_step"] = e0.elapsed_time(e1) / (60 * 16) * 1e3
 except Exception as ex:
     out["graph_error"] = repr(ex)[:300]
+out["N"] = N; out["lib"] = os.environ.get("DDQC_LIB", "default"); out["fused_max_n"] = os.environ.get("DDQC_ENV_FUSED_MAX_N", "default")
 print(json.dumps(out))
