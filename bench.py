@@ -672,7 +672,7 @@ def run_grid_leg(dev, rank: int, world: int, timer) -> dict:
     kw = dict(n=P["n"], m=3, p=3, N=P["N"], L=P["L"], Q=np.kron(np.eye(ell), np.diag(P["Q"])), R=np.kron(np.eye(ell), np.diag(P["R"])),
               S=np.diag(P["S"]), lamb_alpha=P["lamb_alpha"], lamb_sigma=P["lamb_sigma"], U=np.array(P["U"]), Us=np.array(P["Us"]),
               alpha_reg_type=AlphaRegType.APPROXIMATED, lamb_alpha_s=P["lamb_alpha_s"], lamb_sigma_s=P["lamb_sigma_s"])  # fmt: skip
-    setpoints, steps = [[1.0, 1.0, 1.5], [0.0, 0.0, 1.0]], 175
+    setpoints, steps = [[1.0, -1.0, 2.5], [0.0, 0.0, 1.5]], 175  # controller_comparison_config.yaml:25-38
     timer.barrier()
     t0 = time.perf_counter()
     traj = batched_controller_comparison(env, pol, kw, P["u_range"], P["init_hover_pos"], setpoints, steps, np.random.default_rng(rank))
@@ -688,7 +688,8 @@ def run_grid_leg(dev, rank: int, world: int, timer) -> dict:
         "closed_loop_env_steps_per_s": 3 * R * world * len(setpoints) * steps / float(cmp_s),
         "final_error_tracking_median_m": float(np.median(err[:R])), "final_error_ddmpc_median_m": float(np.median(err[2 * R:])),
         "final_error_policy_median_m": float(np.median(err[R:2 * R])),
-        "policy": "random-init actor (BASELINE configs[4]); it is not expected to reach the setpoints",
+        "policy": "random-init actor (BASELINE configs[4]); it is not expected to reach the setpoints - its drones crash and are "
+        "reset to the initial pose [0, 0, 1]",
     }  # fmt: skip
     return out
 
@@ -908,7 +909,7 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
 
 
 def _cpu_mpc_worker(arg):
-    n_solves, seed = arg
+    n_solves, seed, kind = arg
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
 
@@ -916,29 +917,50 @@ def _cpu_mpc_worker(arg):
 
     g = np.load(os.path.join(ROOT, "tests", "golden", "ddmpc_default.npz"))
     prm = mo.default_params()
-    ctrl = mo.NonlinearDDMPCOracle(**mo.ctor_kwargs(prm, g["u"], g["y"], g["y_r"]), solve_on_init=False)
+    if kind == "osqp":
+        import osqp_port as op
+
+        ctrl = op.OSQPStyleDDMPC(prm, g["u"], g["y"], g["y_r"])
+    else:
+        ctrl = mo.NonlinearDDMPCOracle(**mo.ctor_kwargs(prm, g["u"], g["y"], g["y_r"]), solve_on_init=False)
+    dist = 0.0
     t0 = time.perf_counter()
     for k in range(n_solves):
         ctrl.update_and_solve_data_driven_mpc()
+        if k < 3:
+            dist = max(dist, float(np.abs(ctrl.optimal_u[0] - g["u_opt"][k][0]).max()))
         ctrl.store_input_output_measurement(g["u_opt"][k % 3][0], g["y_next"][k % 3])
-    return time.perf_counter() - t0
+    return time.perf_counter() - t0, dist
 
 
-def cpu_ddmpc_baseline(n_solves: int = 3, procs: int | None = None) -> dict:
+def cpu_ddmpc_baseline(n_solves: int = 12, procs: int | None = None) -> dict:
+    """DD-MPC closed-loop solves on all host cores, one controller per process (the reference's scaling model,
+    parallel_grid_search.py:133-155).  Headline: the OSQP-style ADMM port at cvxpy's OSQP tolerances (the solver CLASS of
+    the reference's cvxpy path); beside it the dense interior-point oracle the parity tests use (40x more accurate,
+    several times slower)."""
     import multiprocessing as mp
 
     procs = procs or os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     with mp.get_context("spawn").Pool(procs) as pool:
-        times = pool.map(_cpu_mpc_worker, [(n_solves, s) for s in range(procs)])
+        res = pool.map(_cpu_mpc_worker, [(n_solves, s, "osqp") for s in range(procs)])
+        res_ipm = pool.map(_cpu_mpc_worker, [(3, s, "ipm") for s in range(procs)])
+    times, dists = [r[0] for r in res], [r[1] for r in res]
     return {
         "value": procs * n_solves / max(times),
         "unit": "solves/s",
         "cores": procs,
         "kind": "port",
-        "sample": f"oracle/ddmpc_oracle.py (literal 693-variable QP, dense interior point, numpy/LAPACK; cvxpy+OSQP of "
-        f"the reference is not installable offline): {procs} processes x {n_solves} closed-loop solves, one controller "
-        "per process as the reference's grid search does",
+        "sample": f"oracle/osqp_port.py: OSQP-style ADMM (Stellato et al. 2020; eps_abs = eps_rel = 1e-5, max_iter 10000 as cvxpy "
+        f"calls OSQP; sparse KKT factorised once per QP, warm-started) on the literal 693-variable problem + the alpha_sr problem, "
+        f"{procs} processes x {n_solves} closed-loop solves, one controller per process as the reference's grid search does",
+        "known_bias": "numpy / SuperLU restatement, not OSQP's C code and without cvxpy's per-solve canonicalisation: a real "
+        "cvxpy + OSQP call is estimated within a small factor of it either way (profiles/r2_reference_stack_probe.log: not installable)",
+        "solution_distance_to_high_accuracy_oracle": max(dists),
+        "solution_distance_note": "max |u*_0 - u*_0(oracle)| over the first 3 closed-loop steps: what a 1e-5 first-order solver - the "
+        "reference's own solver class - delivers; the GPU solver is held to 1e-5 against the same oracle",
+        "high_accuracy_ipm_solves_per_s": procs * 3 / max(r[0] for r in res_ipm),
+        "high_accuracy_ipm_note": "oracle/ddmpc_oracle.py, dense primal-dual interior point to 1e-10 (round 1's baseline figure)",
     }
 
 
@@ -1054,7 +1076,7 @@ def run_reference(args) -> dict:
         "cpu_baseline": best,
         "e2e": {"value": best["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         # second half of BASELINE's metric on the same arm, one controller per process
-        "ddmpc": {"metric": "DD-MPC QP solves/s", **cpu_ddmpc_baseline(3)},
+        "ddmpc": {"metric": "DD-MPC QP solves/s", **cpu_ddmpc_baseline()},
         "single_drone": cpu_single_drone_baseline(),
         "wall_s": time.perf_counter() - t_all,
     }
@@ -1071,7 +1093,7 @@ def main():
             if "single_drone" in line:
                 line["single_drone"]["cpu_baseline"] = cpu_single_drone_baseline()
             if "ddmpc" in line:
-                line["ddmpc"]["cpu_baseline"] = cpu_ddmpc_baseline(3)
+                line["ddmpc"]["cpu_baseline"] = cpu_ddmpc_baseline()
                 line["ddmpc"]["speedup_vs_cpu_baseline"] = line["ddmpc"]["value"] / line["ddmpc"]["cpu_baseline"]["value"]
     if line:
         print(json.dumps(line))

@@ -20,7 +20,7 @@ EP_RING = 1024
 ABI_VERSION = 2  # include/ddqc.h: DDQC_ABI_VERSION
 
 ACT_ROTOR_RPMS, ACT_CTBR, ACT_CTBR_FIXED_YAW = 0, 1, 2
-F_ACTION_LATENCY, F_AUTO_TARGET, F_NEED_EULER, F_INDEPENDENT_ENVS = 1, 2, 4, 8
+F_ACTION_LATENCY, F_AUTO_TARGET, F_NEED_EULER, F_INDEPENDENT_ENVS, F_GROUND_WATCH = 1, 2, 4, 8, 16
 
 f32, i32, u32, u64, f64 = C.c_float, C.c_int32, C.c_uint32, C.c_uint64, C.c_double
 vp = C.c_void_p
@@ -97,6 +97,8 @@ class EnvCtl(C.Structure):
         ("total_env_steps", u64),
         ("total_reward", f64),
         ("total_episode_sums", f64 * NUM_REWARDS),
+        ("total_below_ground", u64),
+        ("reserved0", u64),
         ("blocks_done", u32),
         ("pid_reset_pending", u32),
         ("n_reset_last", u32),
@@ -105,6 +107,7 @@ class EnvCtl(C.Structure):
         ("pad0", u32),
         ("acc_reset", u32 * STAT_COPIES),
         ("acc_timeout", u32 * STAT_COPIES),
+        ("acc_ground", u32 * STAT_COPIES),
         ("acc_sums", (f32 * 8) * STAT_COPIES),
         ("ep_ring", (f32 * 8) * EP_RING),
     ]
@@ -161,6 +164,8 @@ class MpcConfig(C.Structure):
         ("alpha_reg_type", i32),
         ("max_iter", i32),
         ("gram_refresh", i32),
+        ("alpha_sr_anchor", i32),
+        ("reserved0", i32),
         ("Q", f64 * 8),
         ("R", f64 * 8),
         ("S", f64 * 8),

@@ -79,8 +79,9 @@ def batched_controller_comparison(env: HoverEnv, policy, dd_mpc_kwargs: dict, u_
                 actions[R : 2 * R] = policy.act_inference(obs[R : 2 * R].contiguous())
                 # data-driven MPC rows: solve, then optimal input -> normalised action straight into the action buffer
                 mpc.update_and_solve_data_driven_mpc()
-                rc = lib.ddqc_ddmpc_action(cfg, mpc.optimal_u.data_ptr(), 0, bounds.contiguous().data_ptr(),
-                                           actions[2 * R :].data_ptr(), u_applied.data_ptr(), R, _lib.stream_ptr(dev))  # fmt: skip
+                with _lib.device_guard(dev):
+                    rc = lib.ddqc_ddmpc_action(cfg, mpc.optimal_u.data_ptr(), 0, bounds.contiguous().data_ptr(),
+                                               actions[2 * R :].data_ptr(), u_applied.data_ptr(), R, _lib.stream_ptr(dev))  # fmt: skip
                 _lib.check(rc, "ddqc_ddmpc_action")
                 act_log.append(actions.clone())
                 obs, *_ = env.step(actions)

@@ -1456,7 +1456,16 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       __syncthreads();
       DDQC_PHASE(3);
       DDQC_SUB(-1);
-      {
+      if (cfg.alpha_sr_anchor == 1) {
+        // alpha_sr anchored at the PREVIOUS solve's optimal equilibrium (the other reading of the package's
+        // "approximation of alpha_Lin^sr(D_t)"): rho = A_u u_s^prev + A_y y_s^prev + e_one with the values the previous
+        // launch left in us_opt / ys_opt; a controller's first solve has no previous equilibrium and uses alpha_sr = 0
+        if (tid <= nsig) {
+          double v = 0.0;
+          if (have_prev[b] > 0) v = tid < m ? us_opt[(size_t)b * m + tid] : (tid < nsig ? ys_opt[(size_t)b * p + (tid - m)] : 1.0);
+          s_coef[tid] = v;
+        }
+      } else {
         // 6-variable box QP for the equilibrium (bounds on u_s only): H 36 | f 6 | lo 6 | hi 6 | x 6 at s_vec (free
         // at this point), assembled by 42 threads, every active set tested by its own thread
         double* io = s_vec;
@@ -1808,6 +1817,7 @@ int check_cfg(const DdqcMpcConfig* c) {
   if (d.C < 1 || d.nx > kMaxNx || (d.m + d.p) * d.ell > kMaxPos || d.m + d.p + 2 > 8) return DDQC_E_SHAPE;
   if (smem_bytes(d) + 6144 > (size_t)kSmemLimit) return DDQC_E_SHAPE;  // 6144 >= static shared memory of the kernel
   if (c->alpha_reg_type != 0 && c->alpha_reg_type != 2) return DDQC_E_CONFIG;
+  if (c->alpha_sr_anchor != 0 && c->alpha_sr_anchor != 1) return DDQC_E_CONFIG;
   return 0;
 }
 

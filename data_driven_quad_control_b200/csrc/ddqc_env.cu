@@ -103,16 +103,18 @@ __device__ __forceinline__ void finalize_step(const DdqcEnvParams& P, const Ddqc
   // clears it; a butterfly leaves every total in every lane
   static_assert(DDQC_STAT_COPIES == 32, "one accumulator copy per lane");
   float f_sums[8];
-  unsigned int f_cnt[2];
+  unsigned int f_cnt[3];
   {
     float4* acc = reinterpret_cast<float4*>(&ctl->acc_sums[lane][0]);
     const float4 lo = __ldcg(acc), hi = __ldcg(acc + 1);
     f_cnt[0] = __ldcg(&ctl->acc_reset[lane]);
     f_cnt[1] = __ldcg(&ctl->acc_timeout[lane]);
+    f_cnt[2] = __ldcg(&ctl->acc_ground[lane]);
     acc[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     acc[1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     ctl->acc_reset[lane] = 0u;
     ctl->acc_timeout[lane] = 0u;
+    ctl->acc_ground[lane] = 0u;
     f_sums[0] = lo.x, f_sums[1] = lo.y, f_sums[2] = lo.z, f_sums[3] = lo.w;
     f_sums[4] = hi.x, f_sums[5] = hi.y, f_sums[6] = hi.z, f_sums[7] = hi.w;
 #pragma unroll
@@ -121,6 +123,7 @@ __device__ __forceinline__ void finalize_step(const DdqcEnvParams& P, const Ddqc
       for (int k = 0; k < 8; ++k) f_sums[k] += __shfl_xor_sync(0xffffffffu, f_sums[k], o);
       f_cnt[0] += __shfl_xor_sync(0xffffffffu, f_cnt[0], o);
       f_cnt[1] += __shfl_xor_sync(0xffffffffu, f_cnt[1], o);
+      f_cnt[2] += __shfl_xor_sync(0xffffffffu, f_cnt[2], o);
     }
   }
   const unsigned int n_reset = f_cnt[0];
@@ -176,6 +179,7 @@ __device__ __forceinline__ void finalize_step(const DdqcEnvParams& P, const Ddqc
     ctl->total_resets += n_reset;
     ctl->total_timeouts += f_cnt[1];
     ctl->total_env_steps += (uint64_t)n;
+    ctl->total_below_ground += f_cnt[2];
   } else if (lane == 9) {
     ctl->n_reset_last = n_reset;
     ctl->pid_reset_pending = (USES_CTBR && !indep) ? (n_reset > 0 ? 1u : 0u) : 0u;
@@ -215,7 +219,7 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
   if (!FUSED) pdl_launch_dependents();  // the finalisation may be scheduled; it waits for this grid to complete
 
   float rew_total = 0.0f;
-  bool did_reset = false, did_timeout = false;
+  bool did_reset = false, did_timeout = false, below_ground = false;
 
   {
     // ------------------------------------------------------------------ load state
@@ -361,6 +365,7 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
                  (fabsf(ang_b.x) > P.term_ang_vel) | (fabsf(ang_b.y) > P.term_ang_vel) |
                  (fabsf(ang_b.z) > P.term_ang_vel) | (fabsf(lin_b.x) > P.term_lin_vel) |
                  (fabsf(lin_b.y) > P.term_lin_vel) | (fabsf(lin_b.z) > P.term_lin_vel);
+    below_ground = live & (p.z < 0.0f);
     did_timeout = live & (ep_len > P.max_episode_length);
     did_reset = live & (did_timeout | crash);
 
@@ -597,6 +602,10 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
     for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
     if (lane == 7) atomicAdd(&ctl->acc_sums[copy][7], r);
     if (lane == 9 && tmask) atomicAdd(&ctl->acc_timeout[copy], (unsigned int)__popc(tmask));
+    if (P.flags & DDQC_F_GROUND_WATCH) {  // no ground plane here: count the env-steps the reference's floor would have changed
+      const unsigned int gmask = __ballot_sync(0xffffffffu, below_ground);
+      if (lane == 10 && gmask) atomicAdd(&ctl->acc_ground[copy], (unsigned int)__popc(gmask));
+    }
   }
 
   if (FUSED) {

@@ -31,6 +31,9 @@ import torch
 from data_driven_quad_control_b200 import _lib
 
 
+ALPHA_SR_ANCHORS = {"optimal_reachable_equilibrium": 0, "previous_equilibrium": 1}
+
+
 class AlphaRegType(Enum):
     APPROXIMATED = 0  # regularise w.r.t. an approximation of alpha_Lin^sr(D_t)
     PREVIOUS = 1  # w.r.t. the previous optimal alpha
@@ -79,7 +82,14 @@ class BatchedNonlinearDataDrivenMPC:
         warm_start: bool = True,
         gram_cache: bool | None = None,
         gram_refresh: int = 128,
+        alpha_sr_anchor: str = "optimal_reachable_equilibrium",
     ):
+        """`alpha_sr_anchor` (extension, alpha_reg_type APPROXIMATED only) selects which equilibrium the approximation
+        of alpha_Lin^sr(D_t) belongs to - the third-party source is not available and the published scheme leaves it
+        open: "optimal_reachable_equilibrium" (default; the equilibrium closest to y_r) or
+        "previous_equilibrium" (the optimal (u_s, y_s) of the previous solve; alpha_sr = 0 on the first solve)."""
+        if alpha_sr_anchor not in ALPHA_SR_ANCHORS:
+            raise ValueError(f"alpha_sr_anchor must be one of {sorted(ALPHA_SR_ANCHORS)}")
         if ext_out_incr_in:
             raise NotImplementedError("ext_out_incr_in=True (extended output / input increments) is not supported")
         if update_cost_threshold:
@@ -116,6 +126,8 @@ class BatchedNonlinearDataDrivenMPC:
         cfg.alpha_reg_type = art.value
         cfg.max_iter = int(max_iter)
         cfg.gram_refresh = int(gram_refresh)
+        cfg.alpha_sr_anchor = ALPHA_SR_ANCHORS[alpha_sr_anchor]
+        self.alpha_sr_anchor = alpha_sr_anchor
         qw = _block_diag_weights(Q, ell, p, "Q")
         rw = _block_diag_weights(R, ell, m, "R")
         sw = _block_diag_weights(S, 1, p, "S")
@@ -180,12 +192,14 @@ class BatchedNonlinearDataDrivenMPC:
         controllers left out of this solve - their outputs and status keep their last values (used by the batched
         evaluator for runs the reference would have aborted)."""
         have_prev = self._have_prev if skip is None else torch.where(skip, -1, self._have_prev).to(torch.int32)
-        rc = self._lib.ddqc_ddmpc_solve(
-            C.byref(self._cfg), self._ws.data_ptr(), self.u.data_ptr(), self.y.data_ptr(), self.y_r.data_ptr(),
-            have_prev.data_ptr(),
-            self._lamb.data_ptr() if self._lamb is not None else None, self._act_state.data_ptr() if self._act_state is not None else None, self.optimal_u.data_ptr(), self.us.data_ptr(), self.ys.data_ptr(), self.status.data_ptr(),
-            self.iters.data_ptr(), self.B, self.gram_cache_ptr, _lib.stream_ptr(self.device),
-        )  # fmt: skip
+        with _lib.device_guard(self.device):
+            rc = self._lib.ddqc_ddmpc_solve(
+                C.byref(self._cfg), self._ws.data_ptr(), self.u.data_ptr(), self.y.data_ptr(), self.y_r.data_ptr(),
+                have_prev.data_ptr(), self._lamb.data_ptr() if self._lamb is not None else None,
+                self._act_state.data_ptr() if self._act_state is not None else None, self.optimal_u.data_ptr(),
+                self.us.data_ptr(), self.ys.data_ptr(), self.status.data_ptr(), self.iters.data_ptr(), self.B,
+                self.gram_cache_ptr, _lib.stream_ptr(self.device),
+            )  # fmt: skip
         _lib.check(rc, "ddqc_ddmpc_solve")
         if skip is None:
             self._have_prev.fill_(1)
@@ -225,10 +239,11 @@ class BatchedNonlinearDataDrivenMPC:
         y_c = torch.as_tensor(np.asarray(y_current) if not torch.is_tensor(y_current) else y_current)
         u_c = u_c.to(device=self.device, dtype=torch.float64).reshape(self.B, self.m).contiguous()
         y_c = y_c.to(device=self.device, dtype=torch.float64).reshape(self.B, self.p).contiguous()
-        rc = self._lib.ddqc_ddmpc_store(
-            C.byref(self._cfg), self.u.data_ptr(), self.y.data_ptr(), u_c.data_ptr(), y_c.data_ptr(), self.B,
-            self.gram_cache_ptr, _lib.stream_ptr(self.device),
-        )
+        with _lib.device_guard(self.device):
+            rc = self._lib.ddqc_ddmpc_store(
+                C.byref(self._cfg), self.u.data_ptr(), self.y.data_ptr(), u_c.data_ptr(), y_c.data_ptr(), self.B,
+                self.gram_cache_ptr, _lib.stream_ptr(self.device),
+            )
         _lib.check(rc, "ddqc_ddmpc_store")
 
     def check_status(self) -> None:
@@ -245,12 +260,12 @@ class NonlinearDataDrivenMPCController:
 
     def __init__(self, n, m, p, u, y, L, Q, R, S, y_r, lamb_alpha, lamb_sigma, U, Us, alpha_reg_type=AlphaRegType.ZERO,
                  lamb_alpha_s=None, lamb_sigma_s=None, ext_out_incr_in=False, update_cost_threshold=None,
-                 n_mpc_step=1, device="cuda", solve_on_init=True):  # fmt: skip
+                 n_mpc_step=1, device="cuda", solve_on_init=True, alpha_sr_anchor="optimal_reachable_equilibrium"):  # fmt: skip
         u, y = np.asarray(u, dtype=np.float64), np.asarray(y, dtype=np.float64)
         self._b = BatchedNonlinearDataDrivenMPC(
             n, m, p, u[None], y[None], L, Q, R, S, np.asarray(y_r, dtype=np.float64).reshape(1, -1), lamb_alpha,
             lamb_sigma, U, Us, alpha_reg_type, lamb_alpha_s, lamb_sigma_s, ext_out_incr_in, update_cost_threshold,
-            n_mpc_step, device, solve_on_init,
+            n_mpc_step, device, solve_on_init, alpha_sr_anchor=alpha_sr_anchor,
         )  # fmt: skip
         self.n, self.m, self.p, self.L, self.N = n, m, p, L, u.shape[0]
         self.n_mpc_step = n_mpc_step

@@ -80,6 +80,13 @@ def sim_nonlinear_dd_mpc_control_loop_batched(
     y_log = torch.zeros((num_steps, B, p), **f64) if record else None
     u_log = torch.zeros((num_steps, B, m), **f64) if record else None
     cfg = C.byref(ctrl._cfg)
+    with _lib.device_guard(dev):  # the raw C calls of the loop launch on the current device
+        return _closed_loop(env, ctrl, lib, cfg, num_steps, n_mpc_step, B, m, bounds, action, u_applied, y_r, d0, max_inc,
+                            sq_sum, n_acc, fail_step, solver_failed, y_log, u_log, record, dev)  # fmt: skip
+
+
+def _closed_loop(env, ctrl, lib, cfg, num_steps, n_mpc_step, B, m, bounds, action, u_applied, y_r, d0, max_inc, sq_sum, n_acc,
+                 fail_step, solver_failed, y_log, u_log, record, dev):  # fmt: skip
     for t in range(0, num_steps, n_mpc_step):
         # runs that already stopped (drift criterion or a failed solve) are aborted evaluations in the reference
         # (controller_evaluation.py:424-447): their controllers are left out of the solve

@@ -94,6 +94,9 @@ def make_env_params(
         flags |= _lib.F_NEED_EULER
     if independent_envs:
         flags |= _lib.F_INDEPENDENT_ENVS
+    if env_cfg["termination_if_close_to_ground"] <= 0.0:
+        # the reference's floor (hover_env.py:199) is not modelled: count what it would have stopped (see ddqc.h)
+        flags |= _lib.F_GROUND_WATCH
     P.flags = flags
     P.clip_actions = env_cfg["clip_actions"]
 
@@ -652,6 +655,21 @@ class HoverEnv:
     def close(self) -> None:
         self._is_closed = True
 
+    def check_ground_plane(self, what: str = "run") -> int:
+        """Number of env-steps that ended below z = 0 (synchronises).  The reference's scene has a ground plane with
+        collision (hover_env.py:199) which this restated rigid body does not model; with
+        `termination_if_close_to_ground <= 0` a drone can therefore sink through the floor here where the reference
+        would leave it lying on it.  A non-zero count raises a `RuntimeWarning`: the results of such a run cannot be
+        compared with the reference's."""
+        import warnings
+
+        k = int(self.rollout_stats()["below_ground_env_steps"])
+        if k:
+            warnings.warn(f"{what}: {k} env-steps ended below the ground plane z = 0, which is not modelled "
+                          "(the reference's drone would be in contact with the floor); results diverge from the reference's",
+                          RuntimeWarning, stacklevel=2)  # fmt: skip
+        return k
+
     # ------------------------------------------------------------------------------ rollout statistics
     def rollout_stats(self) -> dict[str, float]:
         """Totals accumulated on the device since construction (one D2H copy, synchronises):
@@ -665,6 +683,9 @@ class HoverEnv:
             "resets": float(ctl.total_resets),
             "time_outs": float(ctl.total_timeouts),
             "reward_sum": float(ctl.total_reward),
+            # env-steps that ended below the (unmodelled) ground plane; only counted when the configuration disables
+            # the low-altitude termination.  Non-zero = the run left the regime in which it can agree with the reference
+            "below_ground_env_steps": float(ctl.total_below_ground),
         }
         for k, name in enumerate(REWARD_NAMES):
             stats["episode_sum_" + name] = float(ctl.total_episode_sums[k])

@@ -45,6 +45,13 @@ extern "C" {
 #define DDQC_F_ACTION_LATENCY 1u    /* env_cfg["simulate_action_latency"]  (hover_env.py:386-388) */
 #define DDQC_F_AUTO_TARGET 2u       /* auto_target_updates                 (hover_env.py:473-478) */
 #define DDQC_F_NEED_EULER 4u        /* Euler angles feed a live threshold or a non-zero yaw reward */
+#define DDQC_F_GROUND_WATCH 16u     /* count the env-steps that end BELOW the ground plane z = 0.  The reference's scene has a
+                                     * plane entity with collision on (hover_env.py:199); this restatement has no contact
+                                     * model, so when a configuration disables the low-altitude termination
+                                     * (termination_if_close_to_ground <= 0: the tracking example, the DD-MPC evaluation and
+                                     * grid-search scripts) a drone that the reference would leave resting on the floor falls
+                                     * through it here.  The count (DdqcEnvCtl.total_below_ground) lets callers detect that a
+                                     * run has left the regime in which the two agree instead of differing silently */
 #define DDQC_F_INDEPENDENT_ENVS 8u  /* every env behaves like its own num_envs = 1 HoverEnv instance: a reset zeroes the rate
                                      * PID of that env only and refreshes rel_pos of that env only.  The reference's two
                                      * batch-global reset side effects (hover_env.py:563-564, 592-593) couple the drones of one
@@ -112,6 +119,8 @@ typedef struct DdqcEnvCtl {
   uint64_t total_resets, total_timeouts, total_env_steps;
   double total_reward;
   double total_episode_sums[DDQC_NUM_REWARDS]; /* sum of episode_sums[k] over all finished episodes */
+  uint64_t total_below_ground;  /* env-steps that ended with z < 0 (DDQC_F_GROUND_WATCH) */
+  uint64_t reserved0;
   uint32_t blocks_done;
   uint32_t pid_reset_pending;   /* A17: >=1 env reset in the previous launch -> whole-batch PID zero */
   uint32_t n_reset_last;
@@ -120,6 +129,7 @@ typedef struct DdqcEnvCtl {
   uint32_t pad0;
   uint32_t acc_reset[DDQC_STAT_COPIES];
   uint32_t acc_timeout[DDQC_STAT_COPIES];
+  uint32_t acc_ground[DDQC_STAT_COPIES];
   float acc_sums[DDQC_STAT_COPIES][8]; /* 7 episode sums of reset envs + sum of rewards */
   float ep_ring[DDQC_EP_RING][8];      /* mean(episode_sums[k][reset]) / episode_length_s per launch */
 } DdqcEnvCtl;
@@ -268,6 +278,12 @@ typedef struct DdqcMpcConfig {
   int32_t alpha_reg_type;       /* 0 approximated, 1 previous, 2 zero */
   int32_t max_iter;             /* pivoting passes before the interior-point fallback (<=0: 12) */
   int32_t gram_refresh;         /* Gram cache: incremental updates between regenerations (<=0: 128) */
+  int32_t alpha_sr_anchor;      /* alpha_reg_type 0 only - which equilibrium alpha_sr belongs to (the third-party source is not
+                                 * available, the published scheme leaves it to the implementation):
+                                 * 0 = the optimal reachable equilibrium for y_r (6-variable box QP; DESIGN.md, default),
+                                 * 1 = the optimal equilibrium (u_s, y_s) of the PREVIOUS solve, read from us_opt / ys_opt as the
+                                 *     previous launch left them (alpha_sr = 0 on a controller's first solve, have_prev == 0) */
+  int32_t reserved0;
   double Q[8], R[8], S[8];      /* diagonal weights (first p / m / p entries) */
   double lamb_alpha, lamb_sigma, lamb_alpha_s, lamb_sigma_s;
   double U_lo[8], U_hi[8], Us_lo[8], Us_hi[8];

@@ -353,13 +353,35 @@ def solve_alpha_sr(prm: MPCParams, u_win, y_win, y_r):
     raise RuntimeError("oracle active-set iteration (alpha_sr) did not converge")
 
 
+def solve_alpha_sr_fixed_equilibrium(prm: MPCParams, u_win, y_win, u_s, y_s):
+    """alpha_sr for a GIVEN equilibrium (u_s, y_s) - the `previous_equilibrium` anchor (SURVEY 8 a15 as recalled at survey
+    time: "alpha_sr from a 2nd equality-only QP ... with u_s^prev, y_s^prev"):
+        min lamb_alpha_s |a|^2 + lamb_sigma_s |s|^2   s.t.  H_u a = 1 (x) u_s,  H_y a = 1 (x) y_s + s,  1'a = 1.
+    It is the inner problem of `solve_alpha_sr` with the equilibrium held fixed, sigma eliminated; KKT system solved
+    with iterative refinement."""
+    ell, C, m, p = prm.ell, prm.C, prm.m, prm.p
+    Hu, Hy = hankel(u_win, ell), hankel(y_win, ell)
+    la, ls = float(prm.lamb_alpha_s), float(prm.lamb_sigma_s)
+    Y = np.tile(np.asarray(y_s, float).ravel(), ell)
+    Uv = np.tile(np.asarray(u_s, float).ravel(), ell)
+    P = 2 * (la * np.eye(C) + ls * Hy.T @ Hy)
+    q = -2 * ls * Hy.T @ Y
+    A = np.vstack([Hu, np.ones((1, C))])
+    b = np.concatenate([Uv, [1.0]])
+    K = np.zeros((C + len(b), C + len(b)))
+    K[:C, :C], K[:C, C:], K[C:, :C] = P, A.T, A
+    return _refined_solve(K, np.concatenate([-q, b]), iters=4)[:C]
+
+
 class NonlinearDDMPCOracle:
     """Single-controller mirror of the third-party `NonlinearDataDrivenMPCController` API used by
     the reference (ctor: controller_creation.py:91-112; methods: controller_evaluation.py:361-422)."""
 
     def __init__(self, n, m, p, u, y, L, Q, R, S, y_r, lamb_alpha, lamb_sigma, U, Us, alpha_reg_type=ZERO,
                  lamb_alpha_s=None, lamb_sigma_s=None, ext_out_incr_in=False, update_cost_threshold=None,
-                 n_mpc_step=1, solve_on_init=True):  # fmt: skip
+                 n_mpc_step=1, solve_on_init=True, alpha_sr_anchor="optimal_reachable_equilibrium"):  # fmt: skip
+        assert alpha_sr_anchor in ("optimal_reachable_equilibrium", "previous_equilibrium")
+        self.alpha_sr_anchor = alpha_sr_anchor
         if ext_out_incr_in or update_cost_threshold:
             raise NotImplementedError("only the shipped configuration (both off) is restated")
         u, y = np.array(u, float), np.array(y, float)
@@ -388,6 +410,10 @@ class NonlinearDDMPCOracle:
 
     def alpha_sr(self):
         prm = self.prm
+        if prm.alpha_reg_type == APPROXIMATED and self.alpha_sr_anchor == "previous_equilibrium":
+            if self.us_prev is None:  # first solve: no previous equilibrium (assumption: alpha_sr = 0)
+                return np.zeros(prm.C)
+            return solve_alpha_sr_fixed_equilibrium(prm, self.u, self.y, self.us_prev, self.ys_prev)
         if prm.alpha_reg_type == APPROXIMATED:
             return solve_alpha_sr(prm, self.u, self.y, self.y_r.ravel())
         if prm.alpha_reg_type == PREVIOUS and self.alpha_prev is not None:

@@ -262,6 +262,10 @@ class EnvOracle:
         self.extras_episode = {}
         self.body_rate_setpoints = z(N, 3)
         self.last_rpm = z(N, 4)
+        # env-steps that ended below the ground plane z = 0, which neither this restatement nor the product models
+        # (reference: plane entity with collision, hover_env.py:199); counted only when the low-altitude termination
+        # is disabled, like DDQC_F_GROUND_WATCH of the kernel
+        self.below_ground_env_steps = 0
 
     # ------------------------------------------------------------------ helpers
     def _resample_commands(self, idx, stream):
@@ -419,6 +423,8 @@ class EnvOracle:
             | np.any(np.abs(self.base_ang_vel) > F32(cfg["termination_if_ang_vel_greater_than"]), axis=1)
             | np.any(np.abs(self.base_lin_vel) > F32(cfg["termination_if_lin_vel_greater_than"]), axis=1)
         )
+        if cfg["termination_if_close_to_ground"] <= 0.0:
+            self.below_ground_env_steps += int((self.base_pos[:, 2] < F32(0.0)).sum())
         timeout = self.episode_length_buf > self.max_episode_length
         self.reset_buf = timeout | self.crash_condition
         self.time_outs = timeout.astype(F32)

@@ -402,3 +402,59 @@ def test_skipped_controllers_are_left_untouched(build_lib):
         else:  # solved again after two skipped steps (Gram regenerated: the window moved by more than one sample)
             np.testing.assert_allclose(a.optimal_u.cpu().numpy(), b.optimal_u.cpu().numpy(), rtol=0, atol=1e-6)
         assert int((a.status != 0).sum()) == 0
+
+
+def test_previous_equilibrium_anchor_matches_oracle_small(build_lib):
+    """alpha_sr_anchor="previous_equilibrium" (the reading of alpha_reg_type APPROXIMATED recalled in SURVEY 8 a15):
+    alpha_sr = 0 on the first solve, then the alpha_sr of the previous solve's optimal (u_s, y_s).  Closed loop of 5
+    steps on 6 controllers against the literal-QP oracle in the same mode; the two anchors really differ."""
+    import ddmpc_oracle as mo
+
+    prm = _small_params()
+    prm.alpha_reg_type = 0
+    B, T = 6, 5
+    u, y, plants = _synthetic_windows(prm, 3, B, return_plants=True)
+    y_r = np.tile(np.array([[0.3, -0.2, 0.5]]), (B, 1)) + 0.1 * np.arange(B)[:, None]
+    gpu = _batched(prm, u, y, y_r, solve_on_init=False, alpha_sr_anchor="previous_equilibrium")
+    ref = _batched(prm, u, y, y_r, solve_on_init=False)
+    orcs = [mo.NonlinearDDMPCOracle(**mo.ctor_kwargs(prm, u[b], y[b], y_r[b]), solve_on_init=False,
+                                    alpha_sr_anchor="previous_equilibrium") for b in range(B)]  # fmt: skip
+    differs = 0.0
+    for t in range(T):
+        gpu.update_and_solve_data_driven_mpc()
+        assert (gpu.status.cpu().numpy() == 0).all(), gpu.status
+        u0 = gpu.get_optimal_control_input_at_step(0).cpu().numpy()
+        upred = gpu.optimal_u.cpu().numpy()
+        y_new = np.stack([plants[b].step(u0[b]) for b in range(B)])
+        for b, orc in enumerate(orcs):
+            orc.update_and_solve_data_driven_mpc()
+            np.testing.assert_allclose(upred[b], orc.optimal_u, rtol=0, atol=TOL)
+            np.testing.assert_allclose(gpu.us[b].cpu().numpy(), orc.us_prev, rtol=0, atol=TOL)
+            orc.store_input_output_measurement(u0[b], y_new[b])
+        if t == 0:
+            ref.update_and_solve_data_driven_mpc()
+            differs = float(np.abs(ref.optimal_u.cpu().numpy() - upred).max())
+        gpu.store_input_output_measurement(torch.from_numpy(u0).cuda(), torch.from_numpy(y_new).cuda())
+    assert differs > 1e-4  # anchor 1's first solve (alpha_sr = 0) is not the optimal-reachable-equilibrium solution
+
+
+def test_previous_equilibrium_anchor_matches_oracle_default_size(build_lib):
+    """The same at n=6, L=35, N=350 on the PID-stabilised drone data of the golden fixture (2 closed-loop steps)."""
+    import os
+
+    import ddmpc_oracle as mo
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ddmpc_default.npz"))
+    prm = mo.default_params()
+    u, y, y_r = g["u"], g["y"], g["y_r"]
+    gpu = _batched(prm, u[None], y[None], y_r[None], solve_on_init=False, alpha_sr_anchor="previous_equilibrium")
+    orc = mo.NonlinearDDMPCOracle(**mo.ctor_kwargs(prm, u, y, y_r), solve_on_init=False, alpha_sr_anchor="previous_equilibrium")
+    for t in range(2):
+        gpu.update_and_solve_data_driven_mpc()
+        orc.update_and_solve_data_driven_mpc()
+        assert int(gpu.status[0]) == 0
+        np.testing.assert_allclose(gpu.optimal_u[0].cpu().numpy(), orc.optimal_u, rtol=0, atol=TOL)
+        np.testing.assert_allclose(gpu.us[0].cpu().numpy(), orc.us_prev, rtol=0, atol=TOL)
+        u0 = orc.optimal_u[0]
+        gpu.store_input_output_measurement(u0[None], g["y_next"][t][None])
+        orc.store_input_output_measurement(u0, g["y_next"][t])

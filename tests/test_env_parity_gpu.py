@@ -401,3 +401,30 @@ def test_env_on_a_non_current_device(build_lib):
     a0 = FusedActorMLP.random_init(device="cuda:0").act_inference(env.obs_buf.to("cuda:0"))
     assert torch.equal(a1.cpu(), a0.cpu())
     assert torch.cuda.current_device() == 0
+
+
+def test_ground_plane_watch_counts_what_the_reference_floor_would_stop(build_lib):
+    """No ground plane is modelled (reference: hover_env.py:199).  With the low-altitude termination disabled - the
+    tracking example, the DD-MPC evaluation and grid-search configurations - a drone with zero thrust falls through
+    z = 0; the kernel counts those env-steps exactly like the oracle and `check_ground_plane` warns.  With the default
+    termination (z < 0.1 resets the env) nothing is counted."""
+    N, T = 64, 40
+    over = dict(termination_if_close_to_ground=0.0, termination_if_z_greater_than=50.0, termination_if_lin_vel_greater_than=1e3)
+    env, orc = _make_pair(N, "CTBR_FIXED_YAW", False, env_over=over)
+    acts = np.zeros((T, N, 3), np.float32)
+    acts[:, : N // 2, 0] = -1.0  # zero thrust: free fall from z = 1 reaches the floor after ~0.45 s = 12 steps
+    env.reset()
+    orc.reset()
+    for t in range(T):
+        env.step(torch.from_numpy(acts[t]).cuda())
+        orc.step(acts[t])
+        _compare_step(env, orc, t)
+    assert orc.below_ground_env_steps > 0
+    assert int(env.rollout_stats()["below_ground_env_steps"]) == orc.below_ground_env_steps
+    with pytest.warns(RuntimeWarning, match="below the ground plane"):
+        assert env.check_ground_plane("test") == orc.below_ground_env_steps
+    env2, _ = _make_pair(N, "CTBR_FIXED_YAW", False)
+    env2.reset()
+    for t in range(T):
+        env2.step(torch.from_numpy(acts[t]).cuda())
+    assert env2.check_ground_plane() == 0
