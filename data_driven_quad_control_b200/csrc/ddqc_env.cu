@@ -24,8 +24,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "ddqc_device.cuh"
+#include "ddqc_env_pair.cuh"
 
 using namespace ddqc;
 
@@ -57,6 +59,18 @@ namespace {
 #endif
 #ifndef DDQC_ENV_FUSED_MAX_N
 #define DDQC_ENV_FUSED_MAX_N 32768
+#endif
+// ... and the bulk-copy tile kernel (env_step_tile_kernel) from DDQC_ENV_TILE_MIN_N envs on, in the lean configuration
+// (environment variable of the same name overrides; a huge value switches the tile kernel off)
+#ifndef DDQC_ENV_TILE_MIN_N
+#define DDQC_ENV_TILE_MIN_N (1ll << 40)  // off: measured slower than the plain kernel (see env_step_tile_kernel)
+#endif
+// ... and the pair kernel (two envs per thread on packed fp32x2 arithmetic) from DDQC_ENV_PAIR_MIN_N envs on
+#ifndef DDQC_ENV_PAIR_MIN_N
+#define DDQC_ENV_PAIR_MIN_N 65536
+#endif
+#ifndef DDQC_ENV_TILE
+#define DDQC_ENV_TILE 256  // envs per tile of the tile kernel = threads per group (1024 threads per CTA)
 #endif
 // State loads bypass L1 (ld.global.cg): every datum is read once, and the loads issued before griddepcontrol.wait must
 // not be served from lines an earlier grid left in this SM's L1.  Measured and dropped: streaming (evict-first) hints on
@@ -192,63 +206,63 @@ __device__ __forceinline__ void finalize_step(const DdqcEnvParams& P, const Ddqc
   if (lane == 10) ctl->ep_row = row;
 }
 
-// ---- the fused step kernel -------------------------------------------------------------
-// LEAN = the throughput configuration: no Euler angles needed (thresholds >= 180 deg, yaw reward
-// scale 0), no actuator / observation noise, no materialised reference buffers, no measurement
-// override.  It is the same code with those branches compiled out (fewer registers, no spills).
-template <int ACT, bool LEAN, bool FUSED, int THREADS>
-// (the full-featured instantiation gets 80 registers instead of 64: it spilled ~250 bytes per thread at 64)
-__global__ void __launch_bounds__(THREADS, (LEAN ? 1024 : 768) / THREADS)
-env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O, DdqcEnvCtl* __restrict__ ctl,
-                const float* __restrict__ actions, const float* __restrict__ meas_override, const int n) {
+// ---- one env-step for one env ------------------------------------------------------------------
+// The whole of HoverEnv.step for env `i`, state in registers from the first load to the last store.  `IO` says where
+// the env's struct-of-arrays state and its per-env outputs live: GlobalIO reads and writes global memory directly
+// (one coalesced 32-bit access per row and thread), TileIO a shared-memory tile that bulk copies fill and drain.
+enum Field { F_POS, F_QUAT, F_VEL, F_ANG, F_CMD, F_LACT, F_EPLEN, F_HOVER, F_SUMS, F_PIDI, F_PIDE };
+
+template <int ACT, bool LEAN, class IO>
+__device__ __forceinline__ void env_step_body(const DdqcEnvParams& P, const DdqcEnvOut& O, DdqcEnvCtl* __restrict__ ctl, IO& io,
+                                              const float* __restrict__ meas_override, const int n, const int i,
+                                              const bool live, const int lane, const int copy, float& rew_total,
+                                              bool& did_timeout, bool& below_ground) {
   constexpr int A = (ACT == DDQC_ACT_CTBR_FIXED_YAW) ? 3 : 4;
   constexpr int NOBS = 13 + A;
   constexpr bool USES_CTBR = (ACT != DDQC_ACT_ROTOR_RPMS);
   const bool need_euler = !LEAN && (P.flags & DDQC_F_NEED_EULER);
   const float act_noise_std = LEAN ? 0.0f : P.actuator_noise_std;
   const float obs_noise_std = LEAN ? 0.0f : P.obs_noise_std;
-
-  // Threads past the end (last CTA only) recompute env n-1 and skip every side effect, so the
-  // body is straight-line code and the warp-level reductions below need no special casing.
-  const int gid = blockIdx.x * THREADS + threadIdx.x;
-  const bool live = gid < n;
-  const int i = live ? gid : n - 1;
-  const int lane = threadIdx.x & 31;
-  const int copy = (blockIdx.x + (threadIdx.x >> 5)) % DDQC_STAT_COPIES;
   const bool indep = (P.flags & DDQC_F_INDEPENDENT_ENVS) != 0u;  // per-env instead of batch-global reset side effects
-  if (!FUSED) pdl_launch_dependents();  // the finalisation may be scheduled; it waits for this grid to complete
-
-  float rew_total = 0.0f;
-  bool did_reset = false, did_timeout = false, below_ground = false;
-
+  bool did_reset = false;
+  io.begin();
   {
     // ------------------------------------------------------------------ load state
-    V3 p{ld_state(&S.pos[i]), ld_state(&S.pos[n + i]), ld_state(&S.pos[2 * n + i])};
-    Q4 q{ld_state(&S.quat[i]), ld_state(&S.quat[n + i]), ld_state(&S.quat[2 * n + i]), ld_state(&S.quat[3 * n + i])};
-    V3 v{ld_state(&S.vel[i]), ld_state(&S.vel[n + i]), ld_state(&S.vel[2 * n + i])};
-    V3 w{ld_state(&S.ang[i]), ld_state(&S.ang[n + i]), ld_state(&S.ang[2 * n + i])};
-    V3 cmd{ld_state(&S.commands[i]), ld_state(&S.commands[n + i]), ld_state(&S.commands[2 * n + i])};
+    V3 p{io.template ld<F_POS>(0), io.template ld<F_POS>(1), io.template ld<F_POS>(2)};
+    Q4 q{io.template ld<F_QUAT>(0), io.template ld<F_QUAT>(1), io.template ld<F_QUAT>(2), io.template ld<F_QUAT>(3)};
+    V3 v{io.template ld<F_VEL>(0), io.template ld<F_VEL>(1), io.template ld<F_VEL>(2)};
+    V3 w{io.template ld<F_ANG>(0), io.template ld<F_ANG>(1), io.template ld<F_ANG>(2)};
+    V3 cmd{io.template ld<F_CMD>(0), io.template ld<F_CMD>(1), io.template ld<F_CMD>(2)};
     float last_act[A], act[A];
 #pragma unroll
     for (int j = 0; j < A; ++j) {
-      last_act[j] = ld_state(&S.last_actions[j * n + i]);
-      act[j] = clipf(actions[(size_t)i * A + j], -P.clip_actions, P.clip_actions);  // A1
+      last_act[j] = io.template ld<F_LACT>(j);
+      act[j] = clipf(io.action(j), -P.clip_actions, P.clip_actions);  // A1
     }
-    int ep_len = ld_state(&S.episode_length[i]);
-    int hover = ld_state(&S.hover_counter[i]);
+    int ep_len = io.template ldi<F_EPLEN>();
+    int hover = io.template ldi<F_HOVER>();
     float sums[DDQC_NUM_REWARDS];
 #pragma unroll
-    for (int k = 2; k < DDQC_NUM_REWARDS; ++k) sums[k] = ld_state(&S.episode_sums[k * n + i]);
+    for (int k = 2; k < DDQC_NUM_REWARDS; ++k) sums[k] = io.template ld<F_SUMS>(k);
 
     // Everything above was written by the previous STEP kernel (or earlier), which had completed before the previous
     // finalisation released this grid (it triggers its dependents after its own wait), so those loads are in flight
     // while the finalisation still runs.  What the finalisation itself writes is read below the wait: the control
     // block and the two episode sums its A15/A16 fix-ups may touch.
-    if (!FUSED) pdl_wait();
-    const uint64_t ev = ctl->rng_event;
-    const bool pid_pending = !indep && ctl->pid_reset_pending != 0u;
-    sums[0] = ld_state(&S.episode_sums[i]);
-    sums[1] = ld_state(&S.episode_sums[n + i]);
+    io.late_sync();
+    const uint64_t ev = io.rng_event(ctl);
+    const bool pid_pending = !indep && io.pid_reset_pending(ctl);
+    sums[0] = io.template ld<F_SUMS>(0);
+    sums[1] = io.template ld<F_SUMS>(1);
+    float integ[3] = {0.0f, 0.0f, 0.0f}, prev[3] = {0.0f, 0.0f, 0.0f};
+    if (USES_CTBR && !pid_pending) {  // A17: a reset anywhere in the previous launch zeroed every PID
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        integ[j] = io.template ld<F_PIDI>(j);
+        prev[j] = io.template ld<F_PIDE>(j);
+      }
+    }
+    io.inputs_done();  // nothing of this env's stored state is read below this line
 
     // ------------------------------------------------------------------ action -> rpm
     float rpm[4];
@@ -260,14 +274,6 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
         y[j] = P.act_lo[j] + ((ex - (-1.0f)) * P.act_span[j]) / 2.0f;         // A3
       }
       if (USES_CTBR) {
-        float integ[3] = {0.0f, 0.0f, 0.0f}, prev[3] = {0.0f, 0.0f, 0.0f};
-        if (!pid_pending) {  // A17: a reset anywhere in the previous launch zeroed every PID
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            integ[j] = ld_state(&S.pid_integral[j * n + i]);
-            prev[j] = ld_state(&S.pid_prev_error[j * n + i]);
-          }
-        }
         V3 meas;
         if (!LEAN && meas_override) {
           meas = V3{meas_override[i], meas_override[n + i], meas_override[2 * n + i]};
@@ -289,8 +295,8 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
           prev[j] = err;
           c[j] = (P.pid_kp[j] * err + P.pid_ki[j] * integ[j]) + P.pid_kd[j] * deriv;
           if (live) {
-            st_state(&S.pid_integral[j * n + i], integ[j]);
-            st_state(&S.pid_prev_error[j * n + i], prev[j]);
+            io.template st<F_PIDI>(j, integ[j]);
+            io.template st<F_PIDE>(j, prev[j]);
           }
         }
         c[3] = y[0];
@@ -400,8 +406,8 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
       if (USES_CTBR && indep && live) {  // ctbr_controller.reset() of this env's own instance
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          S.pid_integral[j * n + i] = 0.0f;
-          S.pid_prev_error[j * n + i] = 0.0f;
+          io.template st<F_PIDI>(j, 0.0f);
+          io.template st<F_PIDE>(j, 0.0f);
         }
       }
       V3 ip{P.init_pos[0], P.init_pos[1], P.init_pos[2]};
@@ -522,42 +528,42 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
 
     // ------------------------------------------------------------------ store
     if (live) {
-    st_state(&S.pos[i], p.x);
-    st_state(&S.pos[n + i], p.y);
-    st_state(&S.pos[2 * n + i], p.z);
-    st_state(&S.quat[i], q.w);
-    st_state(&S.quat[n + i], q.x);
-    st_state(&S.quat[2 * n + i], q.y);
-    st_state(&S.quat[3 * n + i], q.z);
-    st_state(&S.vel[i], v.x);
-    st_state(&S.vel[n + i], v.y);
-    st_state(&S.vel[2 * n + i], v.z);
-    st_state(&S.ang[i], w.x);
-    st_state(&S.ang[n + i], w.y);
-    st_state(&S.ang[2 * n + i], w.z);
-    st_state(&S.commands[i], cmd_new.x);
-    st_state(&S.commands[n + i], cmd_new.y);
-    st_state(&S.commands[2 * n + i], cmd_new.z);
+    io.template st<F_POS>(0, p.x);
+    io.template st<F_POS>(1, p.y);
+    io.template st<F_POS>(2, p.z);
+    io.template st<F_QUAT>(0, q.w);
+    io.template st<F_QUAT>(1, q.x);
+    io.template st<F_QUAT>(2, q.y);
+    io.template st<F_QUAT>(3, q.z);
+    io.template st<F_VEL>(0, v.x);
+    io.template st<F_VEL>(1, v.y);
+    io.template st<F_VEL>(2, v.z);
+    io.template st<F_ANG>(0, w.x);
+    io.template st<F_ANG>(1, w.y);
+    io.template st<F_ANG>(2, w.z);
+    io.template st<F_CMD>(0, cmd_new.x);
+    io.template st<F_CMD>(1, cmd_new.y);
+    io.template st<F_CMD>(2, cmd_new.z);
 #pragma unroll
-    for (int j = 0; j < A; ++j) st_state(&S.last_actions[j * n + i], act[j]);  // hover_env.py:544, all envs
-    st_state(&S.episode_length[i], ep_len);
-    st_state(&S.hover_counter[i], hover);
+    for (int j = 0; j < A; ++j) io.template st<F_LACT>(j, act[j]);  // hover_env.py:544, all envs
+    io.template sti<F_EPLEN>(ep_len);
+    io.template sti<F_HOVER>(hover);
 #pragma unroll
-    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) st_state(&S.episode_sums[k * n + i], sums[k]);
+    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) io.template st<F_SUMS>(k, sums[k]);
 
-    if (NOBS == 16) {
+    if (NOBS == 16) {  // 64-byte observation rows: four 16-byte stores straight to global memory in both variants
       float4* o4 = reinterpret_cast<float4*>(O.obs + (size_t)i * 16);
-      st_out(&o4[0], make_float4(obs[0], obs[1], obs[2], obs[3]));
-      st_out(&o4[1], make_float4(obs[4], obs[5], obs[6], obs[7]));
-      st_out(&o4[2], make_float4(obs[8], obs[9], obs[10], obs[11]));
-      st_out(&o4[3], make_float4(obs[12], obs[13], obs[14], obs[15]));
+      o4[0] = make_float4(obs[0], obs[1], obs[2], obs[3]);
+      o4[1] = make_float4(obs[4], obs[5], obs[6], obs[7]);
+      o4[2] = make_float4(obs[8], obs[9], obs[10], obs[11]);
+      o4[3] = make_float4(obs[12], obs[13], obs[14], obs[15]);
     } else {
 #pragma unroll
       for (int j = 0; j < NOBS; ++j) O.obs[(size_t)i * NOBS + j] = obs[j];
     }
-    st_out(&O.rew[i], rew);
-    st_out(&O.reset[i], (uint8_t)(did_reset ? 1 : 0));
-    st_out(&O.time_outs[i], did_timeout ? 1.0f : 0.0f);
+    io.rew(rew);
+    io.reset((uint8_t)(did_reset ? 1 : 0));
+    io.time_out(did_timeout ? 1.0f : 0.0f);
 
     if (!LEAN && O.base_lin_vel) {
       O.base_lin_vel[i] = lin_b.x;
@@ -593,20 +599,293 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
     }  // live
   }
 
-  // -------------------------------------------------------------------- statistics
-  // time-out count by ballot, reward total by a shuffle tree; one RED per warp each
-  {
-    unsigned int tmask = __ballot_sync(0xffffffffu, did_timeout);
-    float r = rew_total;
+}
+
+// time-out count by ballot, reward total by a shuffle tree, below-ground count by ballot; one RED per warp each
+__device__ __forceinline__ void warp_stats(const DdqcEnvParams& P, DdqcEnvCtl* __restrict__ ctl, const int lane, const int copy,
+                                           const float rew_total, const bool did_timeout, const bool below_ground) {
+  unsigned int tmask = __ballot_sync(0xffffffffu, did_timeout);
+  float r = rew_total;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-    if (lane == 7) atomicAdd(&ctl->acc_sums[copy][7], r);
-    if (lane == 9 && tmask) atomicAdd(&ctl->acc_timeout[copy], (unsigned int)__popc(tmask));
-    if (P.flags & DDQC_F_GROUND_WATCH) {  // no ground plane here: count the env-steps the reference's floor would have changed
-      const unsigned int gmask = __ballot_sync(0xffffffffu, below_ground);
-      if (lane == 10 && gmask) atomicAdd(&ctl->acc_ground[copy], (unsigned int)__popc(gmask));
-    }
+  for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  if (lane == 7) atomicAdd(&ctl->acc_sums[copy][7], r);
+  if (lane == 9 && tmask) atomicAdd(&ctl->acc_timeout[copy], (unsigned int)__popc(tmask));
+  if (P.flags & DDQC_F_GROUND_WATCH) {  // no ground plane here: count the env-steps the reference's floor would have changed
+    const unsigned int gmask = __ballot_sync(0xffffffffu, below_ground);
+    if (lane == 10 && gmask) atomicAdd(&ctl->acc_ground[copy], (unsigned int)__popc(gmask));
   }
+}
+
+// state and outputs in global memory
+template <int A, bool FUSED>
+struct GlobalIO {
+  const DdqcEnvState& S;
+  const DdqcEnvOut& O;
+  const float* __restrict__ actions;
+  const int n, i;
+  const bool live;
+  template <int F>
+  __device__ __forceinline__ float* fptr() const {
+    if constexpr (F == F_POS) return S.pos;
+    else if constexpr (F == F_QUAT) return S.quat;
+    else if constexpr (F == F_VEL) return S.vel;
+    else if constexpr (F == F_ANG) return S.ang;
+    else if constexpr (F == F_CMD) return S.commands;
+    else if constexpr (F == F_LACT) return S.last_actions;
+    else if constexpr (F == F_SUMS) return S.episode_sums;
+    else if constexpr (F == F_PIDI) return S.pid_integral;
+    else return S.pid_prev_error;
+  }
+  template <int F>
+  __device__ __forceinline__ float ld(int c) const { return ld_state(&fptr<F>()[c * n + i]); }
+  template <int F>
+  __device__ __forceinline__ int ldi() const { return ld_state(F == F_EPLEN ? &S.episode_length[i] : &S.hover_counter[i]); }
+  template <int F>
+  __device__ __forceinline__ void st(int c, float v) const { fptr<F>()[c * n + i] = v; }  // callers guard with `live`
+  template <int F>
+  __device__ __forceinline__ void sti(int v) const { (F == F_EPLEN ? S.episode_length : S.hover_counter)[i] = v; }
+  __device__ __forceinline__ float action(int j) const { return actions[(size_t)i * A + j]; }
+  __device__ __forceinline__ void rew(float v) const { O.rew[i] = v; }
+  __device__ __forceinline__ void reset(uint8_t v) const { O.reset[i] = v; }
+  __device__ __forceinline__ void time_out(float v) const { O.time_outs[i] = v; }
+  __device__ __forceinline__ void begin() const {}
+  __device__ __forceinline__ void inputs_done() const {}
+  __device__ __forceinline__ uint64_t rng_event(const DdqcEnvCtl* ctl) const { return ctl->rng_event; }
+  __device__ __forceinline__ bool pid_reset_pending(const DdqcEnvCtl* ctl) const { return ctl->pid_reset_pending != 0u; }
+  // What the finalisation of the previous step writes (control block, fix-up episode sums) is read after this point
+  __device__ __forceinline__ void late_sync() const { if (!FUSED) pdl_wait(); }
+};
+
+// ---- the tile kernel: persistent CTAs, the state of the NEXT tile staged through shared memory by bulk copies ------
+// One CTA per SM, kGroups groups of kTile threads (32 warps of 64 registers, like the plain kernel); a group walks its
+// own stream of kTile-env tiles.  A tile's ~34 input rows (kTile x 4 bytes each, contiguous in the struct-of-arrays
+// storage) and its action slab arrive in the group's shared-memory buffer as 1-D bulk copies (cp.async.bulk -> mbarrier
+// complete_tx).  The threads read their env's column into registers, a group barrier says "the buffer has been read",
+// and the lane-0 threads of the group's warps (warp w moves the rows r = w mod 8) immediately refill the SAME buffer
+// with the next tile: its loads fly during the ~1100 instructions of arithmetic on the current one, so no warp ever
+// waits on DRAM, and the input side needs no per-access 64-bit address arithmetic (shared-memory loads with immediate
+// offsets).  The new state and the outputs go straight from the registers to global memory (stores do not stall).
+// Measured and dropped on the way: outputs staged through shared memory as well and drained by bulk stores - it needs two
+// 40 KB buffers per group, i.e. 16 warps per SM instead of 32, and this arithmetic (dependent fp32 chains, no FMA
+// contraction) needs 8 warps per scheduler: 84.8 us per 2^20 envs against 63.4 us for the plain kernel.
+constexpr int kTile = DDQC_ENV_TILE;
+constexpr int kGroups = 1024 / kTile;
+constexpr int kTileThreads = kTile * kGroups;
+constexpr int kGroupWarps = kTile / 32;
+
+template <int A>
+struct TileRows {
+  static constexpr int POS = 0, QUAT = 3, VEL = 7, ANG = 10, CMD = 13, LACT = 16, EPLEN = 16 + A, HOVER = 17 + A,
+                       SUMS = 18 + A, PIDI = 25 + A, PIDE = 28 + A, NROWS = 31 + A;
+  static constexpr int ROW_BYTES = kTile * 4;
+  static constexpr int ACT_OFF = NROWS * kTile;                        // float index of the action slab [kTile][A]
+  static constexpr int BUF_BYTES = ((NROWS + A) * ROW_BYTES + 127) / 128 * 128;
+  static constexpr int BAR_OFF = BUF_BYTES * kGroups;                  // mbarriers: [group][main | late]
+  static constexpr int PTR_OFF = BAR_OFF + 8 * 2 * kGroups;            // uint64 global base address of every row
+  static constexpr int SMEM_BYTES = PTR_OFF + 8 * NROWS;
+  template <int F>
+  __host__ __device__ static constexpr int row0() {
+    return F == F_POS ? POS : F == F_QUAT ? QUAT : F == F_VEL ? VEL : F == F_ANG ? ANG : F == F_CMD ? CMD : F == F_LACT ? LACT
+         : F == F_EPLEN ? EPLEN : F == F_HOVER ? HOVER : F == F_SUMS ? SUMS : F == F_PIDI ? PIDI : PIDE;
+  }
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// The bulk copies of one tile into a group's buffer, all by ONE thread (the groups' warps take turns from tile to tile):
+// ~5 instructions per copy, straight-line, instead of every warp of the group walking its share of the row list.  The
+// expected byte counts are posted before the copies that will complete them.
+template <int A, bool USES_CTBR>
+__device__ __forceinline__ void tile_issue_loads(const unsigned long long* __restrict__ rowptr, const float* __restrict__ actions,
+                                                 uint32_t dst0, uint32_t bar_main, int tile, bool main_rows, bool late_rows,
+                                                 bool pid_rows) {
+  using R = TileRows<A>;
+  const uint32_t bar_late = bar_main + 8;
+  const bool pid = USES_CTBR && pid_rows;
+  if (main_rows) mbar_arrive_expect_tx(bar_main, (uint32_t)((R::PIDI - 2) * R::ROW_BYTES + kTile * A * 4));
+  if (late_rows) mbar_arrive_expect_tx(bar_late, (uint32_t)((2 + (pid ? 6 : 0)) * R::ROW_BYTES));
+  const size_t off = (size_t)tile * R::ROW_BYTES;
+#pragma unroll
+  for (int r = 0; r < R::NROWS; ++r) {
+    const bool is_pid = r >= R::PIDI, is_late = is_pid || r == R::SUMS || r == R::SUMS + 1;
+    if (is_late ? !late_rows : !main_rows) continue;
+    if (is_pid && !pid) continue;
+    bulk_load(dst0 + (uint32_t)(r * R::ROW_BYTES), reinterpret_cast<const char*>((uintptr_t)rowptr[r]) + off, R::ROW_BYTES,
+              is_late ? bar_late : bar_main);
+  }
+  if (main_rows)  // the tile's action slab [kTile][A], contiguous
+    bulk_load(dst0 + (uint32_t)(R::ACT_OFF * 4), actions + (size_t)tile * kTile * A, kTile * A * 4, bar_main);
+}
+
+// inputs of one env from the group's shared-memory buffer (column `gt` of every row), outputs to global memory
+template <int A, bool USES_CTBR>
+struct TileIO {
+  using R = TileRows<A>;
+  const float* buf;      // the group's buffer, as floats
+  const DdqcEnvState& S;
+  const DdqcEnvOut& O;
+  const unsigned long long* rowptr;
+  const float* actions;
+  const int n, i, gt, g;
+  const uint32_t buf_addr, bar_main, parity;
+  const int next_tile;   // < 0: this stream has no further tile
+  const bool issuer;     // this thread issues the next tile's copies
+  const bool pid_rows;
+  const uint64_t ev;     // control-block values, read once per launch
+  const bool pid_pending;
+  template <int F>
+  __device__ __forceinline__ float* fptr() const {
+    if constexpr (F == F_POS) return S.pos;
+    else if constexpr (F == F_QUAT) return S.quat;
+    else if constexpr (F == F_VEL) return S.vel;
+    else if constexpr (F == F_ANG) return S.ang;
+    else if constexpr (F == F_CMD) return S.commands;
+    else if constexpr (F == F_LACT) return S.last_actions;
+    else if constexpr (F == F_SUMS) return S.episode_sums;
+    else if constexpr (F == F_PIDI) return S.pid_integral;
+    else return S.pid_prev_error;
+  }
+  template <int F>
+  __device__ __forceinline__ float ld(int c) const { return buf[(R::template row0<F>() + c) * kTile + gt]; }
+  template <int F>
+  __device__ __forceinline__ int ldi() const { return __float_as_int(buf[R::template row0<F>() * kTile + gt]); }
+  template <int F>
+  __device__ __forceinline__ void st(int c, float v) const { fptr<F>()[c * n + i] = v; }
+  template <int F>
+  __device__ __forceinline__ void sti(int v) const { (F == F_EPLEN ? S.episode_length : S.hover_counter)[i] = v; }
+  __device__ __forceinline__ float action(int j) const { return buf[R::ACT_OFF + gt * A + j]; }
+  __device__ __forceinline__ void rew(float v) const { O.rew[i] = v; }
+  __device__ __forceinline__ void reset(uint8_t v) const { O.reset[i] = v; }
+  __device__ __forceinline__ void time_out(float v) const { O.time_outs[i] = v; }
+  __device__ __forceinline__ void begin() const { mbar_wait_parity(bar_main, parity); }          // the main rows have landed
+  __device__ __forceinline__ void late_sync() const { mbar_wait_parity(bar_main + 8, parity); }  // ... and the late ones
+  // every thread of the group has its inputs in registers: the buffer is refilled with the stream's next tile, whose
+  // copies then run under the arithmetic of this one
+  __device__ __forceinline__ void inputs_done() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kTile) : "memory");
+    if (issuer && next_tile >= 0) tile_issue_loads<A, USES_CTBR>(rowptr, actions, buf_addr, bar_main, next_tile, true, true, pid_rows);
+  }
+  __device__ __forceinline__ uint64_t rng_event(const DdqcEnvCtl*) const { return ev; }
+  __device__ __forceinline__ bool pid_reset_pending(const DdqcEnvCtl*) const { return pid_pending; }
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(kTileThreads, 1)
+env_step_tile_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O, DdqcEnvCtl* __restrict__ ctl,
+                     const float* __restrict__ actions, const int n, const int n_tiles) {
+  constexpr int A = (ACT == DDQC_ACT_CTBR_FIXED_YAW) ? 3 : 4;
+  constexpr bool USES_CTBR = (ACT != DDQC_ACT_ROTOR_RPMS);
+  using R = TileRows<A>;
+  extern __shared__ __align__(128) uint8_t tile_smem[];
+  const int tid = threadIdx.x, g = tid / kTile, gt = tid % kTile, gw = gt >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(tile_smem);
+  unsigned long long* rowptr = reinterpret_cast<unsigned long long*>(tile_smem + R::PTR_OFF);
+
+  // ---- one-time setup: global base address of every input row, mbarriers ----
+  if (tid < R::NROWS) {
+    const int r = tid;
+    const float* base;
+    if (r < R::QUAT) base = S.pos + (size_t)(r - R::POS) * n;
+    else if (r < R::VEL) base = S.quat + (size_t)(r - R::QUAT) * n;
+    else if (r < R::ANG) base = S.vel + (size_t)(r - R::VEL) * n;
+    else if (r < R::CMD) base = S.ang + (size_t)(r - R::ANG) * n;
+    else if (r < R::LACT) base = S.commands + (size_t)(r - R::CMD) * n;
+    else if (r < R::EPLEN) base = S.last_actions + (size_t)(r - R::LACT) * n;
+    else if (r == R::EPLEN) base = reinterpret_cast<const float*>(S.episode_length);
+    else if (r == R::HOVER) base = reinterpret_cast<const float*>(S.hover_counter);
+    else if (r < R::PIDI) base = S.episode_sums + (size_t)(r - R::SUMS) * n;
+    else if (r < R::PIDE) base = USES_CTBR ? S.pid_integral + (size_t)(r - R::PIDI) * n : nullptr;
+    else base = USES_CTBR ? S.pid_prev_error + (size_t)(r - R::PIDE) * n : nullptr;
+    rowptr[r] = (unsigned long long)(uintptr_t)base;
+  }
+  if (tid < 2 * kGroups) mbar_init(sbase + R::BAR_OFF + 8 * tid, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const int stream = blockIdx.x * kGroups + g, n_streams = gridDim.x * kGroups;
+  const int copy = (stream + gw) % DDQC_STAT_COPIES;
+  const uint32_t bar_main = sbase + R::BAR_OFF + 16 * g;
+  const uint32_t buf_addr = sbase + (uint32_t)(R::BUF_BYTES * g);
+  const float* buf = reinterpret_cast<const float*>(tile_smem + R::BUF_BYTES * g);
+
+  const int t0 = stream;
+  pdl_launch_dependents();
+  // The main rows were written by the previous STEP kernel, complete before the previous finalisation released this grid:
+  // their copies start before the wait.  The late rows (the two episode sums a fix-up may touch, the PID state whose
+  // need depends on the control block) start after it.
+  if (gt == 0 && t0 < n_tiles) tile_issue_loads<A, USES_CTBR>(rowptr, actions, buf_addr, bar_main, t0, true, false, false);
+  pdl_wait();
+  const bool indep = (P.flags & DDQC_F_INDEPENDENT_ENVS) != 0u;
+  const uint64_t ev = ctl->rng_event;
+  const bool pid_pending = ctl->pid_reset_pending != 0u;
+  const bool pid_rows = indep || !pid_pending;  // A17: a pending whole-batch reset makes the stored PID state moot
+  if (gt == 0 && t0 < n_tiles) tile_issue_loads<A, USES_CTBR>(rowptr, actions, buf_addr, bar_main, t0, false, true, pid_rows);
+
+  int it = 0;
+  for (int tile = t0; tile < n_tiles; tile += n_streams, ++it) {
+    float rew_total = 0.0f;
+    bool did_timeout = false, below_ground = false;
+    const int i = tile * kTile + gt;
+    TileIO<A, USES_CTBR> io{buf, S, O, rowptr, actions, n, i, gt, g, buf_addr, bar_main, (uint32_t)it & 1u,
+                            tile + n_streams < n_tiles ? tile + n_streams : -1, lane == 0 && gw == (it + 1) % kGroupWarps,
+                            pid_rows, ev, pid_pending};
+    env_step_body<ACT, true>(P, O, ctl, io, nullptr, n, i, true, lane, copy, rew_total, did_timeout, below_ground);
+    warp_stats(P, ctl, lane, copy, rew_total, did_timeout, below_ground);
+  }
+}
+
+// ---- the step kernel, one thread per env, state straight from / to global memory --------------------------
+// LEAN = the throughput configuration: no Euler angles needed (thresholds >= 180 deg, yaw reward
+// scale 0), no actuator / observation noise, no materialised reference buffers, no measurement
+// override.  It is the same code with those branches compiled out (fewer registers, no spills).
+#ifndef DDQC_ENV_LEAN_WARPS
+#define DDQC_ENV_LEAN_WARPS 32  // resident warps per SM the lean instantiation is compiled for (32 -> 64 registers);
+#endif                          // measured: 40 warps (48 registers, 96 B of spills) 72.7 us, 48 warps 84.7 us against 64.0 us
+template <int ACT, bool LEAN, bool FUSED, int THREADS, bool TAIL>
+// (the full-featured instantiation gets 80 registers instead of 64: it spilled ~250 bytes per thread at 64)
+__global__ void __launch_bounds__(THREADS, (LEAN ? 32 * DDQC_ENV_LEAN_WARPS : 768) / THREADS)
+env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O, DdqcEnvCtl* __restrict__ ctl,
+                const float* __restrict__ actions, const float* __restrict__ meas_override, const int n, const int i0) {
+  constexpr int A = (ACT == DDQC_ACT_CTBR_FIXED_YAW) ? 3 : 4;
+  constexpr int NOBS = 13 + A;
+  constexpr bool USES_CTBR = (ACT != DDQC_ACT_ROTOR_RPMS);
+  // Threads past the end (last CTA only) recompute env n-1 and skip every side effect, so the
+  // body is straight-line code and the warp-level reductions below need no special casing.
+  // (TAIL: the launch covers the ragged tail [i0, n) behind the tile kernel; a plain launch has i0 = 0 compiled in -
+  // the extra live register made the 64-register instantiation spill.)
+  const int gid = (TAIL ? i0 : 0) + blockIdx.x * THREADS + threadIdx.x;
+  const bool live = gid < n;
+  const int i = live ? gid : n - 1;
+  const int lane = threadIdx.x & 31;
+  const int copy = (blockIdx.x + (threadIdx.x >> 5)) % DDQC_STAT_COPIES;
+  if (!FUSED) pdl_launch_dependents();  // the finalisation may be scheduled; it waits for this grid to complete
+
+  float rew_total = 0.0f;
+  bool did_timeout = false, below_ground = false;
+  GlobalIO<A, FUSED> io{S, O, actions, n, i, live};
+  env_step_body<ACT, LEAN>(P, O, ctl, io, meas_override, n, i, live, lane, copy, rew_total, did_timeout, below_ground);
+  warp_stats(P, ctl, lane, copy, rew_total, did_timeout, below_ground);
 
   if (FUSED) {
     // ------------------------------------------------------------------ last-CTA finalisation
@@ -623,6 +902,429 @@ env_step_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvOut O,
     if (!is_last) return;
     __threadfence();
     finalize_step<NOBS, LEAN, USES_CTBR>(P, S, O, ctl, n, lane);
+  }
+}
+
+// ---- the pair kernel: two envs per thread on packed fp32x2 arithmetic (ddqc_env_pair.cuh) -------------------------
+// Lean configuration only.  The statement order is that of env_step_body; every value is the (env 2j, env 2j+1) pair.
+#ifndef DDQC_ENV_PAIR_THREADS
+#define DDQC_ENV_PAIR_THREADS 128
+#endif
+#ifndef DDQC_ENV_PAIR_BLOCKS
+#define DDQC_ENV_PAIR_BLOCKS 4  // 128 registers per thread
+#endif
+constexpr int kPairThreads = DDQC_ENV_PAIR_THREADS;
+
+__device__ __forceinline__ f2 ldp(const float* p) { return f2{__ldcg(reinterpret_cast<const unsigned long long*>(p))}; }
+__device__ __forceinline__ void stp(float* p, f2 v) { *reinterpret_cast<unsigned long long*>(p) = v.v; }
+
+template <int ACT>
+__global__ void __launch_bounds__(kPairThreads, DDQC_ENV_PAIR_BLOCKS)
+env_step_pair_kernel(const DdqcEnvParams P, const EnvParams2 PP, const DdqcEnvState S, const DdqcEnvOut O,
+                     DdqcEnvCtl* __restrict__ ctl, const float* __restrict__ actions, const int n) {
+  constexpr int A = (ACT == DDQC_ACT_CTBR_FIXED_YAW) ? 3 : 4;
+  constexpr int NOBS = 13 + A;
+  constexpr bool USES_CTBR = (ACT != DDQC_ACT_ROTOR_RPMS);
+  const PairMath M{PP};
+  const int n_pairs = n >> 1;
+  const int gid = blockIdx.x * kPairThreads + threadIdx.x;
+  const bool live = gid < n_pairs;
+  const int i = 2 * (live ? gid : n_pairs - 1);  // first env of the pair; threads past the end redo the last pair, no side effects
+  const int lane = threadIdx.x & 31;
+  const int copy = (blockIdx.x + (threadIdx.x >> 5)) % DDQC_STAT_COPIES;
+  const bool indep = (P.flags & DDQC_F_INDEPENDENT_ENVS) != 0u;
+  pdl_launch_dependents();
+
+  // ------------------------------------------------------------------ load state
+  V3p p{ldp(S.pos + i), ldp(S.pos + n + i), ldp(S.pos + 2 * n + i)};
+  Q4p q{ldp(S.quat + i), ldp(S.quat + n + i), ldp(S.quat + 2 * n + i), ldp(S.quat + 3 * n + i)};
+  V3p v{ldp(S.vel + i), ldp(S.vel + n + i), ldp(S.vel + 2 * n + i)};
+  V3p w{ldp(S.ang + i), ldp(S.ang + n + i), ldp(S.ang + 2 * n + i)};
+  V3p cmd{ldp(S.commands + i), ldp(S.commands + n + i), ldp(S.commands + 2 * n + i)};
+  f2 last_act[A], act[A];
+#pragma unroll
+  for (int j = 0; j < A; ++j) last_act[j] = ldp(S.last_actions + j * n + i);
+  {
+    float a0[A], a1[A];  // the two action rows are adjacent: 2A consecutive floats
+    if (A == 3) {
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(actions + (size_t)i * 3);
+      const f2 u0{src[0]}, u1{src[1]}, u2{src[2]};
+      a0[0] = lo(u0), a0[1] = hi(u0), a0[2] = lo(u1), a1[0] = hi(u1), a1[1] = lo(u2), a1[2] = hi(u2);
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(actions + (size_t)i * 4);
+      const float4 r0 = src[0], r1 = src[1];
+      a0[0] = r0.x, a0[1] = r0.y, a0[2] = r0.z, a0[A - 1] = r0.w;
+      a1[0] = r1.x, a1[1] = r1.y, a1[2] = r1.z, a1[A - 1] = r1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < A; ++j) act[j] = pk(clipf(a0[j], -P.clip_actions, P.clip_actions), clipf(a1[j], -P.clip_actions, P.clip_actions));  // A1
+  }
+  int2 ep_len = __ldcg(reinterpret_cast<const int2*>(S.episode_length + i));
+  int2 hover = __ldcg(reinterpret_cast<const int2*>(S.hover_counter + i));
+  f2 sums[DDQC_NUM_REWARDS];
+#pragma unroll
+  for (int k = 2; k < DDQC_NUM_REWARDS; ++k) sums[k] = ldp(S.episode_sums + k * n + i);
+
+  // as in env_step_body: what the previous finalisation writes is read below the wait
+  pdl_wait();
+  const uint64_t ev = ctl->rng_event;
+  const bool pid_pending = !indep && ctl->pid_reset_pending != 0u;
+  sums[0] = ldp(S.episode_sums + i);
+  sums[1] = ldp(S.episode_sums + n + i);
+  f2 integ[3], prev[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) integ[j] = prev[j] = LIT(L_ZERO);
+  if (USES_CTBR && !pid_pending) {  // A17
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      integ[j] = ldp(S.pid_integral + j * n + i);
+      prev[j] = ldp(S.pid_prev_error + j * n + i);
+    }
+  }
+
+  // ------------------------------------------------------------------ action -> rpm
+  f2 rpm[4];
+  {
+    f2 y[A];
+#pragma unroll
+    for (int j = 0; j < A; ++j) {
+      const f2 ex = (P.flags & DDQC_F_ACTION_LATENCY) ? last_act[j] : act[j];  // A2
+      // A3: lo + ((x - (-1)) * span) / 2;  x - (-1) == x + 1 and / 2 == * 0.5 in IEEE arithmetic
+      y[j] = add2(K2A(act_lo, j), M.mul2(M.mul2(add2(ex, LIT(L_ONE)), K2A(act_span, j)), LIT(L_HALF)));
+    }
+    if (USES_CTBR) {
+      const Q4p qc{q.w, neg2(q.x), neg2(q.y), neg2(q.z)};
+      const V3p meas = M.rotate_by_quat(M.rotate_by_quat(w, q), qc);  // A5
+      f2 sp[3];
+      sp[0] = y[1];
+      sp[1] = y[2];
+      sp[2] = (ACT == DDQC_ACT_CTBR) ? y[A - 1] : LIT(L_ZERO);  // A4
+      const f2 ms[3] = {meas.x, meas.y, meas.z};
+      f2 c[4];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const f2 err = sub2(sp[j], ms[j]);
+        integ[j] = add2(integ[j], M.mul2(err, K2(step_dt)));  // A6
+        const f2 deriv = M.mul2(sub2(err, prev[j]), K2(inv_step_dt));
+        prev[j] = err;
+        c[j] = add2(add2(M.mul2(K2A(pid_kp, j), err), M.mul2(K2A(pid_ki, j), integ[j])), M.mul2(K2A(pid_kd, j), deriv));
+        if (live) {
+          stp(S.pid_integral + j * n + i, integ[j]);
+          stp(S.pid_prev_error + j * n + i, prev[j]);
+        }
+      }
+      c[3] = y[0];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        f2 f = add2(add2(add2(M.mul2(K2A(mixer, 4 * r + 0), c[0]), M.mul2(K2A(mixer, 4 * r + 1), c[1])),
+                         M.mul2(K2A(mixer, 4 * r + 2), c[2])),
+                    M.mul2(K2A(mixer, 4 * r + 3), c[3]));
+        f = pk(lo(f) < 0.0f ? 0.0f : lo(f), hi(f) < 0.0f ? 0.0f : hi(f));  // A7
+        rpm[r] = M.mul2(sqrt2(f), K2(inv_sqrt_kf));
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) rpm[r] = y[r < A ? r : 0];
+    }
+  }
+
+  // ------------------------------------------------------------------ physics (A8)
+  const V3p last_pos = p;
+  {
+    // rotor_wrench
+    const f2 s0 = M.mul2(rpm[0], rpm[0]), s1 = M.mul2(rpm[1], rpm[1]), s2 = M.mul2(rpm[2], rpm[2]), s3 = M.mul2(rpm[3], rpm[3]);
+    const f2 t0 = M.mul2(s0, K2(kf)), t1 = M.mul2(s1, K2(kf)), t2 = M.mul2(s2, K2(kf)), t3 = M.mul2(s3, K2(kf));
+    const f2 fz = add2(add2(add2(t0, t1), t2), t3);
+    const f2 tau_x = fma2(t3, K2A(arm_x, 3), fma2(t2, K2A(arm_x, 2), fma2(t1, K2A(arm_x, 1), M.mul2(t0, K2A(arm_x, 0)))));
+    const f2 tau_y = fma2(t3, K2A(arm_y, 3), fma2(t2, K2A(arm_y, 2), fma2(t1, K2A(arm_y, 1), M.mul2(t0, K2A(arm_y, 0)))));
+    const f2 tau_z = fma2(s3, K2A(km_spin, 3), fma2(s2, K2A(km_spin, 2), fma2(s1, K2A(km_spin, 1), M.mul2(s0, K2A(km_spin, 0)))));
+    const WrenchP W{M.mul2(K2A(k_w, 0), tau_x), M.mul2(K2A(k_w, 1), tau_y), M.mul2(K2A(k_w, 2), tau_z),
+                    M.mul2(K2(two_dt_over_m), fz), M.mul2(K2(dt_over_m), fz)};
+    for (int sidx = 0; sidx < P.decimation; ++sidx) {  // substep
+      const f2 nwx = fma2(neg2(K2A(b_w, 0)), M.mul2(w.y, w.z), add2(w.x, W.ax));
+      const f2 nwy = fma2(neg2(K2A(b_w, 1)), M.mul2(w.z, w.x), add2(w.y, W.ay));
+      const f2 nwz = fma2(neg2(K2A(b_w, 2)), M.mul2(w.x, w.y), add2(w.z, W.az));
+      w = V3p{nwx, nwy, nwz};
+      v.x = fma2(W.cxy, fma2(q.x, q.z, M.mul2(q.w, q.y)), v.x);
+      v.y = fma2(W.cxy, fma2(q.y, q.z, neg2(M.mul2(q.w, q.x))), v.y);
+      const f2 r33 = fma2(LIT(L_MINUS_TWO), fma2(q.x, q.x, M.mul2(q.y, q.y)), LIT(L_ONE));
+      v.z = fma2(W.cz, r33, sub2(v.z, K2(dt_g)));
+      p.x = fma2(v.x, K2(dt), p.x);
+      p.y = fma2(v.y, K2(dt), p.y);
+      p.z = fma2(v.z, K2(dt), p.z);
+      const f2 hx = M.mul2(w.x, K2(half_dt)), hy = M.mul2(w.y, K2(half_dt)), hz = M.mul2(w.z, K2(half_dt));
+      const f2 s = fma2(hz, hz, fma2(hy, hy, M.mul2(hx, hx)));
+      f2 c = fma2(s, K2A(cos_coef, 4), K2A(cos_coef, 3));  // horner5
+      c = fma2(c, s, K2A(cos_coef, 2));
+      c = fma2(c, s, K2A(cos_coef, 1));
+      c = fma2(c, s, K2A(cos_coef, 0));
+      f2 k = fma2(s, K2A(sinc_coef, 4), K2A(sinc_coef, 3));
+      k = fma2(k, s, K2A(sinc_coef, 2));
+      k = fma2(k, s, K2A(sinc_coef, 1));
+      k = fma2(k, s, K2A(sinc_coef, 0));
+      const Q4p nq = M.quat_mul(q, Q4p{c, M.mul2(k, hx), M.mul2(k, hy), M.mul2(k, hz)});
+      const f2 n2 = fma2(nq.z, nq.z, fma2(nq.y, nq.y, fma2(nq.x, nq.x, M.mul2(nq.w, nq.w))));
+      const f2 inv_n = fma2(LIT(L_MINUS_HALF), n2, LIT(L_ONE_HALF));
+      q = Q4p{M.mul2(nq.w, inv_n), M.mul2(nq.x, inv_n), M.mul2(nq.y, inv_n), M.mul2(nq.z, inv_n)};
+    }
+  }
+
+  // ------------------------------------------------------------------ buffers (A9-A12)
+  ep_len.x += 1;
+  ep_len.y += 1;
+  V3p rel{sub2(cmd.x, p.x), sub2(cmd.y, p.y), sub2(cmd.z, p.z)};
+  V3p last_rel{sub2(cmd.x, last_pos.x), sub2(cmd.y, last_pos.y), sub2(cmd.z, last_pos.z)};
+  const Q4p qc{q.w, neg2(q.x), neg2(q.y), neg2(q.z)};
+  V3p lin_b = M.rotate_by_quat(v, qc);
+  V3p ang_b = M.rotate_by_quat(M.rotate_by_quat(w, q), qc);
+
+  // ------------------------------------------------------------------ hover / resample (A13-A15)
+  b2 hover_resampled{false, false};
+  V3p cmd_new = cmd;
+  if (P.flags & DDQC_F_AUTO_TARGET) {
+    const f2 dist = sqrt2(M.sumsq3(rel));
+    const b2 at_target{lo(dist) < P.at_target_threshold, hi(dist) < P.at_target_threshold};
+    b2 fire;
+    if (P.min_hover_steps > 0) {
+      hover.x = at_target.a ? hover.x + 1 : 0;
+      hover.y = at_target.b ? hover.y + 1 : 0;
+      fire = b2{hover.x >= P.min_hover_steps, hover.y >= P.min_hover_steps};
+    } else {
+      fire = at_target;
+    }
+    if (fire.a | fire.b) {
+      V3 c0{lo(cmd.x), lo(cmd.y), lo(cmd.z)}, c1{hi(cmd.x), hi(cmd.y), hi(cmd.z)};
+      if (fire.a) {
+        c0 = resample_command(P, (uint32_t)i, ev, DDQC_STREAM_HOVER);
+        hover.x = 0;
+      }
+      if (fire.b) {
+        c1 = resample_command(P, (uint32_t)(i + 1), ev, DDQC_STREAM_HOVER);
+        hover.y = 0;
+      }
+      cmd_new = V3p{pk(c0.x, c1.x), pk(c0.y, c1.y), pk(c0.z, c1.z)};
+      hover_resampled = fire;
+    }
+  }
+
+  // ------------------------------------------------------------------ termination (A8, A9); LEAN: no Euler thresholds
+  auto crash_of = [&](auto part) {
+    return (fabsf(part(rel.x)) > P.term_x) | (fabsf(part(rel.y)) > P.term_y) | (fabsf(part(rel.z)) > P.term_z) |
+           (part(p.z) < P.term_ground) | (fabsf(part(ang_b.x)) > P.term_ang_vel) | (fabsf(part(ang_b.y)) > P.term_ang_vel) |
+           (fabsf(part(ang_b.z)) > P.term_ang_vel) | (fabsf(part(lin_b.x)) > P.term_lin_vel) |
+           (fabsf(part(lin_b.y)) > P.term_lin_vel) | (fabsf(part(lin_b.z)) > P.term_lin_vel);
+  };
+  // (the scalar kernel also ORs |euler| > threshold with euler = 0, which is false for every threshold >= 0 and for NaN)
+  const b2 crash{crash_of([](f2 x) { return lo(x); }), crash_of([](f2 x) { return hi(x); })};
+  const b2 below_ground{live & (lo(p.z) < 0.0f), live & (hi(p.z) < 0.0f)};
+  const b2 did_timeout{live & (ep_len.x > P.max_episode_length), live & (ep_len.y > P.max_episode_length)};
+  const b2 did_reset{live & (did_timeout.a | crash.a), live & (did_timeout.b | crash.b)};
+
+  f2 last_act_obs[A];
+#pragma unroll
+  for (int j = 0; j < A; ++j) last_act_obs[j] = last_act[j];
+  Q4p q_obs = q;
+
+  // A18: sums of the episode sums over the envs that reset, one half of the pairs after the other
+  {
+    const unsigned int rm0 = __ballot_sync(0xffffffffu, did_reset.a), rm1 = __ballot_sync(0xffffffffu, did_reset.b);
+    if (rm0 | rm1) {
+      float part = 0.0f;
+      for (unsigned int m = rm0; m; m &= m - 1) {
+        const int L = __ffs(m) - 1;
+#pragma unroll
+        for (int k = 0; k < DDQC_NUM_REWARDS; ++k) {
+          const float vk = __shfl_sync(0xffffffffu, lo(sums[k]), L);
+          if (lane == k) part += vk;
+        }
+      }
+      for (unsigned int m = rm1; m; m &= m - 1) {
+        const int L = __ffs(m) - 1;
+#pragma unroll
+        for (int k = 0; k < DDQC_NUM_REWARDS; ++k) {
+          const float vk = __shfl_sync(0xffffffffu, hi(sums[k]), L);
+          if (lane == k) part += vk;
+        }
+      }
+      if (lane < DDQC_NUM_REWARDS) atomicAdd(&ctl->acc_sums[copy][lane], part);
+      if (lane == 8) atomicAdd(&ctl->acc_reset[copy], (unsigned int)(__popc(rm0) + __popc(rm1)));
+    }
+  }
+
+  if (did_reset.a | did_reset.b) {  // reset_idx (hover_env.py:556-595), per lane of the pair
+    const f2 zero = LIT(L_ZERO);
+#pragma unroll
+    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) sums[k] = sel2(did_reset, zero, sums[k]);
+    if (USES_CTBR && indep && live) {  // ctbr_controller.reset() of the env's own instance
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        stp(S.pid_integral + j * n + i, sel2(did_reset, zero, integ[j]));
+        stp(S.pid_prev_error + j * n + i, sel2(did_reset, zero, prev[j]));
+      }
+    }
+    const V3p ip{K2A(init_pos, 0), K2A(init_pos, 1), K2A(init_pos, 2)};
+    p = V3p{sel2(did_reset, ip.x, p.x), sel2(did_reset, ip.y, p.y), sel2(did_reset, ip.z, p.z)};
+    const V3p rel_r{sub2(cmd_new.x, ip.x), sub2(cmd_new.y, ip.y), sub2(cmd_new.z, ip.z)};  // A16, old command
+    rel = V3p{sel2(did_reset, rel_r.x, rel.x), sel2(did_reset, rel_r.y, rel.y), sel2(did_reset, rel_r.z, rel.z)};
+    last_rel = V3p{sel2(did_reset, rel_r.x, last_rel.x), sel2(did_reset, rel_r.y, last_rel.y), sel2(did_reset, rel_r.z, last_rel.z)};
+    q = Q4p{sel2(did_reset, K2A(init_quat, 0), q.w), sel2(did_reset, K2A(init_quat, 1), q.x),
+            sel2(did_reset, K2A(init_quat, 2), q.y), sel2(did_reset, K2A(init_quat, 3), q.z)};
+    q_obs = q;
+    v = V3p{sel2(did_reset, zero, v.x), sel2(did_reset, zero, v.y), sel2(did_reset, zero, v.z)};
+    w = V3p{sel2(did_reset, zero, w.x), sel2(did_reset, zero, w.y), sel2(did_reset, zero, w.z)};
+    lin_b = V3p{sel2(did_reset, zero, lin_b.x), sel2(did_reset, zero, lin_b.y), sel2(did_reset, zero, lin_b.z)};
+    ang_b = V3p{sel2(did_reset, zero, ang_b.x), sel2(did_reset, zero, ang_b.y), sel2(did_reset, zero, ang_b.z)};
+#pragma unroll
+    for (int j = 0; j < A; ++j) last_act_obs[j] = sel2(did_reset, zero, last_act_obs[j]);
+    V3 c0{lo(cmd_new.x), lo(cmd_new.y), lo(cmd_new.z)}, c1{hi(cmd_new.x), hi(cmd_new.y), hi(cmd_new.z)};
+    if (did_reset.a) {
+      ep_len.x = 0;
+      hover.x = 0;
+      c0 = resample_command(P, (uint32_t)i, ev, DDQC_STREAM_RESET);
+      hover_resampled.a = false;
+    }
+    if (did_reset.b) {
+      ep_len.y = 0;
+      hover.y = 0;
+      c1 = resample_command(P, (uint32_t)(i + 1), ev, DDQC_STREAM_RESET);
+      hover_resampled.b = false;
+    }
+    cmd_new = V3p{pk(c0.x, c1.x), pk(c0.y, c1.y), pk(c0.z, c1.z)};
+  }
+
+  // ------------------------------------------------------------------ rewards (A19)
+  const f2 r_target = sub2(M.sumsq3(last_rel), M.sumsq3(rel));
+  f2 r_close = M.mul2(sub2(K2(at_target_threshold_sq), M.sumsq3(rel)), K2(inv_at_target_threshold_sq));
+  r_close = pk(lo(r_close) < 0.0f ? 0.0f : lo(r_close), hi(r_close) < 0.0f ? 0.0f : hi(r_close));
+  const f2 r_hover = pk((float)hover.x, (float)hover.y);
+  f2 r_smooth;
+  {
+    const f2 d0 = sub2(act[0], last_act_obs[0]);
+    r_smooth = M.mul2(d0, d0);
+#pragma unroll
+    for (int j = 1; j < A; ++j) {
+      const f2 d = sub2(act[j], last_act_obs[j]);
+      r_smooth = add2(r_smooth, M.mul2(d, d));
+    }
+  }
+  const f2 r_yaw = LIT(L_ZERO);  // LEAN: yaw reward scale 0, no Euler angles
+  const f2 r_ang = sqrt2(M.sumsq3(V3p{M.mul2(ang_b.x, K2(inv_pi_lit)), M.mul2(ang_b.y, K2(inv_pi_lit)), M.mul2(ang_b.z, K2(inv_pi_lit))}));
+  const f2 r_crash = pk(crash.a ? 1.0f : 0.0f, crash.b ? 1.0f : 0.0f);
+  const f2 rk[DDQC_NUM_REWARDS] = {M.mul2(r_target, K2A(rew_scale, 0)), M.mul2(r_close, K2A(rew_scale, 1)),
+                                   M.mul2(r_hover, K2A(rew_scale, 2)),  M.mul2(r_smooth, K2A(rew_scale, 3)),
+                                   M.mul2(r_yaw, K2A(rew_scale, 4)),    M.mul2(r_ang, K2A(rew_scale, 5)),
+                                   M.mul2(r_crash, K2A(rew_scale, 6))};
+  const f2 sum0_pre = sums[0], sum1_pre = sums[1];
+  f2 rew = LIT(L_ZERO);
+#pragma unroll
+  for (int k = 0; k < DDQC_NUM_REWARDS; ++k) {
+    rew = add2(rew, rk[k]);
+    sums[k] = add2(sums[k], rk[k]);
+  }
+  const float rew_total = live ? lo(rew) + hi(rew) : 0.0f;
+
+  // ------------------------------------------------------------------ observations (A20)
+  f2 obs[NOBS];
+  obs[0] = clip2(M.mul2(rel.x, K2(obs_scale_pos)), -1.0f, 1.0f);
+  obs[1] = clip2(M.mul2(rel.y, K2(obs_scale_pos)), -1.0f, 1.0f);
+  obs[2] = clip2(M.mul2(rel.z, K2(obs_scale_pos)), -1.0f, 1.0f);
+  obs[3] = q_obs.w;
+  obs[4] = q_obs.x;
+  obs[5] = q_obs.y;
+  obs[6] = q_obs.z;
+  obs[7] = clip2(M.mul2(lin_b.x, K2(obs_scale_lin)), -1.0f, 1.0f);
+  obs[8] = clip2(M.mul2(lin_b.y, K2(obs_scale_lin)), -1.0f, 1.0f);
+  obs[9] = clip2(M.mul2(lin_b.z, K2(obs_scale_lin)), -1.0f, 1.0f);
+  obs[10] = clip2(M.mul2(ang_b.x, K2(obs_scale_ang)), -1.0f, 1.0f);
+  obs[11] = clip2(M.mul2(ang_b.y, K2(obs_scale_ang)), -1.0f, 1.0f);
+  obs[12] = clip2(M.mul2(ang_b.z, K2(obs_scale_ang)), -1.0f, 1.0f);
+#pragma unroll
+  for (int j = 0; j < A; ++j) obs[13 + j] = last_act_obs[j];
+
+  // A15/A16 fix-up records (rare): scalar arithmetic on the lane concerned, same expressions as env_step_body
+  if ((hover_resampled.a | hover_resampled.b) && live) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (!(h ? hover_resampled.b : hover_resampled.a)) continue;
+      auto part = [&](f2 x) { return h ? hi(x) : lo(x); };
+      const V3 rel_f{part(cmd_new.x) - part(p.x), part(cmd_new.y) - part(p.y), part(cmd_new.z) - part(p.z)};
+      const V3 lrel_f{part(cmd_new.x) - part(last_pos.x), part(cmd_new.y) - part(last_pos.y), part(cmd_new.z) - part(last_pos.z)};
+      const float rt = (sumsq3(lrel_f) - sumsq3(rel_f)) * P.rew_scale[0];
+      float rc = (P.at_target_threshold_sq - sumsq3(rel_f)) * P.inv_at_target_threshold_sq;
+      rc = (rc < 0.0f ? 0.0f : rc) * P.rew_scale[1];
+      float rw = 0.0f + rt;
+      rw = rw + rc;
+#pragma unroll
+      for (int k = 2; k < DDQC_NUM_REWARDS; ++k) rw = rw + part(rk[k]);
+      const unsigned int slot = atomicAdd(&ctl->fixup_count, 1u);
+      O.fixup_idx[slot] = i + h;
+      float* fv = O.fixup_val + (size_t)slot * 8;
+      fv[0] = rw;
+      fv[1] = part(sum0_pre) + rt;
+      fv[2] = part(sum1_pre) + rc;
+      fv[3] = clipf(rel_f.x * P.obs_scale_pos, -1.0f, 1.0f);
+      fv[4] = clipf(rel_f.y * P.obs_scale_pos, -1.0f, 1.0f);
+      fv[5] = clipf(rel_f.z * P.obs_scale_pos, -1.0f, 1.0f);
+      fv[6] = 0.0f;
+      fv[7] = 0.0f;
+    }
+  }
+
+  // ------------------------------------------------------------------ store
+  if (live) {
+    stp(S.pos + i, p.x);
+    stp(S.pos + n + i, p.y);
+    stp(S.pos + 2 * n + i, p.z);
+    stp(S.quat + i, q.w);
+    stp(S.quat + n + i, q.x);
+    stp(S.quat + 2 * n + i, q.y);
+    stp(S.quat + 3 * n + i, q.z);
+    stp(S.vel + i, v.x);
+    stp(S.vel + n + i, v.y);
+    stp(S.vel + 2 * n + i, v.z);
+    stp(S.ang + i, w.x);
+    stp(S.ang + n + i, w.y);
+    stp(S.ang + 2 * n + i, w.z);
+    stp(S.commands + i, cmd_new.x);
+    stp(S.commands + n + i, cmd_new.y);
+    stp(S.commands + 2 * n + i, cmd_new.z);
+#pragma unroll
+    for (int j = 0; j < A; ++j) stp(S.last_actions + j * n + i, act[j]);  // hover_env.py:544, all envs
+    *reinterpret_cast<int2*>(S.episode_length + i) = ep_len;
+    *reinterpret_cast<int2*>(S.hover_counter + i) = hover;
+#pragma unroll
+    for (int k = 0; k < DDQC_NUM_REWARDS; ++k) stp(S.episode_sums + k * n + i, sums[k]);
+
+    if (NOBS == 16) {
+      float4* o4 = reinterpret_cast<float4*>(O.obs + (size_t)i * 16);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o4[c] = make_float4(lo(obs[4 * c]), lo(obs[4 * c + 1]), lo(obs[4 * c + 2]), lo(obs[4 * c + 3]));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o4[4 + c] = make_float4(hi(obs[4 * c]), hi(obs[4 * c + 1]), hi(obs[4 * c + 2]), hi(obs[4 * c + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < NOBS; ++j) {
+        O.obs[(size_t)i * NOBS + j] = lo(obs[j]);
+        O.obs[(size_t)(i + 1) * NOBS + j] = hi(obs[j]);
+      }
+    }
+    stp(O.rew + i, rew);
+    *reinterpret_cast<uchar2*>(O.reset + i) = make_uchar2(did_reset.a ? 1 : 0, did_reset.b ? 1 : 0);
+    stp(O.time_outs + i, pk(did_timeout.a ? 1.0f : 0.0f, did_timeout.b ? 1.0f : 0.0f));
+  }
+
+  // ------------------------------------------------------------------ statistics (one RED per warp each)
+  {
+    const unsigned int tm = (unsigned int)(__popc(__ballot_sync(0xffffffffu, did_timeout.a)) + __popc(__ballot_sync(0xffffffffu, did_timeout.b)));
+    float r = rew_total;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if (lane == 7) atomicAdd(&ctl->acc_sums[copy][7], r);
+    if (lane == 9 && tm) atomicAdd(&ctl->acc_timeout[copy], tm);
+    if (P.flags & DDQC_F_GROUND_WATCH) {
+      const unsigned int gm = (unsigned int)(__popc(__ballot_sync(0xffffffffu, below_ground.a)) + __popc(__ballot_sync(0xffffffffu, below_ground.b)));
+      if (lane == 10 && gm) atomicAdd(&ctl->acc_ground[copy], gm);
+    }
   }
 }
 
@@ -674,32 +1376,102 @@ extern "C" int ddqc_env_step(const DdqcEnvParams* P, const DdqcEnvState* S, cons
   pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
   cudaError_t err = cudaSuccess;
-  auto launch = [&](auto kernel, dim3 g, dim3 b, auto... args) {
+  auto launch_smem = [&](auto kernel, dim3 g, dim3 b, size_t smem, auto... args) {
     if (err != cudaSuccess) return;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = g;
     cfg.blockDim = b;
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cfg.attrs = pdl_attr;
     cfg.numAttrs = (DDQC_ENV_FINALIZE == 2 && !fused) ? 1 : 0;
     err = cudaLaunchKernelEx(&cfg, kernel, args...);
   };
+  auto launch = [&](auto kernel, dim3 g, dim3 b, auto... args) { launch_smem(kernel, g, b, (size_t)0, args...); };
+  // tile kernel (bulk-copy staged, persistent): lean configuration, large batches, 16-byte aligned rows
+  static const int64_t tile_min_n = [] {
+    const char* e = getenv("DDQC_ENV_TILE_MIN_N");
+    return e ? (int64_t)atoll(e) : (int64_t)DDQC_ENV_TILE_MIN_N;
+  }();
+  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool tile_ok = lean && !fused && n_env >= tile_min_n && (n % 4) == 0 && aligned16(S->pos) && aligned16(S->quat) &&
+                       aligned16(S->vel) && aligned16(S->ang) && aligned16(S->commands) && aligned16(S->last_actions) &&
+                       aligned16(S->episode_sums) && aligned16(S->episode_length) && aligned16(S->hover_counter) &&
+                       aligned16(S->pid_integral) && aligned16(S->pid_prev_error) && aligned16(O->rew) &&
+                       aligned16(O->time_outs) && aligned16(O->reset) && aligned16(actions);
+  // pair kernel (two envs per thread, packed fp32x2): lean configuration, even batch size (8-byte aligned row pairs)
+  static const int64_t pair_min_n = [] {
+    const char* e = getenv("DDQC_ENV_PAIR_MIN_N");
+    return e ? (int64_t)atoll(e) : (int64_t)DDQC_ENV_PAIR_MIN_N;
+  }();
+  auto aligned8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
+  const bool pair_ok = lean && !fused && !tile_ok && n_env >= pair_min_n && (n % 2) == 0 && aligned8(S->pos) && aligned8(S->quat) &&
+                       aligned8(S->vel) && aligned8(S->ang) && aligned8(S->commands) && aligned8(S->last_actions) &&
+                       aligned8(S->episode_sums) && aligned8(S->episode_length) && aligned8(S->hover_counter) &&
+                       aligned8(S->pid_integral) && aligned8(S->pid_prev_error) && aligned8(O->rew) && aligned8(O->time_outs) &&
+                       (reinterpret_cast<uintptr_t>(O->reset) & 1u) == 0 && (reinterpret_cast<uintptr_t>(O->obs) & 15u) == 0 &&
+                       (reinterpret_cast<uintptr_t>(actions) & 15u) == 0;
+  EnvParams2 PP;
+  if (pair_ok) {
+    const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(P);
+    for (int k = 0; k < kEnvParamWords; ++k) PP.w[k] = (unsigned long long)wsrc[k] | ((unsigned long long)wsrc[k] << 32);
+    const float lits[L_COUNT] = {-0.0f, 0.0f, 1.0f, 2.0f, 0.5f, 1.5f, -0.5f, -2.0f};
+    for (int k = 0; k < L_COUNT; ++k) {
+      uint32_t b;
+      memcpy(&b, &lits[k], 4);
+      PP.lit[k] = (unsigned long long)b | ((unsigned long long)b << 32);
+    }
+  }
+  int sms = 148;
+  if (tile_ok) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+#define DDQC_LAUNCH_TILE(ACT)                                                                                  \
+  do {                                                                                                        \
+    using R = TileRows<(ACT == DDQC_ACT_CTBR_FIXED_YAW ? 3 : 4)>;                                             \
+    static bool attr_set = false;                                                                             \
+    if (!attr_set) {                                                                                          \
+      err = cudaFuncSetAttribute(env_step_tile_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, R::SMEM_BYTES); \
+      attr_set = err == cudaSuccess;                                                                          \
+    }                                                                                                         \
+    const int n_tiles = n / kTile;                                                                            \
+    const int grid_t = (n_tiles + kGroups - 1) / kGroups < sms ? (n_tiles + kGroups - 1) / kGroups : sms;     \
+    launch_smem(env_step_tile_kernel<ACT>, dim3(grid_t), dim3(kTileThreads), (size_t)R::SMEM_BYTES, *P, *S, *O, ctl, actions, n, \
+                n_tiles);                                                                                     \
+    if (n_tiles * kTile < n)                                                                                  \
+      launch(env_step_kernel<ACT, true, false, kThreadsSplit, true>, dim3((n - n_tiles * kTile + kThreadsSplit - 1) / kThreadsSplit), \
+             dim3(kThreadsSplit), *P, *S, *O, ctl, actions, meas_override, n, n_tiles * kTile);               \
+    launch(env_finalize_kernel<(ACT == DDQC_ACT_CTBR_FIXED_YAW ? 16 : 17), true, (ACT != DDQC_ACT_ROTOR_RPMS)>, dim3(1), \
+           dim3(32), *P, *S, *O, ctl, n);                                                                     \
+  } while (0)
 #define DDQC_LAUNCH2(ACT, LEANV)                                                                              \
   do {                                                                                                        \
     if (fused) {                                                                                              \
-      launch(env_step_kernel<ACT, LEANV, true, kThreadsFused>, dim3((n + kThreadsFused - 1) / kThreadsFused),  \
-             dim3(kThreadsFused), *P, *S, *O, ctl, actions, meas_override, n);                                \
+      launch(env_step_kernel<ACT, LEANV, true, kThreadsFused, false>, dim3((n + kThreadsFused - 1) / kThreadsFused),  \
+             dim3(kThreadsFused), *P, *S, *O, ctl, actions, meas_override, n, 0);                             \
     } else {                                                                                                  \
-      launch(env_step_kernel<ACT, LEANV, false, kThreadsSplit>, dim3((n + kThreadsSplit - 1) / kThreadsSplit), \
-             dim3(kThreadsSplit), *P, *S, *O, ctl, actions, meas_override, n);                                \
+      launch(env_step_kernel<ACT, LEANV, false, kThreadsSplit, false>, dim3((n + kThreadsSplit - 1) / kThreadsSplit), \
+             dim3(kThreadsSplit), *P, *S, *O, ctl, actions, meas_override, n, 0);                             \
       launch(env_finalize_kernel<(ACT == DDQC_ACT_CTBR_FIXED_YAW ? 16 : 17), LEANV, (ACT != DDQC_ACT_ROTOR_RPMS)>, \
              dim3(1), dim3(32), *P, *S, *O, ctl, n);                                                          \
     }                                                                                                         \
   } while (0)
+#define DDQC_LAUNCH_PAIR(ACT)                                                                                  \
+  do {                                                                                                        \
+    launch(env_step_pair_kernel<ACT>, dim3((n / 2 + kPairThreads - 1) / kPairThreads), dim3(kPairThreads), *P, PP, *S, *O, ctl, \
+           actions, n);                                                                                       \
+    launch(env_finalize_kernel<(ACT == DDQC_ACT_CTBR_FIXED_YAW ? 16 : 17), true, (ACT != DDQC_ACT_ROTOR_RPMS)>, dim3(1), \
+           dim3(32), *P, *S, *O, ctl, n);                                                                     \
+  } while (0)
 #define DDQC_LAUNCH(ACT)                                                                                      \
   do {                                                                                                        \
-    if (lean)                                                                                                 \
+    if (tile_ok)                                                                                              \
+      DDQC_LAUNCH_TILE(ACT);                                                                                  \
+    else if (pair_ok)                                                                                         \
+      DDQC_LAUNCH_PAIR(ACT);                                                                                  \
+    else if (lean)                                                                                            \
       DDQC_LAUNCH2(ACT, true);                                                                                \
     else                                                                                                      \
       DDQC_LAUNCH2(ACT, false);                                                                               \
@@ -717,5 +1489,7 @@ extern "C" int ddqc_env_step(const DdqcEnvParams* P, const DdqcEnvState* S, cons
   }
 #undef DDQC_LAUNCH
 #undef DDQC_LAUNCH2
+#undef DDQC_LAUNCH_TILE
+#undef DDQC_LAUNCH_PAIR
   return (int)err;
 }
