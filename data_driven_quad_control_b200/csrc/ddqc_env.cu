@@ -67,7 +67,11 @@ namespace {
 #endif
 // ... and the pair kernel (two envs per thread on packed fp32x2 arithmetic) from DDQC_ENV_PAIR_MIN_N envs on
 #ifndef DDQC_ENV_PAIR_MIN_N
-#define DDQC_ENV_PAIR_MIN_N 65536
+#define DDQC_ENV_PAIR_MIN_N (1ll << 40)  // off: 28 % fewer instructions, but 16 warps per SM instead of 32 - 69.7 us against 64.3 us
+#endif
+// ... and the pair kernel on bulk-copy staged inputs (env_step_pair_tile_kernel) from DDQC_ENV_PAIR_TILE_MIN_N envs on
+#ifndef DDQC_ENV_PAIR_TILE_MIN_N
+#define DDQC_ENV_PAIR_TILE_MIN_N (1ll << 40)  // off: 78.0 us
 #endif
 #ifndef DDQC_ENV_TILE
 #define DDQC_ENV_TILE 256  // envs per tile of the tile kernel = threads per group (1024 threads per CTA)
@@ -255,14 +259,19 @@ __device__ __forceinline__ void env_step_body(const DdqcEnvParams& P, const Ddqc
     sums[0] = io.template ld<F_SUMS>(0);
     sums[1] = io.template ld<F_SUMS>(1);
     float integ[3] = {0.0f, 0.0f, 0.0f}, prev[3] = {0.0f, 0.0f, 0.0f};
-    if (USES_CTBR && !pid_pending) {  // A17: a reset anywhere in the previous launch zeroed every PID
+    // A17: a reset anywhere in the previous launch zeroed every PID.  A shared-memory tile must be read completely before
+    // it is refilled (IO::kReadAllFirst); from global memory the loads sit where the values are used - hoisting them
+    // here costs the 64-register kernel 0.9 us per 2^20 envs
+    if (IO::kReadAllFirst) {
+      if (USES_CTBR && !pid_pending) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        integ[j] = io.template ld<F_PIDI>(j);
-        prev[j] = io.template ld<F_PIDE>(j);
+        for (int j = 0; j < 3; ++j) {
+          integ[j] = io.template ld<F_PIDI>(j);
+          prev[j] = io.template ld<F_PIDE>(j);
+        }
       }
+      io.inputs_done();  // nothing of this env's stored state is read below this line
     }
-    io.inputs_done();  // nothing of this env's stored state is read below this line
 
     // ------------------------------------------------------------------ action -> rpm
     float rpm[4];
@@ -274,6 +283,13 @@ __device__ __forceinline__ void env_step_body(const DdqcEnvParams& P, const Ddqc
         y[j] = P.act_lo[j] + ((ex - (-1.0f)) * P.act_span[j]) / 2.0f;         // A3
       }
       if (USES_CTBR) {
+        if (!IO::kReadAllFirst && !pid_pending) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            integ[j] = io.template ld<F_PIDI>(j);
+            prev[j] = io.template ld<F_PIDE>(j);
+          }
+        }
         V3 meas;
         if (!LEAN && meas_override) {
           meas = V3{meas_override[i], meas_override[n + i], meas_override[2 * n + i]};
@@ -619,6 +635,7 @@ __device__ __forceinline__ void warp_stats(const DdqcEnvParams& P, DdqcEnvCtl* _
 // state and outputs in global memory
 template <int A, bool FUSED>
 struct GlobalIO {
+  static constexpr bool kReadAllFirst = false;
   const DdqcEnvState& S;
   const DdqcEnvOut& O;
   const float* __restrict__ actions;
@@ -738,9 +755,27 @@ __device__ __forceinline__ void tile_issue_loads(const unsigned long long* __res
     bulk_load(dst0 + (uint32_t)(R::ACT_OFF * 4), actions + (size_t)tile * kTile * A, kTile * A * 4, bar_main);
 }
 
+// global base address (env 0) of input row r of the tile layout
+template <int A, bool USES_CTBR>
+__device__ __forceinline__ const float* tile_row_base(const DdqcEnvState& S, int r, int n) {
+  using R = TileRows<A>;
+  if (r < R::QUAT) return S.pos + (size_t)(r - R::POS) * n;
+  if (r < R::VEL) return S.quat + (size_t)(r - R::QUAT) * n;
+  if (r < R::ANG) return S.vel + (size_t)(r - R::VEL) * n;
+  if (r < R::CMD) return S.ang + (size_t)(r - R::ANG) * n;
+  if (r < R::LACT) return S.commands + (size_t)(r - R::CMD) * n;
+  if (r < R::EPLEN) return S.last_actions + (size_t)(r - R::LACT) * n;
+  if (r == R::EPLEN) return reinterpret_cast<const float*>(S.episode_length);
+  if (r == R::HOVER) return reinterpret_cast<const float*>(S.hover_counter);
+  if (r < R::PIDI) return S.episode_sums + (size_t)(r - R::SUMS) * n;
+  if (r < R::PIDE) return USES_CTBR ? S.pid_integral + (size_t)(r - R::PIDI) * n : nullptr;
+  return USES_CTBR ? S.pid_prev_error + (size_t)(r - R::PIDE) * n : nullptr;
+}
+
 // inputs of one env from the group's shared-memory buffer (column `gt` of every row), outputs to global memory
 template <int A, bool USES_CTBR>
 struct TileIO {
+  static constexpr bool kReadAllFirst = true;
   using R = TileRows<A>;
   const float* buf;      // the group's buffer, as floats
   const DdqcEnvState& S;
@@ -803,22 +838,7 @@ env_step_tile_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvO
   unsigned long long* rowptr = reinterpret_cast<unsigned long long*>(tile_smem + R::PTR_OFF);
 
   // ---- one-time setup: global base address of every input row, mbarriers ----
-  if (tid < R::NROWS) {
-    const int r = tid;
-    const float* base;
-    if (r < R::QUAT) base = S.pos + (size_t)(r - R::POS) * n;
-    else if (r < R::VEL) base = S.quat + (size_t)(r - R::QUAT) * n;
-    else if (r < R::ANG) base = S.vel + (size_t)(r - R::VEL) * n;
-    else if (r < R::CMD) base = S.ang + (size_t)(r - R::ANG) * n;
-    else if (r < R::LACT) base = S.commands + (size_t)(r - R::CMD) * n;
-    else if (r < R::EPLEN) base = S.last_actions + (size_t)(r - R::LACT) * n;
-    else if (r == R::EPLEN) base = reinterpret_cast<const float*>(S.episode_length);
-    else if (r == R::HOVER) base = reinterpret_cast<const float*>(S.hover_counter);
-    else if (r < R::PIDI) base = S.episode_sums + (size_t)(r - R::SUMS) * n;
-    else if (r < R::PIDE) base = USES_CTBR ? S.pid_integral + (size_t)(r - R::PIDI) * n : nullptr;
-    else base = USES_CTBR ? S.pid_prev_error + (size_t)(r - R::PIDE) * n : nullptr;
-    rowptr[r] = (unsigned long long)(uintptr_t)base;
-  }
+  if (tid < R::NROWS) rowptr[tid] = (unsigned long long)(uintptr_t)tile_row_base<A, USES_CTBR>(S, tid, n);
   if (tid < 2 * kGroups) mbar_init(sbase + R::BAR_OFF + 8 * tid, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
@@ -918,69 +938,55 @@ constexpr int kPairThreads = DDQC_ENV_PAIR_THREADS;
 __device__ __forceinline__ f2 ldp(const float* p) { return f2{__ldcg(reinterpret_cast<const unsigned long long*>(p))}; }
 __device__ __forceinline__ void stp(float* p, f2 v) { *reinterpret_cast<unsigned long long*>(p) = v.v; }
 
-template <int ACT>
-__global__ void __launch_bounds__(kPairThreads, DDQC_ENV_PAIR_BLOCKS)
-env_step_pair_kernel(const DdqcEnvParams P, const EnvParams2 PP, const DdqcEnvState S, const DdqcEnvOut O,
-                     DdqcEnvCtl* __restrict__ ctl, const float* __restrict__ actions, const int n) {
+template <int ACT, class IO>
+__device__ __forceinline__ void env_step_pair_body(const DdqcEnvParams& P, const EnvParams2& PP, const DdqcEnvState& S,
+                                                   const DdqcEnvOut& O, DdqcEnvCtl* __restrict__ ctl, IO& io, const int n,
+                                                   const int i, const bool live, const int lane, const int copy) {
   constexpr int A = (ACT == DDQC_ACT_CTBR_FIXED_YAW) ? 3 : 4;
   constexpr int NOBS = 13 + A;
   constexpr bool USES_CTBR = (ACT != DDQC_ACT_ROTOR_RPMS);
   const PairMath M{PP};
-  const int n_pairs = n >> 1;
-  const int gid = blockIdx.x * kPairThreads + threadIdx.x;
-  const bool live = gid < n_pairs;
-  const int i = 2 * (live ? gid : n_pairs - 1);  // first env of the pair; threads past the end redo the last pair, no side effects
-  const int lane = threadIdx.x & 31;
-  const int copy = (blockIdx.x + (threadIdx.x >> 5)) % DDQC_STAT_COPIES;
   const bool indep = (P.flags & DDQC_F_INDEPENDENT_ENVS) != 0u;
-  pdl_launch_dependents();
 
   // ------------------------------------------------------------------ load state
-  V3p p{ldp(S.pos + i), ldp(S.pos + n + i), ldp(S.pos + 2 * n + i)};
-  Q4p q{ldp(S.quat + i), ldp(S.quat + n + i), ldp(S.quat + 2 * n + i), ldp(S.quat + 3 * n + i)};
-  V3p v{ldp(S.vel + i), ldp(S.vel + n + i), ldp(S.vel + 2 * n + i)};
-  V3p w{ldp(S.ang + i), ldp(S.ang + n + i), ldp(S.ang + 2 * n + i)};
-  V3p cmd{ldp(S.commands + i), ldp(S.commands + n + i), ldp(S.commands + 2 * n + i)};
+  io.begin();
+  V3p p{io.template ld<F_POS>(0), io.template ld<F_POS>(1), io.template ld<F_POS>(2)};
+  Q4p q{io.template ld<F_QUAT>(0), io.template ld<F_QUAT>(1), io.template ld<F_QUAT>(2), io.template ld<F_QUAT>(3)};
+  V3p v{io.template ld<F_VEL>(0), io.template ld<F_VEL>(1), io.template ld<F_VEL>(2)};
+  V3p w{io.template ld<F_ANG>(0), io.template ld<F_ANG>(1), io.template ld<F_ANG>(2)};
+  V3p cmd{io.template ld<F_CMD>(0), io.template ld<F_CMD>(1), io.template ld<F_CMD>(2)};
   f2 last_act[A], act[A];
 #pragma unroll
-  for (int j = 0; j < A; ++j) last_act[j] = ldp(S.last_actions + j * n + i);
+  for (int j = 0; j < A; ++j) last_act[j] = io.template ld<F_LACT>(j);
   {
     float a0[A], a1[A];  // the two action rows are adjacent: 2A consecutive floats
-    if (A == 3) {
-      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(actions + (size_t)i * 3);
-      const f2 u0{src[0]}, u1{src[1]}, u2{src[2]};
-      a0[0] = lo(u0), a0[1] = hi(u0), a0[2] = lo(u1), a1[0] = hi(u1), a1[1] = lo(u2), a1[2] = hi(u2);
-    } else {
-      const float4* src = reinterpret_cast<const float4*>(actions + (size_t)i * 4);
-      const float4 r0 = src[0], r1 = src[1];
-      a0[0] = r0.x, a0[1] = r0.y, a0[2] = r0.z, a0[A - 1] = r0.w;
-      a1[0] = r1.x, a1[1] = r1.y, a1[2] = r1.z, a1[A - 1] = r1.w;
-    }
+    io.load_actions(a0, a1);
 #pragma unroll
     for (int j = 0; j < A; ++j) act[j] = pk(clipf(a0[j], -P.clip_actions, P.clip_actions), clipf(a1[j], -P.clip_actions, P.clip_actions));  // A1
   }
-  int2 ep_len = __ldcg(reinterpret_cast<const int2*>(S.episode_length + i));
-  int2 hover = __ldcg(reinterpret_cast<const int2*>(S.hover_counter + i));
+  int2 ep_len = io.template ldi<F_EPLEN>();
+  int2 hover = io.template ldi<F_HOVER>();
   f2 sums[DDQC_NUM_REWARDS];
 #pragma unroll
-  for (int k = 2; k < DDQC_NUM_REWARDS; ++k) sums[k] = ldp(S.episode_sums + k * n + i);
+  for (int k = 2; k < DDQC_NUM_REWARDS; ++k) sums[k] = io.template ld<F_SUMS>(k);
 
   // as in env_step_body: what the previous finalisation writes is read below the wait
-  pdl_wait();
-  const uint64_t ev = ctl->rng_event;
-  const bool pid_pending = !indep && ctl->pid_reset_pending != 0u;
-  sums[0] = ldp(S.episode_sums + i);
-  sums[1] = ldp(S.episode_sums + n + i);
+  io.late_sync();
+  const uint64_t ev = io.rng_event(ctl);
+  const bool pid_pending = !indep && io.pid_reset_pending(ctl);
+  sums[0] = io.template ld<F_SUMS>(0);
+  sums[1] = io.template ld<F_SUMS>(1);
   f2 integ[3], prev[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) integ[j] = prev[j] = LIT(L_ZERO);
   if (USES_CTBR && !pid_pending) {  // A17
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      integ[j] = ldp(S.pid_integral + j * n + i);
-      prev[j] = ldp(S.pid_prev_error + j * n + i);
+      integ[j] = io.template ld<F_PIDI>(j);
+      prev[j] = io.template ld<F_PIDE>(j);
     }
   }
+  io.inputs_done();
 
   // ------------------------------------------------------------------ action -> rpm
   f2 rpm[4];
@@ -993,8 +999,8 @@ env_step_pair_kernel(const DdqcEnvParams P, const EnvParams2 PP, const DdqcEnvSt
       y[j] = add2(K2A(act_lo, j), M.mul2(M.mul2(add2(ex, LIT(L_ONE)), K2A(act_span, j)), LIT(L_HALF)));
     }
     if (USES_CTBR) {
-      const Q4p qc{q.w, neg2(q.x), neg2(q.y), neg2(q.z)};
-      const V3p meas = M.rotate_by_quat(M.rotate_by_quat(w, q), qc);  // A5
+      const V3p nq{neg2(q.x), neg2(q.y), neg2(q.z)};
+      const V3p meas = M.rotate_by_quat(M.rotate_by_quat(w, q, nq), Q4p{q.w, nq.x, nq.y, nq.z}, V3p{q.x, q.y, q.z});  // A5
       f2 sp[3];
       sp[0] = y[1];
       sp[1] = y[2];
@@ -1062,7 +1068,7 @@ env_step_pair_kernel(const DdqcEnvParams P, const EnvParams2 PP, const DdqcEnvSt
       k = fma2(k, s, K2A(sinc_coef, 2));
       k = fma2(k, s, K2A(sinc_coef, 1));
       k = fma2(k, s, K2A(sinc_coef, 0));
-      const Q4p nq = M.quat_mul(q, Q4p{c, M.mul2(k, hx), M.mul2(k, hy), M.mul2(k, hz)});
+      const Q4p nq = M.quat_mul(q, V3p{neg2(q.x), neg2(q.y), neg2(q.z)}, Q4p{c, M.mul2(k, hx), M.mul2(k, hy), M.mul2(k, hz)});
       const f2 n2 = fma2(nq.z, nq.z, fma2(nq.y, nq.y, fma2(nq.x, nq.x, M.mul2(nq.w, nq.w))));
       const f2 inv_n = fma2(LIT(L_MINUS_HALF), n2, LIT(L_ONE_HALF));
       q = Q4p{M.mul2(nq.w, inv_n), M.mul2(nq.x, inv_n), M.mul2(nq.y, inv_n), M.mul2(nq.z, inv_n)};
@@ -1074,9 +1080,10 @@ env_step_pair_kernel(const DdqcEnvParams P, const EnvParams2 PP, const DdqcEnvSt
   ep_len.y += 1;
   V3p rel{sub2(cmd.x, p.x), sub2(cmd.y, p.y), sub2(cmd.z, p.z)};
   V3p last_rel{sub2(cmd.x, last_pos.x), sub2(cmd.y, last_pos.y), sub2(cmd.z, last_pos.z)};
-  const Q4p qc{q.w, neg2(q.x), neg2(q.y), neg2(q.z)};
-  V3p lin_b = M.rotate_by_quat(v, qc);
-  V3p ang_b = M.rotate_by_quat(M.rotate_by_quat(w, q), qc);
+  const V3p nqv{neg2(q.x), neg2(q.y), neg2(q.z)}, qv{q.x, q.y, q.z};
+  const Q4p qc{q.w, nqv.x, nqv.y, nqv.z};
+  V3p lin_b = M.rotate_by_quat(v, qc, qv);
+  V3p ang_b = M.rotate_by_quat(M.rotate_by_quat(w, q, nqv), qc, qv);
 
   // ------------------------------------------------------------------ hover / resample (A13-A15)
   b2 hover_resampled{false, false};
@@ -1115,10 +1122,10 @@ env_step_pair_kernel(const DdqcEnvParams P, const EnvParams2 PP, const DdqcEnvSt
            (fabsf(part(lin_b.y)) > P.term_lin_vel) | (fabsf(part(lin_b.z)) > P.term_lin_vel);
   };
   // (the scalar kernel also ORs |euler| > threshold with euler = 0, which is false for every threshold >= 0 and for NaN)
-  const b2 crash{crash_of([](f2 x) { return lo(x); }), crash_of([](f2 x) { return hi(x); })};
-  const b2 below_ground{live & (lo(p.z) < 0.0f), live & (hi(p.z) < 0.0f)};
-  const b2 did_timeout{live & (ep_len.x > P.max_episode_length), live & (ep_len.y > P.max_episode_length)};
-  const b2 did_reset{live & (did_timeout.a | crash.a), live & (did_timeout.b | crash.b)};
+  const b2 crash{(bool)crash_of([](f2 x) { return lo(x); }), (bool)crash_of([](f2 x) { return hi(x); })};
+  const b2 below_ground{live && (lo(p.z) < 0.0f), live && (hi(p.z) < 0.0f)};
+  const b2 did_timeout{live && (ep_len.x > P.max_episode_length), live && (ep_len.y > P.max_episode_length)};
+  const b2 did_reset{live && (did_timeout.a || crash.a), live && (did_timeout.b || crash.b)};
 
   f2 last_act_obs[A];
 #pragma unroll
@@ -1328,6 +1335,146 @@ env_step_pair_kernel(const DdqcEnvParams P, const EnvParams2 PP, const DdqcEnvSt
   }
 }
 
+
+// the pair's state from global memory: one 64-bit access per row and thread
+template <int A>
+struct PairGlobalIO {
+  const DdqcEnvState& S;
+  const float* __restrict__ actions;
+  const int n, i;
+  template <int F>
+  __device__ __forceinline__ const float* fptr() const {
+    if constexpr (F == F_POS) return S.pos;
+    else if constexpr (F == F_QUAT) return S.quat;
+    else if constexpr (F == F_VEL) return S.vel;
+    else if constexpr (F == F_ANG) return S.ang;
+    else if constexpr (F == F_CMD) return S.commands;
+    else if constexpr (F == F_LACT) return S.last_actions;
+    else if constexpr (F == F_SUMS) return S.episode_sums;
+    else if constexpr (F == F_PIDI) return S.pid_integral;
+    else return S.pid_prev_error;
+  }
+  template <int F>
+  __device__ __forceinline__ f2 ld(int c) const { return ldp(fptr<F>() + c * n + i); }
+  template <int F>
+  __device__ __forceinline__ int2 ldi() const {
+    return __ldcg(reinterpret_cast<const int2*>((F == F_EPLEN ? S.episode_length : S.hover_counter) + i));
+  }
+  __device__ __forceinline__ void load_actions(float (&a0)[A], float (&a1)[A]) const {
+    if (A == 3) {
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(actions + (size_t)i * 3);
+      const f2 u0{src[0]}, u1{src[1]}, u2{src[2]};
+      a0[0] = lo(u0), a0[1] = hi(u0), a0[2] = lo(u1), a1[0] = hi(u1), a1[1] = lo(u2), a1[2] = hi(u2);
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(actions + (size_t)i * 4);
+      const float4 r0 = src[0], r1 = src[1];
+      a0[0] = r0.x, a0[1] = r0.y, a0[2] = r0.z, a0[A - 1] = r0.w;
+      a1[0] = r1.x, a1[1] = r1.y, a1[2] = r1.z, a1[A - 1] = r1.w;
+    }
+  }
+  __device__ __forceinline__ void begin() const {}
+  __device__ __forceinline__ void late_sync() const { pdl_wait(); }
+  __device__ __forceinline__ void inputs_done() const {}
+  __device__ __forceinline__ uint64_t rng_event(const DdqcEnvCtl* ctl) const { return ctl->rng_event; }
+  __device__ __forceinline__ bool pid_reset_pending(const DdqcEnvCtl* ctl) const { return ctl->pid_reset_pending != 0u; }
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(kPairThreads, DDQC_ENV_PAIR_BLOCKS)
+env_step_pair_kernel(const DdqcEnvParams P, const EnvParams2 PP, const DdqcEnvState S, const DdqcEnvOut O,
+                     DdqcEnvCtl* __restrict__ ctl, const float* __restrict__ actions, const int n) {
+  constexpr int A = (ACT == DDQC_ACT_CTBR_FIXED_YAW) ? 3 : 4;
+  const int n_pairs = n >> 1;
+  const int gid = blockIdx.x * kPairThreads + threadIdx.x;
+  const bool live = gid < n_pairs;
+  const int i = 2 * (live ? gid : n_pairs - 1);  // first env of the pair; threads past the end redo the last pair, no side effects
+  const int lane = threadIdx.x & 31;
+  const int copy = (blockIdx.x + (threadIdx.x >> 5)) % DDQC_STAT_COPIES;
+  pdl_launch_dependents();
+  PairGlobalIO<A> io{S, actions, n, i};
+  env_step_pair_body<ACT>(P, PP, S, O, ctl, io, n, i, live, lane, copy);
+}
+
+// the pair kernel on bulk-copy staged inputs: a group of kTile / 2 threads per kTile-env tile, kPairGroups groups per CTA
+constexpr int kPairGroupThreads = kTile / 2;
+constexpr int kPairGroups = 512 / kPairGroupThreads;  // 512 threads of 128 registers per SM
+constexpr int kPairTileThreads = kPairGroupThreads * kPairGroups;
+
+template <int A, bool USES_CTBR>
+struct PairTileIO {
+  using R = TileRows<A>;
+  const float* buf;      // the group's buffer, as floats
+  const unsigned long long* rowptr;
+  const float* actions;
+  const int gt, g;
+  const uint32_t buf_addr, bar_main, parity;
+  const int next_tile;   // < 0: this stream has no further tile
+  const bool issuer;     // this thread issues the next tile's copies
+  const bool pid_rows;
+  const uint64_t ev;     // control-block values, read once per launch
+  const bool pid_pending;
+  template <int F>
+  __device__ __forceinline__ f2 ld(int c) const {
+    return f2{*reinterpret_cast<const unsigned long long*>(buf + (R::template row0<F>() + c) * kTile + 2 * gt)};
+  }
+  template <int F>
+  __device__ __forceinline__ int2 ldi() const { return *reinterpret_cast<const int2*>(buf + R::template row0<F>() * kTile + 2 * gt); }
+  __device__ __forceinline__ void load_actions(float (&a0)[A], float (&a1)[A]) const {
+    const float* src = buf + R::ACT_OFF + 2 * gt * A;
+#pragma unroll
+    for (int j = 0; j < A; ++j) a0[j] = src[j], a1[j] = src[A + j];
+  }
+  __device__ __forceinline__ void begin() const { mbar_wait_parity(bar_main, parity); }
+  __device__ __forceinline__ void late_sync() const { mbar_wait_parity(bar_main + 8, parity); }
+  __device__ __forceinline__ void inputs_done() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kPairGroupThreads) : "memory");
+    if (issuer && next_tile >= 0) tile_issue_loads<A, USES_CTBR>(rowptr, actions, buf_addr, bar_main, next_tile, true, true, pid_rows);
+  }
+  __device__ __forceinline__ uint64_t rng_event(const DdqcEnvCtl*) const { return ev; }
+  __device__ __forceinline__ bool pid_reset_pending(const DdqcEnvCtl*) const { return pid_pending; }
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(kPairTileThreads, 1)
+env_step_pair_tile_kernel(const DdqcEnvParams P, const EnvParams2 PP, const DdqcEnvState S, const DdqcEnvOut O,
+                          DdqcEnvCtl* __restrict__ ctl, const float* __restrict__ actions, const int n, const int n_tiles) {
+  constexpr int A = (ACT == DDQC_ACT_CTBR_FIXED_YAW) ? 3 : 4;
+  constexpr bool USES_CTBR = (ACT != DDQC_ACT_ROTOR_RPMS);
+  using R = TileRows<A>;
+  static_assert(kPairGroups <= kGroups, "the shared-memory map of the tile kernel has room for kGroups buffers");
+  extern __shared__ __align__(128) uint8_t tile_smem[];
+  const int tid = threadIdx.x, g = tid / kPairGroupThreads, gt = tid % kPairGroupThreads, gw = gt >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(tile_smem);
+  unsigned long long* rowptr = reinterpret_cast<unsigned long long*>(tile_smem + R::PTR_OFF);
+  if (tid < R::NROWS) rowptr[tid] = (unsigned long long)(uintptr_t)tile_row_base<A, USES_CTBR>(S, tid, n);
+  if (tid < 2 * kPairGroups) mbar_init(sbase + R::BAR_OFF + 8 * tid, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const int stream = blockIdx.x * kPairGroups + g, n_streams = gridDim.x * kPairGroups;
+  const int copy = (stream + gw) % DDQC_STAT_COPIES;
+  const uint32_t bar_main = sbase + R::BAR_OFF + 16 * g;
+  const uint32_t buf_addr = sbase + (uint32_t)(R::BUF_BYTES * g);
+  const float* buf = reinterpret_cast<const float*>(tile_smem + R::BUF_BYTES * g);
+  const int t0 = stream;
+  pdl_launch_dependents();
+  if (gt == 0 && t0 < n_tiles) tile_issue_loads<A, USES_CTBR>(rowptr, actions, buf_addr, bar_main, t0, true, false, false);
+  pdl_wait();
+  const bool indep = (P.flags & DDQC_F_INDEPENDENT_ENVS) != 0u;
+  const uint64_t ev = ctl->rng_event;
+  const bool pid_pending = ctl->pid_reset_pending != 0u;
+  const bool pid_rows = indep || !pid_pending;
+  if (gt == 0 && t0 < n_tiles) tile_issue_loads<A, USES_CTBR>(rowptr, actions, buf_addr, bar_main, t0, false, true, pid_rows);
+  int it = 0;
+  for (int tile = t0; tile < n_tiles; tile += n_streams, ++it) {
+    const int i = tile * kTile + 2 * gt;
+    PairTileIO<A, USES_CTBR> io{buf, rowptr, actions, gt, g, buf_addr, bar_main, (uint32_t)it & 1u,
+                                tile + n_streams < n_tiles ? tile + n_streams : -1,
+                                lane == 0 && gw == (it + 1) % (kPairGroupThreads / 32), pid_rows, ev, pid_pending};
+    env_step_pair_body<ACT>(P, PP, S, O, ctl, io, n, i, true, lane, copy);
+  }
+}
+
 // Second launch of a step: one warp folds the statistics of the step kernel that has just completed
 // (the kernel boundary is the only ordering the stores, the REDs and the fix-up list need: the step
 // kernel itself has no barrier, no fence and no ticket, so a CTA's registers are released the moment
@@ -1394,25 +1541,31 @@ extern "C" int ddqc_env_step(const DdqcEnvParams* P, const DdqcEnvState* S, cons
     return e ? (int64_t)atoll(e) : (int64_t)DDQC_ENV_TILE_MIN_N;
   }();
   auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  const bool tile_ok = lean && !fused && n_env >= tile_min_n && (n % 4) == 0 && aligned16(S->pos) && aligned16(S->quat) &&
+  static const int64_t pair_tile_min_n = [] {
+    const char* e = getenv("DDQC_ENV_PAIR_TILE_MIN_N");
+    return e ? (int64_t)atoll(e) : (int64_t)DDQC_ENV_PAIR_TILE_MIN_N;
+  }();
+  const bool tile_align = lean && !fused && (n % 4) == 0 && aligned16(S->pos) && aligned16(S->quat) &&
                        aligned16(S->vel) && aligned16(S->ang) && aligned16(S->commands) && aligned16(S->last_actions) &&
                        aligned16(S->episode_sums) && aligned16(S->episode_length) && aligned16(S->hover_counter) &&
                        aligned16(S->pid_integral) && aligned16(S->pid_prev_error) && aligned16(O->rew) &&
                        aligned16(O->time_outs) && aligned16(O->reset) && aligned16(actions);
+  const bool pair_tile_ok = tile_align && n_env >= pair_tile_min_n;
+  const bool tile_ok = tile_align && !pair_tile_ok && n_env >= tile_min_n;
   // pair kernel (two envs per thread, packed fp32x2): lean configuration, even batch size (8-byte aligned row pairs)
   static const int64_t pair_min_n = [] {
     const char* e = getenv("DDQC_ENV_PAIR_MIN_N");
     return e ? (int64_t)atoll(e) : (int64_t)DDQC_ENV_PAIR_MIN_N;
   }();
   auto aligned8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
-  const bool pair_ok = lean && !fused && !tile_ok && n_env >= pair_min_n && (n % 2) == 0 && aligned8(S->pos) && aligned8(S->quat) &&
+  const bool pair_ok = lean && !fused && !tile_ok && !pair_tile_ok && n_env >= pair_min_n && (n % 2) == 0 && aligned8(S->pos) && aligned8(S->quat) &&
                        aligned8(S->vel) && aligned8(S->ang) && aligned8(S->commands) && aligned8(S->last_actions) &&
                        aligned8(S->episode_sums) && aligned8(S->episode_length) && aligned8(S->hover_counter) &&
                        aligned8(S->pid_integral) && aligned8(S->pid_prev_error) && aligned8(O->rew) && aligned8(O->time_outs) &&
                        (reinterpret_cast<uintptr_t>(O->reset) & 1u) == 0 && (reinterpret_cast<uintptr_t>(O->obs) & 15u) == 0 &&
                        (reinterpret_cast<uintptr_t>(actions) & 15u) == 0;
   EnvParams2 PP;
-  if (pair_ok) {
+  if (pair_ok || pair_tile_ok) {
     const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(P);
     for (int k = 0; k < kEnvParamWords; ++k) PP.w[k] = (unsigned long long)wsrc[k] | ((unsigned long long)wsrc[k] << 32);
     const float lits[L_COUNT] = {-0.0f, 0.0f, 1.0f, 2.0f, 0.5f, 1.5f, -0.5f, -2.0f};
@@ -1423,7 +1576,7 @@ extern "C" int ddqc_env_step(const DdqcEnvParams* P, const DdqcEnvState* S, cons
     }
   }
   int sms = 148;
-  if (tile_ok) {
+  if (tile_ok || pair_tile_ok) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1458,6 +1611,24 @@ extern "C" int ddqc_env_step(const DdqcEnvParams* P, const DdqcEnvState* S, cons
              dim3(1), dim3(32), *P, *S, *O, ctl, n);                                                          \
     }                                                                                                         \
   } while (0)
+#define DDQC_LAUNCH_PAIR_TILE(ACT)                                                                             \
+  do {                                                                                                        \
+    using R = TileRows<(ACT == DDQC_ACT_CTBR_FIXED_YAW ? 3 : 4)>;                                             \
+    static bool attr_set = false;                                                                             \
+    if (!attr_set) {                                                                                          \
+      err = cudaFuncSetAttribute(env_step_pair_tile_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, R::SMEM_BYTES); \
+      attr_set = err == cudaSuccess;                                                                          \
+    }                                                                                                         \
+    const int n_tiles = n / kTile;                                                                            \
+    const int grid_t = (n_tiles + kPairGroups - 1) / kPairGroups < sms ? (n_tiles + kPairGroups - 1) / kPairGroups : sms; \
+    launch_smem(env_step_pair_tile_kernel<ACT>, dim3(grid_t), dim3(kPairTileThreads), (size_t)R::SMEM_BYTES, *P, PP, *S, *O, ctl, \
+                actions, n, n_tiles);                                                                         \
+    if (n_tiles * kTile < n)                                                                                  \
+      launch(env_step_kernel<ACT, true, false, kThreadsSplit, true>, dim3((n - n_tiles * kTile + kThreadsSplit - 1) / kThreadsSplit), \
+             dim3(kThreadsSplit), *P, *S, *O, ctl, actions, meas_override, n, n_tiles * kTile);               \
+    launch(env_finalize_kernel<(ACT == DDQC_ACT_CTBR_FIXED_YAW ? 16 : 17), true, (ACT != DDQC_ACT_ROTOR_RPMS)>, dim3(1), \
+           dim3(32), *P, *S, *O, ctl, n);                                                                     \
+  } while (0)
 #define DDQC_LAUNCH_PAIR(ACT)                                                                                  \
   do {                                                                                                        \
     launch(env_step_pair_kernel<ACT>, dim3((n / 2 + kPairThreads - 1) / kPairThreads), dim3(kPairThreads), *P, PP, *S, *O, ctl, \
@@ -1467,7 +1638,9 @@ extern "C" int ddqc_env_step(const DdqcEnvParams* P, const DdqcEnvState* S, cons
   } while (0)
 #define DDQC_LAUNCH(ACT)                                                                                      \
   do {                                                                                                        \
-    if (tile_ok)                                                                                              \
+    if (pair_tile_ok)                                                                                         \
+      DDQC_LAUNCH_PAIR_TILE(ACT);                                                                             \
+    else if (tile_ok)                                                                                         \
       DDQC_LAUNCH_TILE(ACT);                                                                                  \
     else if (pair_ok)                                                                                         \
       DDQC_LAUNCH_PAIR(ACT);                                                                                  \
@@ -1491,5 +1664,6 @@ extern "C" int ddqc_env_step(const DdqcEnvParams* P, const DdqcEnvState* S, cons
 #undef DDQC_LAUNCH2
 #undef DDQC_LAUNCH_TILE
 #undef DDQC_LAUNCH_PAIR
+#undef DDQC_LAUNCH_PAIR_TILE
   return (int)err;
 }

@@ -83,21 +83,23 @@ struct Q4p {
 struct PairMath {
   const EnvParams2& PP;
   __device__ __forceinline__ f2 mul2(f2 a, f2 b) const { return fma2(a, b, LIT(L_NEGZERO)); }
-  __device__ __forceinline__ Q4p quat_mul(Q4p a, Q4p b) const {
+  // `na` = (-a.x, -a.y, -a.z): the caller holds the conjugate of `a` anyway, so no negation is issued here
+  __device__ __forceinline__ Q4p quat_mul(Q4p a, V3p na, Q4p b) const {
     Q4p r;
-    r.w = fma2(neg2(a.z), b.z, fma2(neg2(a.y), b.y, fma2(neg2(a.x), b.x, mul2(a.w, b.w))));
-    r.x = fma2(neg2(a.z), b.y, fma2(a.y, b.z, fma2(a.x, b.w, mul2(a.w, b.x))));
-    r.y = fma2(a.z, b.x, fma2(a.y, b.w, fma2(neg2(a.x), b.z, mul2(a.w, b.y))));
-    r.z = fma2(a.z, b.w, fma2(neg2(a.y), b.x, fma2(a.x, b.y, mul2(a.w, b.z))));
+    r.w = fma2(na.z, b.z, fma2(na.y, b.y, fma2(na.x, b.x, mul2(a.w, b.w))));
+    r.x = fma2(na.z, b.y, fma2(a.y, b.z, fma2(a.x, b.w, mul2(a.w, b.x))));
+    r.y = fma2(a.z, b.x, fma2(a.y, b.w, fma2(na.x, b.z, mul2(a.w, b.y))));
+    r.z = fma2(a.z, b.w, fma2(na.y, b.x, fma2(a.x, b.y, mul2(a.w, b.z))));
     return r;
   }
-  __device__ __forceinline__ V3p rotate_by_quat(V3p v, Q4p q) const {
-    f2 ux = fma2(q.y, v.z, neg2(mul2(q.z, v.y)));
-    f2 uy = fma2(q.z, v.x, neg2(mul2(q.x, v.z)));
-    f2 uz = fma2(q.x, v.y, neg2(mul2(q.y, v.x)));
-    f2 sx = fma2(q.y, uz, fma2(neg2(q.z), uy, mul2(q.w, ux)));
-    f2 sy = fma2(q.z, ux, fma2(neg2(q.x), uz, mul2(q.w, uy)));
-    f2 sz = fma2(q.x, uy, fma2(neg2(q.y), ux, mul2(q.w, uz)));
+  // v rotated by q; `nq` = (-q.x, -q.y, -q.z).  -(q.z v.y) of the scalar code is issued as (-q.z) v.y: the same value
+  __device__ __forceinline__ V3p rotate_by_quat(V3p v, Q4p q, V3p nq) const {
+    f2 ux = fma2(q.y, v.z, mul2(nq.z, v.y));
+    f2 uy = fma2(q.z, v.x, mul2(nq.x, v.z));
+    f2 uz = fma2(q.x, v.y, mul2(nq.y, v.x));
+    f2 sx = fma2(q.y, uz, fma2(nq.z, uy, mul2(q.w, ux)));
+    f2 sy = fma2(q.z, ux, fma2(nq.x, uz, mul2(q.w, uy)));
+    f2 sz = fma2(q.x, uy, fma2(nq.y, ux, mul2(q.w, uz)));
     return V3p{fma2(LIT(L_TWO), sx, v.x), fma2(LIT(L_TWO), sy, v.y), fma2(LIT(L_TWO), sz, v.z)};
   }
   __device__ __forceinline__ f2 sumsq3(V3p a) const { return add2(add2(mul2(a.x, a.x), mul2(a.y, a.y)), mul2(a.z, a.z)); }

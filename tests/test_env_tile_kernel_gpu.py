@@ -1,10 +1,12 @@
-"""GPU parity of the two alternative launch shapes of ddqc_env_step against the numpy oracle: the PAIR kernel (two envs per
-thread on packed fp32x2 arithmetic, the default from 65 536 envs on) and the bulk-copy TILE kernel (env_step_tile_kernel: persistent CTAs, the next tile's state staged through shared
-memory by cp.async.bulk under the arithmetic of the current one, ragged tail on the one-thread-per-env kernel) against
-the numpy oracle.  `ddqc_env_step` picks the tile
-kernel from DDQC_ENV_TILE_MIN_N envs on; the variable is read once per process, so the small-size cases run in a
-subprocess that sets it (tests/tile_kernel_check.py).  The 2**20-env cases of test_env_parity_gpu.py exercise it at its
-default threshold."""
+"""GPU parity of the alternative launch shapes of ddqc_env_step against the numpy oracle.  Besides the default kernels
+(one thread per env: fused finalisation up to 32 768 envs, split finalisation + programmatic dependent launch above)
+the library holds three experimental ones, all bit-exact, all measured SLOWER on B200 and therefore off unless asked for
+(DESIGN.md section 3 has the numbers and the ncu evidence):
+  pair       two envs per thread on packed fp32x2 arithmetic (FFMA2 / FADD2), 64-bit state accesses
+  tile       persistent CTAs, the next tile's state staged through shared memory by cp.async.bulk + mbarrier
+  pair_tile  both
+`ddqc_env_step` reads the thresholds DDQC_ENV_{PAIR,TILE,PAIR_TILE}_MIN_N once per process, so every case runs in a
+subprocess that sets them (tests/tile_kernel_check.py)."""
 
 import json
 import os
@@ -21,8 +23,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 KINDS = {  # environment that forces one launch shape of ddqc_env_step at small batch sizes
-    "tile": dict(DDQC_ENV_TILE_MIN_N="256", DDQC_ENV_FUSED_MAX_N="0"),
-    "pair": dict(DDQC_ENV_PAIR_MIN_N="2", DDQC_ENV_FUSED_MAX_N="0", DDQC_ENV_TILE_MIN_N=str(1 << 40)),
+    "tile": dict(DDQC_ENV_TILE_MIN_N="256", DDQC_ENV_FUSED_MAX_N="0", DDQC_ENV_PAIR_TILE_MIN_N=str(1 << 40)),
+    "pair_tile": dict(DDQC_ENV_PAIR_TILE_MIN_N="256", DDQC_ENV_FUSED_MAX_N="0"),
+    "pair": dict(DDQC_ENV_PAIR_MIN_N="2", DDQC_ENV_FUSED_MAX_N="0", DDQC_ENV_TILE_MIN_N=str(1 << 40), DDQC_ENV_PAIR_TILE_MIN_N=str(1 << 40)),
 }
 
 
@@ -34,7 +37,7 @@ def _run(at_name, N, T, auto=True, independent=False, park=False, kind="tile"):
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize("kind", ["pair", "tile"])
+@pytest.mark.parametrize("kind", ["pair_tile", "pair", "tile"])
 @pytest.mark.parametrize("at_name", ["CTBR_FIXED_YAW", "CTBR", "ROTOR_RPMS"])
 def test_bit_exact_with_ragged_tail(build_lib, at_name, kind):
     """1300 envs (tile kernel: 5 full 256-env tiles + a tail of 20; pair kernel: 650 pairs, last CTA partly idle), 250
@@ -58,28 +61,30 @@ def test_pair_kernel_odd_batch_falls_back(build_lib):
     assert res["resets"] > 300
 
 
-def test_tile_kernel_many_tiles_per_stream_and_hover_fixups(build_lib):
+@pytest.mark.parametrize("kind", ["pair_tile", "tile"])
+def test_tile_kernel_many_tiles_per_stream_and_hover_fixups(build_lib, kind):
     """148 x 4 tile streams: 166 404 envs = 650 tiles + a tail of 4 -> some streams walk two tiles (buffer refill under
     the arithmetic, mbarrier phase flips); parked drones produce hover / resample events and A15/A16 fix-ups on steps
     with resets elsewhere."""
-    res = _run("CTBR_FIXED_YAW", 166404, 40, park=True)
+    res = _run("CTBR_FIXED_YAW", 166404, 40, park=True, kind=kind)
     assert res["resets"] > 1000 and res["hover_events"] > 1000
 
 
-def test_tile_kernel_independent_envs_and_no_auto_targets(build_lib):
-    res = _run("CTBR_FIXED_YAW", 2048 + 4, 200, auto=False, independent=True)
+@pytest.mark.parametrize("kind", ["pair_tile", "tile"])
+def test_tile_kernel_independent_envs_and_no_auto_targets(build_lib, kind):
+    res = _run("CTBR_FIXED_YAW", 2048 + 4, 200, auto=False, independent=True, kind=kind)
     assert res["resets"] > 1000
 
 
 def test_unaligned_batch_falls_back_to_the_plain_kernel(build_lib):
     """n % 4 != 0: the rows of the struct-of-arrays state are not 16-byte aligned, the bulk copies cannot be used and
     the step runs on the one-thread-per-env kernel - same results."""
-    res = _run("CTBR_FIXED_YAW", 1301, 60)
+    res = _run("CTBR_FIXED_YAW", 1301, 60, kind="pair_tile")
     assert res["resets"] > 300
 
 
-def test_tile_kernel_default_threshold_ragged_full_size(build_lib):
-    """2**20 - 76 envs (n % 4 == 0, 4095 full tiles + a tail of 180) at the default threshold, 2 steps."""
+def test_default_launch_shape_ragged_full_size(build_lib):
+    """2**20 - 76 envs on the default launch shape (one thread per env, split finalisation), 2 steps."""
     from test_env_parity_gpu import _compare_step, _make_pair
 
     N, T = (1 << 20) - 76, 2
