@@ -167,7 +167,8 @@ class Timer:
     events on the launching stream; a region's time is the MAX over ranks.  A region is repeated until at least
     `min_total_s` seconds have been timed (>= 5 regions) and the MEDIAN region is reported, so that one rank's hiccup
     inside a 1.5 ms region cannot decide the figure (round 1's 4-GPU line).  Inside a region the steps are replays of a
-    CUDA graph of G = min(K, 32) consecutive steps plus K % G eager launches (`--no-graph`: all eager)."""
+    CUDA graph of G consecutive steps (G = K up to 256 steps, i.e. one replay per region; 64 above) plus K % G eager
+    launches (`--no-graph`: all eager)."""
 
     def __init__(self, dev, world, use_graph: bool, min_total_s: float = 0.25, max_regions: int = 300):
         import torch
@@ -183,7 +184,7 @@ class Timer:
 
     def run(self, step_fn, K: int) -> dict:
         torch = self.torch
-        G = min(K, 32) if self.use_graph else 0
+        G = (K if K <= 256 else 64) if self.use_graph else 0
         graph = None
         if G:
             side = torch.cuda.Stream(device=self.dev)

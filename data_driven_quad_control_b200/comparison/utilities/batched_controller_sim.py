@@ -88,6 +88,7 @@ def batched_controller_comparison(env: HoverEnv, policy, dd_mpc_kwargs: dict, u_
                 mpc.store_input_output_measurement(u_applied, env.get_pos()[2 * R :])
                 pos_log.append(env.get_pos(add_noise=False).clone())
                 tgt_log.append(np.asarray(sp, np.float64).reshape(-1))
+    env.check_ground_plane("controller comparison")  # warns if a drone sank below the (unmodelled) floor
     # construct_trajectory_data of the reference: clamp to [-1, 1] (the env clips), back to physical units
     a = torch.stack(act_log).clamp(-1, 1)
     u_phys = linear_interpolate(x=a, x_min=-1, x_max=1, y_min=bounds[:, 0], y_max=bounds[:, 1]).cpu().numpy().transpose(1, 0, 2)

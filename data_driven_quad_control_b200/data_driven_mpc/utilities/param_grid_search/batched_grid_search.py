@@ -117,6 +117,8 @@ def evaluate_bucket(make_env: Callable[[int], HoverEnv], cache: DataDrivenCache,
                                                     eval_params.max_target_dist_increment, fixed.n_n_mpc_step)  # fmt: skip
     rmse = res.rmse.cpu().numpy().reshape(nC, nE, nS)
     failed = res.failed.cpu().numpy().reshape(nC, nE, nS)
+    # the evaluation configuration disables the low-altitude termination; the reference's floor is not modelled here
+    env.check_ground_plane(f"DD-MPC evaluation of {nC} combination(s)")
     env.close()
     return rmse, failed
 

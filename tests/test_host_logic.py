@@ -262,3 +262,36 @@ def test_grid_search_bookkeeping_follows_the_reference_worker():
     grid = DDMPCParameterGrid([350], [4, 6], [30, 35], [1e1, 5e1], [1e5], [1e-3], [1e3, 1e5])
     combos = combinations_from_grid(grid)
     assert len(combos) == 16 and combos[0] == (350, 4, 30, 1e1, 1e5, 1e-3, 1e3) and combos[1].lamb_sigma_s == 1e5 and combos[2].lamb_alpha == 5e1
+
+
+def test_cache_states_keep_their_rate_pid_rows():
+    """the per-env rows of the rate-PID state saved right after a data collection travel with the cached
+    drone state (`row_of_state`) and are re-assembled for the evaluation batch (`stack_states`), instead of every
+    evaluation run starting from a zeroed PID (a derivative kick the reference's runs do not have)."""
+    from data_driven_quad_control_b200.data_driven_mpc.utilities.param_grid_search.param_grid_search_config import (
+        row_of_state,
+        stack_states,
+    )
+    from data_driven_quad_control_b200.envs.hover_env_config import EnvState
+    from data_driven_quad_control_b200.utilities.vectorized_pid_controller import VectorizedControllerState
+
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.rand(*s, generator=g)  # noqa: E731
+    full = EnvState(base_pos=r(3, 3), base_quat=r(3, 4), base_lin_vel=r(3, 3), base_ang_vel=r(3, 3), commands=r(3, 3),
+                    episode_length=torch.arange(3, dtype=torch.int32), last_actions=r(3, 3),
+                    ctbr_controller_state=VectorizedControllerState(integral=r(3, 3), prev_error=r(3, 3)))  # fmt: skip
+    rows = [row_of_state(full, b) for b in range(3)]
+    assert rows[1].ctbr_controller_state.prev_error.shape == (1, 3)
+    assert torch.equal(rows[1].ctbr_controller_state.prev_error[0], full.ctbr_controller_state.prev_error[1])
+    # an evaluation batch: entry 2 three times, then entry 0
+    batch = stack_states([rows[2], rows[2], rows[2], rows[0]])
+    assert torch.equal(batch.ctbr_controller_state.integral, full.ctbr_controller_state.integral[[2, 2, 2, 0]])
+    assert torch.equal(batch.base_pos, full.base_pos[[2, 2, 2, 0]])
+    # states without a controller state (RPM action type) stack to None; a mixed list pads with zeros
+    bare = row_of_state(EnvState(**{**full.__dict__, "ctbr_controller_state": None}), 0)
+    assert stack_states([bare, bare]).ctbr_controller_state is None
+    mixed = stack_states([rows[1], bare])
+    assert torch.equal(mixed.ctbr_controller_state.prev_error[1], torch.zeros(3))
+    # an explicit controller state still overrides
+    z = VectorizedControllerState(integral=torch.zeros(2, 3), prev_error=torch.zeros(2, 3))
+    assert stack_states([rows[1], rows[2]], z).ctbr_controller_state is z
