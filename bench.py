@@ -9,11 +9,19 @@ QP-solve throughput (the second half of the metric) is reported in the same JSON
 "ddmpc".  One "step" is one `HoverEnv.step` over every env of the rank (4 physics substeps +
 CTBR controller + termination/auto-reset + rewards + observations).
 
-Workload (config.workload): CTBR_FIXED_YAW env, default get_cfgs() + training reward config,
+Headline workload (config.workload): CTBR_FIXED_YAW env, default get_cfgs() + training reward config,
 random actions U(-1,1) pre-generated on the device (seeded), auto target updates on,
 2**20 envs PER GPU (weak scaling, envs sharded by index, no data-path collective; rollout
 statistics are all-reduced once at the end).  State + outputs are 374 MB per step, larger than
 the 126 MB L2, so every timed step streams from HBM (no L2 flush needed).
+
+Timing: regions of exactly K steps (one CUDA-graph replay), barrier + synchronize on both sides, CUDA events on the
+launching stream, MAX over ranks per region; the region is repeated until 0.25 s have been timed and the median is
+reported (class Timer).
+
+Further legs of the same JSON line (each can be switched off, see --help): `e2e` (host buffers), `policy_rollout`
+(BASELINE configs[2]), `strong_scaling` (configs[2] as stated: 2**20 envs in total), `small_batch` (configs[1]),
+`single_drone` (configs[0]), `ddmpc` (configs[3]), `grid_search` (configs[4]), `cpu_baseline` (N = 1 only).
 """
 
 from __future__ import annotations

@@ -60,8 +60,11 @@ __device__ __forceinline__ float sqrt_nonneg(float x) {
   return r;
 }
 
+// torch.clip(x, lo, hi): NaN passes through (both compares are false).  Measured and dropped (round 2): the
+// two-instruction form max.NaN / min.NaN (FMNMX.NAN: same values, NaN included) - 26 instructions fewer per env-step, but
+// the 64-register step kernel then spills 4 bytes per thread and a 2^20-env step takes 64.1 us instead of 63.5 us.
 __device__ __forceinline__ float clipf(float x, float lo, float hi) {
-  return x < lo ? lo : (x > hi ? hi : x);  // NaN passes through, like torch.clip
+  return x < lo ? lo : (x > hi ? hi : x);
 }
 
 // ---- Philox-4x32-10 -----------------------------------------------------------------
