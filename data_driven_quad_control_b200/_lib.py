@@ -17,7 +17,7 @@ NUM_REWARDS = 7
 STAT_COPIES = 32
 EP_RING = 1024
 
-ABI_VERSION = 2  # include/ddqc.h: DDQC_ABI_VERSION
+ABI_VERSION = 3  # include/ddqc.h: DDQC_ABI_VERSION
 
 ACT_ROTOR_RPMS, ACT_CTBR, ACT_CTBR_FIXED_YAW = 0, 1, 2
 F_ACTION_LATENCY, F_AUTO_TARGET, F_NEED_EULER, F_INDEPENDENT_ENVS, F_GROUND_WATCH = 1, 2, 4, 8, 16
@@ -180,6 +180,10 @@ class MpcConfig(C.Structure):
     ]
 
 
+class MpcAux(C.Structure):
+    _fields_ = [("u_ic", vp), ("y_ic", vp), ("v_sr", vp), ("sr_out", vp)]
+
+
 i64 = C.c_int64
 P = C.POINTER
 
@@ -206,6 +210,11 @@ SIGNATURES = {
     "ddqc_ddmpc_workspace_bytes": (i64, [P(MpcConfig), i64]),
     "ddqc_ddmpc_gram_cache_bytes": (i64, [P(MpcConfig), i64]),
     "ddqc_ddmpc_solve": (C.c_int, [P(MpcConfig), vp] + [vp] * 11 + [i64, vp, vp]),
+    "ddqc_ddmpc_solve_ex": (C.c_int, [P(MpcConfig), vp] + [vp] * 11 + [i64, vp, P(MpcAux), vp]),
+    "ddqc_ddmpc_hankel_apply": (C.c_int, [P(MpcConfig), vp, vp, vp, vp, i64, vp]),
+    "ddqc_ddmpc_recover_workspace_bytes": (i64, [P(MpcConfig), i64]),
+    "ddqc_ddmpc_recover": (C.c_int, [P(MpcConfig), vp] + [vp] * 14 + [i64, vp]),
+    "ddqc_ddmpc_refresh_data": (C.c_int, [P(MpcConfig), vp, vp, vp, vp, vp, C.c_double, vp, vp, i64, vp]),
     "ddqc_ddmpc_store": (C.c_int, [P(MpcConfig), vp, vp, vp, vp, i64, vp, vp]),
     "ddqc_ddmpc_action": (C.c_int, [P(MpcConfig), vp, C.c_int32, vp, vp, vp, i64, vp]),
     "ddqc_ddmpc_post_step": (C.c_int, [P(MpcConfig), vp, vp, vp, vp, i64, i64, vp, vp, C.c_double, vp, vp, vp, vp, C.c_int32, i64, vp, vp]),
@@ -213,7 +222,7 @@ SIGNATURES = {
     "ddqc_policy_mlp_forward": (C.c_int, [vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp]),
 }
 
-_STRUCTS = {0: EnvParams, 1: EnvCtl, 2: EnvState, 3: EnvOut, 4: MpcConfig}
+_STRUCTS = {0: EnvParams, 1: EnvCtl, 2: EnvState, 3: EnvOut, 4: MpcConfig, 5: MpcAux}
 
 _lib = None
 

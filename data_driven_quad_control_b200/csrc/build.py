@@ -24,6 +24,7 @@ UNITS = [
     ("ddqc_env_aux.cu", ["-fmad=false"]),
     ("ddqc_ctrl.cu", ["-fmad=false"]),
     ("ddqc_ddmpc.cu", []),
+    ("ddqc_ddmpc_recover.cu", []),
     ("ddqc_policy.cu", []),
 ]
 

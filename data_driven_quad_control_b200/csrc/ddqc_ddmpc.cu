@@ -1083,7 +1083,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
                    const double* __restrict__ y_r, const int32_t* __restrict__ have_prev,
                    const double* __restrict__ lamb, int8_t* __restrict__ act_state, double* __restrict__ u_opt, double* __restrict__ us_opt,
                    double* __restrict__ ys_opt, int32_t* __restrict__ status, int32_t* __restrict__ iters,
-                   const int batch, long long* __restrict__ phase_clk, double* __restrict__ gram_cache) {
+                   const int batch, long long* __restrict__ phase_clk, double* __restrict__ gram_cache, const DdqcMpcAux aux) {
   extern __shared__ __align__(16) double smem[];
   const Dims d = make_dims(cfg);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
@@ -1159,6 +1159,12 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
     const double lam_as = lamb ? lamb[4 * (size_t)b + 2] : cfg.lamb_alpha_s, lam_ss = lamb ? lamb[4 * (size_t)b + 3] : cfg.lamb_sigma_s;
     const double* ub = u_win + (size_t)b * N * m;
     const double* yb = y_win + (size_t)b * N * p;
+    // initial condition (the last n samples): of the data windows themselves, or of the rolling measurement arrays when
+    // the Hankel data is a frozen snapshot (update_cost_threshold)
+    const double* ubp = aux.u_ic ? aux.u_ic + (size_t)b * N * m : ub;
+    const double* ybp = aux.y_ic ? aux.y_ic + (size_t)b * N * p : yb;
+    // alpha_reg_type PREVIOUS: v_sr = H alpha_sr arrives from ddqc_ddmpc_hankel_apply; the tau row becomes tau - v_sr
+    const double* vsr = (cfg.alpha_reg_type == 1 && aux.v_sr) ? aux.v_sr + (size_t)b * (nsig * ell + 1) : nullptr;
 
     // ---- 0. stage the (u, y) window signal-major; Gram -> workspace slot -------------------------
     DDQC_SUB(-1);
@@ -1318,17 +1324,20 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
         const int a = e / ell, j = e % ell;
         const int P = pos_of(d, a, j);
         put_sym(d, GA, GS, Pa0 + a, P, 1.0);
+        double tv = 0.0;
         if (a < m) {
           if (j >= L) put_sym(d, GA, GS, Pa1 + a, P, 1.0);
-          if (j < n) put_sym(d, GA, GS, Pa0 + nsig + 1, P, ub[(size_t)(N - n + j) * m + a]);
+          if (j < n) tv = ubp[(size_t)(N - n + j) * m + a];
         } else {
           if (j >= n) put_sym(d, GA, GS, Pa1 + a, P, 1.0);
-          if (j < n) put_sym(d, GA, GS, Pa0 + nsig + 1, P, yb[(size_t)(N - n + j) * p + (a - m)]);
+          if (j < n) tv = ybp[(size_t)(N - n + j) * p + (a - m)];
         }
+        if (vsr) tv -= vsr[e];
+        if (j < n || vsr) put_sym(d, GA, GS, Pa0 + nsig + 1, P, tv);
       }
       if (tid == 0) {
         put_sym(d, GA, GS, Pa0 + nsig, Pone, 1.0);
-        put_sym(d, GA, GS, Pa0 + nsig + 1, Pone, 1.0);
+        put_sym(d, GA, GS, Pa0 + nsig + 1, Pone, vsr ? 1.0 - vsr[nsig * ell] : 1.0);
       }
     }
     __syncthreads();
@@ -1516,6 +1525,10 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
       backsub_blocked(sM, ncol_all, s_yv);
       for (int q = tid; q < d.n2p; q += kThreads) s_e[q] = q < d.n2 ? ds * s_yv[q] : 0.0;
       __syncthreads();
+      if (aux.sr_out) {  // (u_sr, y_sr, e) for ddqc_ddmpc_recover: v_sr = rho - e
+        double* so = aux.sr_out + (size_t)b * (nsig + d.n2);
+        for (int q = tid; q < nsig + d.n2; q += kThreads) so[q] = q < nsig ? s_coef[q] : s_e[q - nsig];
+      }
       DDQC_PHASE(4);
     }
 
@@ -1626,7 +1639,7 @@ ddmpc_solve_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __rest
         const int i = warp;
         double sum = 0.0;
         for (int j = lane; j < n; j += 32)
-          sum += i < m ? ub[(size_t)(N - n + j) * m + i] : yb[(size_t)(N - n + j) * p + (i - m)];
+          sum += i < m ? ubp[(size_t)(N - n + j) * m + i] : ybp[(size_t)(N - n + j) * p + (i - m)];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if (lane == 0) {
@@ -1816,7 +1829,7 @@ int check_cfg(const DdqcMpcConfig* c) {
   const Dims d = make_dims(*c);
   if (d.C < 1 || d.nx > kMaxNx || (d.m + d.p) * d.ell > kMaxPos || d.m + d.p + 2 > 8) return DDQC_E_SHAPE;
   if (smem_bytes(d) + 6144 > (size_t)kSmemLimit) return DDQC_E_SHAPE;  // 6144 >= static shared memory of the kernel
-  if (c->alpha_reg_type != 0 && c->alpha_reg_type != 2) return DDQC_E_CONFIG;
+  if (c->alpha_reg_type < 0 || c->alpha_reg_type > 2) return DDQC_E_CONFIG;
   if (c->alpha_sr_anchor != 0 && c->alpha_sr_anchor != 1) return DDQC_E_CONFIG;
   return 0;
 }
@@ -1856,8 +1869,22 @@ extern "C" int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg, void* ws, const double
                                 double* us_opt,
                                 double* ys_opt, int32_t* status, int32_t* iters, int64_t batch, void* gram_cache,
                                 void* stream) {
+  return ddqc_ddmpc_solve_ex(cfg, ws, u_win, y_win, y_r, have_prev, lamb, act_state, u_opt, us_opt, ys_opt, status, iters,
+                             batch, gram_cache, nullptr, stream);
+}
+
+extern "C" int ddqc_ddmpc_solve_ex(const DdqcMpcConfig* cfg, void* ws, const double* u_win, const double* y_win,
+                                   const double* y_r, const int32_t* have_prev, const double* lamb, int8_t* act_state,
+                                   double* u_opt, double* us_opt, double* ys_opt, int32_t* status, int32_t* iters,
+                                   int64_t batch, void* gram_cache, const DdqcMpcAux* aux_host, void* stream) {
   int rc = check_cfg(cfg);
   if (rc) return rc;
+  DdqcMpcAux aux = {nullptr, nullptr, nullptr, nullptr};
+  if (aux_host) aux = *aux_host;
+  if ((aux.u_ic == nullptr) != (aux.y_ic == nullptr)) return DDQC_E_NULL;
+  // PREVIOUS needs v_sr (zeros on a first solve); a frozen snapshot has no one-sample shift for the Gram cache to follow
+  if (cfg->alpha_reg_type == 1 && !aux.v_sr) return DDQC_E_NULL;
+  if (aux.u_ic && gram_cache) return DDQC_E_CONFIG;
   if (!ws || !u_win || !y_win || !y_r || !u_opt || !us_opt || !ys_opt || !status || !iters || !have_prev)
     return DDQC_E_NULL;
   if (batch < 0) return DDQC_E_SHAPE;
@@ -1878,7 +1905,7 @@ extern "C" int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg, void* ws, const double
   double* slots = reinterpret_cast<double*>(static_cast<char*>(ws) + 256);
   ddmpc_solve_kernel<<<grid, kThreads, smem, st>>>(*cfg, slots, static_cast<int*>(ws), u_win, y_win, y_r,
                                                    have_prev, lamb, act_state, u_opt, us_opt, ys_opt, status,
-                                                   iters, (int)batch, g_phase_clk, static_cast<double*>(gram_cache));
+                                                   iters, (int)batch, g_phase_clk, static_cast<double*>(gram_cache), aux);
   return (int)cudaGetLastError();
 }
 

@@ -320,6 +320,7 @@ extern "C" int64_t ddqc_struct_size(int which) {
     case 2: return (int64_t)sizeof(DdqcEnvState);
     case 3: return (int64_t)sizeof(DdqcEnvOut);
     case 4: return (int64_t)sizeof(DdqcMpcConfig);
+    case 5: return (int64_t)sizeof(DdqcMpcAux);
     default: return -1;
   }
 }

@@ -12,10 +12,21 @@ controllers (leading dimension B on every tensor) and solves them in one launch.
 
 `NonlinearDataDrivenMPCController` is the single-controller, numpy-in / numpy-out drop-in.
 
-Supported configuration: the one every shipped reference config uses (`ext_out_incr_in=False`,
-`update_cost_threshold=None`), `alpha_reg_type` APPROXIMATED (0) or ZERO (2), block-diagonal
-Q / R with identical diagonal blocks (what `controller_creation.py:73-88` builds).  Anything
-else raises NotImplementedError / ValueError instead of silently solving a different problem.
+Supported configuration: `ext_out_incr_in=False` (what every shipped reference config uses), all three
+`alpha_reg_type`s, `update_cost_threshold`, `n_mpc_step`, block-diagonal Q / R with identical diagonal blocks
+(what `controller_creation.py:73-88` builds).  Anything else raises NotImplementedError / ValueError instead of
+silently solving a different problem.
+
+The two modes that need the optimal alpha - which the condensed solver never forms - run a dual-recovery
+kernel after every solve (`ddqc_ddmpc_recover`, csrc/ddqc_ddmpc_recover.cu):
+
+* `alpha_reg_type` PREVIOUS (1): alpha_sr of a solve = the optimal alpha of the previous solve (zeros on the
+  first); `self.alpha_prev` (B, C) holds it, `ddqc_ddmpc_hankel_apply` turns it into v_sr = H alpha_sr on the
+  current data before the solve.
+* `update_cost_threshold`: the measurement arrays `self.u / self.y` always roll (the initial condition is always the
+  latest n samples); the Hankel data of a solve is a snapshot of them (`self.u_data / self.y_data`), refreshed
+  before the solve unless the previous solve's tracking cost (`self.tracking_cost`) was <= the threshold
+  (configs/data_driven_mpc/dd_mpc_controller_params.yaml:85-90; semantics restated in oracle/ddmpc_oracle.py).
 """
 
 from __future__ import annotations
@@ -92,11 +103,9 @@ class BatchedNonlinearDataDrivenMPC:
             raise ValueError(f"alpha_sr_anchor must be one of {sorted(ALPHA_SR_ANCHORS)}")
         if ext_out_incr_in:
             raise NotImplementedError("ext_out_incr_in=True (extended output / input increments) is not supported")
-        if update_cost_threshold:
-            raise NotImplementedError("update_cost_threshold is not supported (always None in the reference configs)")
         art = AlphaRegType(alpha_reg_type) if not isinstance(alpha_reg_type, AlphaRegType) else alpha_reg_type
-        if art == AlphaRegType.PREVIOUS:
-            raise NotImplementedError("alpha_reg_type PREVIOUS is not supported by the condensed GPU solver yet")
+        # null or 0 = "input-output data is always updated online" (dd_mpc_controller_params.yaml:89-90)
+        self.update_cost_threshold = float(update_cost_threshold) if update_cost_threshold else None
         if art == AlphaRegType.APPROXIMATED and (lamb_alpha_s is None or lamb_sigma_s is None):
             raise ValueError("lamb_alpha_s and lamb_sigma_s are required for alpha_reg_type APPROXIMATED")
         self._lib = _lib.load()
@@ -162,6 +171,10 @@ class BatchedNonlinearDataDrivenMPC:
         # Per-controller Gram cache (ddqc.h): G persists in HBM between solves and follows the one-sample window shift
         # by a rank-2 correction.  `gram_cache=None` enables it when it fits in a quarter of the free device memory.
         gc_bytes = self._lib.ddqc_ddmpc_gram_cache_bytes(C.byref(cfg), self.B)
+        if self.update_cost_threshold is not None:
+            if gram_cache:
+                raise ValueError("gram_cache follows one-sample window shifts; it cannot be combined with update_cost_threshold")
+            gram_cache = False  # a frozen / re-snapshotted data window is not a one-sample shift
         if gram_cache is None:
             gram_cache = gc_bytes <= torch.cuda.mem_get_info(dev)[0] // 4 and os.environ.get("DDQC_GRAM_CACHE", "1") != "0"
         self._gram_cache = torch.zeros((gc_bytes,), dtype=torch.uint8, device=dev) if gram_cache else None
@@ -177,6 +190,28 @@ class BatchedNonlinearDataDrivenMPC:
         # active set of the condensed box QP, carried between solves as the warm start
         self.nx = (self.L - self.n) * m + m + p
         self._act_state = torch.zeros((self.B, self.nx), dtype=torch.int8, device=dev) if warm_start else None
+        # ---- optional modes (module docstring) --------------------------------------------------------------
+        thr, nsig, C_ = self.update_cost_threshold, m + p, self.N - ell + 1
+        self._needs_recover = art == AlphaRegType.PREVIOUS or thr is not None
+        self.alpha_prev = torch.zeros((self.B, C_), **f64) if art == AlphaRegType.PREVIOUS else None
+        self._v_sr = torch.zeros((self.B, nsig * ell + 1), **f64) if art == AlphaRegType.PREVIOUS else None
+        self._sr = torch.zeros((self.B, nsig + p * ell), **f64) if (thr is not None and art == AlphaRegType.APPROXIMATED) else None
+        self.tracking_cost = torch.full((self.B,), float("inf"), **f64) if thr is not None else None
+        self.data_updated = torch.ones((self.B,), dtype=torch.int32, device=dev) if thr is not None else None
+        self.u_data = self.u.clone() if thr is not None else self.u  # Hankel data of the solves
+        self.y_data = self.y.clone() if thr is not None else self.y
+        if self._needs_recover:
+            rb = self._lib.ddqc_ddmpc_recover_workspace_bytes(C.byref(cfg), self.B)
+            if rb < 0:
+                raise ValueError("unsupported problem size for the dual-recovery kernel (ddqc_ddmpc_recover.cu)")
+            self._rec_ws = torch.empty((rb,), dtype=torch.uint8, device=dev)
+        self._aux = _lib.MpcAux()
+        if thr is not None:
+            self._aux.u_ic, self._aux.y_ic = self.u.data_ptr(), self.y.data_ptr()
+        if self._v_sr is not None:
+            self._aux.v_sr = self._v_sr.data_ptr()
+        if self._sr is not None:
+            self._aux.sr_out = self._sr.data_ptr()
         if solve_on_init:
             self.update_and_solve_data_driven_mpc()
 
@@ -192,15 +227,34 @@ class BatchedNonlinearDataDrivenMPC:
         controllers left out of this solve - their outputs and status keep their last values (used by the batched
         evaluator for runs the reference would have aborted)."""
         have_prev = self._have_prev if skip is None else torch.where(skip, -1, self._have_prev).to(torch.int32)
+        cfg, st, thr = C.byref(self._cfg), _lib.stream_ptr(self.device), self.update_cost_threshold
+        lamb = self._lamb.data_ptr() if self._lamb is not None else None
         with _lib.device_guard(self.device):
-            rc = self._lib.ddqc_ddmpc_solve(
-                C.byref(self._cfg), self._ws.data_ptr(), self.u.data_ptr(), self.y.data_ptr(), self.y_r.data_ptr(),
-                have_prev.data_ptr(), self._lamb.data_ptr() if self._lamb is not None else None,
+            if thr is not None:  # refresh the Hankel data of the controllers whose last tracking cost exceeds the threshold
+                _lib.check(self._lib.ddqc_ddmpc_refresh_data(
+                    cfg, self.u.data_ptr(), self.y.data_ptr(), self.u_data.data_ptr(), self.y_data.data_ptr(),
+                    self.tracking_cost.data_ptr(), thr, have_prev.data_ptr(), self.data_updated.data_ptr(), self.B, st,
+                ), "ddqc_ddmpc_refresh_data")  # fmt: skip
+            if self.alpha_prev is not None:  # v_sr = H alpha_prev on the data of this solve
+                _lib.check(self._lib.ddqc_ddmpc_hankel_apply(
+                    cfg, self.u_data.data_ptr(), self.y_data.data_ptr(), self.alpha_prev.data_ptr(), self._v_sr.data_ptr(), self.B, st,
+                ), "ddqc_ddmpc_hankel_apply")  # fmt: skip
+            rc = self._lib.ddqc_ddmpc_solve_ex(
+                cfg, self._ws.data_ptr(), self.u_data.data_ptr(), self.y_data.data_ptr(), self.y_r.data_ptr(),
+                have_prev.data_ptr(), lamb,
                 self._act_state.data_ptr() if self._act_state is not None else None, self.optimal_u.data_ptr(),
                 self.us.data_ptr(), self.ys.data_ptr(), self.status.data_ptr(), self.iters.data_ptr(), self.B,
-                self.gram_cache_ptr, _lib.stream_ptr(self.device),
+                self.gram_cache_ptr, C.byref(self._aux), st,
             )  # fmt: skip
-        _lib.check(rc, "ddqc_ddmpc_solve")
+            _lib.check(rc, "ddqc_ddmpc_solve")
+            if self._needs_recover:
+                _lib.check(self._lib.ddqc_ddmpc_recover(
+                    cfg, self._rec_ws.data_ptr(), self.u_data.data_ptr(), self.y_data.data_ptr(),
+                    self._aux.u_ic, self._aux.y_ic, self.y_r.data_ptr(), have_prev.data_ptr(), lamb,
+                    self.optimal_u.data_ptr(), self.us.data_ptr(), self.ys.data_ptr(), self._aux.v_sr, self._aux.sr_out,
+                    self.alpha_prev.data_ptr() if self.alpha_prev is not None else None,
+                    self.tracking_cost.data_ptr() if self.tracking_cost is not None else None, self.B, st,
+                ), "ddqc_ddmpc_recover")  # fmt: skip
         if skip is None:
             self._have_prev.fill_(1)
         else:  # a skipped controller keeps the history it had (it may be solved again later)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DDQC_ABI_VERSION 2
+#define DDQC_ABI_VERSION 3
 
 #define DDQC_E_NULL (-1)    /* required pointer is NULL */
 #define DDQC_E_SHAPE (-2)   /* bad size / unsupported shape */
@@ -317,6 +317,58 @@ int ddqc_ddmpc_solve(const DdqcMpcConfig* cfg_host, void* ws, const double* u_wi
                      double* u_opt, double* us_opt, double* ys_opt, int32_t* status, int32_t* iters,
                      int64_t batch, void* gram_cache, void* stream);
 
+/* Optional inputs / outputs of a solve for the modes every shipped reference config leaves off
+ * (configs/data_driven_mpc/dd_mpc_controller_params.yaml:60-70 `alpha_reg_type: 1`, :85-90 `update_cost_threshold`;
+ * ctor keywords data_driven_mpc/utilities/param_grid_search/controller_creation.py:108-110).  All members may be NULL.
+ *  u_ic [B][N][m], y_ic [B][N][p] : windows whose LAST n samples are the initial condition, when u_win / y_win hold a
+ *                                   frozen snapshot of the Hankel data (update_cost_threshold); not with a Gram cache
+ *  v_sr [B][(m+p) ell + 1]        : alpha_reg_type 1 (PREVIOUS), required there: H alpha_sr, Hankel row (signal a,
+ *                                   depth j) at a ell + j (inputs first), ones row last - ddqc_ddmpc_hankel_apply
+ *  sr_out [B][m + p + p ell]      : alpha_reg_type 0: (u_sr, y_sr, e) of the alpha_sr sub-problem, e by (depth j,
+ *                                   output c) at j p + c; v_sr = rho - e.  Input of ddqc_ddmpc_recover. */
+typedef struct DdqcMpcAux {
+  const double* u_ic;
+  const double* y_ic;
+  const double* v_sr;
+  double* sr_out;
+} DdqcMpcAux;
+
+/* ddqc_ddmpc_solve with the optional block above (aux NULL = ddqc_ddmpc_solve). */
+int ddqc_ddmpc_solve_ex(const DdqcMpcConfig* cfg_host, void* ws, const double* u_win,
+                        const double* y_win, const double* y_r, const int32_t* have_prev, const double* lamb,
+                        int8_t* act_state, double* u_opt, double* us_opt, double* ys_opt, int32_t* status,
+                        int32_t* iters, int64_t batch, void* gram_cache, const DdqcMpcAux* aux_host, void* stream);
+
+/* v[b] = H_b alpha[b] for the Hankel matrix of (u_win, y_win): alpha [B][C], C = N - ell + 1; v in the layout of
+ * DdqcMpcAux.v_sr.  alpha_reg_type 1: alpha_sr = the previous optimal alpha (zeros before the first solve). */
+int ddqc_ddmpc_hankel_apply(const DdqcMpcConfig* cfg_host, const double* u_win, const double* y_win,
+                            const double* alpha, double* v, int64_t batch, void* stream);
+
+/* Dual recovery after a solve (the condensed solver never forms alpha; the two optional modes need it).  With the
+ * optimum (u_opt, us_opt, ys_opt) every Hankel row has a prescribed value (inputs, ones row: D = 0) or a target with
+ * weight w (outputs: D = lamb_alpha / w); alpha* = alpha_sr + H'z with (G + D) z = t - v_sr (one Cholesky per
+ * controller, one CTA each; numpy mirror oracle/ddmpc_condensed.py::recover_dual).
+ *  u_win, y_win, u_ic, y_ic, y_r, have_prev (< 0: skipped), lamb, u_opt, us_opt, ys_opt : as given to / left by the solve
+ *  v_sr (alpha_reg_type 1) / sr (alpha_reg_type 0: the solve's sr_out) / neither (type 2) : what alpha_sr was
+ *  alpha_io [B][C] or NULL   : += H'z  (holds alpha_sr on entry, alpha* on return - alpha_reg_type 1)
+ *  cost_out [B] or NULL      : the tracking cost  sum_k |ubar_k - u_s|_R^2 + |ybar_k - y_s|_Q^2 + |y_s - y_r|_S^2
+ *                              (k = -n..L) that update_cost_threshold compares; +inf if the factorisation broke down
+ *  ws: ddqc_ddmpc_recover_workspace_bytes() bytes, 256-byte aligned. */
+int64_t ddqc_ddmpc_recover_workspace_bytes(const DdqcMpcConfig* cfg_host, int64_t batch);
+int ddqc_ddmpc_recover(const DdqcMpcConfig* cfg_host, void* ws, const double* u_win, const double* y_win,
+                       const double* u_ic, const double* y_ic, const double* y_r, const int32_t* have_prev,
+                       const double* lamb, const double* u_opt, const double* us_opt, const double* ys_opt,
+                       const double* v_sr, const double* sr, double* alpha_io, double* cost_out, int64_t batch,
+                       void* stream);
+
+/* update_cost_threshold: before a solve, copy the rolling windows into the Hankel-data snapshot of every controller
+ * whose last tracking cost exceeds `threshold` or that has not been solved yet (have_prev == 0); the others keep
+ * their data ("online input-output data updates are disabled when the tracking cost value is less than this value",
+ * dd_mpc_controller_params.yaml:85-90).  refreshed [B] int32 (or NULL) reports which were copied. */
+int ddqc_ddmpc_refresh_data(const DdqcMpcConfig* cfg_host, const double* u_roll, const double* y_roll,
+                            double* u_data, double* y_data, const double* cost, double threshold,
+                            const int32_t* have_prev, int32_t* refreshed, int64_t batch, void* stream);
+
 /* Optional per-controller Gram cache (`gram_cache`, or NULL, of ddqc_ddmpc_solve / _store / _post_step): the block-packed
  * Gram matrix of every controller's Hankel matrix persists between solves; a solve whose window moved by exactly one
  * sample (one store_input_output_measurement) since the cached matrix applies the rank-2 correction
@@ -366,7 +418,7 @@ int ddqc_policy_mlp_forward(const float* obs, int64_t n, int32_t n_in, int32_t n
                             void* stream);
 
 /* library identification and layout self-check: sizeof of struct `which`
- * (0 DdqcEnvParams, 1 DdqcEnvCtl, 2 DdqcEnvState, 3 DdqcEnvOut, 4 DdqcMpcConfig), -1 otherwise. */
+ * (0 DdqcEnvParams, 1 DdqcEnvCtl, 2 DdqcEnvState, 3 DdqcEnvOut, 4 DdqcMpcConfig, 5 DdqcMpcAux), -1 otherwise. */
 int ddqc_abi_version(void);
 int64_t ddqc_struct_size(int which);
 

@@ -142,12 +142,17 @@ def v_sr_optimal_reachable(prm: MPCParams, G, y_r):
     return rho - Ds * z, t[:m], t[m:]
 
 
-def solve_condensed(prm: MPCParams, u_win, y_win, y_r, us_prev=None, ys_prev=None, x0=None):
+def solve_condensed(prm: MPCParams, u_win, y_win, y_r, us_prev=None, ys_prev=None, x0=None, v_sr_ext=None,
+                    u_ic=None, y_ic=None):
+    """`v_sr_ext` (alpha_reg_type PREVIOUS): H alpha_sr for an arbitrary alpha_sr, canonical row order.
+    `u_ic` / `y_ic` (update_cost_threshold): windows whose last n samples are the initial condition when the
+    Hankel data (u_win, y_win) is a frozen snapshot."""
     n, m, p, L, ell = prm.n, prm.m, prm.p, prm.L, prm.ell
     G, _ = hankel_gram(u_win, y_win, ell)
     r = G.shape[0]
     w, B, T = row_classes(prm)
-    u_past, y_past = u_win[-n:], y_win[-n:]
+    u_past = (u_win if u_ic is None else u_ic)[-n:]
+    y_past = (y_win if y_ic is None else y_ic)[-n:]
     tau = np.zeros(r)
     tau[: n * m] = u_past.ravel()
     tau[m * ell : m * ell + n * p] = y_past.ravel()
@@ -157,6 +162,8 @@ def solve_condensed(prm: MPCParams, u_win, y_win, y_r, us_prev=None, ys_prev=Non
     v_sr = np.zeros(r)
     if prm.alpha_reg_type == APPROXIMATED:
         v_sr, _, _ = v_sr_optimal_reachable(prm, G, np.asarray(y_r, float).ravel())
+    elif v_sr_ext is not None:
+        v_sr = np.asarray(v_sr_ext, float)
 
     D0 = np.where(np.isfinite(w), prm.lamb_alpha / w, 0.0)
     Lc = np.linalg.cholesky(G + np.diag(D0))
@@ -188,6 +195,37 @@ def solve_condensed(prm: MPCParams, u_win, y_win, y_r, us_prev=None, ys_prev=Non
     u_s, y_s = x[nB : nB + m], x[nB + m :]
     u_pred = np.vstack([x[:nB].reshape(L - n, m), np.tile(u_s, (n + 1, 1))])  # ubar_0..ubar_L
     return dict(u_opt=u_pred, us=u_s, ys=y_s, x=x, iters=iters, Hq=Hq, f=f, lo=lo, hi=hi, v_sr=v_sr)
+
+
+def recover_dual(prm: MPCParams, u_win, y_win, y_r, u_opt, us, ys, v_sr=None, u_ic=None, y_ic=None):
+    """Mirror of `ddmpc_recover_kernel` (csrc/ddqc_ddmpc_recover.cu): with the box-QP optimum x* = (ubar, u_s, y_s)
+    known, every row of H has a prescribed value (hard rows, D = 0) or a target with weight w (soft rows,
+    D = lamb_alpha / w); the minimising alpha is alpha_sr + H'z with
+
+        (G + D) z = t - v_sr,     t = prescribed values / targets,
+
+    from which  alpha* - alpha_sr = H'z  (alpha_reg_type PREVIOUS needs alpha*),  ybar_k - y_s = -(lamb_alpha / Q) z
+    on the predicted output rows, and the TRACKING COST sum |ubar - u_s|_R^2 + |ybar - y_s|_Q^2 + |y_s - y_r|_S^2
+    (update_cost_threshold).  Canonical row order of `hankel_gram`.  Returns (z, H'z, tracking cost)."""
+    n, m, p, L, ell = prm.n, prm.m, prm.p, prm.L, prm.ell
+    G, H = hankel_gram(u_win, y_win, ell)
+    r = G.shape[0]
+    w, _, _ = row_classes(prm)
+    u_past = (u_win if u_ic is None else u_ic)[-n:]
+    y_past = (y_win if y_ic is None else y_ic)[-n:]
+    ubar = np.vstack([u_past, np.asarray(u_opt, float)])  # (ell, m): k = -n..L
+    t = np.empty(r)
+    t[: m * ell] = ubar.ravel()
+    t[m * ell : (m + p) * ell] = np.concatenate([y_past.ravel(), np.tile(ys, ell - n)])
+    t[-1] = 1.0
+    D = np.where(np.isfinite(w), prm.lamb_alpha / w, 0.0)
+    rhs = t - (0.0 if v_sr is None else np.asarray(v_sr, float))
+    Lc = np.linalg.cholesky(G + np.diag(D))
+    z = np.linalg.solve(Lc.T, np.linalg.solve(Lc, rhs))
+    cost = float((prm.R * (ubar - us) ** 2).sum() + (prm.Q * (y_past - ys) ** 2).sum() + (prm.S * (ys - np.asarray(y_r, float).ravel()) ** 2).sum())
+    zy = z[m * ell + n * p : m * ell + L * p].reshape(L - n, p)  # predicted output rows k = 0..L-n-1
+    cost += float((prm.lamb_alpha**2 * zy**2 / prm.Q).sum())
+    return z, H.T @ z, cost
 
 
 # =============================================================================================

@@ -108,8 +108,10 @@ class MPCParams:
 # --------------------------------------------------------------------------------------------
 # literal QP assembly
 # --------------------------------------------------------------------------------------------
-def build_literal_qp(prm: MPCParams, u_win, y_win, y_r, alpha_sr):
-    """0.5 z'Pz + q'z,  A z = b,  G z <= h   with z = [alpha, sigma, ubar, ybar, u_s, y_s]."""
+def build_literal_qp(prm: MPCParams, u_win, y_win, y_r, alpha_sr, u_past=None, y_past=None):
+    """0.5 z'Pz + q'z,  A z = b,  G z <= h   with z = [alpha, sigma, ubar, ybar, u_s, y_s].
+    `u_past` / `y_past` (n samples): initial condition when it is not the tail of the Hankel data (frozen data,
+    update_cost_threshold)."""
     n, m, p, L, ell, C = prm.n, prm.m, prm.p, prm.L, prm.ell, prm.C
     Hu, Hy = hankel(u_win, ell), hankel(y_win, ell)
     o_a, o_s, o_u, o_y = 0, C, C + p * ell, C + p * ell + m * ell
@@ -167,7 +169,8 @@ def build_literal_qp(prm: MPCParams, u_win, y_win, y_r, alpha_sr):
     row[o_a : o_a + C] = 1
     rows.append(row)
     rhs.append(1.0)
-    u_past, y_past = u_win[-n:], y_win[-n:]
+    u_past = u_win[-n:] if u_past is None else np.asarray(u_past, float)
+    y_past = y_win[-n:] if y_past is None else np.asarray(y_past, float)
     for j in range(n):  # initial condition
         for i in range(m):
             eq([(o_u + j * m + i, 1)], u_past[j, i])
@@ -382,8 +385,16 @@ class NonlinearDDMPCOracle:
                  n_mpc_step=1, solve_on_init=True, alpha_sr_anchor="optimal_reachable_equilibrium"):  # fmt: skip
         assert alpha_sr_anchor in ("optimal_reachable_equilibrium", "previous_equilibrium")
         self.alpha_sr_anchor = alpha_sr_anchor
-        if ext_out_incr_in or update_cost_threshold:
-            raise NotImplementedError("only the shipped configuration (both off) is restated")
+        if ext_out_incr_in:
+            raise NotImplementedError("ext_out_incr_in is not restated (off in every shipped configuration)")
+        # update_cost_threshold (configs/data_driven_mpc/dd_mpc_controller_params.yaml:85-90: "online input-output data
+        # updates are disabled when the tracking cost value is less than this value"; null or 0 = always update).
+        # Restated as: the measurement arrays always roll (the initial condition is always the latest n samples); the
+        # Hankel data of a solve is a snapshot of them, refreshed before the solve unless the previous solve's tracking
+        # cost  sum_k |ubar_k - u_s|_R^2 + |ybar_k - y_s|_Q^2 + |y_s - y_r|_S^2  was <= the threshold.  UNVERIFIED
+        # against the package source (absent), like the rest of this file.
+        self.update_cost_threshold = float(update_cost_threshold) if update_cost_threshold else None
+        self.tracking_cost = None
         u, y = np.array(u, float), np.array(y, float)
         ell = L + n + 1
         Q, R, S = np.asarray(Q, float), np.asarray(R, float), np.asarray(S, float)
@@ -397,6 +408,7 @@ class NonlinearDDMPCOracle:
         self.n, self.m, self.p, self.L, self.N = n, m, p, L, u.shape[0]
         self.n_mpc_step = n_mpc_step
         self.u, self.y = u.copy(), y.copy()
+        self.u_data, self.y_data = u.copy(), y.copy()
         self.y_r = np.asarray(y_r, float).reshape(-1, 1)
         self.us_prev = self.ys_prev = None
         self.alpha_prev = None
@@ -413,17 +425,22 @@ class NonlinearDDMPCOracle:
         if prm.alpha_reg_type == APPROXIMATED and self.alpha_sr_anchor == "previous_equilibrium":
             if self.us_prev is None:  # first solve: no previous equilibrium (assumption: alpha_sr = 0)
                 return np.zeros(prm.C)
-            return solve_alpha_sr_fixed_equilibrium(prm, self.u, self.y, self.us_prev, self.ys_prev)
+            return solve_alpha_sr_fixed_equilibrium(prm, self.u_data, self.y_data, self.us_prev, self.ys_prev)
         if prm.alpha_reg_type == APPROXIMATED:
-            return solve_alpha_sr(prm, self.u, self.y, self.y_r.ravel())
+            return solve_alpha_sr(prm, self.u_data, self.y_data, self.y_r.ravel())
         if prm.alpha_reg_type == PREVIOUS and self.alpha_prev is not None:
             return self.alpha_prev
         return np.zeros(prm.C)
 
     def update_and_solve_data_driven_mpc(self):
         prm = self.prm
+        thr = self.update_cost_threshold
+        self.data_updated = thr is None or self.tracking_cost is None or self.tracking_cost > thr
+        if self.data_updated:
+            self.u_data, self.y_data = self.u.copy(), self.y.copy()
         a_sr = self.alpha_sr()
-        P, q, A, b, G, h, offs = build_literal_qp(prm, self.u, self.y, self.y_r.ravel(), a_sr)
+        P, q, A, b, G, h, offs = build_literal_qp(prm, self.u_data, self.y_data, self.y_r.ravel(), a_sr,
+                                                  self.u[-prm.n :], self.y[-prm.n :])
         z, nu, lam, s, info = solve_qp_ipm(P, q, A, b, G, h)
         if not info["converged"]:
             raise RuntimeError("oracle IPM did not converge")
@@ -433,6 +450,9 @@ class NonlinearDDMPCOracle:
         self.us_prev = z[offs["us"] : offs["us"] + prm.m].copy()
         self.ys_prev = z[offs["ys"] : offs["ys"] + prm.p].copy()
         self.alpha_prev = z[: prm.C].copy()
+        ybar = z[offs["ybar"] : offs["ybar"] + prm.p * ell].reshape(ell, prm.p)
+        self.tracking_cost = float((prm.R * (ubar - self.us_prev) ** 2).sum() + (prm.Q * (ybar - self.ys_prev) ** 2).sum()
+                                   + (prm.S * (self.ys_prev - self.y_r.ravel()) ** 2).sum())
         self.last = dict(z=z, offs=offs, info=info, qp=(P, q, A, b, G, h), mult=(nu, lam), alpha_sr=a_sr)
 
     def get_optimal_control_input_at_step(self, n_step=0):

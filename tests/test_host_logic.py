@@ -47,8 +47,20 @@ def test_argument_validation_without_gpu(build_lib):
     assert lib.ddqc_ddmpc_gram_cache_bytes(ctypes.byref(cfg), -1) == -1
     assert lib.ddqc_ddmpc_solve(ctypes.byref(cfg), *([None] * 12), 16, None, None) == -1  # null buffers, with or without a cache
     assert lib.ddqc_ddmpc_store(ctypes.byref(cfg), None, None, None, None, 16, None, None) == -1
-    cfg.alpha_reg_type = 1
+    cfg.alpha_reg_type = 3
     assert lib.ddqc_ddmpc_workspace_bytes(ctypes.byref(cfg), 4096) == -1
+    # alpha_reg_type PREVIOUS needs v_sr = H alpha_sr (DdqcMpcAux), which the plain entry point cannot carry
+    cfg.alpha_reg_type = 1
+    assert lib.ddqc_ddmpc_workspace_bytes(ctypes.byref(cfg), 4096) > 0
+    assert lib.ddqc_ddmpc_solve(ctypes.byref(cfg), *([ctypes.c_void_p(256)] * 12), 16, None, None) == -1
+    aux = _lib.MpcAux()
+    aux.u_ic = 256  # u_ic without y_ic
+    assert lib.ddqc_ddmpc_solve_ex(ctypes.byref(cfg), *([ctypes.c_void_p(256)] * 12), 16, None, ctypes.byref(aux), None) == -1
+    # dual recovery: workspace = 256 B + one (rp + 1) x ld matrix per slot (r = 6*42+1 = 253 -> rp = 256, ld = 272), 296 slots at most... 320
+    assert lib.ddqc_ddmpc_recover_workspace_bytes(ctypes.byref(cfg), 1) == 256 + 8 * 257 * 272
+    assert lib.ddqc_ddmpc_recover(ctypes.byref(cfg), *([None] * 15), 16, None) == -1
+    assert lib.ddqc_ddmpc_hankel_apply(ctypes.byref(cfg), None, None, None, None, 16, None) == -1
+    assert lib.ddqc_ddmpc_refresh_data(ctypes.byref(cfg), None, None, None, None, None, 1.0, None, None, 16, None) == -1
     cfg.alpha_reg_type, cfg.N = 0, 4000  # H would have > 512 rows? no: rows fixed by l; C large is fine
     assert lib.ddqc_ddmpc_workspace_bytes(ctypes.byref(cfg), 1) > 0
     cfg.L = 100  # r = 6*107+1 > kMaxR
