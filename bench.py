@@ -862,6 +862,33 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
     cold_passes = float(cold.pivoting_passes.float().mean())
     cold_failed = int((cold.status != 0).sum())
     del cold
+    # the optional controller modes (off in every shipped config): the solve is followed by the dual-recovery
+    # kernel (ddqc_ddmpc_recover: one Cholesky of G + D per controller), PREVIOUS also preceded by v_sr = H alpha_prev
+    modes = {}
+    for name, kw in (("alpha_reg_type_previous", dict(alpha_reg_type=AlphaRegType.PREVIOUS)),
+                     ("update_cost_threshold", dict(alpha_reg_type=AlphaRegType.APPROXIMATED, update_cost_threshold=1e-2))):  # fmt: skip
+        mc = BatchedNonlinearDataDrivenMPC(
+            n=P["n"], m=3, p=3, u=u_N, y=y_N, L=P["L"], Q=np.kron(np.eye(ell), np.diag(P["Q"])),
+            R=np.kron(np.eye(ell), np.diag(P["R"])), S=np.diag(P["S"]), y_r=np.array(P["y_r"]), lamb_alpha=P["lamb_alpha"],
+            lamb_sigma=P["lamb_sigma"], U=P["U"], Us=P["Us"], lamb_alpha_s=P["lamb_alpha_s"], lamb_sigma_s=P["lamb_sigma_s"],
+            device=dev, solve_on_init=False, **kw,
+        )  # fmt: skip
+        ms = []
+        for t in range(6):
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            mc.update_and_solve_data_driven_mpc()
+            m1.record()
+            mc.store_input_output_measurement(mc.get_optimal_control_input_at_step(0), y_N[:, -1])
+            torch.cuda.synchronize()
+            ms.append(m0.elapsed_time(m1))
+        avg_m = sum(ms[1:]) / len(ms[1:])
+        modes[name] = {"solves_per_s": batch / (avg_m * 1e-3), "ms_per_batch_solve": avg_m, "steps": len(ms) - 1,
+                       "failed_controllers": int((mc.status != 0).sum()), "launches_per_solve": 3 if "previous" in name else 3}
+        if mc.tracking_cost is not None:
+            modes[name]["tracking_cost_mean"] = float(mc.tracking_cost.mean())
+            modes[name]["data_frozen_fraction"] = float(1.0 - mc.data_updated.float().mean())
+        del mc
     solve_ms = sorted(ev_a[t].elapsed_time(ev_b[t]) for t in range(warm, T + warm))
     med = solve_ms[len(solve_ms) // 2]
     avg = sum(solve_ms) / len(solve_ms)
@@ -885,6 +912,7 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
         "ms_per_batch_solve_median": med,
         "closed_loop_solves_per_s": batch * T / t_loop,
         "e2e": e2e,
+        "optional_modes": modes,
         "cold_start": {"value": batch / (cold_ms * 1e-3), "unit": "solves/s", "ms_per_batch_solve": cold_ms,
                        "pivoting_passes_mean": cold_passes, "failed_controllers": cold_failed},
         "config": "n=6, L=35, N=350, m=p=3 (693-variable QP, 331 equalities, 111 box rows), alpha_reg_type=0, "

@@ -143,17 +143,8 @@ __device__ __forceinline__ Wrench rotor_wrench(const DdqcEnvParams& P, const flo
 }
 
 __device__ __forceinline__ void substep(const DdqcEnvParams& P, const Wrench& W, V3& p, Q4& q, V3& v, V3& w) {
-  // body-frame Euler equations, gyroscopic term with the old rates
-  float nwx = fm(-P.b_w[0], w.y * w.z, w.x + W.ax);
-  float nwy = fm(-P.b_w[1], w.z * w.x, w.y + W.ay);
-  float nwz = fm(-P.b_w[2], w.x * w.y, w.z + W.az);
-  w = V3{nwx, nwy, nwz};
-  // world-frame linear velocity (old pose): third column of R(q) * thrust / m + gravity
-  v.x = fm(W.cxy, fm(q.x, q.z, q.w * q.y), v.x);
-  v.y = fm(W.cxy, fm(q.y, q.z, -(q.w * q.x)), v.y);
-  float r33 = fm(-2.0f, fm(q.x, q.x, q.y * q.y), 1.0f);
-  v.z = fm(W.cz, r33, v.z - P.dt_g);
-  // semi-implicit Euler: positions with the new velocities
+  // Order pinned by the reference's published Genesis run (oracle/drone_physics.py): the pose advances
+  // with the OLD velocities, then the velocities with the forces at the NEW pose.
   p.x = fm(v.x, P.dt, p.x);
   p.y = fm(v.y, P.dt, p.y);
   p.z = fm(v.z, P.dt, p.z);
@@ -166,6 +157,16 @@ __device__ __forceinline__ void substep(const DdqcEnvParams& P, const Wrench& W,
   float n2 = fm(n.z, n.z, fm(n.y, n.y, fm(n.x, n.x, n.w * n.w)));
   float inv_n = fm(-0.5f, n2, 1.5f);
   q = Q4{n.w * inv_n, n.x * inv_n, n.y * inv_n, n.z * inv_n};
+  // body-frame Euler equations, gyroscopic term with the old rates
+  float nwx = fm(-P.b_w[0], w.y * w.z, w.x + W.ax);
+  float nwy = fm(-P.b_w[1], w.z * w.x, w.y + W.ay);
+  float nwz = fm(-P.b_w[2], w.x * w.y, w.z + W.az);
+  w = V3{nwx, nwy, nwz};
+  // world-frame linear velocity: third column of R(q) at the new pose * thrust / m + gravity
+  v.x = fm(W.cxy, fm(q.x, q.z, q.w * q.y), v.x);
+  v.y = fm(W.cxy, fm(q.y, q.z, -(q.w * q.x)), v.y);
+  float r33 = fm(-2.0f, fm(q.x, q.x, q.y * q.y), 1.0f);
+  v.z = fm(W.cz, r33, v.z - P.dt_g);
 }
 
 __device__ __forceinline__ float sumsq3(V3 a) { return (a.x * a.x + a.y * a.y) + a.z * a.z; }

@@ -1047,14 +1047,7 @@ __device__ __forceinline__ void env_step_pair_body(const DdqcEnvParams& P, const
     const WrenchP W{M.mul2(K2A(k_w, 0), tau_x), M.mul2(K2A(k_w, 1), tau_y), M.mul2(K2A(k_w, 2), tau_z),
                     M.mul2(K2(two_dt_over_m), fz), M.mul2(K2(dt_over_m), fz)};
     for (int sidx = 0; sidx < P.decimation; ++sidx) {  // substep
-      const f2 nwx = fma2(neg2(K2A(b_w, 0)), M.mul2(w.y, w.z), add2(w.x, W.ax));
-      const f2 nwy = fma2(neg2(K2A(b_w, 1)), M.mul2(w.z, w.x), add2(w.y, W.ay));
-      const f2 nwz = fma2(neg2(K2A(b_w, 2)), M.mul2(w.x, w.y), add2(w.z, W.az));
-      w = V3p{nwx, nwy, nwz};
-      v.x = fma2(W.cxy, fma2(q.x, q.z, M.mul2(q.w, q.y)), v.x);
-      v.y = fma2(W.cxy, fma2(q.y, q.z, neg2(M.mul2(q.w, q.x))), v.y);
-      const f2 r33 = fma2(LIT(L_MINUS_TWO), fma2(q.x, q.x, M.mul2(q.y, q.y)), LIT(L_ONE));
-      v.z = fma2(W.cz, r33, sub2(v.z, K2(dt_g)));
+      // pose with the old velocities, then the velocities with the forces at the new pose (ddqc_device.cuh::substep)
       p.x = fma2(v.x, K2(dt), p.x);
       p.y = fma2(v.y, K2(dt), p.y);
       p.z = fma2(v.z, K2(dt), p.z);
@@ -1072,6 +1065,14 @@ __device__ __forceinline__ void env_step_pair_body(const DdqcEnvParams& P, const
       const f2 n2 = fma2(nq.z, nq.z, fma2(nq.y, nq.y, fma2(nq.x, nq.x, M.mul2(nq.w, nq.w))));
       const f2 inv_n = fma2(LIT(L_MINUS_HALF), n2, LIT(L_ONE_HALF));
       q = Q4p{M.mul2(nq.w, inv_n), M.mul2(nq.x, inv_n), M.mul2(nq.y, inv_n), M.mul2(nq.z, inv_n)};
+      const f2 nwx = fma2(neg2(K2A(b_w, 0)), M.mul2(w.y, w.z), add2(w.x, W.ax));
+      const f2 nwy = fma2(neg2(K2A(b_w, 1)), M.mul2(w.z, w.x), add2(w.y, W.ay));
+      const f2 nwz = fma2(neg2(K2A(b_w, 2)), M.mul2(w.x, w.y), add2(w.z, W.az));
+      w = V3p{nwx, nwy, nwz};
+      v.x = fma2(W.cxy, fma2(q.x, q.z, M.mul2(q.w, q.y)), v.x);
+      v.y = fma2(W.cxy, fma2(q.y, q.z, neg2(M.mul2(q.w, q.x))), v.y);
+      const f2 r33 = fma2(LIT(L_MINUS_TWO), fma2(q.x, q.x, M.mul2(q.y, q.y)), LIT(L_ONE));
+      v.z = fma2(W.cz, r33, sub2(v.z, K2(dt_g)));
     }
   }
 

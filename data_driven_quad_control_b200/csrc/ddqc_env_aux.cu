@@ -151,7 +151,8 @@ restore_state_kernel(const DdqcEnvParams P, const DdqcEnvState S, const DdqcEnvO
       for (int c = 0; c < 3; ++c) {
         const float pc = base_pos[t * 3 + c], cm = commands[t * 3 + c];
         S.pos[c * n + e] = pc;
-        S.commands[c * n + e] = cm;
+        // the saved commands only enter rel_pos / last_rel_pos: the reference's restore_from_state never writes
+        // self.commands (hover_env.py:712-716), so an env whose target changed since the save keeps its CURRENT target
         // body-frame buffers go into the simulator dofs verbatim (hover_env.py:729-735)
         S.vel[c * n + e] = base_lin_vel[t * 3 + c];
         S.ang[c * n + e] = base_ang_vel[t * 3 + c];

@@ -210,7 +210,9 @@ int ddqc_env_get_state(const DdqcEnvParams* params_host, const DdqcEnvState* sta
 
 /* HoverEnv.restore_from_state (hover_env.py:697-753): scatters the AoS inputs to idx.  The
  * body-frame velocities are written into the simulator dofs as the reference does
- * (hover_env.py:729-735).  Episode sums of idx are averaged into the ctl ring and zeroed. */
+ * (hover_env.py:729-735).  `commands` only enters the rel_pos / last_rel_pos buffers: the reference never
+ * writes self.commands here (hover_env.py:712-716), the env keeps its current target.  Episode sums of idx
+ * are averaged into the ctl ring and zeroed. */
 int ddqc_env_restore_state(const DdqcEnvParams* params_host, const DdqcEnvState* state_host,
                            const DdqcEnvOut* out_host, DdqcEnvCtl* ctl, const int64_t* idx,
                            int64_t n_idx, int64_t n_env, const float* base_pos,

@@ -1,12 +1,28 @@
 """TEST INFRASTRUCTURE ONLY (oracle) -- restated Genesis drone rigid-body substep.
 
-PARITY UNPINNED for this file: the arithmetic of the physics substep lives in
-the un-vendored third-party package `genesis_world @ git+.../Genesis@1249131`
-(reference `pyproject.toml:15`), which is neither under /root/reference nor
-installed here.  The reference only pins it *behaviourally*
-(`tests/controller_tests/test_drone_ctbr_controller.py:45-104`: hover |w|<0.1
-after 10 steps, rate error <= 1e-3 after 20 steps), both of which this
-restatement satisfies (tests/test_oracle_vs_reference.py).
+The arithmetic of the physics substep lives in the un-vendored third-party package
+`genesis_world @ git+.../Genesis@1249131` (reference `pyproject.toml:15`), which is neither under
+/root/reference nor installable here (profiles/r2_reference_stack_probe.log), so this file cannot be
+compared with Genesis call by call.  What pins it:
+
+  * the ONE output of the real stack that ships with the reference, `docs/resources/
+    controller_comparison_plot.png` (Genesis + the reference's tracking controller / PPO policy), digitised by
+    `oracle/digitize_reference_plot.py` into `tests/golden/ref_comparison_plot_curves.npz`:
+    `tests/test_reference_plot_pin.py` flies the same scenario on this restatement and requires the
+    tracking-controller drone and the PPO drone to stay within a few pixels of the published curves over all
+    14 s (1 px = 0.047 s, ~6 mm), and the PPO drone to hover as steadily as the reference's does.  That
+    figure selected the ORDER of the update below: with the velocity-first (semi-implicit) order used until
+    round 2 the same flights missed the published curves by up to 12.6 px (tracking overshoot 0.10 m instead
+    of 0.17 m at the second setpoint) and the PPO policy showed a 20 mm limit cycle in hover that the
+    reference's run does not have; pose-first reproduces both (max 2.1 / 4.9 px, 0.2 mm).  Candidate orders
+    compared on the figure (sum of the six 90th-percentile pixel distances): velocity-first 17.6, fully
+    explicit 10.4, pose-first 9.8, velocity-first with the rotor command delayed one substep 9.0 (needs extra
+    per-env state; not adopted).  Pose-first is what a simulator shows when the pose it reports lags its
+    generalised coordinates by one substep.
+  * behaviourally, the reference's own tests (`tests/controller_tests/test_drone_ctbr_controller.py:45-104`:
+    hover |w|<0.1 after 10 steps, rate error <= 1e-3 after 20 steps) pass on it
+    (tests/test_oracle_vs_reference.py), and tests/test_physics_convergence.py shows first-order convergence
+    to the continuous Newton-Euler solution.
 
 Restated model (call sites: reference `hover_env.py:437-439` set_propellels_rpm +
 scene.step(); `hover_env.py:452-470` get_pos/get_quat/get_vel/get_ang):
@@ -15,8 +31,8 @@ scene.step(); `hover_env.py:452-470` get_pos/get_quat/get_vel/get_ang):
                  yaw torque  sum_i (rpm_i*rpm_i)*(KM*spin_i)  (body z)
   body rates:    J wdot = tau - w x (J w), J diagonal  (free-joint angular dofs in the body frame)
   world linear:  m vdot = R(q) [0,0,sum T] + m g       (g = -9.81 z)
-  integrator:    semi-implicit Euler, dt = sim dt:  w,v first (forces at the old pose),
-                 then p += v*dt and q <- q (x) dq renormalised, dq = [cos|h|, sinc|h| h], h = w*dt/2,
+  integrator:    dt = sim dt, POSE FIRST: p += v*dt and q <- q (x) dq renormalised with the OLD v, w
+                 (dq = [cos|h|, sinc|h| h], h = w*dt/2), then w, v with the forces at the NEW pose;
                  cos / sinc by their degree-4 Taylor polynomials in |h|^2 (1 ulp for |w| <= 100 rad/s
                  at dt = 0.01) and the renormalisation by one Newton step q*(1.5 - 0.5|q|^2)
                  (|q|^2 = 1 + O(1e-7) every step, so this equals q/|q| to fp32 rounding).
@@ -171,19 +187,7 @@ def substep(P: PhysParams, wrench, p, q, v, w):
     vx, vy, vz = v
     wx, wy, wz = w
 
-    # body-frame Euler equations (gyroscopic term with the OLD rates)
-    nwx = fma(-P.b_w[0], wy * wz, wx + a_x)
-    nwy = fma(-P.b_w[1], wz * wx, wy + a_y)
-    nwz = fma(-P.b_w[2], wx * wy, wz + a_z)
-    wx, wy, wz = nwx, nwy, nwz
-
-    # world-frame linear velocity: third column of R(q) times thrust/m, plus gravity (old pose)
-    vx = fma(c_xy, fma(qx, qz, qw * qy), vx)
-    vy = fma(c_xy, fma(qy, qz, -(qw * qx)), vy)
-    r33 = fma(F32(-2.0), fma(qx, qx, qy * qy), F32(1.0))
-    vz = fma(c_z, r33, vz - P.dt_g)
-
-    # positions with the NEW velocities (semi-implicit Euler)
+    # pose first, with the OLD velocities (see the module docstring: the order pinned by the reference's published plot)
     px = fma(vx, P.dt, px)
     py = fma(vy, P.dt, py)
     pz = fma(vz, P.dt, pz)
@@ -197,6 +201,19 @@ def substep(P: PhysParams, wrench, p, q, v, w):
     nw, nx, ny, nz = quat_mul(qw, qx, qy, qz, c, k * hx, k * hy, k * hz)
     n2 = fma(nz, nz, fma(ny, ny, fma(nx, nx, nw * nw)))
     inv_n = fma(F32(-0.5), n2, F32(1.5))
-    q = (nw * inv_n, nx * inv_n, ny * inv_n, nz * inv_n)
+    qw, qx, qy, qz = nw * inv_n, nx * inv_n, ny * inv_n, nz * inv_n
+    q = (qw, qx, qy, qz)
+
+    # body-frame Euler equations (gyroscopic term with the OLD rates)
+    nwx = fma(-P.b_w[0], wy * wz, wx + a_x)
+    nwy = fma(-P.b_w[1], wz * wx, wy + a_y)
+    nwz = fma(-P.b_w[2], wx * wy, wz + a_z)
+    wx, wy, wz = nwx, nwy, nwz
+
+    # world-frame linear velocity: third column of R(q) at the NEW pose times thrust/m, plus gravity
+    vx = fma(c_xy, fma(qx, qz, qw * qy), vx)
+    vy = fma(c_xy, fma(qy, qz, -(qw * qx)), vy)
+    r33 = fma(F32(-2.0), fma(qx, qx, qy * qy), F32(1.0))
+    vz = fma(c_z, r33, vz - P.dt_g)
 
     return (px, py, pz), q, (vx, vy, vz), (wx, wy, wz)

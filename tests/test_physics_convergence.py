@@ -86,14 +86,15 @@ def test_substep_converges_at_first_order_to_the_newton_euler_solution():
 def test_hover_is_an_equilibrium_and_free_fall_is_exact():
     """Zero rates, level attitude, rotor speed sqrt(m g / (4 KF)): the drone stays put up to fp32 rounding of the torque
     sums (4 s: 0.5 mm of drift, 2e-5 rad/s; the reference's own pin is |w| < 0.1 after 10 env steps).  Zero thrust:
-    v_z = -g t exactly in the semi-implicit scheme, z = z0 - g dt^2 k (k + 1) / 2."""
+    v_z = -g t exactly, z = z0 - g dt^2 k (k - 1) / 2 in the pose-first order (the pose advances with the velocity of the
+    previous substep; k (k + 1) / 2 in the velocity-first order used until round 2)."""
     hover_rpm = np.sqrt(dp.CF2X_MASS * dp.GRAVITY / (4 * dp.CF2X_KF))
     s0 = np.array([0.0, 0.0, 1.0, 1.0, 0, 0, 0, 0, 0, 0, 0, 0, 0])
     p, q, v, w = _oracle_run(0.01, 400, np.full(4, hover_rpm), s0)
     assert np.abs(p - [0, 0, 1]).max() < 2e-3 and np.abs(v).max() < 2e-3 and np.abs(w).max() < 1e-4 and abs(q[0] - 1) < 1e-7
     k = 50
     p, q, v, w = _oracle_run(0.01, k, np.zeros(4), s0)
-    assert abs(v[2] + dp.GRAVITY * 0.01 * k) < 1e-5 and abs(p[2] - (1.0 - dp.GRAVITY * 1e-4 * k * (k + 1) / 2)) < 1e-5
+    assert abs(v[2] + dp.GRAVITY * 0.01 * k) < 1e-5 and abs(p[2] - (1.0 - dp.GRAVITY * 1e-4 * k * (k - 1) / 2)) < 1e-5
 
 
 def test_quaternion_stays_normalised_and_yaw_equivariance():
