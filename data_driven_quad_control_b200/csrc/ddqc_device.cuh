@@ -142,9 +142,20 @@ __device__ __forceinline__ Wrench rotor_wrench(const DdqcEnvParams& P, const flo
   return Wrench{P.k_w[0] * tau_x, P.k_w[1] * tau_y, P.k_w[2] * tau_z, P.two_dt_over_m * fz, P.dt_over_m * fz};
 }
 
-__device__ __forceinline__ void substep(const DdqcEnvParams& P, const Wrench& W, V3& p, Q4& q, V3& v, V3& w) {
-  // Order pinned by the reference's published Genesis run (oracle/drone_physics.py): the pose advances
-  // with the OLD velocities, then the velocities with the forces at the NEW pose.
+// One substep is: pose with the OLD velocities, then the velocities with the forces at the NEW pose (order pinned by
+// the reference's published Genesis run: oracle/drone_physics.py).  It is evaluated in two halves so
+// that the decimation loop can defer the linear-velocity half of substep k to the top of substep k + 1, where it runs
+// beside the (long, dependent) quaternion chain instead of behind it - the same operations on the same operands, only
+// their place in the instruction stream differs (bit-identical to substep()).
+__device__ __forceinline__ void substep_velocity(const DdqcEnvParams& P, const Wrench& W, const Q4& q, V3& v) {
+  // world-frame linear velocity: third column of R(q) at the new pose * thrust / m + gravity
+  v.x = fm(W.cxy, fm(q.x, q.z, q.w * q.y), v.x);
+  v.y = fm(W.cxy, fm(q.y, q.z, -(q.w * q.x)), v.y);
+  float r33 = fm(-2.0f, fm(q.x, q.x, q.y * q.y), 1.0f);
+  v.z = fm(W.cz, r33, v.z - P.dt_g);
+}
+
+__device__ __forceinline__ void substep_pose_rates(const DdqcEnvParams& P, const Wrench& W, V3& p, Q4& q, const V3& v, V3& w) {
   p.x = fm(v.x, P.dt, p.x);
   p.y = fm(v.y, P.dt, p.y);
   p.z = fm(v.z, P.dt, p.z);
@@ -162,11 +173,27 @@ __device__ __forceinline__ void substep(const DdqcEnvParams& P, const Wrench& W,
   float nwy = fm(-P.b_w[1], w.z * w.x, w.y + W.ay);
   float nwz = fm(-P.b_w[2], w.x * w.y, w.z + W.az);
   w = V3{nwx, nwy, nwz};
-  // world-frame linear velocity: third column of R(q) at the new pose * thrust / m + gravity
-  v.x = fm(W.cxy, fm(q.x, q.z, q.w * q.y), v.x);
-  v.y = fm(W.cxy, fm(q.y, q.z, -(q.w * q.x)), v.y);
-  float r33 = fm(-2.0f, fm(q.x, q.x, q.y * q.y), 1.0f);
-  v.z = fm(W.cz, r33, v.z - P.dt_g);
+}
+
+__device__ __forceinline__ void substep(const DdqcEnvParams& P, const Wrench& W, V3& p, Q4& q, V3& v, V3& w) {
+  substep_pose_rates(P, W, p, q, v, w);
+  substep_velocity(P, W, q, v);
+}
+
+// `decimation` substeps under one zero-order-held rotor command
+#ifndef DDQC_ENV_DEFER_VELOCITY
+#define DDQC_ENV_DEFER_VELOCITY 1
+#endif
+__device__ __forceinline__ void substeps(const DdqcEnvParams& P, const Wrench& W, V3& p, Q4& q, V3& v, V3& w) {
+#if DDQC_ENV_DEFER_VELOCITY
+  for (int sidx = 0; sidx < P.decimation; ++sidx) {
+    if (sidx > 0) substep_velocity(P, W, q, v);  // deferred half of the previous substep
+    substep_pose_rates(P, W, p, q, v, w);
+  }
+  if (P.decimation > 0) substep_velocity(P, W, q, v);
+#else
+  for (int sidx = 0; sidx < P.decimation; ++sidx) substep(P, W, p, q, v, w);
+#endif
 }
 
 __device__ __forceinline__ float sumsq3(V3 a) { return (a.x * a.x + a.y * a.y) + a.z * a.z; }

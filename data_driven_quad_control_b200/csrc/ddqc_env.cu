@@ -343,7 +343,7 @@ __device__ __forceinline__ void env_step_body(const DdqcEnvParams& P, const Ddqc
     const V3 last_pos = p;
     {
       const Wrench W = rotor_wrench(P, rpm);  // zero-order hold: constant over the substeps
-      for (int sidx = 0; sidx < P.decimation; ++sidx) substep(P, W, p, q, v, w);
+      substeps(P, W, p, q, v, w);
     }
 
     // ------------------------------------------------------------------ buffers (A9-A12)

@@ -107,6 +107,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16 consecutive fp32 columns of this thread's TMEM lane, asynchronously: the registers are valid after tmem_wait16(r).
+// (tcgen05.wait::ld waits for ALL outstanding loads of the thread, so the pipeline is wait(current) -> issue(next) ->
+// arithmetic on current; the "+r" operands of the wait keep the compiler from reading the registers above it.)
+#ifndef DDQC_POLICY_TMEM_PIPE
+#define DDQC_POLICY_TMEM_PIPE 1
+#endif
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 // x = hi + lo with hi, lo bf16 (16 mantissa bits together); two values per conversion instruction
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);  // .x = a in the low half
@@ -312,6 +335,63 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
     mbar_wait(mbar, phase);
     phase ^= 1;
     tc_fence_after();
+#if DDQC_POLICY_TMEM_PIPE && DDQC_POLICY_F32X2 && DDQC_POLICY_KSPLIT
+    // ---- 3 + 4, TMEM reads software-pipelined: 16 columns at a time, the load of the next 16 in flight under the
+    // arithmetic of the current ones (ncu: 20 % of the stall cycles of the one-shot x32 version were spent behind
+    // tcgen05.wait::ld); the layer-2 MMAs of a 32-column pair of K steps are issued as soon as it is written, as before
+    {
+      uint32_t ra[16], rb[16];
+      tmem_ld16_issue(d1 + lane_addr + half * 64, ra);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t(&cur)[16] = (q & 1) ? rb : ra;
+        uint32_t(&nxt)[16] = (q & 1) ? ra : rb;
+        const int c0 = half * 64 + q * 16;
+        tmem_wait16(cur);
+        if (q < 3) tmem_ld16_issue(d1 + lane_addr + c0 + 16, nxt);
+        const f2_t sc = pk2(kTanhScale, kTanhScale);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float4 ba = *reinterpret_cast<const float4*>(sB1 + c0 + 8 * c), bb = *reinterpret_cast<const float4*>(sB1 + c0 + 8 * c + 4);
+          uint4 h, l;
+          f2_t t0, t1, t2, t3;
+          tanh4(fma2(pk2(__uint_as_float(cur[8 * c]), __uint_as_float(cur[8 * c + 1])), sc, pk2(ba.x, ba.y)),
+                fma2(pk2(__uint_as_float(cur[8 * c + 2]), __uint_as_float(cur[8 * c + 3])), sc, pk2(ba.z, ba.w)), t0, t1);
+          tanh4(fma2(pk2(__uint_as_float(cur[8 * c + 4]), __uint_as_float(cur[8 * c + 5])), sc, pk2(bb.x, bb.y)),
+                fma2(pk2(__uint_as_float(cur[8 * c + 6]), __uint_as_float(cur[8 * c + 7])), sc, pk2(bb.z, bb.w)), t2, t3);
+          split_pair2(t0, h.x, l.x);
+          split_pair2(t1, h.y, l.y);
+          split_pair2(t2, h.z, l.z);
+          split_pair2(t3, h.w, l.w);
+          const uint32_t off = core_off(row, c0 + 8 * c, kHid / 8);
+          *reinterpret_cast<uint4*>(wgs + kA2Hi + off) = h;
+          *reinterpret_cast<uint4*>(wgs + kA2Lo + off) = l;
+        }
+        if (q & 1) {  // the 32-column pair cb = q / 2 of both thread halves is complete: contract it
+          const int cb = q >> 1;
+          fence_async_smem();
+          tc_fence_before();
+          wg_sync(wg);
+          if (wtid == 0) {
+            tc_fence_after();
+#pragma unroll 1
+            for (int kq = 0; kq < 4; ++kq) {
+              const int ks = (kq >> 1) * 4 + cb * 2 + (kq & 1);
+              const uint32_t ko = ks * 256;  // two 16-byte K chunks per MMA
+              const uint64_t ah = make_desc(wga + kA2Hi + ko, 128, (kHid / 8) * 128), al = make_desc(wga + kA2Lo + ko, 128, (kHid / 8) * 128);
+              const uint64_t bh = make_desc(sbase + kW2Hi + ko, 128, (kHid / 8) * 128), bl = make_desc(sbase + kW2Lo + ko, 128, (kHid / 8) * 128);
+              umma_bf16(d2, ah, bh, (cb | kq) != 0);
+              if (SPLIT) {
+                umma_bf16(d2, al, bh, 1);
+                umma_bf16(d2, ah, bl, 1);
+              }
+            }
+            if (cb == 1) umma_commit(mbar);
+          }
+        }
+      }
+    }
+#else
     // ---- 3. h1 = tanh(D1 + b1) -> layer-2 operand tile (this thread: 64 of the row's 128 columns) ----
 #pragma unroll 1
     for (int cb = 0; cb < 2; ++cb) {
@@ -369,6 +449,7 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
         }
       }
     }
+#endif
     {  // prefetch the next tile's observation chunk
       const long long nrow = (tile + tile_step) * kTileM + row;
       o0 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -388,6 +469,42 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
     f2_t out2[kMaxOut];  // (even, odd) column partial sums
 #pragma unroll
     for (int j = 0; j < kMaxOut; ++j) out2[j] = pk2(0.0f, 0.0f);
+#if DDQC_POLICY_TMEM_PIPE
+    {
+      uint32_t ra[16], rb[16];
+      tmem_ld16_issue(d2 + lane_addr + half * 64, ra);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t(&cur)[16] = (q & 1) ? rb : ra;
+        uint32_t(&nxt)[16] = (q & 1) ? ra : rb;
+        const int c0 = half * 64 + q * 16;
+        tmem_wait16(cur);
+        if (q < 3) tmem_ld16_issue(d2 + lane_addr + c0 + 16, nxt);
+        const f2_t sc = pk2(kTanhScale, kTanhScale);
+        f2_t h[8];
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const float4 bq = *reinterpret_cast<const float4*>(sB2 + c0 + 4 * qq);
+          tanh4(fma2(pk2(__uint_as_float(cur[4 * qq]), __uint_as_float(cur[4 * qq + 1])), sc, pk2(bq.x, bq.y)),
+                fma2(pk2(__uint_as_float(cur[4 * qq + 2]), __uint_as_float(cur[4 * qq + 3])), sc, pk2(bq.z, bq.w)), h[2 * qq], h[2 * qq + 1]);
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxOut; ++j) {
+          if (j < n_out) {  // uniform
+            const float4* w = reinterpret_cast<const float4*>(sW3 + j * kHid + c0);
+            f2_t acc = out2[j];
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const float4 ww = w[qq];
+              acc = fma2(h[2 * qq], pk2(ww.x, ww.y), acc);
+              acc = fma2(h[2 * qq + 1], pk2(ww.z, ww.w), acc);
+            }
+            out2[j] = acc;
+          }
+        }
+      }
+    }
+#else
 #pragma unroll 1
     for (int cb = 0; cb < 2; ++cb) {
       const int c0 = half * 64 + cb * 32;
@@ -416,6 +533,7 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
         }
       }
     }
+#endif
 #pragma unroll
     for (int j = 0; j < kMaxOut; ++j) {
       float e, o;

@@ -8,7 +8,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _setup(B, n_mpc_step=1, seed=3):
+def _setup(B, n_mpc_step=1, seed=3, alpha_reg_type=None, **ctor_extra):
     import ddmpc_oracle as mo
     from data_driven_quad_control_b200.data_driven_mpc.nonlinear_data_driven_mpc_controller import (
         BatchedNonlinearDataDrivenMPC,
@@ -27,6 +27,8 @@ def _setup(B, n_mpc_step=1, seed=3):
     dev = torch.device("cuda")
     prm = mo.default_params()
     prm.n, prm.L, prm.N = 2, 5, 80
+    if alpha_reg_type is not None:
+        prm.alpha_reg_type = alpha_reg_type
     env_cfg, obs_cfg, _, cmd_cfg = get_cfgs()
     obs_cfg["obs_noise_std"] = 1e-4
     env_cfg.update(episode_length_s=100, termination_if_close_to_ground=0.0, termination_if_x_greater_than=100.0,
@@ -56,7 +58,7 @@ def _setup(B, n_mpc_step=1, seed=3):
         assert np.abs(cmd - cmd.astype(np.float32)).max() < 1e-9  # what is left is the fp32 controller command
     y_r = np.tile(np.array([[0.3, 0.2, 1.8]]), (B, 1)) + 0.05 * np.arange(B)[:, None]
     kw = mo.ctor_kwargs(prm, u_N[0].cpu().numpy(), y_N[0].cpu().numpy(), y_r[0])
-    kw.update(u=u_N, y=y_N, y_r=y_r, n_mpc_step=n_mpc_step)
+    kw.update(u=u_N, y=y_N, y_r=y_r, n_mpc_step=n_mpc_step, **ctor_extra)
     ctrl = BatchedNonlinearDataDrivenMPC(**kw, device=dev, solve_on_init=False)
     env.update_target_pos(torch.arange(B, device=dev), torch.from_numpy(y_r).to(dev))
     return prm, env, ctrl, u_N.cpu().numpy(), y_N.cpu().numpy(), y_r
@@ -86,6 +88,39 @@ def test_batched_closed_loop_matches_reference_loop(build_lib, n_n_mpc_step):
         # rolling windows: initial data shifted by T samples, then the applied inputs / measured outputs
         np.testing.assert_array_equal(ctrl.u[b].cpu().numpy(), np.vstack([u0[b][T:], u_sys[:, b]]))
         np.testing.assert_array_equal(ctrl.y[b].cpu().numpy(), np.vstack([y0[b][T:], y_sys[:, b]]))
+
+
+@pytest.mark.parametrize("alpha_reg_type,thr", [(1, None), (0, 1e9), (1, 1e9)])  # 1e9: the data freezes after the first solve
+def test_batched_closed_loop_optional_modes(build_lib, alpha_reg_type, thr):
+    """The evaluator with the controller modes of SURVEY 8 a16 switched on (alpha_reg_type PREVIOUS, update_cost_threshold;
+    dual recovery after every solve), replayed through the literal-QP oracle controller in the same mode."""
+    import ddmpc_eval_oracle as eo
+    import ddmpc_oracle as mo
+    from data_driven_quad_control_b200.data_driven_mpc.utilities.param_grid_search.controller_evaluation import (
+        sim_nonlinear_dd_mpc_control_loop_batched,
+    )
+
+    B, T = 3, 8
+    prm, env, ctrl, u0, y0, y_r = _setup(B, alpha_reg_type=alpha_reg_type, update_cost_threshold=thr)
+    d0 = np.linalg.norm(env.get_pos(add_noise=False).cpu().numpy().astype(np.float64) - y_r, axis=1)
+    res = sim_nonlinear_dd_mpc_control_loop_batched(env, ctrl, T, torch.from_numpy(d0), None, False, record=True)
+    assert not bool(res.failed.any())
+    y_sys, u_sys = res.y_sys.cpu().numpy(), res.u_sys.cpu().numpy()
+    frozen = 0
+    for b in range(B):
+        replay = iter(y_sys[:, b])
+        orc = mo.NonlinearDDMPCOracle(**{**mo.ctor_kwargs(prm, u0[b], y0[b], y_r[b]), "update_cost_threshold": thr}, solve_on_init=False)
+        rmse, u_ref, _ = eo.sim_control_loop(orc, lambda u: next(replay), T, d0[b], None, False)
+        np.testing.assert_allclose(u_sys[:, b], u_ref, rtol=0, atol=2e-5)
+        np.testing.assert_allclose(float(res.rmse[b]), rmse, rtol=1e-13, atol=0)
+        np.testing.assert_array_equal(ctrl.u[b].cpu().numpy(), np.vstack([u0[b][T:], u_sys[:, b]]))  # the measurements always roll
+        if thr is not None:
+            assert abs(float(ctrl.tracking_cost[b]) - orc.tracking_cost) <= 1e-6 * max(1.0, orc.tracking_cost)
+            np.testing.assert_array_equal(ctrl.u_data[b].cpu().numpy(), orc.u_data)  # the Hankel data only when the cost allows
+            frozen += not np.array_equal(orc.u_data, orc.u)
+        if alpha_reg_type == 1:
+            np.testing.assert_allclose(ctrl.alpha_prev[b].cpu().numpy(), orc.alpha_prev, rtol=0, atol=2e-5)
+    assert thr is None or frozen > 0
 
 
 def test_early_stop_freezes_the_controller(build_lib):

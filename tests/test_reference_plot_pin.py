@@ -49,8 +49,9 @@ def comparison_env():
     return env
 
 
-def fly(which: str) -> np.ndarray:
-    """(350, 3) true positions logged after every control step, as parallel_controller_sim.py:339-340 records them."""
+def fly(which: str, with_inputs: bool = False) -> np.ndarray:
+    """(350, 3) true positions logged after every control step, as parallel_controller_sim.py:339-340 records them
+    (`with_inputs`: (350, 6), the applied thrust [N] / roll / pitch rate commands [rad/s] appended, :337, :425-431)."""
     env = comparison_env()
     ctrl = TrackingOracle(0.027, [[2.0, 0.0, 2.2], [2.0, 0.0, 2.2], [18.0, 0.0, 6.0]], 5.0, 1, env.step_dt)
     q_sp = np.array([[1.0, 0.0, 0.0, 0.0]], np.float32)
@@ -61,9 +62,10 @@ def fly(which: str) -> np.ndarray:
         env.update_target_pos([0], tgt)
         for _ in range(steps):
             c = ctrl.compute(env.base_pos.astype(np.float32), env.base_quat, tgt, q_sp)[:, :3].astype(np.float64)
-            env.step(np.clip(-1.0 + (c - lo) * 2.0 / span, -1, 1).astype(np.float32))
+            a = np.clip(-1.0 + (c - lo) * 2.0 / span, -1, 1)
+            env.step(a.astype(np.float32))
             if log is not None:
-                log.append(env.base_pos[0].copy())
+                log.append(np.concatenate([env.base_pos[0], (lo + (a + 1.0) * span / 2.0)[0]]))
 
     # stabilisation at the initial hover position + the 350 steps of the DD-MPC drone's data collection, during which the
     # other drones are held by the stabilising (tracking) controller (controller_comparison.py:286-330)
@@ -79,10 +81,12 @@ def fly(which: str) -> np.ndarray:
         for sp in SETPOINTS:
             env.update_target_pos([0], np.array([sp], np.float32))
             for _ in range(STEPS):
-                env.step(np.clip(po.actor_forward(obs, *W), -1, 1).astype(np.float32))
+                a = np.clip(po.actor_forward(obs, *W), -1, 1)
+                env.step(a.astype(np.float32))
                 obs = env.obs_buf.copy()
-                log.append(env.base_pos[0].copy())
-    return np.array(log)
+                log.append(np.concatenate([env.base_pos[0], (lo + (a.astype(np.float64) + 1.0) * span / 2.0)[0]]))
+    log = np.array(log)
+    return log if with_inputs else log[:, :3]
 
 
 def pixel_distance(points: np.ndarray, values: np.ndarray, px_per_s: float, px_per_unit: float) -> np.ndarray:
@@ -143,3 +147,14 @@ def test_ppo_policy_flight_matches_the_published_genesis_run(curves):
     # same steady-state offsets as the reference's run (the policy is a proportional-type controller): read off the figure
     ref_hold = [np.median(curves[f"{ax}_rl"][(curves[f"{ax}_rl"][:, 0] > 4.0) & (curves[f"{ax}_rl"][:, 0] < 6.8), 1]) for ax in "xyz"]
     assert np.abs(pos[100:170].mean(0) - ref_hold).max() < 0.012, (pos[100:170].mean(0), ref_hold)
+
+
+def test_ppo_policy_commands_match_the_published_genesis_run(curves):
+    """The "Control Inputs" row of the same figure: total thrust and roll / pitch rate commands of the PPO drone (the
+    green lines; 462 px per newton, 8.2 px per rad/s).  The commands ring after each setpoint change (lightly damped
+    attitude loop), which makes them the most sensitive probe of the fast dynamics the figure offers.  Measured: median
+    0.9 - 1.1 px, 90th percentile 2.0 / 2.2 / 2.1 px (velocity-first order: thrust 90th percentile 4.3 px)."""
+    log = fly("rl", with_inputs=True)
+    for i, ax in enumerate(("thrust", "roll", "pitch")):
+        d = pixel_distance(curves[f"{ax}_rl"], log[:, 3 + i], float(curves[f"{ax}_px_per_s"]), float(curves[f"{ax}_px_per_m"]))
+        assert np.median(d) < 1.5 and np.percentile(d, 90) < 3.0, (ax, np.median(d), np.percentile(d, 90))
