@@ -350,8 +350,21 @@ __device__ long long* g_fprof = nullptr;
 #define FPROF(k)
 #endif
 
+// The solver inlines to 441 KB of SASS and ncu shows an instruction-cache hit rate of 83 % (stall "no instruction" 0.5
+// per issue).  DDQC_MPC_OUTLINE = 1 keeps ONE body of each of the large phase routines (called 2-4 times each; 366 KB).
+// Measured and left off: 514-518 k solves/s against 614 k on the phase probe (tools/mpc_perf.py) - behind a call the
+// routines lose the constant propagation of their shape arguments and the pivoting pays the ABI spills (96 -> 145 k
+// cycles per solve), far more than the instruction fetch gains.
+#ifndef DDQC_MPC_OUTLINE
+#define DDQC_MPC_OUTLINE 0
+#endif
+#if DDQC_MPC_OUTLINE
+#define DDQC_PHASE_FN __noinline__
+#else
+#define DDQC_PHASE_FN
+#endif
 template <bool RECT>
-__device__ void factor_columns(double* __restrict__ M, int nb1, int nrows, int ncols, int* s_flag) {
+__device__ DDQC_PHASE_FN void factor_columns(double* __restrict__ M, int nb1, int nrows, int ncols, int* s_flag) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   constexpr int kBulk = kWarps - 1;
   __syncthreads();
@@ -511,7 +524,7 @@ __device__ void backsub_blocked(const double* __restrict__ M, int ncols, double*
 }
 
 // Schur complement of the trailing block columns [c0, nrows): C_IK -= sum_{J < c0} L_IJ L_KJ^T
-__device__ void schur_trailing(double* __restrict__ M, int nrows, int c0) {
+__device__ DDQC_PHASE_FN void schur_trailing(double* __restrict__ M, int nrows, int c0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int nrem = nrows - c0;
   const int nblk = nrem * (nrem + 1) / 2;
@@ -682,7 +695,7 @@ __device__ int bpp_pass(const QpWork& q, double tol_g, int* last) {
 }
 
 // pivoting driver; returns 1 when converged.  `passes` accumulates the number of passes.
-__device__ int bpp_solve(const QpWork& q, double tol_g, int max_pass, int* passes) {
+__device__ DDQC_PHASE_FN int bpp_solve(const QpWork& q, double tol_g, int max_pass, int* passes) {
   const int tid = threadIdx.x, nx = q.nx;
   int best = nx + 1, patience = 3;
   for (int it = 0; it < max_pass; ++it) {
