@@ -884,7 +884,9 @@ def run_ddmpc_leg(dev, batch: int, T: int, warm: int = 2) -> dict:
             ms.append(m0.elapsed_time(m1))
         avg_m = sum(ms[1:]) / len(ms[1:])
         modes[name] = {"solves_per_s": batch / (avg_m * 1e-3), "ms_per_batch_solve": avg_m, "steps": len(ms) - 1,
-                       "failed_controllers": int((mc.status != 0).sum()), "launches_per_solve": 3 if "previous" in name else 3}
+                       "failed_controllers": int((mc.status != 0).sum()),
+                       # PREVIOUS: v_sr = H alpha_prev, solve, dual recovery; threshold: data refresh, solve, dual recovery
+                       "launches_per_solve": 3}
         if mc.tracking_cost is not None:
             modes[name]["tracking_cost_mean"] = float(mc.tracking_cost.mean())
             modes[name]["data_frozen_fraction"] = float(1.0 - mc.data_updated.float().mean())

@@ -116,6 +116,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // DDQC_POLICY_DEFER_OUT = 1: the half-0 thread sums and stores a row's actions after the NEXT warpgroup barrier (under the
 // next tile's layer-1 MMAs), one barrier per tile less.  Measured and left off: 0.1749-0.1751 ms either way - that barrier
 // is not on the critical path.
+// DDQC_POLICY_MMA1_AHEAD = 1: the layer-1 MMAs of tile t+1 are issued right behind the last layer-2 MMAs of tile t (its
+// operand tile is stored before the barrier that precedes them), so they run under the layer-2 epilogue of tile t and no
+// tile starts by waiting for its own layer-1 product (second mbarrier per warpgroup).
+#ifndef DDQC_POLICY_MMA1_AHEAD
+#define DDQC_POLICY_MMA1_AHEAD 1
+#endif
 #ifndef DDQC_POLICY_DEFER_OUT
 #define DDQC_POLICY_DEFER_OUT 0
 #endif
@@ -281,6 +287,8 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbase + kBar));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbase + kBar + 8));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbase + kB3 + 16));  // layer-1 barriers (MMA1_AHEAD): the
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbase + kB3 + 24));  // unused tail of the b3 slot
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -299,6 +307,9 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
   const uint32_t wga = sbase + kWgBase + wg * kWgStride;
   float* part = reinterpret_cast<float*>(smem + kPart + wg * kPartStride);
   uint32_t phase = 0;
+  constexpr bool kAhead = DDQC_POLICY_MMA1_AHEAD && DDQC_POLICY_TMEM_PIPE && DDQC_POLICY_F32X2 && DDQC_POLICY_KSPLIT;
+  const uint32_t mbar1 = kAhead ? sbase + kB3 + 16 + 8 * wg : mbar;  // layer-1 MMAs complete
+  uint32_t phase1 = 0;
 
   const long long n_tiles = (n + kTileM - 1) / kTileM;
   const long long tile_step = (long long)gridDim.x * 2;
@@ -327,36 +338,64 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
     }
   };
 #endif
-  for (long long tile = (long long)blockIdx.x * 2 + wg; tile < n_tiles; tile += tile_step) {
-    const long long grow = tile * kTileM + row;
-    const bool valid = grow < n;
-    // ---- 1. observation row -> layer-1 operand tile (each thread one 8-element K chunk) ----
-    {
-      float y[8];
-      y[0] = o0.x; y[1] = o0.y; y[2] = o0.z; y[3] = o0.w; y[4] = o1.x; y[5] = o1.y; y[6] = o1.z; y[7] = o1.w;
-      const uint32_t off = core_off(row, 8 * half, kIn / 8);
-      store_chunk(wgs, kA1Hi + off, kA1Lo + off, y);
+  // ---- 1. observation row (registers o0, o1) -> layer-1 operand tile (each thread one 8-element K chunk) ----
+  auto store_a1 = [&]() {
+    float y[8];
+    y[0] = o0.x; y[1] = o0.y; y[2] = o0.z; y[3] = o0.w; y[4] = o1.x; y[5] = o1.y; y[6] = o1.z; y[7] = o1.w;
+    const uint32_t off = core_off(row, 8 * half, kIn / 8);
+    store_chunk(wgs, kA1Hi + off, kA1Lo + off, y);
+  };
+  // ---- 2. D1 = A1 W1^T (one elected thread; behind a warpgroup barrier that follows the operand stores) ----
+  auto issue_mma1 = [&]() {
+    const uint64_t ah = make_desc(wga + kA1Hi, 128, (kIn / 8) * 128), al = make_desc(wga + kA1Lo, 128, (kIn / 8) * 128);
+    const uint64_t bh = make_desc(sbase + kW1Hi, 128, (kIn / 8) * 128), bl = make_desc(sbase + kW1Lo, 128, (kIn / 8) * 128);
+    umma_bf16(d1, ah, bh, 0);
+    if (SPLIT) {
+      umma_bf16(d1, al, bh, 1);
+      umma_bf16(d1, ah, bl, 1);
     }
+    umma_commit(mbar1);
+  };
+  auto load_obs = [&](long long t) {  // observation chunk of tile t -> o0, o1 (zeros past the end)
+    const long long r = t * kTileM + row;
+    o0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    o1 = o0;
+    if (t < n_tiles && r < n) {
+      const float4* src = reinterpret_cast<const float4*>(obs + r * kIn + 8 * half);
+      o0 = __ldg(src);
+      o1 = __ldg(src + 1);
+    }
+  };
+  if (kAhead && (long long)blockIdx.x * 2 + wg < n_tiles) {  // prologue: the first tile's layer-1 product
+    store_a1();
     fence_async_smem();
     tc_fence_before();
     wg_sync(wg);
-    // ---- 2. D1 = A1 W1^T ----
     if (wtid == 0) {
       tc_fence_after();
-      const uint64_t ah = make_desc(wga + kA1Hi, 128, (kIn / 8) * 128), al = make_desc(wga + kA1Lo, 128, (kIn / 8) * 128);
-      const uint64_t bh = make_desc(sbase + kW1Hi, 128, (kIn / 8) * 128), bl = make_desc(sbase + kW1Lo, 128, (kIn / 8) * 128);
-      umma_bf16(d1, ah, bh, 0);
-      if (SPLIT) {
-        umma_bf16(d1, al, bh, 1);
-        umma_bf16(d1, ah, bl, 1);
+      issue_mma1();
+    }
+    load_obs((long long)blockIdx.x * 2 + wg + tile_step);
+  }
+  for (long long tile = (long long)blockIdx.x * 2 + wg; tile < n_tiles; tile += tile_step) {
+    const long long grow = tile * kTileM + row;
+    const bool valid = grow < n;
+    const bool has_next = tile + tile_step < n_tiles;
+    if (!kAhead) {
+      store_a1();
+      fence_async_smem();
+      tc_fence_before();
+      wg_sync(wg);
+      if (wtid == 0) {
+        tc_fence_after();
+        issue_mma1();
       }
-      umma_commit(mbar);
     }
 #if DDQC_POLICY_DEFER_OUT
     flush_pending();  // the previous tile's actions, under the layer-1 MMAs
 #endif
-    mbar_wait(mbar, phase);
-    phase ^= 1;
+    mbar_wait(mbar1, kAhead ? phase1 : phase);
+    if (kAhead) phase1 ^= 1; else phase ^= 1;
     tc_fence_after();
 #if DDQC_POLICY_TMEM_PIPE && DDQC_POLICY_F32X2 && DDQC_POLICY_KSPLIT
     // ---- 3 + 4, TMEM reads software-pipelined: 16 columns at a time, the load of the next 16 in flight under the
@@ -392,6 +431,9 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
         }
         if (q & 1) {  // the 32-column pair cb = q / 2 of both thread halves is complete: contract it
           const int cb = q >> 1;
+          // MMA1_AHEAD: D1 has been read completely and the layer-1 MMAs of this tile are done (waited for above), so
+          // the NEXT tile's layer-1 operand tile can be stored now and contracted right behind this tile's layer 2
+          if (kAhead && cb == 1 && has_next) store_a1();
           fence_async_smem();
           tc_fence_before();
           wg_sync(wg);
@@ -410,6 +452,7 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
               }
             }
             if (cb == 1) umma_commit(mbar);
+            if (kAhead && cb == 1 && has_next) issue_mma1();
           }
         }
       }
@@ -473,16 +516,7 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
       }
     }
 #endif
-    {  // prefetch the next tile's observation chunk
-      const long long nrow = (tile + tile_step) * kTileM + row;
-      o0 = make_float4(0.f, 0.f, 0.f, 0.f);
-      o1 = o0;
-      if (tile + tile_step < n_tiles && nrow < n) {
-        const float4* src = reinterpret_cast<const float4*>(obs + nrow * kIn + 8 * half);
-        o0 = __ldg(src);
-        o1 = __ldg(src + 1);
-      }
-    }
+    load_obs(tile + (kAhead ? 2 : 1) * tile_step);  // prefetch: the next tile whose operand tile is not stored yet
     mbar_wait(mbar, phase);
     phase ^= 1;
     tc_fence_after();
