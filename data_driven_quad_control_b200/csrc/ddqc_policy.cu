@@ -122,6 +122,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #ifndef DDQC_POLICY_MMA1_AHEAD
 #define DDQC_POLICY_MMA1_AHEAD 1
 #endif
+// DDQC_POLICY_PDL = 1: programmatic dependent launch.  In a rollout the kernel in front of this one is the env step's
+// one-warp finalisation and the one behind it the next env step, both PDL-aware (ddqc_env.cu): launched with the
+// programmatic-serialisation attribute, this kernel converts its weights / allocates TMEM while the finalisation still
+// runs, waits (griddepcontrol.wait) before it touches the observations, and only then releases its own dependents - the
+// next env step becomes resident on the SMs whose tile streams have ended and issues its state loads under the tail.
+#ifndef DDQC_POLICY_PDL
+#define DDQC_POLICY_PDL 1
+#endif
 #ifndef DDQC_POLICY_DEFER_OUT
 #define DDQC_POLICY_DEFER_OUT 0
 #endif
@@ -313,6 +321,12 @@ policy_mlp_kernel(const float* __restrict__ obs, const long long n, const float*
 
   const long long n_tiles = (n + kTileM - 1) / kTileM;
   const long long tile_step = (long long)gridDim.x * 2;
+#if DDQC_POLICY_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");               // the producer of `obs` has completed
+#if DDQC_POLICY_PDL == 2
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the consumer of `actions` may be scheduled
+#endif
+#endif
   // observation chunk of this thread (row, 8 of the 16 inputs), software-pipelined: the loads of the NEXT tile are
   // issued while the layer-2 MMAs of the current one run, so no tile starts with an exposed global-memory round trip
   float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
@@ -681,7 +695,17 @@ extern "C" int ddqc_policy_mlp_forward(const float* obs, int64_t n, int32_t n_in
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_tiles = (n + kTileM - 1) / kTileM;
   const int grid = (int)((n_tiles + 1) / 2 < sms ? (n_tiles + 1) / 2 : sms);
-  kern<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(obs, (long long)n, W1, b1, W2, b2, W3, b3, n_out,
-                                                                         actions);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cfg.attrs = attr;
+  cfg.numAttrs = DDQC_POLICY_PDL ? 1 : 0;
+  e = cudaLaunchKernelEx(&cfg, kern, obs, (long long)n, W1, b1, W2, b2, W3, b3, (int)n_out, actions);
+  if (e != cudaSuccess) return (int)e;
   return (int)cudaGetLastError();
 }
