@@ -23,7 +23,10 @@
 // memory, panel rows one per thread, trailing update in 4x4 register tiles against the panel held column-major in
 // shared memory); the right-hand side rides along as an extra row, so the forward substitution is free; blocked
 // back-substitution.  These modes are off in every shipped configuration: the kernel is written for clarity, and
-// costs about as much as the solve it follows.
+// costs about 1.7 times the solve it follows (ncu: 39 % of the warp samples wait at the barriers around the one-warp
+// diagonal-block factorisation).  Measured and dropped: a LEFT-looking factorisation that keeps each row's block-column
+// accumulator in registers and never writes the trailing matrix back (every thread streams its own row of L from the
+// workspace: 14.2 ms per 4096 PREVIOUS solves against 13.3 ms - the strided row reads cost more than the write-backs).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -34,7 +37,10 @@ namespace {
 
 constexpr int kT = 256;
 constexpr int kNB = 16;
-constexpr int kMaxSlotsR = 320;
+#ifndef DDQC_REC_BLOCKS
+#define DDQC_REC_BLOCKS 3  // resident CTAs per SM the kernel is compiled for: 2 -> 14.8 ms per 4096 PREVIOUS solves (solve
+#endif                     // + recovery), 3 -> 13.3, 4 -> 13.4 (profiles/r2_ddmpc_recover_variants.log)
+constexpr int kMaxSlotsR = 640;
 constexpr int kSmemLimitR = 227 * 1024;
 
 struct RDims {
@@ -69,7 +75,7 @@ __device__ __forceinline__ double block_sum(double v, double* s_red) {
   return t;
 }
 
-__global__ void __launch_bounds__(kT, 2)
+__global__ void __launch_bounds__(kT, DDQC_REC_BLOCKS)
 ddmpc_recover_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __restrict__ work_counter,
                      const double* __restrict__ u_win, const double* __restrict__ y_win,
                      const double* __restrict__ u_ic, const double* __restrict__ y_ic, const double* __restrict__ y_r,
@@ -195,7 +201,7 @@ ddmpc_recover_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __re
         for (int c = 0; c < kNB; ++c) {
           const double dcc = sD[c * (kNB + 1) + c];
           if (!(dcc > 0.0) && lane == 0) s_bad = 1;
-          const double inv = 1.0 / sqrt(dcc);
+          const double inv = rsqrt(dcc);
           __syncwarp();
           if (lane == c) sD[c * (kNB + 1) + c] = inv;
           if (lane > c && lane < kNB) sD[lane * (kNB + 1) + c] *= inv;
@@ -438,7 +444,7 @@ extern "C" int ddqc_ddmpc_recover(const DdqcMpcConfig* cfg, void* ws, const doub
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int grid = 2 * sms;
+  int grid = DDQC_REC_BLOCKS * sms;
   if (grid > kMaxSlotsR) grid = kMaxSlotsR;
   if (grid > batch) grid = (int)batch;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
