@@ -158,3 +158,18 @@ def test_ppo_policy_commands_match_the_published_genesis_run(curves):
     for i, ax in enumerate(("thrust", "roll", "pitch")):
         d = pixel_distance(curves[f"{ax}_rl"], log[:, 3 + i], float(curves[f"{ax}_px_per_s"]), float(curves[f"{ax}_px_per_m"]))
         assert np.median(d) < 1.5 and np.percentile(d, 90) < 3.0, (ax, np.median(d), np.percentile(d, 90))
+
+
+@pytest.mark.reference
+def test_fixture_is_what_the_digitiser_reads_from_the_reference_figure(tmp_path, curves, monkeypatch):
+    """Build container only: `oracle/digitize_reference_plot.py` run on /root/reference/docs/resources/
+    controller_comparison_plot.png reproduces the committed fixture exactly."""
+    import digitize_reference_plot as dg
+
+    out = tmp_path / "curves.npz"
+    monkeypatch.setattr(dg, "OUT", str(out))
+    dg.main()
+    fresh = np.load(out)
+    assert sorted(fresh.files) == sorted(curves.files)
+    for k in fresh.files:
+        assert np.array_equal(fresh[k], curves[k]), k
