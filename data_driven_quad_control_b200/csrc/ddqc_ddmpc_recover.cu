@@ -246,6 +246,17 @@ ddmpc_recover_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __re
           while ((ti + 1) * (ti + 2) / 2 <= task) ++ti;
           while (ti * (ti + 1) / 2 > task) --ti;
           const int tj = task - ti * (ti + 1) / 2;
+          // the tile's current values are requested FIRST, as double2 rows, so that their L2 latency runs under the
+          // panel product (read-modify-write statements on the same array are not reordered by the compiler: as sixteen
+          // `A[..] -= acc` the tile cost sixteen dependent round trips)
+          double2 cur[4][2];
+          double* tp = A + (size_t)(k1 + 4 * ti) * ld + (k1 + 4 * tj);
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const bool in = k1 + 4 * ti + x <= rp;
+            cur[x][0] = in ? *reinterpret_cast<const double2*>(tp + (size_t)x * ld) : make_double2(0.0, 0.0);
+            cur[x][1] = in ? *reinterpret_cast<const double2*>(tp + (size_t)x * ld + 2) : make_double2(0.0, 0.0);
+          }
           double acc[4][4];
 #pragma unroll
           for (int x = 0; x < 4; ++x)
@@ -269,10 +280,11 @@ ddmpc_recover_kernel(const DdqcMpcConfig cfg, double* __restrict__ ws, int* __re
           for (int x = 0; x < 4; ++x) {
             const int i = k1 + 4 * ti + x;
             if (i > rp) continue;
+            const double cv[4] = {cur[x][0].x, cur[x][0].y, cur[x][1].x, cur[x][1].y};
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
               const int j = k1 + 4 * tj + y;
-              if (j <= i && j < rp) A[(size_t)i * ld + j] -= acc[x][y];
+              if (j <= i && j < rp) tp[(size_t)x * ld + y] = cv[y] - acc[x][y];
             }
           }
         }
