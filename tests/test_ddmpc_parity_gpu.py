@@ -576,3 +576,33 @@ def test_update_cost_threshold_default_size(build_lib):
         assert abs(float(gpu.tracking_cost[0]) - orc.tracking_cost) <= 1e-6 * orc.tracking_cost
         gpu.store_input_output_measurement(orc.optimal_u[0][None], g["y_next"][t][None])
         orc.store_input_output_measurement(orc.optimal_u[0], g["y_next"][t])
+
+
+def test_single_controller_numpy_api_optional_modes(build_lib):
+    """The numpy-in / numpy-out drop-in (`NonlinearDataDrivenMPCController`, the class the reference constructs at
+    controller_creation.py:91-112) with `alpha_reg_type=PREVIOUS` and `update_cost_threshold` passed as the reference passes
+    them: three closed-loop steps against the oracle."""
+    import ddmpc_oracle as mo
+    from data_driven_quad_control_b200.data_driven_mpc.nonlinear_data_driven_mpc_controller import (
+        AlphaRegType,
+        NonlinearDataDrivenMPCController,
+    )
+
+    prm = _small_params()
+    prm.alpha_reg_type = 1
+    u, y, plants = _synthetic_windows(prm, 21, 1, return_plants=True)
+    y_r = np.array([0.25, -0.1, 0.45])
+    kw = {**mo.ctor_kwargs(prm, u[0], y[0], y_r), "update_cost_threshold": 25.0}
+    ctrl = NonlinearDataDrivenMPCController(**{**kw, "alpha_reg_type": AlphaRegType.PREVIOUS})
+    orc = mo.NonlinearDDMPCOracle(**kw)
+    for t in range(3):
+        u0 = ctrl.get_optimal_control_input_at_step(n_step=0)
+        np.testing.assert_allclose(u0, orc.get_optimal_control_input_at_step(0), rtol=0, atol=TOL)
+        y_new = plants[0].step(u0)
+        ctrl.store_input_output_measurement(u_current=u0, y_current=y_new, du_current=ctrl.get_du_value_at_step(n_step=0))
+        orc.store_input_output_measurement(u0, y_new)
+        ctrl.update_and_solve_data_driven_mpc()
+        orc.update_and_solve_data_driven_mpc()
+    np.testing.assert_allclose(ctrl.get_optimal_control_input_at_step(0), orc.get_optimal_control_input_at_step(0), rtol=0, atol=TOL)
+    np.testing.assert_allclose(ctrl._b.alpha_prev[0].cpu().numpy(), orc.alpha_prev, rtol=0, atol=TOL)
+    assert abs(float(ctrl._b.tracking_cost[0]) - orc.tracking_cost) <= 1e-6 * max(1.0, orc.tracking_cost)
